@@ -1,0 +1,389 @@
+"""CPU oracle for the NFDPM Glow hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The
+shipped package (``normalizing-flow-with-diffusion-prior-model_b200/``) never does.
+
+It is a *functional* restatement of the reference algorithm (the reference is a tree of
+``nn.Module`` objects): every function takes plain tensors / a flat ``state_dict`` with the
+reference's key names and runs in fp32 on the CPU with fp64 accumulators, exactly as the
+reference's trainers do.  Each function cites the reference lines it follows
+(paths relative to the reference root).
+
+Parity status: PINNED.  ``oracle/make_golden.py`` imports the unmodified reference
+package in the build container, runs it on seeded weights/inputs and writes
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this file against those
+vectors (the reference's own tests hold no golden values — only round-trip properties —
+so outputs of the reference run here are the pin).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+LOG_2PI = float(np.log(2 * np.pi))  # normalizing_flow/prior.py:23
+
+
+# --------------------------------------------------------------------------- primitives
+def squeeze2x2(x: Tensor) -> Tensor:
+    """Space-to-depth, out channel = c*4 + h1*2 + w1 (normalizing_flow/transforms.py:226)."""
+    b, c, h, w = x.shape
+    v = x.reshape(b, c, h // 2, 2, w // 2, 2)          # b c h h1 w w1
+    return v.permute(0, 1, 3, 5, 2, 4).reshape(b, c * 4, h // 2, w // 2)
+
+
+def unsqueeze2x2(y: Tensor) -> Tensor:
+    """Depth-to-space, inverse of :func:`squeeze2x2` (normalizing_flow/transforms.py:238)."""
+    b, c4, h, w = y.shape
+    v = y.reshape(b, c4 // 4, 2, 2, h, w)               # b c c1 c2 h w
+    return v.permute(0, 1, 4, 2, 5, 3).reshape(b, c4 // 4, h * 2, w * 2)
+
+
+def actnorm_stats(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """Data-dependent ActNorm parameters (normalizing_flow/transforms.py:74-78).
+
+    scale = -log(std_unbiased + 1e-6), bias = -mean, both per channel, shape (C,1,1)."""
+    scale = -torch.log(x.std(dim=(0, 2, 3)) + 1e-6)
+    bias = -x.mean(dim=(0, 2, 3))
+    return scale.reshape(-1, 1, 1), bias.reshape(-1, 1, 1)
+
+
+def actnorm_fwd(x: Tensor, scale: Tensor, bias: Tensor) -> Tuple[Tensor, Tensor]:
+    """y = exp(scale)*(x+bias); log-det term = H*W*sum(scale) (transforms.py:80-81)."""
+    h, w = x.shape[2:]
+    return torch.exp(scale) * (x + bias), h * w * scale.sum()
+
+
+def actnorm_inv(y: Tensor, scale: Tensor, bias: Tensor) -> Tensor:
+    """x = y*exp(-scale) - bias (transforms.py:93)."""
+    return y * torch.exp(-scale) - bias
+
+
+def invconv_fwd(x: Tensor, weight: Tensor) -> Tuple[Tensor, Tensor]:
+    """1x1 conv with a dense CxC weight; log-det = H*W*log|det W| computed in fp64 and cast
+    to fp32 (transforms.py:130-132)."""
+    h, w = x.shape[2:]
+    c = weight.shape[0]
+    ld = h * w * torch.slogdet(weight.reshape(c, c).double())[1].float()
+    return F.conv2d(x, weight), ld
+
+
+def invconv_inv(y: Tensor, weight: Tensor) -> Tensor:
+    """1x1 conv with the fp32 dense inverse (transforms.py:144)."""
+    c = weight.shape[0]
+    return F.conv2d(y, weight.reshape(c, c).inverse().reshape(c, c, 1, 1))
+
+
+def zeroconv(x: Tensor, weight: Tensor, bias: Tensor, logs: Tensor) -> Tensor:
+    """ZeroConv2d: (conv3x3(x, pad 1) + bias) * exp(3*logs) (normalizing_flow/utils.py:36-44)."""
+    return F.conv2d(x, weight, bias, padding=1) * torch.exp(logs * 3.0)
+
+
+def coupling_net(x_a: Tensor, sd: Dict[str, Tensor], pre: str, init: bool = False) -> Tensor:
+    """conv3x3(no bias) -> ActNorm -> ReLU -> conv1x1 -> ActNorm -> ReLU -> ZeroConv3x3
+    (normalizing_flow/utils.py:83-89, :64-69).  ``pre`` is the prefix of ``...affcoupling.net.``.
+    With ``init`` the inner ActNorms whose ``is_initialized`` flag is 0 are set from the data
+    first (transforms.py:74-78 reached through utils.py:69)."""
+    h = x_a
+    for idx, pad in (("0", 1), ("2", 0)):
+        base = f"{pre}{idx}._Conv2dActNorm__"
+        h = F.conv2d(h, sd[base + "conv.weight"], None, padding=pad)
+        if init and int(sd[base + "actnorm.is_initialized"]) == 0:
+            s, b = actnorm_stats(h)
+            sd[base + "actnorm.scale"] = s
+            sd[base + "actnorm.bias"] = b
+            sd[base + "actnorm.is_initialized"] = torch.tensor(1, dtype=torch.uint8)
+        h = torch.relu(actnorm_fwd(h, sd[base + "actnorm.scale"], sd[base + "actnorm.bias"])[0])
+    return zeroconv(h, sd[pre + "4.weight"], sd[pre + "4.bias"], sd[pre + "4.logs"])
+
+
+def coupling_fwd(x: Tensor, sd: Dict[str, Tensor], pre: str, init: bool = False) -> Tuple[Tensor, Tensor]:
+    """Affine coupling forward (transforms.py:179-184): first half of the net output is the
+    log-scale, second half the shift; scale = sigmoid(log_scale + 2); y_b = (x_b + t)*scale;
+    per-sample log-det = sum log(scale + 1e-6)."""
+    x_a, x_b = x.chunk(2, dim=1)
+    log_s, t = coupling_net(x_a, sd, pre, init).chunk(2, dim=1)
+    s = torch.sigmoid(log_s + 2.0)
+    y = torch.cat([x_a, (x_b + t) * s], dim=1)
+    return y, torch.log(s + 1e-6).reshape(x.shape[0], -1).sum(1)
+
+
+def coupling_inv(y: Tensor, sd: Dict[str, Tensor], pre: str) -> Tensor:
+    """Affine coupling inverse (transforms.py:196-200): x_b = y_b/(scale + 1e-6) - t."""
+    y_a, y_b = y.chunk(2, dim=1)
+    log_s, t = coupling_net(y_a, sd, pre).chunk(2, dim=1)
+    s = torch.sigmoid(log_s + 2.0)
+    return torch.cat([y_a, y_b / (s + 1e-6) - t], dim=1)
+
+
+def gaussian_logp(x: Tensor, mean: Tensor, logs: Tensor) -> Tensor:
+    """Diagonal Gaussian log-density summed over non-batch dims (normalizing_flow/prior.py:36-37)."""
+    v = -0.5 * (LOG_2PI + 2.0 * logs + ((x - mean) ** 2.0) * torch.exp(-2.0 * logs))
+    return v.reshape(x.shape[0], -1).sum(1)
+
+
+def split_prior_params(y: Tensor, sd: Dict[str, Tensor], pre: str) -> Tuple[Tensor, Tensor]:
+    """mean, logs = chunk(ZeroConv3x3(y)) or zeros when the prior is not learned
+    (transforms.py:266-268)."""
+    if (pre + "conv.weight") in sd:
+        h = zeroconv(y, sd[pre + "conv.weight"], sd[pre + "conv.bias"], sd[pre + "conv.logs"])
+    else:
+        h = torch.zeros(y.shape[0], 2 * y.shape[1], *y.shape[2:])
+    mean, logs = h.chunk(2, dim=1)
+    return mean, logs
+
+
+# --------------------------------------------------------------------------- step / model
+def _step_prefixes(L: int, K: int) -> List[List[str]]:
+    """Key prefixes per level in execution order (normalizing_flow/glow.py:163-170)."""
+    lv = [[f"blocks.{i}.flows.{j}." for j in range(K)] for i in range(L - 1)]
+    lv.append([f"final_flows.{j}." for j in range(K)])
+    return lv
+
+
+def step_fwd(x: Tensor, sd: Dict[str, Tensor], pre: str, ld: Tensor, init: bool = False) -> Tensor:
+    """StepFlow forward: ActNorm -> InvConv2d -> AffineCoupling (glow.py:46-48).
+    ``ld`` is mutated in place like the reference's ``log_det_jac +=``."""
+    if init and int(sd[pre + "actnorm.is_initialized"]) == 0:
+        s, b = actnorm_stats(x)
+        sd[pre + "actnorm.scale"], sd[pre + "actnorm.bias"] = s, b
+        sd[pre + "actnorm.is_initialized"] = torch.tensor(1, dtype=torch.uint8)
+    y, d = actnorm_fwd(x, sd[pre + "actnorm.scale"], sd[pre + "actnorm.bias"])
+    ld += d
+    y, d = invconv_fwd(y, sd[pre + "invconv2d.weight"])
+    ld += d
+    y, d = coupling_fwd(y, sd, pre + "affcoupling.net.", init)
+    ld += d
+    return y
+
+
+def step_inv(y: Tensor, sd: Dict[str, Tensor], pre: str) -> Tensor:
+    """StepFlow inverse: coupling^-1 -> invconv^-1 -> actnorm^-1 (glow.py:60-62)."""
+    x = coupling_inv(y, sd, pre + "affcoupling.net.")
+    x = invconv_inv(x, sd[pre + "invconv2d.weight"])
+    return actnorm_inv(x, sd[pre + "actnorm.scale"], sd[pre + "actnorm.bias"])
+
+
+def glow_transform(sd: Dict[str, Tensor], x: Tensor, L: int, K: int, ld: Tensor,
+                   logp: Optional[Tensor], init: bool = False) -> Tuple[List[Tensor], Tensor, Optional[Tensor]]:
+    """Glow.transform (glow.py:172-201 with GlowBlock.transform :90-114 and Split.transform
+    transforms.py:286-290).  Returns ([z_0..z_{L-1}], ld, logp); ld/logp mutated in place.
+    ``logp=None`` disables the split priors (transforms.py:287).  ``init=True`` performs the
+    data-dependent ActNorm initialisation on flags that are still 0 and writes the new
+    parameters back into ``sd``."""
+    levels = _step_prefixes(L, K)
+    zs: List[Tensor] = []
+    y = x
+    for i in range(L - 1):
+        y = squeeze2x2(y)
+        for pre in levels[i]:
+            y = step_fwd(y, sd, pre, ld, init)
+        y, z = y.chunk(2, dim=1)
+        if logp is not None:
+            mean, logs = split_prior_params(y, sd, f"blocks.{i}.split.")
+            logp += gaussian_logp(z, mean, logs)
+        zs.append(z)
+    y = squeeze2x2(y)
+    for pre in levels[L - 1]:
+        y = step_fwd(y, sd, pre, ld, init)
+    zs.append(y)
+    return zs, ld, logp
+
+
+def glow_invert(sd: Dict[str, Tensor], latents: Sequence[Tensor], L: int, K: int,
+                temperature: float = 1.0, eps: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """Glow.invert (glow.py:203-228, GlowBlock.invert :116-137, Split.invert
+    transforms.py:292-309).  ``latents`` holds either all L parts or only the last one; in the
+    latter case the split latents are drawn as mean + exp(logs)*temperature*eps
+    (prior.py:49-50) with ``eps[i]`` the standard-normal draw for block i (zeros if None)."""
+    levels = _step_prefixes(L, K)
+    y = latents[-1]
+    for pre in reversed(levels[L - 1]):
+        y = step_inv(y, sd, pre)
+    y = unsqueeze2x2(y)
+    for n, i in enumerate(reversed(range(L - 1))):
+        idx = -(n + 2)
+        z = latents[idx] if len(latents) >= -idx else None   # utils.py:295-300 get_item
+        if z is None:
+            mean, logs = split_prior_params(y, sd, f"blocks.{i}.split.")
+            e = eps[i] if eps is not None else torch.zeros_like(mean)
+            z = mean + (torch.exp(logs) * temperature) * e
+        y = torch.cat([y, z], dim=1)
+        for pre in reversed(levels[i]):
+            y = step_inv(y, sd, pre)
+        y = unsqueeze2x2(y)
+    return y
+
+
+def gaussian_prior_params(psd: Dict[str, Tensor], shape: Sequence[int]) -> Tuple[Tensor, Tensor]:
+    """GaussianPrior: ZeroConv2d(2C,2C) applied to an all-zero map, chunked into mean/logs
+    (normalizing_flow/prior.py:79-81).  The conv of zeros is exactly its bias, so this is
+    bias*exp(3*logs) per channel — restated literally with the conv to stay faithful."""
+    b, c, h, w = shape
+    z = torch.zeros(b, 2 * c, h, w)
+    key = "_GaussianPrior__conv."
+    if (key + "weight") in psd:
+        z = zeroconv(z, psd[key + "weight"], psd[key + "bias"], psd[key + "logs"])
+    mean, logs = z.chunk(2, dim=1)
+    return mean, logs
+
+
+def gaussian_prior_logp(psd: Dict[str, Tensor], z: Tensor) -> Tensor:
+    """GaussianPrior.compute_log_prob (prior.py:70-83)."""
+    mean, logs = gaussian_prior_params(psd, z.shape)
+    return gaussian_logp(z, mean, logs)
+
+
+def gaussian_prior_sample(psd: Dict[str, Tensor], shape: Sequence[int], temperature: float, eps: Tensor) -> Tensor:
+    """GaussianPrior.sample (prior.py:85-99, :49-50) with the normal draw supplied."""
+    mean, logs = gaussian_prior_params(psd, shape)
+    return mean + (torch.exp(logs) * temperature) * eps
+
+
+# --------------------------------------------------------------------------- step glue (a23)
+def preprocess_batch(batch: Tensor, n_bits: int, n_bins: float) -> Tensor:
+    """[0,1] images -> n_bits quantised, centred (normalizing_flow/utils.py:188-196)."""
+    v = batch * 255
+    if n_bits < 8:
+        v = torch.floor(v / 2 ** (8 - n_bits))
+    return v / n_bins - 0.5
+
+
+def postprocess_batch(batch: Tensor, n_bins: float) -> Tensor:
+    """Inverse of the above to uint8 (normalizing_flow/utils.py:210)."""
+    return torch.clip(torch.floor((batch + 0.5) * n_bins) * (256.0 / n_bins), 0, 255).to(torch.uint8)
+
+
+def bpd_loss(log_likelihood: Tensor, n_bins: float, n_pixel: float) -> Tensor:
+    """Bits per dimension (normalizing_flow/utils.py:255-256)."""
+    return ((np.log(n_bins) * n_pixel - log_likelihood) * (np.log2(np.e) / n_pixel)).mean(dim=0)
+
+
+def nll_bpd(sd: Dict[str, Tensor], psd: Dict[str, Tensor], x: Tensor, L: int, K: int,
+            n_bins: float, n_pixel: float) -> Tensor:
+    """The likelihood-evaluation recipe of normalizing_flow/trainer.py:154-161 /:46-52."""
+    b = x.shape[0]
+    ld = torch.zeros(b, dtype=torch.float64)
+    lp = torch.zeros(b, dtype=torch.float64)
+    zs, ld, lp = glow_transform(sd, x, L, K, ld, lp)
+    lp += gaussian_prior_logp(psd, zs[-1])
+    return bpd_loss(ld + lp, n_bins, n_pixel)
+
+
+def output_shapes(L: int, in_channels: int, size: int) -> List[Tuple[int, int, int]]:
+    """Latent shapes (normalizing_flow/utils.py:93-117)."""
+    out = []
+    for _ in range(L - 1):
+        if size % 2 != 0:
+            raise ValueError("The input dimension is not divisible by 2!")
+        in_channels *= 2
+        size //= 2
+        out.append((in_channels, size, size))
+    out.append((in_channels * 4, size // 2, size // 2))
+    return out
+
+
+# --------------------------------------------------------------------------- seeded weights
+def glow_param_shapes(in_channel: int, L: int, K: int, learn_prior: bool = True,
+                      n_features: int = 512) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(key, shape, dtype) in the reference's state_dict order (verified against the live
+    reference module by oracle/make_golden.py)."""
+    out: List[Tuple[str, Tuple[int, ...], str]] = []
+
+    def step(pre: str, c: int):
+        out.append((pre + "actnorm.scale", (c, 1, 1), "f"))
+        out.append((pre + "actnorm.bias", (c, 1, 1), "f"))
+        out.append((pre + "actnorm.is_initialized", (), "u8"))
+        out.append((pre + "invconv2d.weight", (c, c, 1, 1), "f"))
+        n = pre + "affcoupling.net."
+        for idx, cin, k in (("0", c // 2, 3), ("2", n_features, 1)):
+            out.append((f"{n}{idx}._Conv2dActNorm__conv.weight", (n_features, cin, k, k), "f"))
+            out.append((f"{n}{idx}._Conv2dActNorm__actnorm.scale", (n_features, 1, 1), "f"))
+            out.append((f"{n}{idx}._Conv2dActNorm__actnorm.bias", (n_features, 1, 1), "f"))
+            out.append((f"{n}{idx}._Conv2dActNorm__actnorm.is_initialized", (), "u8"))
+        out.append((n + "4.weight", (c, n_features, 3, 3), "f"))
+        out.append((n + "4.bias", (c,), "f"))
+        out.append((n + "4.logs", (1, c, 1, 1), "f"))
+
+    for i in range(L - 1):
+        c = 4 * (2 ** i) * in_channel
+        for j in range(K):
+            step(f"blocks.{i}.flows.{j}.", c)
+        if learn_prior:
+            out.append((f"blocks.{i}.split.conv.weight", (c, c // 2, 3, 3), "f"))
+            out.append((f"blocks.{i}.split.conv.bias", (c,), "f"))
+            out.append((f"blocks.{i}.split.conv.logs", (1, c, 1, 1), "f"))
+    c = 2 ** (L + 1) * in_channel
+    for j in range(K):
+        step(f"final_flows.{j}.", c)
+    return out
+
+
+def seeded_state(in_channel: int, L: int, K: int, seed: int, learn_prior: bool = True,
+                 initialized: bool = True, zero_sigma: float = 0.02) -> Tuple[Dict[str, Tensor], Dict[str, Tensor]]:
+    """Deterministic, *non-degenerate* weights for parity work (numpy PCG64, so the same
+    bytes are regenerated on any box).  ZeroConv2d tensors get N(0, zero_sigma) noise because
+    at the reference's zero init the coupling nets output exactly 0 and conv precision would
+    be untestable (SURVEY.md §7 hard part 1).  Returns (flow state_dict, GaussianPrior state_dict)."""
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, Tensor] = {}
+    for key, shape, kind in glow_param_shapes(in_channel, L, K, learn_prior):
+        if kind == "u8":
+            sd[key] = torch.tensor(1 if initialized else 0, dtype=torch.uint8)
+            continue
+        if key.endswith("invconv2d.weight"):
+            c = shape[0]
+            q, _ = np.linalg.qr(rng.standard_normal((c, c)))
+            w = q + 0.05 * rng.standard_normal((c, c))          # well conditioned, |det| != 1
+            arr = w.reshape(shape)
+        elif key.endswith("actnorm.scale"):
+            arr = 0.1 * rng.standard_normal(shape)
+        elif key.endswith("actnorm.bias"):
+            arr = 0.1 * rng.standard_normal(shape)
+        elif key.endswith("_Conv2dActNorm__conv.weight"):
+            fan_in = shape[1] * shape[2] * shape[3]
+            arr = rng.standard_normal(shape) / math.sqrt(fan_in)
+        elif key.endswith(".logs"):
+            arr = 0.1 * rng.standard_normal(shape)
+        elif key.endswith(".bias"):
+            arr = zero_sigma * rng.standard_normal(shape)
+        else:  # ZeroConv weights (coupling net.4 / split.conv)
+            fan_in = shape[1] * 9
+            arr = zero_sigma * rng.standard_normal(shape) * (16.0 / math.sqrt(fan_in))
+        sd[key] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+    cz = 2 ** (L + 1) * in_channel
+    psd: Dict[str, Tensor] = {}
+    if learn_prior:
+        psd["_GaussianPrior__conv.weight"] = torch.from_numpy(
+            (0.01 * rng.standard_normal((2 * cz, 2 * cz, 3, 3))).astype(np.float32))
+        psd["_GaussianPrior__conv.bias"] = torch.from_numpy((0.1 * rng.standard_normal((2 * cz,))).astype(np.float32))
+        psd["_GaussianPrior__conv.logs"] = torch.from_numpy(
+            (0.1 * rng.standard_normal((1, 2 * cz, 1, 1))).astype(np.float32))
+    return sd, psd
+
+
+def seeded_input(shape: Sequence[int], seed: int, n_bits: int = 5) -> Tensor:
+    """Synthetic dequantised images in [-0.5, 0.5) as the trainer feeds them
+    (normalizing_flow/trainer.py:152-155), from numpy PCG64."""
+    rng = np.random.default_rng(seed)
+    n_bins = 2.0 ** n_bits
+    img = torch.from_numpy(rng.random(tuple(shape), dtype=np.float32))
+    noise = torch.from_numpy(rng.random(tuple(shape), dtype=np.float32))
+    return preprocess_batch(img, n_bits, n_bins) + noise / n_bins
+
+
+def state_checksum(sd: Dict[str, Tensor]) -> Tuple[float, float]:
+    """(sum, abs-sum) in fp64 over all float tensors — used to prove regenerated weights
+    equal the ones the golden outputs were made with."""
+    s = a = 0.0
+    for k in sorted(sd):
+        t = sd[k]
+        if t.dtype.is_floating_point:
+            s += float(t.double().sum())
+            a += float(t.double().abs().sum())
+    return s, a
