@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — Glow L3/K16 32x32 forward(+log-det, +log-p) and inverse images/s on 1..8 B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, launched
+under torchrun for N>1 (one rank per GPU).  One "step" = one pass of the hot path over one batch of synthetic
+images: Glow.transform + GaussianPrior.compute_log_prob (x -> z, log-det, log-p) followed by Glow.invert (z -> x).
+Rank 0 prints ONE JSON line.
+
+  value        images/s (whole job), inputs already resident in HBM, device-timed with CUDA events, L2 flushed
+               between timed steps, max over ranks
+  e2e          same metric through the public module API with HOST (pinned) inputs: H2D of the batch and D2H of
+               the per-image log-likelihood and the decoded images inside the timed region
+  roofline     the dominant kernel (coupling-net 512x512 GEMM at level 0) timed alone with CUDA events:
+               achieved TFLOP/s vs the measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (port of the reference's algorithm, torch-CPU fp32, all host threads) on a bounded
+               sample of the same workload, rank 0 / N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "normalizing-flow-with-diffusion-prior-model_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CFG = dict(in_channel=3, L=3, K=16, S=32, batch=128)          # BASELINE.json configs[1]
+WORKLOAD = "Glow L3 K16, CIFAR-10 shape 3x32x32, batch 128 per GPU, fwd+logdet+logp then inverse"
+METRIC = "Glow L3/K16 32x32 fwd+logdet & inverse imgs/sec"
+FLOP_PER_IMG_FWD = 4.0119e9                                   # SURVEY.md §8 (verified with torch flop counter)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        for r in rows:
+            f = [v.strip() for v in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step_fn(B: int):
+    """The reference's CPU path for this workload (oracle port): returns (fn, description)."""
+    import torch
+    from oracle import glow_oracle as O
+    c, L, K, S = CFG["in_channel"], CFG["L"], CFG["K"], CFG["S"]
+    sd, psd = O.seeded_state(c, L, K, 0)
+    x = O.seeded_input((B, c, S, S), 1)
+
+    def step():
+        with torch.no_grad():
+            ld = torch.zeros(B, dtype=torch.float64)
+            lp = torch.zeros(B, dtype=torch.float64)
+            zs, ld, lp = O.glow_transform(sd, x, L, K, ld, lp)
+            lp += O.gaussian_prior_logp(psd, zs[-1])
+            return O.glow_invert(sd, zs, L, K)
+    return step
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host CPU (oracle port; the reference is pure Python
+    on torch, so the port IS torch-CPU fp32 running the same op sequence), all host threads."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 32                                   # bounded sample of the 128-image batch: ~1-2 s per step on 8+ cores
+    step = oracle_step_fn(B)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = B / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"batch {B} of {CFG['batch']} per step"},
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
+                             "sample": f"batch {B} of {CFG['batch']}, {steps} steps, os.cpu_count={os.cpu_count()}"},
+            "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG["batch"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import normalizing_flow as nf
+    from normalizing_flow import _native as N, _engine as E
+    from oracle import glow_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c, L, K, S, B = CFG["in_channel"], CFG["L"], CFG["K"], CFG["S"], args.batch
+    mode = E.precision()
+
+    # random-init weights of the named architecture (seeded, non-degenerate ZeroConvs), synthetic dequantised images
+    sd, psd = O.seeded_state(c, L, K, 0)
+    flow = nf.Glow(c, L, K).to(dev)
+    flow.load_state_dict(sd)
+    prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
+    prior.load_state_dict(psd)
+    x_host = O.seeded_input((B, c, S, S), 1 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    ll_host = torch.empty(B, dtype=torch.float64).pin_memory()
+    xr_host = torch.empty(B, c, S, S).pin_memory()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_dev():
+        ld, lp = nf.initialize_with_zeros(2, B, dev)
+        zs, ld, lp = flow.transform(x_dev, ld, lp)
+        lp += prior.compute_log_prob(zs[-1])
+        xr = flow.invert(zs)
+        return ld + lp, xr
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        ld, lp = nf.initialize_with_zeros(2, B, dev)
+        zs, ld, lp = flow.transform(xd, ld, lp)
+        lp += prior.compute_log_prob(zs[-1])
+        xr = flow.invert(zs)
+        ll_host.copy_(ld + lp, non_blocking=True)
+        xr_host.copy_(xr, non_blocking=True)
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for s, e in ev:
+            flush_buf.zero_()                      # evict L2 between timed iterations (not timed)
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tot = sum(s.elapsed_time(e) for s, e in ev)          # ms
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_dev()
+            step_e2e()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if rank == 0 else None
+        t_wall0 = time.time()
+        l0 = N.launch_count
+        ms = timed(step_dev, args.steps)
+        launches = N.launch_count - l0
+        ms_e2e = timed(step_e2e, args.steps)
+        t_wall1 = time.time()
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+        ll, xr = step_dev()
+        torch.cuda.synchronize()
+        recon = float((xr - x_dev).abs().max())
+
+        # ---- roofline of the dominant kernel: coupling-net conv2 (512x512) GEMM at level 0, M = B*256
+        hbm, tf_burst, tf_sust, src = peaks()
+        M, F = B * (S // 2) * (S // 2), 512
+        dt = torch.float32 if mode == "fp32" else torch.bfloat16
+        a = (torch.randn(M, F, device=dev) * 0.5).to(dt)
+        w = (torch.randn(F, F, device=dev) * 0.05).to(dt)
+        d = torch.empty(M, F, dtype=dt, device=dev)
+        es, eb = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
+        for _ in range(3):
+            N.gemm_nt(a, F, w, F, d, F, M, F, F, N.EPI_ACTNORM_RELU, es, eb)
+        reps = 10
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for s, e in evs:
+            flush_buf.zero_()
+            s.record()
+            N.gemm_nt(a, F, w, F, d, F, M, F, F, N.EPI_ACTNORM_RELU, es, eb)
+            e.record()
+        torch.cuda.synchronize()
+        k_ms = sum(s.elapsed_time(e) for s, e in evs) / reps
+        achieved = 2.0 * M * F * F / (k_ms * 1e-3) / 1e12
+
+    if rank == 0:
+        imgs = B * world * args.steps
+        value = imgs / (ms * 1e-3)
+        e2e_v = imgs / (ms_e2e * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": mode, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world} (independent shards, "
+                       "no data-path collective)", "l2": "flushed between timed steps (256 MiB memset)",
+                       "weights": "seeded random init, non-zero ZeroConvs"},
+            "e2e": {"value": e2e_v, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": ll_host.numel() * 8 + xr_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": ("gemm_nt_f32_kernel (CUDA-core fp32)" if mode == "fp32" else
+                                                        "gemm_nt_tc_kernel (tcgen05 bf16)") + f" M={M} N=512 K=512",
+                         "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
+                         "traffic": None, "peak_source": f"{src} bf16 burst (kernel timed alone)", "kernel_ms": k_ms},
+            "clocks": clocks,
+            "checks": {"recon_max_abs_err": recon, "step_tflops": 2 * FLOP_PER_IMG_FWD * B / (ms / args.steps * 1e-3) / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            Bs = 32
+            st = oracle_step_fn(Bs)
+            st()
+            best = 1e30
+            for _ in range(3):
+                t0 = time.perf_counter()
+                st()
+                best = min(best, time.perf_counter() - t0)
+            line["cpu_baseline"] = {"value": Bs / best, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"oracle (torch-CPU fp32) on batch {Bs} of {B}, best of 3, "
+                                              f"os.cpu_count={os.cpu_count()}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

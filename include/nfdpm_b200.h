@@ -1,0 +1,176 @@
+/*
+ * nfdpm_b200.h — C ABI of libnfdpm_b200.so: hand-written sm_100a kernels for the Glow flow
+ * hot path of NFDPM (reference: davitpapikyan/Normalizing-Flow-with-Diffusion-Prior-Model).
+ *
+ * The reference is pure Python on PyTorch; it has no FFI of its own.  The "interface each entry
+ * point replaces" is therefore the reference's Python call site (file:line below, relative to the
+ * reference root), and the binding a maintainer adds is a ctypes stub (see INTEGRATION.md and
+ * normalizing-flow-with-diffusion-prior-model_b200/normalizing_flow/_native.py).
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: raw DEVICE pointers, explicit sizes/strides (in ELEMENTS), stream last;
+ *   - return 0 on success, non-zero on failure (nfdpm_last_error_string() explains, thread-local);
+ *   - never allocate, never synchronise, never touch the legacy default stream implicitly: all
+ *     work is enqueued on `stream`; scratch memory is passed in by the caller;
+ *   - flow tensors are NCHW fp32 ("[B,C,P]" below, P = H*W) with an explicit batch stride so
+ *     channel halves of a wider tensor can be read/written in place (chunk/concat without copies);
+ *   - coupling-network activations are pixel-major rows "[M,ld]" (M = B*P, channel fastest),
+ *     fp32 (NFDPM_F32, exact CUDA-core path) or bf16 (NFDPM_BF16, tcgen05 tensor-core path);
+ *   - no CPU fallback exists anywhere in the library.
+ */
+#ifndef NFDPM_B200_H_
+#define NFDPM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFDPM_VERSION 100
+
+/* element / accumulator type codes */
+#define NFDPM_F32 0
+#define NFDPM_F64 1
+#define NFDPM_BF16 2
+
+/* GEMM epilogues */
+#define NFDPM_EPI_RAW 0          /* D = acc                                   */
+#define NFDPM_EPI_ACTNORM_RELU 1 /* D = max(0, exp(scale[n]) * (acc + bias[n])) (utils.py:69,84-87) */
+
+typedef void* nfdpm_stream_t; /* cudaStream_t */
+
+int nfdpm_version(void);
+const char* nfdpm_last_error_string(void);
+/* Number of SMs of the current device (grid sizing on the host side); <0 on error. */
+int nfdpm_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K-LU + fold: per-step parameter preparation, batched over n steps in ONE launch per 16 items.
+ * Replaces torch.slogdet(weight.double()) (normalizing_flow/transforms.py:131) and
+ * weight.inverse() (transforms.py:144), and folds ActNorm (transforms.py:80, :93) into the 1x1 mix:
+ *   forward  y = W*diag(exp(s))*(x + b)        -> fwd_mt[i*C+o] = W[o][i]*exp(s[i]),  fwd_beta[o] = sum_i fwd_mt[i][o]*b[i]
+ *   inverse  x = diag(exp(-s))*W^-1*y - b      -> inv_mt[i*C+o] = exp(-s[o])*Winv[o][i], inv_beta[o] = -b[o]
+ *   logdet[0] = log|det W| (fp64 partial-pivot LU, rounded to fp32) + sum(s)
+ * weight==NULL means identity, scale/bias==NULL mean zeros.  Any output pointer may be NULL.
+ * lu_ws: 2*C*C doubles of scratch per item (required when weight != NULL).
+ */
+typedef struct {
+  const float* weight; /* [C,C] row = output channel (InvConv2d.weight squeezed) */
+  const float* scale;  /* [C] ActNorm.scale */
+  const float* bias;   /* [C] ActNorm.bias  */
+  int32_t C;
+  int32_t pad_;
+  float* fwd_mt;
+  float* fwd_beta;
+  float* inv_mt;
+  float* inv_beta;
+  float* winv;   /* [C,C] row-major W^-1 (fp32) */
+  float* logdet; /* [1] */
+  double* lu_ws; /* [2*C*C] */
+} nfdpm_mix_item;
+int nfdpm_mix_prepare(const nfdpm_mix_item* items_host, int n, nfdpm_stream_t stream);
+
+/* K-A / K-A^-1: y[b,o,p] = sum_i mt[i*C+o]*x[b,i,p] + beta[o]  (fused ActNorm + 1x1 conv,
+ * transforms.py:80 + :132 forward; :144 + :93 inverse).  x,y: [B,C,P] with batch strides. */
+int nfdpm_channel_mix(const float* x, float* y, const float* mt, const float* beta, int B, int C, int P,
+                      int64_t x_bstride, int64_t y_bstride, nfdpm_stream_t stream);
+
+/* Stand-alone ActNorm (transforms.py:80 / :93): inverse==0: y = exp(s[c])*(x+b[c]); else y = x*exp(-s[c]) - b[c]. */
+int nfdpm_actnorm_apply(const float* x, float* y, const float* scale, const float* bias, int B, int C, int P,
+                        int inverse, nfdpm_stream_t stream);
+
+/* Data-dependent ActNorm statistics (transforms.py:74-78): scale_out[c] = -log(std_unbiased + 1e-6),
+ * bias_out[c] = -mean.  layout 0: x is [B,C,P] (NCHW, batch stride xs); layout 1: x is rows [M=B*P, ld=xs],
+ * channel fastest.  Written straight into the parameter storage. */
+int nfdpm_channel_stats(const float* x, int layout, int B, int C, int P, int64_t xs, float* scale_out,
+                        float* bias_out, nfdpm_stream_t stream);
+
+/* Squeeze / unsqueeze (transforms.py:226 / :238): out channel = c*4 + h1*2 + w1.
+ * squeeze: x [B,C,H,W] -> y [B,4C,H/2,W/2]; unsqueeze: x [B,C,H,W] -> y [B,C/4,2H,2W]. */
+int nfdpm_squeeze(const float* x, float* y, int B, int C, int H, int W, int64_t x_bstride, int64_t y_bstride,
+                  nfdpm_stream_t stream);
+int nfdpm_unsqueeze(const float* x, float* y, int B, int C, int H, int W, int64_t x_bstride, int64_t y_bstride,
+                    nfdpm_stream_t stream);
+/* chunk / concat without torch: copy a [B,Cn,P] channel block between strided tensors (transforms.py:285, :308). */
+int nfdpm_copy_channels(const float* src, float* dst, int B, int Cn, int P, int64_t src_bstride,
+                        int64_t dst_bstride, nfdpm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Coupling network (normalizing_flow/utils.py:83-89) as three GEMMs over pixel-major rows.
+ *   conv3x3(C/2->512): A1 = im2col(x_a) [M, ld>=9*C/2], column = c*9 + ky*3 + kx (== the layout of
+ *                      nn.Conv2d.weight.view(512,-1)), zero padded up to ld        -> nfdpm_im2col3x3
+ *   conv1x1(512->512): plain GEMM
+ *   ZeroConv3x3(512->C): "taps as N": PM[m, tap*C+co] = sum_ci h2[m,ci]*W3[co,ci,tap] (one GEMM, N=9C);
+ *                      the 3x3 gather-add over neighbouring pixels happens in nfdpm_coupling_apply.
+ */
+int nfdpm_im2col3x3(const float* x, void* out, int out_dtype, int B, int Cin, int H, int W, int64_t x_bstride,
+                    int64_t ld_out, nfdpm_stream_t stream);
+
+/* Generic gather + cast used to lay out weights for the GEMMs (no arithmetic):
+ *   out[(a*nb + b)*ld_out + k] = in[a*sa + b*sb + k*sk]  for a<na, b<nb, k<nk; columns nk..ld_out-1 and
+ *   rows na*nb..rows_out-1 are zero-filled. */
+int nfdpm_pack_matrix(const float* in, void* out, int out_dtype, int na, int nb, int nk, int64_t sa, int64_t sb,
+                      int64_t sk, int64_t ld_out, int rows_out, nfdpm_stream_t stream);
+
+/* D[M,N] = epilogue(A[M,K] * Bw[N,K]^T).  A, Bw: in_dtype (NFDPM_F32 -> CUDA-core fp32 kernel,
+ * NFDPM_BF16 -> tcgen05/TMEM kernel, fp32 accumulate); D: out_dtype (F32 or BF16).  K must be a multiple
+ * of 16 (F32) / 64 (BF16) and lda, ldb, ldd multiples of 8.  Replaces nn.Conv2d.forward at
+ * utils.py:69 (x2) and ZeroConv2d's conv at utils.py:44, transforms.py:266. */
+int nfdpm_gemm_nt(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N,
+                  int K, int in_dtype, int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias,
+                  nfdpm_stream_t stream);
+
+/* Affine-coupling epilogue (transforms.py:179-184 forward, :196-200 inverse).
+ *   pm   [M, ldp]: taps-as-N output of the ZeroConv GEMM (column = tap*C + co, tap = ky*3+kx)
+ *   net[co] = (sum_tap pm[m + (ky-1)*W + (kx-1), tap*C+co] (zero outside the image) + bias3[co]) * exp(3*logs3[co])
+ *   log_s = net[0:C/2], t = net[C/2:C], s = sigmoid(log_s + 2)
+ *   forward: y_b = (x_b + t)*s, ld_part += sum log(s + 1e-6);   inverse: y_b = x_b/(s + 1e-6) - t
+ * x,y [B,C,P] NCHW (batch strides); the first C/2 channels are copied through when y != x.
+ * ld_part (forward only, may be NULL): fp32 [T][B] partial sums, T = nfdpm_ld_tiles(P); entry t*B+b. */
+int nfdpm_ld_tiles(int P);
+int nfdpm_coupling_apply(const float* pm, int64_t ldp, const float* bias3, const float* logs3, const float* x,
+                         float* y, float* ld_part, int B, int C, int H, int W, int64_t x_bstride,
+                         int64_t y_bstride, int inverse, nfdpm_stream_t stream);
+
+/* Split prior (transforms.py:266-268, 286-289; prior.py:36-37).  h [M, ldh] = raw ZeroConv GEMM output
+ * (N = C, column = co; NULL when the prior is not learned -> mean = logs = 0), bias/logs = split.conv.{bias,logs}.
+ *   mean = ((h+bias)*exp(3*logs))[0:C/2], lg = (...)[C/2:C];  z = x[:, C/2:C]
+ *   logp_part[t*B+b] = sum -0.5*(log(2pi) + 2*lg + (z-mean)^2*exp(-2*lg))      (may be NULL)
+ *   z_out [B,C/2,P] contiguous copy of z (may be NULL). */
+int nfdpm_split_prior_logp(const float* h, int64_t ldh, const float* bias, const float* logs, const float* x,
+                           int64_t x_bstride, float* z_out, float* logp_part, int B, int C, int H, int W,
+                           nfdpm_stream_t stream);
+/* Split.invert without a latent (transforms.py:305-307, prior.py:49-50): writes
+ * mean + exp(lg)*temperature*eps into channels C/2..C of y [B,C,P]; eps [B,C/2,P] contiguous. */
+int nfdpm_split_prior_sample(const float* h, int64_t ldh, const float* bias, const float* logs, const float* eps,
+                             float temperature, float* y, int64_t y_bstride, int B, int C, int H, int W,
+                             nfdpm_stream_t stream);
+
+/* GaussianPrior (prior.py:70-99): the reference convolves an all-zero map, so mean/logs are the
+ * per-channel constants (bias*exp(3*logs))[0:C] and [C:2C] of the 2C-channel ZeroConv2d.
+ * bias/logs NULL -> standard normal.  logp_part: fp32 [B]. */
+int nfdpm_gauss_logp_const(const float* z, const float* bias, const float* logs, float* logp_part, int B, int C,
+                           int P, nfdpm_stream_t stream);
+int nfdpm_gauss_sample_const(const float* eps, const float* bias, const float* logs, float temperature, float* out,
+                             int B, int C, int P, nfdpm_stream_t stream);
+
+/* Layout converters for stand-alone ZeroConv2d / Conv2dActNorm module calls (normalizing_flow/utils.py:43-44, :68-69).
+ *   rows_to_nchw: out[b,n,p] = f(h[(b*P+p)*ldh + n]); mode 0: identity; 1: (v+p1[n])*exp(3*p2[n]) (ZeroConv2d gain);
+ *                 2: exp(p1[n])*(v+p2[n]) (ActNorm).   nchw_to_rows: rows[m, c] = x[b,c,p], columns Cc..ld-1 zero. */
+int nfdpm_rows_to_nchw(const float* h, int64_t ldh, int mode, const float* p1, const float* p2, float* out, int B,
+                       int Nc, int P, nfdpm_stream_t stream);
+int nfdpm_nchw_to_rows(const float* x, void* out, int out_dtype, int B, int Cc, int P, int64_t x_bstride, int64_t ld,
+                       nfdpm_stream_t stream);
+
+/* acc[b] += sum_{r<R} part[r*B+b] + sum_{j<nc} cmul[j]*cval[j]   (fixed order -> deterministic).
+ * acc is the caller's running log_det_jac / logp (`+=` in place, transforms.py:81,131,184,288), fp32 or fp64.
+ * cval/cmul: device fp32 arrays (e.g. logdet constants and their H*W multipliers); may be NULL with nc=0. */
+int nfdpm_accumulate(void* acc, int acc_dtype, const float* part, int R, int B, const float* cval,
+                     const float* cmul, int nc, nfdpm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFDPM_B200_H_ */

@@ -1,0 +1,93 @@
+// Shared helpers for libnfdpm_b200 (sm_100a).  Internal header, not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/nfdpm_b200.h"
+
+namespace nfdpm {
+
+// thread-local last error (nfdpm_last_error_string)
+char* err_buf();
+int fail(const char* fmt, ...);
+
+#define NFDPM_REQUIRE(cond, ...)                \
+  do {                                          \
+    if (!(cond)) return nfdpm::fail(__VA_ARGS__); \
+  } while (0)
+
+// Check the launch itself (not execution): cheap, does not synchronise.
+#define NFDPM_CHECK_LAUNCH(name)                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) return nfdpm::fail("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define NFDPM_CUDA(call)                                                                  \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) return nfdpm::fail("%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline cudaStream_t as_stream(nfdpm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// streaming 128-bit access: read-once / write-once tensors should not pollute L1
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic per-image reduction of one value per thread, for kernels whose CTA owns TPB consecutive
+// flattened pixels m = b*P + p of ONE tile:  val[t] -> sums[img] for the images the tile overlaps.
+// `first_m` = flattened index of thread 0, `n_valid` = number of valid threads.  Results are written by
+// out(b, tile_in_image, sum).  Fixed summation order => bitwise reproducible.
+template <int TPB, typename Out>
+__device__ __forceinline__ void tile_image_reduce(float v, float* sh /*[TPB]*/, int64_t first_m, int n_valid, int P,
+                                                  Out out) {
+  const int t = threadIdx.x;
+  sh[t] = (t < n_valid) ? v : 0.f;
+  __syncthreads();
+  if (P >= TPB) {
+    // the tile lies inside one image (tiles are cut per image when P > TPB; P == TPB is one image)
+    // tree reduction in a fixed order
+    for (int s = TPB / 2; s > 0; s >>= 1) {
+      if (t < s) sh[t] += sh[t + s];
+      __syncthreads();
+    }
+    if (t == 0) out(first_m / P, (int)((first_m % P) / TPB), sh[0]);
+  } else {
+    // several whole images per tile: one thread sums one image sequentially
+    const int n_img = (n_valid + P - 1) / P;
+    if (t < n_img) {
+      float s = 0.f;
+      const int lo = t * P, hi = min(lo + P, n_valid);
+      for (int i = lo; i < hi; ++i) s += sh[i];
+      out(first_m / P + t, 0, s);
+    }
+  }
+}
+
+}  // namespace nfdpm

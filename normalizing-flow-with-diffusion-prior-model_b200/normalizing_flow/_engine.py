@@ -1,0 +1,262 @@
+"""Host-side orchestration of the libnfdpm_b200 kernels: parameter caches, scratch memory and the
+launch sequences of one StepFlow / coupling network.  No arithmetic happens here — every number is
+produced by a kernel of the C-ABI library; torch supplies device memory and the current stream.
+
+Precision modes (env ``NFDPM_PRECISION``):
+  * ``fp32`` — coupling-network GEMMs on CUDA cores with exact fp32 FMA accumulation
+    (parity bar: z / log-det within 1e-4 relative of the reference).
+  * ``bf16`` — coupling-network GEMMs on tcgen05 tensor cores, bf16 operands, fp32 TMEM accumulators
+    (parity bar stated in DESIGN.md / tests).  Everything outside the coupling nets is fp32 in both modes.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def precision() -> str:
+    p = os.environ.get("NFDPM_PRECISION", "fp32").lower()
+    if p not in ("fp32", "bf16"):
+        raise ValueError(f"NFDPM_PRECISION must be 'fp32' or 'bf16', got {p!r}")
+    return p
+
+
+def round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class _Workspace:
+    """Grow-only scratch buffers keyed by (tag, dtype, device, stream).  Kernels of one flow run in stream
+    order and each buffer is consumed before it is overwritten, so one set per stream is enough."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, tag: str, numel: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+        key = (tag, dtype, device.index, torch.cuda.current_stream(device).cuda_stream)
+        t = self._bufs.get(key)
+        if t is None or t.numel() < numel:
+            t = torch.empty(max(numel, 1), dtype=dtype, device=device)
+            self._bufs[key] = t
+        return t
+
+    def clear(self):
+        self._bufs.clear()
+
+
+WS = _Workspace()
+_SCALARS = {}
+
+
+def scalar_f32(device: torch.device, value: float) -> torch.Tensor:
+    """Cached 1-element device tensor (multipliers for nfdpm_accumulate)."""
+    key = (device.index, float(value))
+    t = _SCALARS.get(key)
+    if t is None:
+        t = torch.full((1,), float(value), dtype=torch.float32, device=device)
+        _SCALARS[key] = t
+    return t
+
+
+def check_input(x: torch.Tensor, what: str = "input") -> torch.Tensor:
+    N.require_cuda(x, what)
+    if x.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32 (got {x.dtype})")
+    if x.dim() != 4:
+        raise ValueError(f"{what} must be [B, C, H, W] (got shape {tuple(x.shape)})")
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def check_acc(a: Optional[torch.Tensor], B: int, what: str) -> None:
+    if a is None:
+        return
+    N.require_cuda(a, what)
+    if a.dtype not in (torch.float32, torch.float64) or a.dim() != 1 or a.shape[0] != B or not a.is_contiguous():
+        raise ValueError(f"{what} must be a contiguous float32/float64 vector of length {B} "
+                         f"(got {a.dtype}, shape {tuple(a.shape)})")
+
+
+def autograd_needed(x: torch.Tensor, module: torch.nn.Module) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if x.requires_grad:
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def _vkey(*tensors) -> tuple:
+    return tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+
+
+# ------------------------------------------------------------------------------------------- mix cache
+class MixCache:
+    """Prepared mixing matrices of one (ActNorm, InvConv2d) pair: see nfdpm_mix_prepare."""
+
+    def __init__(self):
+        self.key = None
+        self.C = 0
+        self.fwd_mt = self.fwd_beta = self.inv_mt = self.inv_beta = self.winv = self.logdet = self.lu_ws = None
+
+    def invalidate(self):
+        self.key = None
+
+    def _alloc(self, C: int, device: torch.device, logdet_slot: Optional[torch.Tensor]):
+        if self.fwd_mt is not None and self.C == C and self.fwd_mt.device == device:
+            if logdet_slot is not None and (self.logdet is None or self.logdet.data_ptr() != logdet_slot.data_ptr()):
+                self.logdet = logdet_slot
+                self.key = None
+            return
+        f = dict(dtype=torch.float32, device=device)
+        self.C = C
+        self.fwd_mt = torch.empty(C * C, **f)
+        self.fwd_beta = torch.empty(C, **f)
+        self.inv_mt = torch.empty(C * C, **f)
+        self.inv_beta = torch.empty(C, **f)
+        self.winv = torch.empty(C * C, **f)
+        self.logdet = logdet_slot if logdet_slot is not None else torch.empty(1, **f)
+        self.lu_ws = torch.empty(2 * C * C, dtype=torch.float64, device=device)
+        self.key = None
+
+
+def prepare_mix(entries: Sequence[Tuple[MixCache, Optional[torch.Tensor], Optional[torch.Tensor],
+                                        Optional[torch.Tensor], int, Optional[torch.Tensor]]]) -> None:
+    """entries: (cache, weight|None, scale|None, bias|None, C, logdet_slot|None).  Re-runs the batched
+    LU/fold kernel only for entries whose parameters changed (tensor version counters)."""
+    items = []
+    for cache, w, s, b, C, slot in entries:
+        dev = (w if w is not None else s).device
+        cache._alloc(C, dev, slot)
+        key = _vkey(w, s, b)
+        if cache.key == key:
+            continue
+        cache.key = key
+        items.append(N.MixItem(weight=N._p(w), scale=N._p(s), bias=N._p(b), C=C, pad_=0,
+                               fwd_mt=cache.fwd_mt.data_ptr(), fwd_beta=cache.fwd_beta.data_ptr(),
+                               inv_mt=cache.inv_mt.data_ptr(), inv_beta=cache.inv_beta.data_ptr(),
+                               winv=cache.winv.data_ptr(), logdet=cache.logdet.data_ptr(),
+                               lu_ws=cache.lu_ws.data_ptr()))
+    if items:
+        N.mix_prepare(items)
+
+
+# ------------------------------------------------------------------------------------------- coupling net
+class CouplingCache:
+    """GEMM-ready copies of the three conv weights of one coupling network (nfdpm_pack_matrix)."""
+
+    def __init__(self):
+        self.key = None
+        self.w1 = self.w2 = self.w3 = None
+        self.K1 = self.K1p = self.ldp = 0
+
+
+def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, dt: torch.dtype):
+    key = (_vkey(w1, w2, w3), dt)
+    if cache.key == key:
+        return
+    F, Ch = w1.shape[0], w1.shape[1]
+    C = w3.shape[0]
+    dev = w1.device
+    K1 = Ch * 9
+    K1p = round_up(K1, 64)
+    ldp = round_up(9 * C, 16)
+    if cache.w1 is None or cache.w1.dtype != dt or cache.w1.numel() != F * K1p:
+        cache.w1 = torch.empty(F * K1p, dtype=dt, device=dev)
+        cache.w3 = torch.empty(ldp * F, dtype=dt, device=dev)
+        cache.w2 = torch.empty(F * F, dtype=dt, device=dev) if dt != torch.float32 else None
+    # conv1 [F, Ch, 3, 3] -> rows n, cols c*9+tap (natural), zero-padded to K1p
+    N.pack_matrix(w1, cache.w1, 1, F, K1, 0, K1, 1, K1p, F)
+    if dt != torch.float32:
+        N.pack_matrix(w2, cache.w2, 1, F, F, 0, F, 1, F, F)
+    # zero conv [C, F, 3, 3] -> rows (tap, co), cols ci ("taps as N"); rows 9C..ldp zero
+    N.pack_matrix(w3, cache.w3, 9, C, F, 1, F * 9, 9, F, ldp)
+    cache.K1, cache.K1p, cache.ldp = K1, K1p, ldp
+    cache.key = key
+
+
+def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int, init: bool = False) -> Tuple[torch.Tensor, int]:
+    """Run the coupling network of AffineCoupling ``cp`` on the first C/2 channels of ``y`` ([B,C,P], batch
+    stride ``ybs``).  Returns (pm, ldp): the taps-as-N ZeroConv rows consumed by nfdpm_coupling_apply.
+    ``init`` performs the data-dependent initialisation of inner ActNorms that are not initialised yet
+    (always in exact fp32)."""
+    conv1, an1, conv2, an2, zc = cp._parts()
+    F = conv1.weight.shape[0]
+    if F % 64 != 0:
+        raise ValueError(f"coupling_net_n_features must be a multiple of 64 (got {F})")
+    need_init = init and not (an1._initialized() and an2._initialized())
+    dt = torch.float32 if (precision() == "fp32" or need_init) else torch.bfloat16
+    cache = cp._cache
+    _pack_coupling(cache, conv1.weight, conv2.weight, zc.weight, dt)
+    dev = y.device
+    M = B * H * W
+    K1p, ldp = cache.K1p, cache.ldp
+    A1 = WS.get("A1", M * K1p, dt, dev)
+    N.im2col3x3(y, A1, B, C // 2, H, W, ybs, K1p)
+    h1 = WS.get("h1", M * F, dt, dev)
+    if need_init and not an1._initialized():
+        raw = WS.get("raw", M * F, torch.float32, dev)
+        N.gemm_nt(A1, K1p, cache.w1, K1p, raw, F, M, F, K1p)
+        N.channel_stats(raw, 1, B, F, H * W, F, an1.scale, an1.bias)
+        an1._mark_initialized()
+    N.gemm_nt(A1, K1p, cache.w1, K1p, h1, F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
+    w2 = cache.w2 if dt != torch.float32 else conv2.weight
+    h2 = WS.get("h2", M * F, dt, dev)
+    if need_init and not an2._initialized():
+        raw = WS.get("raw", M * F, torch.float32, dev)
+        N.gemm_nt(h1, F, w2, F, raw, F, M, F, F)
+        N.channel_stats(raw, 1, B, F, H * W, F, an2.scale, an2.bias)
+        an2._mark_initialized()
+    N.gemm_nt(h1, F, w2, F, h2, F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
+    pm = WS.get("pm", M * ldp, torch.float32, dev)
+    N.gemm_nt(h2, F, cache.w3, F, pm, ldp, M, ldp, F)
+    return pm, ldp
+
+
+class SplitCache:
+    def __init__(self):
+        self.key = None
+        self.w = None
+        self.Kp = self.ldh = 0
+
+
+def split_rows(sp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int) -> Tuple[Optional[torch.Tensor], int]:
+    """Raw ZeroConv3x3 (C/2 -> C) rows of the Split prior, always exact fp32 (the conv is tiny).
+    Returns (h, ldh) or (None, 0) when the prior is not learned."""
+    conv = sp.conv
+    if conv is None:
+        return None, 0
+    cache = sp._cache
+    w = conv.weight
+    Ch = C // 2
+    K = Ch * 9
+    Kp = round_up(K, 16)
+    ldh = round_up(C, 8)
+    key = _vkey(w)
+    if cache.key != key:
+        if cache.w is None or cache.w.numel() != ldh * Kp:
+            cache.w = torch.empty(ldh * Kp, dtype=torch.float32, device=w.device)
+        N.pack_matrix(w, cache.w, 1, C, K, 0, K, 1, Kp, ldh)
+        cache.key, cache.Kp, cache.ldh = key, Kp, ldh
+    M = B * H * W
+    A = WS.get("As", M * Kp, torch.float32, y.device)
+    N.im2col3x3(y, A, B, Ch, H, W, ybs, Kp)
+    h = WS.get("hs", M * ldh, torch.float32, y.device)
+    N.gemm_nt(A, Kp, cache.w, Kp, h, ldh, M, C, Kp)
+    return h, ldh
+
+
+def conv3x3_rows(conv, x: torch.Tensor, xbs: int, B: int, Cin: int, Cout: int, H: int, W: int) -> Tuple[torch.Tensor, int]:
+    """Exact-fp32 3x3 "same" convolution of the first ``Cin`` channels of x as im2col + GEMM.  Returns the raw
+    rows [M, ld] (no bias).  Used by the stand-alone ZeroConv2d / Conv2dActNorm module calls."""
+    K, Kp, ld = Cin * 9, round_up(Cin * 9, 16), round_up(Cout, 8)
+    wp = WS.get("wp", ld * Kp, torch.float32, x.device)
+    N.pack_matrix(conv.weight, wp, 1, Cout, K, 0, K, 1, Kp, ld)
+    M = B * H * W
+    A = WS.get("As", M * Kp, torch.float32, x.device)
+    N.im2col3x3(x, A, B, Cin, H, W, xbs, Kp)
+    h = WS.get("hs", M * ld, torch.float32, x.device)
+    N.gemm_nt(A, Kp, wp, Kp, h, ld, M, Cout, Kp)
+    return h, ld

@@ -1,0 +1,187 @@
+"""ctypes binding of libnfdpm_b200.so (include/nfdpm_b200.h).
+
+There is no fallback: if the shared library is missing or a kernel call fails this module raises.
+Every wrapper enqueues on torch's *current* CUDA stream and passes raw device pointers; torch is used
+only for memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+F32, F64, BF16 = 0, 1, 2
+EPI_RAW, EPI_ACTNORM_RELU = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("NFDPM_B200_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libnfdpm_b200.so"))
+
+
+class MixItem(C.Structure):
+    """struct nfdpm_mix_item (include/nfdpm_b200.h)."""
+    _fields_ = [("weight", C.c_void_p), ("scale", C.c_void_p), ("bias", C.c_void_p), ("C", C.c_int32),
+                ("pad_", C.c_int32), ("fwd_mt", C.c_void_p), ("fwd_beta", C.c_void_p), ("inv_mt", C.c_void_p),
+                ("inv_beta", C.c_void_p), ("winv", C.c_void_p), ("logdet", C.c_void_p), ("lu_ws", C.c_void_p)]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"libnfdpm_b200.so not found at {LIB_PATH}. Build it with `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` (nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    sig = {
+        "nfdpm_version": ([], C.c_int),
+        "nfdpm_last_error_string": ([], C.c_char_p),
+        "nfdpm_sm_count": ([], C.c_int),
+        "nfdpm_ld_tiles": ([i32], C.c_int),
+        "nfdpm_mix_prepare": ([C.POINTER(MixItem), i32, vp], C.c_int),
+        "nfdpm_channel_mix": ([vp, vp, vp, vp, i32, i32, i32, i64, i64, vp], C.c_int),
+        "nfdpm_actnorm_apply": ([vp, vp, vp, vp, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_channel_stats": ([vp, i32, i32, i32, i32, i64, vp, vp, vp], C.c_int),
+        "nfdpm_squeeze": ([vp, vp, i32, i32, i32, i32, i64, i64, vp], C.c_int),
+        "nfdpm_unsqueeze": ([vp, vp, i32, i32, i32, i32, i64, i64, vp], C.c_int),
+        "nfdpm_copy_channels": ([vp, vp, i32, i32, i32, i64, i64, vp], C.c_int),
+        "nfdpm_im2col3x3": ([vp, vp, i32, i32, i32, i32, i32, i64, i64, vp], C.c_int),
+        "nfdpm_pack_matrix": ([vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i32, vp], C.c_int),
+        "nfdpm_gemm_nt": ([vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp], C.c_int),
+        "nfdpm_coupling_apply": ([vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i32, vp], C.c_int),
+        "nfdpm_split_prior_logp": ([vp, i64, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_split_prior_sample": ([vp, i64, vp, vp, vp, f32, vp, i64, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_gauss_logp_const": ([vp, vp, vp, vp, i32, i32, i32, vp], C.c_int),
+        "nfdpm_gauss_sample_const": ([vp, vp, vp, f32, vp, i32, i32, i32, vp], C.c_int),
+        "nfdpm_rows_to_nchw": ([vp, i64, i32, vp, vp, vp, i32, i32, i32, vp], C.c_int),
+        "nfdpm_nchw_to_rows": ([vp, vp, i32, i32, i32, i32, i64, i64, vp], C.c_int),
+        "nfdpm_accumulate": ([vp, i32, vp, i32, i32, vp, vp, i32, vp], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, name)   # AttributeError here == header / library mismatch: fail loudly
+        fn.argtypes = args
+        fn.restype = res
+    return lib
+
+
+lib = _load()
+EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_ld_tiles", "nfdpm_mix_prepare",
+           "nfdpm_channel_mix", "nfdpm_actnorm_apply", "nfdpm_channel_stats", "nfdpm_squeeze", "nfdpm_unsqueeze",
+           "nfdpm_copy_channels", "nfdpm_im2col3x3", "nfdpm_pack_matrix", "nfdpm_gemm_nt", "nfdpm_coupling_apply",
+           "nfdpm_split_prior_logp", "nfdpm_split_prior_sample", "nfdpm_gauss_logp_const",
+           "nfdpm_gauss_sample_const", "nfdpm_accumulate", "nfdpm_rows_to_nchw", "nfdpm_nchw_to_rows"]
+
+#: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
+launch_count = 0
+
+
+def _ok(rc: int, n_launch: int = 1) -> None:
+    global launch_count
+    if rc != 0:
+        raise RuntimeError("libnfdpm_b200: " + lib.nfdpm_last_error_string().decode())
+    launch_count += n_launch
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device: this package runs only its sm_100a kernels and has "
+                           f"no CPU fallback (got device {t.device}).")
+
+
+def ld_tiles(P: int) -> int:
+    return lib.nfdpm_ld_tiles(P)
+
+
+def mix_prepare(items) -> None:
+    arr = (MixItem * len(items))(*items)
+    _ok(lib.nfdpm_mix_prepare(arr, len(items), _st()), (len(items) + 15) // 16)
+
+
+def channel_mix(x, y, mt, beta, B, Cc, P, xbs, ybs) -> None:
+    _ok(lib.nfdpm_channel_mix(_p(x), _p(y), _p(mt), _p(beta), B, Cc, P, xbs, ybs, _st()))
+
+
+def actnorm_apply(x, y, scale, bias, B, Cc, P, inverse) -> None:
+    _ok(lib.nfdpm_actnorm_apply(_p(x), _p(y), _p(scale), _p(bias), B, Cc, P, int(inverse), _st()))
+
+
+def channel_stats(x, layout, B, Cc, P, xs, scale_out, bias_out) -> None:
+    _ok(lib.nfdpm_channel_stats(_p(x), layout, B, Cc, P, xs, _p(scale_out), _p(bias_out), _st()))
+
+
+def squeeze(x, y, B, Cc, H, W, xbs, ybs) -> None:
+    _ok(lib.nfdpm_squeeze(_p(x), _p(y), B, Cc, H, W, xbs, ybs, _st()))
+
+
+def unsqueeze(x, y, B, Cc, H, W, xbs, ybs) -> None:
+    _ok(lib.nfdpm_unsqueeze(_p(x), _p(y), B, Cc, H, W, xbs, ybs, _st()))
+
+
+def copy_channels(src, dst, B, Cn, P, sbs, dbs) -> None:
+    _ok(lib.nfdpm_copy_channels(_p(src), _p(dst), B, Cn, P, sbs, dbs, _st()))
+
+
+def im2col3x3(x, out, B, Cin, H, W, xbs, ld) -> None:
+    _ok(lib.nfdpm_im2col3x3(_p(x), _p(out), _dt(out), B, Cin, H, W, xbs, ld, _st()))
+
+
+def pack_matrix(src, out, na, nb, nk, sa, sb, sk, ld, rows_out) -> None:
+    _ok(lib.nfdpm_pack_matrix(_p(src), _p(out), _dt(out), na, nb, nk, sa, sb, sk, ld, rows_out, _st()))
+
+
+def gemm_nt(A, lda, Bw, ldb, D, ldd, M, N, K, epilogue=EPI_RAW, ep_scale=None, ep_bias=None) -> None:
+    _ok(lib.nfdpm_gemm_nt(_p(A), lda, _p(Bw), ldb, _p(D), ldd, M, N, K, _dt(A), _dt(D), epilogue, _p(ep_scale),
+                          _p(ep_bias), _st()))
+
+
+def coupling_apply(pm, ldp, bias3, logs3, x, y, ld_part, B, Cc, H, W, xbs, ybs, inverse) -> None:
+    _ok(lib.nfdpm_coupling_apply(_p(pm), ldp, _p(bias3), _p(logs3), _p(x), _p(y), _p(ld_part), B, Cc, H, W, xbs, ybs,
+                                 int(inverse), _st()))
+
+
+def split_prior_logp(h, ldh, bias, logs, x, xbs, z_out, logp_part, B, Cc, H, W) -> None:
+    _ok(lib.nfdpm_split_prior_logp(_p(h), ldh, _p(bias), _p(logs), _p(x), xbs, _p(z_out), _p(logp_part), B, Cc, H, W,
+                                   _st()))
+
+
+def split_prior_sample(h, ldh, bias, logs, eps, temperature, y, ybs, B, Cc, H, W) -> None:
+    _ok(lib.nfdpm_split_prior_sample(_p(h), ldh, _p(bias), _p(logs), _p(eps), float(temperature), _p(y), ybs, B, Cc,
+                                     H, W, _st()))
+
+
+def gauss_logp_const(z, bias, logs, part, B, Cc, P) -> None:
+    _ok(lib.nfdpm_gauss_logp_const(_p(z), _p(bias), _p(logs), _p(part), B, Cc, P, _st()))
+
+
+def gauss_sample_const(eps, bias, logs, temperature, out, B, Cc, P) -> None:
+    _ok(lib.nfdpm_gauss_sample_const(_p(eps), _p(bias), _p(logs), float(temperature), _p(out), B, Cc, P, _st()))
+
+
+def accumulate(acc, part, R, B, cval=None, cmul=None, nc=0) -> None:
+    _ok(lib.nfdpm_accumulate(_p(acc), _dt(acc), _p(part), R, B, _p(cval), _p(cmul), nc, _st()))
+
+
+def rows_to_nchw(h, ldh, mode, p1, p2, out, B, Nc, P) -> None:
+    _ok(lib.nfdpm_rows_to_nchw(_p(h), ldh, mode, _p(p1), _p(p2), _p(out), B, Nc, P, _st()))
+
+
+def nchw_to_rows(x, out, B, Cc, P, xbs, ld) -> None:
+    _ok(lib.nfdpm_nchw_to_rows(_p(x), _p(out), _dt(out), B, Cc, P, xbs, ld, _st()))

@@ -1,0 +1,273 @@
+"""Composite flows StepFlow / GlowBlock / Glow with the reference's constructor signatures, attribute and
+parameter names (reference normalizing_flow/glow.py:12-246), scheduled as one kernel chain per call:
+
+    forward step   : [K-LU+fold, cached] -> K-A (ActNorm+1x1 conv, fused) -> im2col -> GEMM1 -> GEMM2 -> GEMM3
+                     -> coupling epilogue (in place on the K-A output)
+    inverse step   : im2col -> GEMM1 -> GEMM2 -> GEMM3 -> inverse coupling epilogue -> K-A^-1
+    level boundary : squeeze reads the kept half in place (batch stride); Split writes z and the prior term
+    whole call     : ONE accumulate kernel adds every per-step log-det partial and the K*L data-independent
+                     constants H*W*(sum(scale) + log|det W|) into the caller's accumulator (in place)
+
+``Glow.transform`` / ``Glow.invert`` never copy activations for chunk/concat: halves are addressed through batch
+strides.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _engine as E
+from . import _native as N
+from .base import Transform
+from .transforms import ActNorm, AffineCoupling, InvConv2d, Split, Squeeze, _no_autograd
+from .utils import get_item
+
+
+class StepFlow(Transform):
+    """ActNorm -> InvConv2d -> AffineCoupling (reference glow.py:21-63).  ActNorm and the 1x1 convolution run as
+    ONE memory-bound kernel with pre-folded weights."""
+
+    def __init__(self, in_channels: int = 3, coupling_net_n_features: int = 512):
+        super().__init__()
+        self.actnorm = ActNorm(in_channels=in_channels)
+        self.invconv2d = InvConv2d(in_channels=in_channels)
+        self.affcoupling = AffineCoupling(in_channels=in_channels, n_features=coupling_net_n_features)
+        self._mix = E.MixCache()
+        self._C = in_channels
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._mix.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *a, **k):
+        self._mix = E.MixCache()
+        return super()._apply(fn, *a, **k)
+
+    def _mix_entry(self, slot: Optional[Tensor] = None):
+        return (self._mix, self.invconv2d.weight, self.actnorm.scale, self.actnorm.bias, self._C, slot)
+
+    def _ready(self) -> bool:
+        _, an1, _, an2, _ = self.affcoupling._parts()
+        return self.actnorm._initialized() and an1._initialized() and an2._initialized()
+
+    def _forward_views(self, x: Tensor, xbs: int, y: Tensor, ybs: int, B: int, H: int, W: int,
+                       ld_part: Optional[Tensor], slot: Optional[Tensor] = None) -> None:
+        C, P = self._C, H * W
+        if not self.actnorm._initialized():
+            self.actnorm._maybe_init(x, xbs, B, C, P)
+            self._mix.invalidate()
+        E.prepare_mix([self._mix_entry(slot)])
+        N.channel_mix(x, y, self._mix.fwd_mt, self._mix.fwd_beta, B, C, P, xbs, ybs)
+        self.affcoupling._run(y, ybs, y, ybs, B, C, H, W, False, ld_part)
+
+    def _inverse_views(self, y: Tensor, ybs: int, t: Tensor, tbs: int, x: Tensor, xbs: int, B: int, H: int,
+                       W: int) -> None:
+        """y --coupling^-1--> t (t may be y: in place) --K-A^-1--> x."""
+        C, P = self._C, H * W
+        E.prepare_mix([self._mix_entry(None)])
+        self.affcoupling._run(y, ybs, t, tbs, B, C, H, W, True, None)
+        N.channel_mix(t, x, self._mix.inv_mt, self._mix.inv_beta, B, C, P, tbs, xbs)
+
+    def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        _no_autograd(x, self, "StepFlow.transform")
+        x = E.check_input(x)
+        B, C, H, W = x.shape
+        if C != self._C:
+            raise ValueError(f"StepFlow built for {self._C} channels got {C}")
+        E.check_acc(log_det_jac, B, "log_det_jac")
+        T = N.ld_tiles(H * W)
+        part = E.WS.get("ldp1", T * B, torch.float32, x.device)
+        y = torch.empty_like(x)
+        self._forward_views(x, C * H * W, y, C * H * W, B, H, W, part)
+        if log_det_jac is not None:
+            N.accumulate(log_det_jac, part, T, B, self._mix.logdet, E.scalar_f32(x.device, H * W), 1)
+        return y, log_det_jac, logp
+
+    def invert(self, y: Tensor) -> Tensor:
+        _no_autograd(y, self, "StepFlow.invert")
+        y = E.check_input(y)
+        B, C, H, W = y.shape
+        t, x = torch.empty_like(y), torch.empty_like(y)
+        self._inverse_views(y, C * H * W, t, C * H * W, x, C * H * W, B, H, W)
+        return x
+
+
+class GlowBlock(Transform):
+    """Squeeze -> K StepFlows -> Split (reference glow.py:75-137)."""
+
+    def __init__(self, in_channels: int = 3, K: int = 32, learn_prior_mean_logs: bool = True):
+        super().__init__()
+        flow_channels = 4 * in_channels
+        self.squeeze = Squeeze()
+        self.flows = nn.ModuleList([StepFlow(in_channels=flow_channels) for _ in range(K)])
+        self.split = Split(flow_channels, learn_prior_mean_logs=learn_prior_mean_logs)
+
+    def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        y, log_det_jac, logp = self.squeeze.transform(x, log_det_jac, logp)
+        for flow in self.flows:
+            y, log_det_jac, logp = flow.transform(y, log_det_jac, logp)
+        return self.split.transform(y, log_det_jac, logp)
+
+    def invert(self, y: Tensor, latent: Tensor = None, temperature: float = 1.0) -> Tensor:
+        inv = self.split.invert(y, latent, temperature=temperature)
+        for flow in reversed(self.flows):
+            inv = flow.invert(inv)
+        return self.squeeze.invert(inv)
+
+
+class Glow(Transform):
+    """L-1 GlowBlocks, a final squeeze and K final StepFlows (reference glow.py:149-246)."""
+
+    def __init__(self, in_channel: int = 3, L: int = 3, K: int = 32, learn_prior_mean_logs: bool = True):
+        super().__init__()
+        self.L, self.K, self.in_channel = L, K, in_channel
+        self.blocks = nn.ModuleList(GlowBlock(in_channels=(2 ** i * in_channel), K=K,
+                                              learn_prior_mean_logs=learn_prior_mean_logs) for i in range(L - 1))
+        self.final_squeeze = Squeeze()
+        self.final_flows = nn.ModuleList(StepFlow(in_channels=(2 ** (L + 1) * in_channel)) for _ in range(K))
+        self._logdet_all: Optional[Tensor] = None
+        self._cmul = {}
+
+    def _apply(self, fn, *a, **k):
+        self._logdet_all = None
+        self._cmul = {}
+        return super()._apply(fn, *a, **k)
+
+    # ---- helpers
+    def _levels(self) -> List[Tuple[nn.ModuleList, Optional[Split]]]:
+        lv = [(blk.flows, blk.split) for blk in self.blocks]
+        lv.append((self.final_flows, None))
+        return lv
+
+    def _slots(self, device: torch.device) -> Tensor:
+        n = self.L * self.K
+        if self._logdet_all is None or self._logdet_all.device != device:
+            self._logdet_all = torch.zeros(n, dtype=torch.float32, device=device)
+        return self._logdet_all
+
+    def _multipliers(self, H: int, W: int, device: torch.device) -> Tensor:
+        key = (H, W, device.index)
+        t = self._cmul.get(key)
+        if t is None:
+            vals = []
+            h, w = H, W
+            for _ in range(self.L):
+                h, w = h // 2, w // 2
+                vals += [float(h * w)] * self.K
+            t = torch.tensor(vals, dtype=torch.float32, device=device)
+            self._cmul[key] = t
+        return t
+
+    def _check_image(self, x: Tensor) -> Tuple[int, int, int, int]:
+        B, C, H, W = x.shape
+        if C != self.in_channel:
+            raise ValueError(f"Glow built for {self.in_channel} input channels got {C}")
+        if H % (2 ** self.L) or W % (2 ** self.L):
+            raise ValueError(f"input {H}x{W} is not divisible by 2^L = {2 ** self.L}")
+        return B, C, H, W
+
+    # ---- forward: x -> ([z_0..z_{L-1}], log_det_jac, logp)
+    def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[list, Tensor, Tensor]:
+        _no_autograd(x, self, "Glow.transform")
+        x = E.check_input(x)
+        B, c, H, W = self._check_image(x)
+        if log_det_jac is None:
+            raise ValueError("log_det_jac accumulator is required")
+        E.check_acc(log_det_jac, B, "log_det_jac")
+        E.check_acc(logp, B, "logp")
+        dev = x.device
+        levels = self._levels()
+        slots = self._slots(dev)
+        steps = [s for flows, _ in levels for s in flows]
+        if all(s._ready() for s in steps):
+            # one batched LU/fold launch for every StepFlow whose parameters changed since the last call
+            E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
+        # partial-sum rows: per step T_l rows of B
+        geo = []
+        h, w, ch = H, W, c
+        for li in range(self.L):
+            h, w = h // 2, w // 2
+            C = ch * 4
+            geo.append((C, h, w, N.ld_tiles(h * w)))
+            ch = C // 2
+        R_ld = sum(g[3] for g in geo) * self.K
+        R_lp = sum(g[3] for g in geo[:-1])
+        ld_part = E.WS.get("ld_part", max(R_ld, 1) * B, torch.float32, dev)
+        lp_part = E.WS.get("lp_part", max(R_lp, 1) * B, torch.float32, dev) if logp is not None else None
+        latents: List[Tensor] = []
+        cur, cur_bs, cur_c, cur_h, cur_w = x, c * H * W, c, H, W
+        row = lrow = si = 0
+        for li, (flows, split) in enumerate(levels):
+            C, h, w, T = geo[li]
+            P = h * w
+            a = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+            b = torch.empty_like(a)
+            N.squeeze(cur, a, B, cur_c, cur_h, cur_w, cur_bs, C * P)
+            for step in flows:
+                step._forward_views(a, C * P, b, C * P, B, h, w, ld_part[row * B:], slots[si:si + 1])
+                a, b = b, a
+                row += T
+                si += 1
+            if split is None:
+                latents.append(a)
+                break
+            z = torch.empty(B, C // 2, h, w, dtype=torch.float32, device=dev)
+            split._forward_views(a, C * P, B, C, h, w, z, lp_part[lrow * B:] if lp_part is not None else None)
+            lrow += T
+            latents.append(z)
+            cur, cur_bs, cur_c, cur_h, cur_w = a, C * P, C // 2, h, w
+        N.accumulate(log_det_jac, ld_part, R_ld, B, slots, self._multipliers(H, W, dev), self.L * self.K)
+        if logp is not None and R_lp > 0:
+            N.accumulate(logp, lp_part, R_lp, B)
+        return latents, log_det_jac, logp
+
+    # ---- inverse: latents -> x
+    def invert(self, latents: list, temperature: float = 1.0) -> Tensor:
+        z_last = E.check_input(latents[-1], "latents[-1]")
+        _no_autograd(z_last, self, "Glow.invert")
+        B, Cf, h, w = z_last.shape
+        if Cf != 2 ** (self.L + 1) * self.in_channel:
+            raise ValueError(f"final latent has {Cf} channels, expected {2 ** (self.L + 1) * self.in_channel}")
+        dev = z_last.device
+        levels = self._levels()
+        slots = self._slots(dev)
+        steps = [s for flows, _ in levels for s in flows]
+        if all(s._ready() for s in steps):
+            E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
+        C, P = Cf, h * w
+        cur = z_last
+        own = False          # `cur` is caller memory until the first step has produced a copy
+        for li in range(self.L - 1, -1, -1):
+            flows, _ = levels[li]
+            other = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+            for step in reversed(flows):
+                if own:
+                    step._inverse_views(cur, C * P, cur, C * P, other, C * P, B, h, w)
+                    cur, other = other, cur
+                else:
+                    tmp = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+                    step._inverse_views(cur, C * P, tmp, C * P, other, C * P, B, h, w)
+                    cur, other, own = other, tmp, True
+            # undo the squeeze of this level into the first half of the previous level's tensor
+            if li == 0:
+                out = torch.empty(B, C // 4, h * 2, w * 2, dtype=torch.float32, device=dev)
+                N.unsqueeze(cur, out, B, C, h, w, C * P, (C // 4) * P * 4)
+                return out
+            Cn, hn, wn = 2 * (C // 4), h * 2, w * 2
+            nxt = torch.empty(B, Cn, hn, wn, dtype=torch.float32, device=dev)
+            N.unsqueeze(cur, nxt, B, C, h, w, C * P, Cn * hn * wn)
+            latent = get_item(latents, -(self.L - li + 1))   # None -> draw from the conditional prior
+            levels[li - 1][1]._fill_second_half(nxt, Cn * hn * wn, B, Cn, hn, wn, latent, temperature)
+            cur, own, C, h, w, P = nxt, True, Cn, hn, wn, hn * wn
+        raise AssertionError("unreachable")
+
+    @torch.no_grad()
+    def sample(self, latents: list, postprocess_func=None, temperature: float = 1.0) -> Tensor:
+        """eval() -> invert -> optional postprocess -> train(), like the reference (glow.py:230-246; note the
+        unconditional switch back to train mode)."""
+        self.eval()
+        new_samples = self.invert(latents, temperature)
+        out = postprocess_func(new_samples.float()) if postprocess_func else new_samples.float()
+        self.train()
+        return out

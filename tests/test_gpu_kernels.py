@@ -1,0 +1,326 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against a torch fp64/fp32 CPU restatement of the same
+arithmetic on seeded inputs.  Tolerances are written per test; memory-layout kernels must be bit exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from normalizing_flow import _native as N
+from oracle import glow_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = np.random.default_rng(seed)
+    return torch.from_numpy((scale * g.standard_normal(shape)).astype(np.float32))
+
+
+def sync():
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("C,P,B", [(3, 784, 2), (4, 256, 3), (8, 64, 5), (12, 256, 4), (16, 16, 9), (24, 64, 4),
+                                   (48, 16, 7), (6, 49, 3), (96, 64, 2), (192, 16, 3), (12, 4096, 1)])
+def test_channel_mix(C, P, B):
+    x = rnd(B, C, P, seed=C + P)
+    mt = rnd(C, C, seed=1)            # mt[i, o]
+    beta = rnd(C, seed=2)
+    y = torch.empty(B, C, P, device=DEV)
+    N.channel_mix(x.cuda(), y, mt.cuda(), beta.cuda(), B, C, P, C * P, C * P)
+    sync()
+    ref = torch.einsum("io,bip->bop", mt.double(), x.double()) + beta.double()[None, :, None]
+    assert torch.allclose(y.cpu().double(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_channel_mix_strided_halves():
+    # read the first half of a wider tensor, write into the second half of another (chunk / concat in place)
+    B, C, P = 3, 8, 64
+    wide = rnd(B, 2 * C, P, seed=3)
+    out = torch.zeros(B, 2 * C, P, device=DEV)
+    mt, beta = rnd(C, C, seed=4), rnd(C, seed=5)
+    N.channel_mix(wide.cuda(), out.view(-1)[C * P:], mt.cuda(), beta.cuda(), B, C, P, 2 * C * P, 2 * C * P)
+    sync()
+    ref = torch.einsum("io,bip->bop", mt.double(), wide[:, :C].double()) + beta.double()[None, :, None]
+    assert torch.allclose(out[:, C:].cpu().double(), ref, rtol=1e-5, atol=1e-5)
+    assert out[:, :C].abs().sum() == 0
+
+
+@pytest.mark.parametrize("C", [3, 4, 12, 24, 48, 96, 192])
+def test_mix_prepare(C):
+    g = np.random.default_rng(C)
+    q, _ = np.linalg.qr(g.standard_normal((C, C)))
+    w = torch.from_numpy((q + 0.1 * g.standard_normal((C, C))).astype(np.float32))
+    s, b = rnd(C, seed=1, scale=0.3), rnd(C, seed=2, scale=0.3)
+    f = dict(dtype=torch.float32, device=DEV)
+    fwd_mt, fwd_beta, inv_mt, inv_beta, winv, logdet = (torch.empty(C * C, **f), torch.empty(C, **f),
+                                                        torch.empty(C * C, **f), torch.empty(C, **f),
+                                                        torch.empty(C * C, **f), torch.empty(1, **f))
+    ws = torch.empty(2 * C * C, dtype=torch.float64, device=DEV)
+    wd, sd_, bd = w.cuda(), s.cuda(), b.cuda()
+    N.mix_prepare([N.MixItem(weight=wd.data_ptr(), scale=sd_.data_ptr(), bias=bd.data_ptr(), C=C, pad_=0,
+                             fwd_mt=fwd_mt.data_ptr(), fwd_beta=fwd_beta.data_ptr(), inv_mt=inv_mt.data_ptr(),
+                             inv_beta=inv_beta.data_ptr(), winv=winv.data_ptr(), logdet=logdet.data_ptr(),
+                             lu_ws=ws.data_ptr())])
+    sync()
+    W = w.double()
+    ref_ld = torch.slogdet(W)[1].float() + s.sum()
+    assert abs(logdet.item() - ref_ld.item()) <= 1e-5 * max(1.0, abs(ref_ld.item()))
+    Winv = torch.linalg.inv(W)
+    assert torch.allclose(winv.cpu().reshape(C, C).double(), Winv, rtol=1e-4, atol=1e-5)
+    ref_fwd = (W * torch.exp(s.double())[None, :]).T            # [i, o]
+    assert torch.allclose(fwd_mt.cpu().reshape(C, C).double(), ref_fwd, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(fwd_beta.cpu().double(), ref_fwd.T @ b.double(), rtol=1e-4, atol=1e-5)
+    ref_inv = (torch.exp(-s.double())[:, None] * Winv).T        # [i, o] = exp(-s[o]) Winv[o, i]
+    assert torch.allclose(inv_mt.cpu().reshape(C, C).double(), ref_inv, rtol=1e-4, atol=1e-5)
+    assert torch.equal(inv_beta.cpu(), -b)
+
+
+def test_mix_prepare_identity_and_batch():
+    # weight NULL -> identity; 40 items -> 3 launches of <=16
+    C = 5
+    f = dict(dtype=torch.float32, device=DEV)
+    s = [rnd(C, seed=i, scale=0.2).cuda() for i in range(40)]
+    outs = [torch.empty(1, **f) for _ in range(40)]
+    mts = [torch.empty(C * C, **f) for _ in range(40)]
+    N.mix_prepare([N.MixItem(weight=None, scale=s[i].data_ptr(), bias=None, C=C, pad_=0, fwd_mt=mts[i].data_ptr(),
+                             fwd_beta=None, inv_mt=None, inv_beta=None, winv=None, logdet=outs[i].data_ptr(),
+                             lu_ws=None) for i in range(40)])
+    sync()
+    for i in range(40):
+        assert abs(outs[i].item() - s[i].sum().item()) < 1e-6
+        assert torch.allclose(mts[i].cpu().reshape(C, C), torch.diag(torch.exp(s[i].cpu())), rtol=1e-6)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 4, 6), (3, 1, 32, 32), (2, 12, 16, 16), (1, 6, 8, 8)])
+def test_squeeze_unsqueeze_exact(B, C, H, W):
+    x = rnd(B, C, H, W, seed=7)
+    y = torch.empty(B, 4 * C, H // 2, W // 2, device=DEV)
+    N.squeeze(x.cuda(), y, B, C, H, W, C * H * W, C * H * W)
+    back = torch.empty(B, C, H, W, device=DEV)
+    N.unsqueeze(y, back, B, 4 * C, H // 2, W // 2, C * H * W, C * H * W)
+    sync()
+    assert torch.equal(y.cpu(), O.squeeze2x2(x))
+    assert torch.equal(back.cpu(), x)
+
+
+def test_squeeze_strided_and_copy_channels():
+    B, C, H, W = 2, 4, 8, 8
+    wide = rnd(B, 2 * C, H, W, seed=8)
+    y = torch.empty(B, 4 * C, H // 2, W // 2, device=DEV)
+    N.squeeze(wide.cuda(), y, B, C, H, W, 2 * C * H * W, C * H * W)        # squeeze the kept half in place
+    z = torch.empty(B, C, H, W, device=DEV)
+    N.copy_channels(wide.cuda().view(-1)[C * H * W:], z, B, C, H * W, 2 * C * H * W, C * H * W)
+    sync()
+    assert torch.equal(y.cpu(), O.squeeze2x2(wide[:, :C].contiguous()))
+    assert torch.equal(z.cpu(), wide[:, C:])
+
+
+@pytest.mark.parametrize("B,Cin,H,W,ld", [(2, 2, 16, 16, 64), (3, 6, 16, 16, 64), (2, 12, 8, 8, 128),
+                                          (5, 24, 4, 4, 256), (1, 3, 7, 5, 32)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_im2col(B, Cin, H, W, ld, dt):
+    x = rnd(B, 2 * Cin, H, W, seed=9)                     # use the first Cin channels of a wider tensor
+    out = torch.full((B * H * W, ld), 7.0, dtype=dt, device=DEV)
+    N.im2col3x3(x.cuda(), out, B, Cin, H, W, 2 * Cin * H * W, ld)
+    sync()
+    ref = F.unfold(x[:, :Cin], 3, padding=1).permute(0, 2, 1).reshape(B * H * W, Cin * 9)   # col = c*9 + ky*3 + kx
+    got = out.cpu().float()
+    assert torch.equal(got[:, :Cin * 9], ref.to(dt).float())
+    assert got[:, Cin * 9:].abs().sum() == 0
+
+
+def test_pack_matrix_layouts():
+    C, Fe = 12, 64
+    w3 = rnd(C, Fe, 3, 3, seed=10)
+    ldp = 112
+    out = torch.full((ldp, Fe), 5.0, device=DEV)
+    N.pack_matrix(w3.cuda(), out, 9, C, Fe, 1, Fe * 9, 9, Fe, ldp)
+    sync()
+    ref = w3.permute(2, 3, 0, 1).reshape(9 * C, Fe)       # row = tap*C + co, col = ci
+    assert torch.equal(out.cpu()[:9 * C], ref) and out.cpu()[9 * C:].abs().sum() == 0
+    w1 = rnd(Fe, 6, 3, 3, seed=11)
+    o1 = torch.full((Fe, 64), 5.0, dtype=torch.bfloat16, device=DEV)
+    N.pack_matrix(w1.cuda(), o1, 1, Fe, 54, 0, 54, 1, 64, Fe)
+    sync()
+    assert torch.equal(o1.cpu().float()[:, :54], w1.reshape(Fe, 54).bfloat16().float())
+    assert o1.cpu().float()[:, 54:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("M,N_,K", [(128, 128, 64), (300, 512, 64), (77, 112, 512), (1000, 12, 64), (129, 224, 128),
+                                    (4096, 512, 512), (16, 432, 512), (257, 40, 16)])
+@pytest.mark.parametrize("epi", [N.EPI_RAW, N.EPI_ACTNORM_RELU])
+def test_gemm_nt_fp32(M, N_, K, epi):
+    a, b = rnd(M, K, seed=M), rnd(N_, K, seed=N_ + 1)
+    ldd = (N_ + 7) // 8 * 8
+    d = torch.full((M, ldd), 3.0, device=DEV)
+    es, eb = rnd(N_, seed=3, scale=0.2), rnd(N_, seed=4)
+    N.gemm_nt(a.cuda(), K, b.cuda(), K, d, ldd, M, N_, K, epi, es.cuda(), eb.cuda())
+    sync()
+    ref = a.double() @ b.double().T
+    if epi == N.EPI_ACTNORM_RELU:
+        ref = torch.relu(torch.exp(es.double()) * (ref + eb.double()))
+    got = d.cpu().double()
+    assert torch.allclose(got[:, :N_], ref, rtol=1e-5, atol=1e-4 * math.sqrt(K) / 8)
+    assert (got[:, N_:] == 3.0).all()            # padding columns untouched
+
+
+def test_gemm_nt_fp32_bf16_out():
+    M, N_, K = 200, 512, 64
+    a, b = rnd(M, K, seed=1), rnd(N_, K, seed=2)
+    d = torch.empty(M, N_, dtype=torch.bfloat16, device=DEV)
+    N.gemm_nt(a.cuda(), K, b.cuda(), K, d, N_, M, N_, K)
+    sync()
+    ref = (a.double() @ b.double().T)
+    assert torch.allclose(d.cpu().double(), ref, rtol=1e-2, atol=1e-2)
+
+
+def _coupling_ref(pm_full, bias3, logs3, x, inverse):
+    """pm_full: conv output [B, C, H, W] before bias; mirrors transforms.py:179-184 / 196-200."""
+    C = x.shape[1]
+    net = (pm_full + bias3.reshape(1, C, 1, 1)) * torch.exp(3 * logs3.reshape(1, C, 1, 1))
+    log_s, t = net.chunk(2, 1)
+    s = torch.sigmoid(log_s + 2.0)
+    xa, xb = x.chunk(2, 1)
+    if inverse:
+        return torch.cat([xa, xb / (s + 1e-6) - t], 1), None
+    return torch.cat([xa, (xb + t) * s], 1), torch.log(s + 1e-6).reshape(x.shape[0], -1).sum(1)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 4, 28, 28), (5, 12, 16, 16), (6, 24, 8, 8), (19, 48, 4, 4), (2, 6, 5, 7),
+                                     (2, 12, 64, 64)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_coupling_apply(B, C, H, W, inverse):
+    Fe = 32
+    h2 = rnd(B, Fe, H, W, seed=C)
+    w3 = rnd(C, Fe, 3, 3, seed=C + 1, scale=0.05)
+    bias3, logs3 = rnd(C, seed=2, scale=0.1), rnd(C, seed=3, scale=0.1)
+    x = rnd(B, C, H, W, seed=4)
+    # taps-as-N rows computed on the CPU: pm[m, tap*C+co] = sum_ci h2[m,ci] * w3[co,ci,tap]
+    rows = h2.permute(0, 2, 3, 1).reshape(-1, Fe).double()
+    wt = w3.permute(2, 3, 0, 1).reshape(9 * C, Fe).double()
+    ldp = (9 * C + 15) // 16 * 16
+    pm = torch.zeros(rows.shape[0], ldp)
+    pm[:, :9 * C] = (rows @ wt.T).float()
+    conv = F.conv2d(h2.double(), w3.double(), padding=1).float()
+    ref_y, ref_ld = _coupling_ref(conv, bias3, logs3, x, inverse)
+    P = H * W
+    T = N.ld_tiles(P)
+    part = torch.zeros(T * B, device=DEV)
+    y = torch.empty(B, C, H, W, device=DEV)
+    N.coupling_apply(pm.cuda(), ldp, bias3.cuda(), logs3.cuda(), x.cuda(), y, None if inverse else part, B, C, H, W,
+                     C * P, C * P, inverse)
+    sync()
+    assert torch.allclose(y.cpu(), ref_y, rtol=2e-5, atol=2e-5)
+    if not inverse:
+        got = part.cpu().reshape(T, B).sum(0)
+        assert torch.allclose(got, ref_ld, rtol=1e-5, atol=1e-4)
+        # in place on the second half gives the same answer
+        xin = x.cuda().clone()
+        N.coupling_apply(pm.cuda(), ldp, bias3.cuda(), logs3.cuda(), xin, xin, part, B, C, H, W, C * P, C * P, False)
+        sync()
+        assert torch.equal(xin.cpu(), y.cpu())
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 4, 16, 16), (5, 12, 16, 16), (6, 24, 8, 8), (2, 8, 32, 32), (3, 6, 3, 5)])
+def test_split_prior(B, C, H, W):
+    P, Ch = H * W, C // 2
+    x = rnd(B, C, H, W, seed=1)
+    ldh = (C + 7) // 8 * 8
+    h = torch.zeros(B * P, ldh)
+    h[:, :C] = rnd(B * P, C, seed=2, scale=0.3)
+    bias, logs = rnd(C, seed=3, scale=0.1), rnd(C, seed=4, scale=0.1)
+    full = ((h[:, :C] + bias) * torch.exp(3 * logs)).reshape(B, H, W, C).permute(0, 3, 1, 2)
+    mean, lg = full.chunk(2, 1)
+    ref = O.gaussian_logp(x[:, Ch:], mean, lg)
+    T = N.ld_tiles(P)
+    part = torch.zeros(T * B, device=DEV)
+    z = torch.empty(B, Ch, H, W, device=DEV)
+    N.split_prior_logp(h.cuda(), ldh, bias.cuda(), logs.cuda(), x.cuda(), C * P, z, part, B, C, H, W)
+    sync()
+    assert torch.equal(z.cpu(), x[:, Ch:])
+    assert torch.allclose(part.cpu().reshape(T, B).sum(0), ref, rtol=1e-5, atol=1e-3)
+    # not-learned prior: standard normal
+    N.split_prior_logp(None, 0, None, None, x.cuda(), C * P, None, part, B, C, H, W)
+    sync()
+    ref0 = O.gaussian_logp(x[:, Ch:], torch.zeros_like(mean), torch.zeros_like(lg))
+    assert torch.allclose(part.cpu().reshape(T, B).sum(0), ref0, rtol=1e-5, atol=1e-3)
+    # sampling writes mean + exp(lg)*T*eps into the second half only
+    eps = rnd(B, Ch, H, W, seed=5)
+    out = x.cuda().clone()
+    N.split_prior_sample(h.cuda(), ldh, bias.cuda(), logs.cuda(), eps.cuda(), 0.7, out, C * P, B, C, H, W)
+    sync()
+    assert torch.equal(out.cpu()[:, :Ch], x[:, :Ch])
+    assert torch.allclose(out.cpu()[:, Ch:], mean + torch.exp(lg) * 0.7 * eps, rtol=1e-5, atol=1e-6)
+
+
+def test_gauss_const_and_accumulate():
+    B, C, P = 7, 48, 16
+    z = rnd(B, C, 4, 4, seed=1)
+    bias, logs = rnd(2 * C, seed=2, scale=0.1), rnd(2 * C, seed=3, scale=0.1)
+    psd = {"_GaussianPrior__conv.weight": torch.zeros(2 * C, 2 * C, 3, 3), "_GaussianPrior__conv.bias": bias,
+           "_GaussianPrior__conv.logs": logs.reshape(1, -1, 1, 1)}
+    ref = O.gaussian_prior_logp(psd, z)
+    out = torch.empty(B, device=DEV)
+    N.gauss_logp_const(z.cuda(), bias.cuda(), logs.cuda(), out, B, C, P)
+    sync()
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5)
+    eps = rnd(B, C, 4, 4, seed=4)
+    smp = torch.empty(B, C, 4, 4, device=DEV)
+    N.gauss_sample_const(eps.cuda(), bias.cuda(), logs.cuda(), 0.5, smp, B, C, P)
+    sync()
+    assert torch.allclose(smp.cpu(), O.gaussian_prior_sample(psd, z.shape, 0.5, eps), rtol=1e-5, atol=1e-6)
+    # accumulate: fp64 and fp32 accumulators, partial rows + constants, in place
+    part = rnd(3, B, seed=5)
+    cval, cmul = rnd(4, seed=6), torch.tensor([256.0, 64.0, 16.0, 1.0])
+    for dt in (torch.float64, torch.float32):
+        acc = torch.arange(B, dtype=dt, device=DEV)
+        ptr = acc.data_ptr()
+        N.accumulate(acc, part.cuda(), 3, B, cval.cuda(), cmul.cuda(), 4)
+        sync()
+        ref_acc = torch.arange(B, dtype=torch.float64) + part.double().sum(0) + (cval.double() * cmul.double()).sum()
+        assert acc.data_ptr() == ptr
+        assert torch.allclose(acc.cpu().double(), ref_acc, rtol=1e-6 if dt == torch.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_channel_stats(layout):
+    B, C, H, W = 6, 5, 8, 8
+    x = rnd(B, C, H, W, seed=1) * 3 + 10          # large mean/std ratio stresses the variance computation
+    s_ref, b_ref = O.actnorm_stats(x)
+    s, b = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    if layout == 0:
+        N.channel_stats(x.cuda(), 0, B, C, H * W, C * H * W, s, b)
+    else:
+        rows = torch.zeros(B * H * W, 8)
+        rows[:, :C] = x.permute(0, 2, 3, 1).reshape(-1, C)
+        N.channel_stats(rows.cuda(), 1, B, C, H * W, 8, s, b)
+    sync()
+    assert torch.allclose(s.cpu(), s_ref.reshape(-1), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(b.cpu(), b_ref.reshape(-1), rtol=1e-6)
+
+
+def test_layout_converters_and_actnorm_apply():
+    B, C, H, W = 2, 5, 4, 6
+    P = H * W
+    x = rnd(B, C, H, W, seed=1)
+    rows = torch.empty(B * P, 8, device=DEV)
+    N.nchw_to_rows(x.cuda(), rows, B, C, P, C * P, 8)
+    back = torch.empty(B, C, H, W, device=DEV)
+    N.rows_to_nchw(rows, 8, 0, None, None, back, B, C, P)
+    sync()
+    assert torch.equal(back.cpu(), x)
+    assert rows.cpu()[:, C:].abs().sum() == 0
+    s, b = rnd(C, seed=2, scale=0.2), rnd(C, seed=3)
+    N.rows_to_nchw(rows, 8, 2, s.cuda(), b.cuda(), back, B, C, P)
+    y = torch.empty(B, C, H, W, device=DEV)
+    N.actnorm_apply(x.cuda(), y, s.cuda(), b.cuda(), B, C, P, 0)
+    inv = torch.empty(B, C, H, W, device=DEV)
+    N.actnorm_apply(y, inv, s.cuda(), b.cuda(), B, C, P, 1)
+    sync()
+    ref = O.actnorm_fwd(x, s.reshape(C, 1, 1), b.reshape(C, 1, 1))[0]
+    assert torch.allclose(y.cpu(), ref, rtol=1e-6, atol=1e-6) and torch.allclose(back.cpu(), ref, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(inv.cpu(), x, rtol=1e-5, atol=1e-6)

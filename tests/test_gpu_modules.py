@@ -1,0 +1,327 @@
+"""Module-level parity (GPU): the drop-in ``normalizing_flow`` package against (a) the committed outputs of the
+unmodified reference (tests/golden/*.npz), (b) the CPU oracle on fresh seeded inputs, and (c) size-independent
+properties at BASELINE.json's full sizes.
+
+Tolerances (fp32 mode, north star): z and log-det within 1e-4 relative, bits/dim within 1e-3, inverse
+reconstruction error under 1e-4.  The tests assert tighter bounds where fp32 allows.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import normalizing_flow as nf
+from oracle import glow_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+CASES = ["glow_c1_L3_K2_b3_s32", "glow_c3_L3_K1_b2_s32", "glow_c3_L2_K1_b5_s16", "glow_c1_L2_K1_b2_s8_noprior"]
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode(monkeypatch):
+    monkeypatch.setenv("NFDPM_PRECISION", "fp32")
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(True)
+
+
+def relerr(a, b):
+    a, b = a.detach().cpu().double(), torch.as_tensor(b).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build(c, L, K, seed, learn_prior=True, initialized=True):
+    sd, psd = O.seeded_state(c, L, K, seed, learn_prior=learn_prior, initialized=initialized)
+    flow = nf.Glow(c, L, K, learn_prior_mean_logs=learn_prior).to(DEV)
+    flow.load_state_dict(sd, strict=True)
+    prior = None
+    if learn_prior:
+        prior = nf.GaussianPrior(2 ** (L + 1) * c).to(DEV)
+        prior.load_state_dict(psd, strict=True)
+    return flow, prior, sd, psd
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("acc_dtype", [torch.float64, torch.float32])
+def test_glow_against_reference_golden(golden_dir, name, acc_dtype):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    c, L, K, B, S, seed, lp = [int(v) for v in g["cfg"]]
+    flow, prior, sd, psd = build(c, L, K, seed, learn_prior=bool(lp))
+    assert np.allclose(np.array(O.state_checksum(sd)), g["checksum"], atol=1e-9)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    ld = torch.zeros(B, dtype=acc_dtype, device=DEV)
+    logp = torch.zeros(B, dtype=acc_dtype, device=DEV)
+    ld_ptr, lp_ptr = ld.data_ptr(), logp.data_ptr()
+    zs, ld2, logp2 = flow.transform(x, ld, logp)
+    assert ld2.data_ptr() == ld_ptr and logp2.data_ptr() == lp_ptr          # accumulators updated IN PLACE
+    assert len(zs) == L and [tuple(z.shape[1:]) for z in zs] == nf.calculate_output_shapes(L, c, S)
+    for i, z in enumerate(zs):
+        assert z.dtype == torch.float32 and z.is_contiguous()
+        assert relerr(z, g[f"z{i}"]) < 2e-5, f"z{i}"
+    rt = 1e-6 if acc_dtype == torch.float64 else 1e-5
+    np.testing.assert_allclose(ld.cpu().double().numpy(), g["ld"], rtol=max(rt, 2e-6))
+    np.testing.assert_allclose(logp.cpu().double().numpy(), g["logp"], rtol=max(rt, 2e-6), atol=1e-3)
+    # logp=None disables every prior term (NFBackbone path, reference __init__.py:81)
+    ld3 = torch.zeros(B, dtype=acc_dtype, device=DEV)
+    zs3, ld3, none = flow.transform(x, ld3, None)
+    assert none is None
+    np.testing.assert_allclose(ld3.cpu().double().numpy(), g["ld_nolp"], rtol=max(rt, 2e-6))
+    for a, b in zip(zs, zs3):
+        assert torch.equal(a, b)                                            # deterministic
+    # inverse with all latents, and with only the last one at temperature 0 (z = conditional mean)
+    gz = [torch.from_numpy(g[f"z{i}"]).to(DEV) for i in range(L)]
+    keep = [t.clone() for t in gz]
+    xr = flow.invert(gz)
+    for a, b in zip(gz, keep):
+        assert torch.equal(a, b)                                            # caller's latents are not modified
+    assert (xr.cpu() - torch.from_numpy(g["x_rec"])).abs().max() < 2e-5
+    assert (xr.cpu() - torch.from_numpy(g["x"])).abs().max() < 1e-4         # north star: reconstruction < 1e-4
+    xt0 = flow.invert(gz[-1:], temperature=0.0)
+    assert (xt0.cpu() - torch.from_numpy(g["x_T0"])).abs().max() < 2e-5
+    # round trip through our own forward
+    assert (flow.invert(zs) - x).abs().max() < 1e-4
+    if lp:
+        pl = prior.compute_log_prob(gz[-1])
+        np.testing.assert_allclose(pl.cpu().numpy(), g["prior_logp"], rtol=1e-5)
+        # bits/dim within 1e-3 of the reference
+        ll_ref = torch.from_numpy(g["ld"] + g["logp"]) + torch.from_numpy(g["prior_logp"]).double()
+        ll = ld.cpu().double() + logp.cpu().double() + pl.cpu().double()
+        n_pix = float(c * S * S)
+        assert abs(float(O.bpd_loss(ll, 32.0, n_pix) - O.bpd_loss(ll_ref, 32.0, n_pix))) < 1e-3
+        s0 = prior.sample(tuple(gz[-1].shape), temperature=0.0)
+        np.testing.assert_allclose(s0.cpu().numpy(), g["prior_sample_T0"], rtol=1e-5, atol=1e-7)
+
+
+def test_data_dependent_init_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "glow_init_c1_L2_K1_b6_s16.npz"))
+    c, L, K, B, S, seed, _ = [int(v) for v in g["cfg"]]
+    flow, _, sd, _ = build(c, L, K, seed, initialized=False)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    logp = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, logp = flow.transform(x, ld, logp)
+    after = flow.state_dict()
+    for k in g.files:
+        if not k.startswith("sd/"):
+            continue
+        got = after[k[3:]].cpu()
+        if got.dtype == torch.uint8:
+            assert int(got) == 1, k
+        else:
+            np.testing.assert_allclose(got.numpy().reshape(g[k].shape), g[k], rtol=5e-5, atol=5e-6, err_msg=k)
+    for i, z in enumerate(zs):
+        assert relerr(z, g[f"z{i}"]) < 1e-4
+    np.testing.assert_allclose(ld.cpu().numpy(), g["ld"], rtol=1e-5)
+    np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], rtol=1e-5)
+    # second call uses the now-initialised parameters and gives the same answer
+    ld2 = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs2, ld2, _ = flow.transform(x, ld2, None)
+    assert relerr(zs2[-1], g[f"z{L - 1}"]) < 1e-4
+    np.testing.assert_allclose(ld2.cpu().numpy(), g["ld"], rtol=1e-5)
+
+
+def test_reference_unit_tests_and_goldens(golden_dir):
+    """The reference's own tests (tests/transformations.py: EPS=1e-3 round trips, ActNorm moments) plus value
+    parity with its outputs for ActNorm / InvConv2d / AffineCoupling / Squeeze."""
+    g = np.load(os.path.join(golden_dir, "transforms.npz"))
+    x = torch.from_numpy(g["x"]).to(DEV)
+    f = nf.ActNorm(in_channels=3).to(DEV)
+    ld, lp = torch.zeros(8, device=DEV), torch.zeros(8, device=DEV)
+    y, ld, lp = f.transform(x, ld, lp)
+    inv = f.invert(y)
+    assert (inv - x).norm() < 1e-3
+    assert y.mean(dim=(0, 2, 3)).abs().max() < 1e-3 and (y.var(dim=(0, 2, 3)) - 1).norm() < 1e-3
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ld.cpu().numpy(), g["ld"], rtol=1e-5)
+    np.testing.assert_allclose(f.scale.detach().cpu().numpy(), g["scale"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(f.bias.detach().cpu().numpy(), g["bias"], rtol=1e-5, atol=1e-6)
+    assert int(f.is_initialized) == 1
+    ic = nf.InvConv2d(in_channels=3).to(DEV)
+    ic.load_state_dict({"weight": torch.from_numpy(g["ic_w"])})
+    ld = torch.zeros(8, device=DEV)
+    y, ld, _ = ic.transform(x, ld, lp)
+    np.testing.assert_allclose(y.cpu().numpy(), g["ic_y"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(ld.cpu().numpy(), g["ic_ld"], rtol=1e-5)
+    inv = ic.invert(y)
+    assert (inv - x).norm() < 1e-3
+    np.testing.assert_allclose(inv.cpu().numpy(), g["ic_inv"], rtol=1e-4, atol=1e-4)
+    # a freshly constructed InvConv2d (QR init) round-trips as in the reference test
+    ic2 = nf.InvConv2d(in_channels=3).to(DEV)
+    y2, _, _ = ic2.transform(x, torch.zeros(8, device=DEV), lp)
+    assert (ic2.invert(y2) - x).norm() < 1e-3
+    ac = nf.AffineCoupling(4).to(DEV)
+    sdc, _ = O.seeded_state(1, 2, 1, 41)
+    pre = "blocks.0.flows.0.affcoupling."
+    ac.load_state_dict({k[len(pre):]: v for k, v in sdc.items() if k.startswith(pre)}, strict=True)
+    xa = torch.from_numpy(g["ac_x"]).to(DEV)
+    ld = torch.zeros(4, device=DEV)
+    y, ld, _ = ac.transform(xa, ld, lp)
+    np.testing.assert_allclose(y.cpu().numpy(), g["ac_y"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ld.cpu().numpy(), g["ac_ld"], rtol=1e-5)
+    inv = ac.invert(y)
+    assert (inv - xa).norm() < 1e-3 and y.shape == xa.shape == inv.shape
+    # zero-init coupling (the reference test's actual setting): scale = sigmoid(2) everywhere
+    ac0 = nf.AffineCoupling(4).to(DEV)
+    x0 = torch.randn(32, 4, 28, 28, device=DEV)
+    ld0 = torch.zeros(32, device=DEV)
+    y0, ld0, _ = ac0.transform(x0, ld0, None)
+    assert (ac0.invert(y0) - x0).norm() < 1e-3
+    s2 = 1.0 / (1.0 + np.exp(-2.0))
+    np.testing.assert_allclose(ld0.cpu().numpy(), 2 * 784 * np.log(s2 + 1e-6), rtol=1e-5)
+    sq = nf.Squeeze()
+    xs = torch.from_numpy(g["sq_x"]).to(DEV)
+    ys = sq.transform(xs, None, None)[0]
+    assert np.array_equal(ys.cpu().numpy(), g["sq_y"]) and np.array_equal(sq.invert(ys).cpu().numpy(), g["sq_x"])
+
+
+def test_step_block_split_granular_api():
+    """StepFlow / GlowBlock / Split used one by one equal the fused Glow call and the oracle."""
+    c, L, K, B, S = 3, 2, 2, 3, 16
+    flow, _, sd, _ = build(c, L, K, 77)
+    x = O.seeded_input((B, c, S, S), 78)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, lp = flow.transform(x.to(DEV), ld, lp)
+    ld_o, lp_o = torch.zeros(B, dtype=torch.float64), torch.zeros(B, dtype=torch.float64)
+    zo, ld_o, lp_o = O.glow_transform(sd, x, L, K, ld_o, lp_o)
+    # block by block
+    ld_b = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lp_b = torch.zeros(B, dtype=torch.float64, device=DEV)
+    y, ld_b, z0, lp_b = flow.blocks[0].transform(x.to(DEV), ld_b, lp_b)
+    assert relerr(z0, zo[0]) < 2e-5 and relerr(z0, zs[0]) < 1e-6
+    y, _, _ = flow.final_squeeze.transform(y, ld_b, lp_b)
+    for st in flow.final_flows:
+        y, ld_b, lp_b = st.transform(y, ld_b, lp_b)
+    assert relerr(y, zo[1]) < 2e-5
+    np.testing.assert_allclose(ld_b.cpu().numpy(), ld_o.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(lp_b.cpu().numpy(), lp_o.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(ld.cpu().numpy(), ld_o.numpy(), rtol=1e-6)
+    # inverse block by block
+    inv = y
+    for st in reversed(flow.final_flows):
+        inv = st.invert(inv)
+    inv = flow.final_squeeze.invert(inv)
+    inv = flow.blocks[0].invert(inv, z0)
+    assert (inv.cpu() - x).abs().max() < 1e-4
+    # Split.invert sampling: T=0 gives the conditional mean of the oracle
+    kept = torch.from_numpy(O.unsqueeze2x2(zo[1]).numpy()).to(DEV)
+    full = flow.blocks[0].split.invert(kept, None, temperature=0.0)
+    mean, _ = O.split_prior_params(O.unsqueeze2x2(zo[1]), sd, "blocks.0.split.")
+    assert relerr(full[:, kept.shape[1]:], mean) < 2e-5
+    # T=1: sample statistics follow N(mean, exp(logs))
+    torch.manual_seed(0)
+    big = kept.repeat(64, 1, 1, 1)
+    smp = flow.blocks[0].split.invert(big, None, temperature=1.0)[:, kept.shape[1]:]
+    m, lg = O.split_prior_params(O.unsqueeze2x2(zo[1]).repeat(64, 1, 1, 1), sd, "blocks.0.split.")
+    zscore = (smp.cpu() - m) / torch.exp(lg)
+    assert abs(float(zscore.mean())) < 0.02 and abs(float(zscore.std()) - 1) < 0.02
+
+
+def test_nfbackbone_and_sample_api(tmp_path):
+    c, L, K, B, S = 1, 3, 2, 4, 32
+    flow, prior, sd, psd = build(c, L, K, 91)
+    ck = tmp_path / "model_gaussian_001.pt"
+    torch.save({"flow": flow.state_dict(), "prior_dist": prior.state_dict()}, ck)
+    bb = nf.NFBackbone(str(ck), c, L, K, True, True)
+    assert bb.is_frozen() and not any(p.requires_grad for p in bb.parameters())
+    assert list(bb.state_dict().keys())[0].startswith("model.")
+    x = O.seeded_input((B, c, S, S), 92).to(DEV)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    torch.set_grad_enabled(True)           # frozen backbone works with autograd enabled (diffusion trainer path)
+    parts, ld = bb.transform(x, ld)
+    torch.set_grad_enabled(False)
+    ld_o = torch.zeros(B, dtype=torch.float64)
+    zo, ld_o, _ = O.glow_transform(sd, x.cpu(), L, K, ld_o, None)
+    for a, b in zip(parts, zo):
+        assert relerr(a, b) < 2e-5
+    np.testing.assert_allclose(ld.cpu().numpy(), ld_o.numpy(), rtol=1e-6)
+    out = bb.sample(parts, postprocess_func=lambda t: nf.postprocess_batch(t, 32.0))
+    assert out.dtype == torch.uint8 and out.shape == (B, c, S, S) and bb.model.training
+    ref = O.postprocess_batch(O.glow_invert(sd, zo, L, K), 32.0)
+    assert (out.int() - ref.int()).abs().max() <= 8       # one 5-bit quantisation level at most (floor at a bin edge)
+    assert float((out != ref).float().mean()) < 1e-3
+    # Glow.sample from the Gaussian prior on the last latent only (metrics/compute.py:214-215)
+    torch.manual_seed(1)
+    last = prior.sample((B, 16, 4, 4), temperature=0.7)
+    img = flow.sample([last], temperature=0.7)
+    assert img.shape == (B, c, S, S) and torch.isfinite(img).all()
+
+
+@pytest.mark.parametrize("cfg", [(1, 3, 4, 64, 32), (3, 3, 16, 128, 32)])
+def test_full_size_properties(cfg):
+    """BASELINE configs 1 and 2 at full size: reference-style random init + data-dependent initialisation,
+    then (a) invert(transform(x)) < 1e-4, (b) closed-form log-det at zero-init coupling nets,
+    (c) per-image independence: a batch subset through the CPU oracle gives the same z / log-det / log-p."""
+    c, L, K, B, S = cfg
+    torch.manual_seed(0)
+    flow = nf.Glow(c, L, K).to(DEV)
+    prior = nf.GaussianPrior(2 ** (L + 1) * c).to(DEV)
+    x = O.seeded_input((B, c, S, S), 123).to(DEV)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, lp = flow.transform(x, ld, lp)          # performs the data-dependent init
+    sd = {k: v.cpu() for k, v in flow.state_dict().items()}
+    assert all(int(v) == 1 for k, v in sd.items() if k.endswith("is_initialized"))
+    xr = flow.invert(zs)
+    assert (xr - x).abs().max() < 1e-4
+    # (b) zero-init ZeroConvs: every coupling contributes (C/2)*P*log(sigmoid(2)+1e-6); 1x1 convs are orthogonal
+    s2 = np.log(1.0 / (1.0 + np.exp(-2.0)) + 1e-6)
+    want = 0.0
+    h, ch = S, c
+    for li in range(L):
+        h //= 2
+        C = ch * 4
+        for k, v in sd.items():
+            pre = f"blocks.{li}.flows." if li < L - 1 else "final_flows."
+            if k.startswith(pre) and k.endswith(".actnorm.scale") and "affcoupling" not in k:
+                want += h * h * float(v.double().sum())
+            if k.startswith(pre) and k.endswith("invconv2d.weight"):
+                want += h * h * float(torch.slogdet(v.reshape(C, C).double())[1])
+        want += K * (C // 2) * h * h * s2
+        ch = C // 2
+    np.testing.assert_allclose(ld.cpu().numpy(), np.full(B, want), rtol=2e-6)
+    # Gaussian log-p at zero-init priors = -0.5*n*log(2pi) - 0.5*sum z^2 over split latents (+ final via prior)
+    lp_want = sum((-0.5 * z[0].numel() * np.log(2 * np.pi) - 0.5 * (z.double() ** 2).flatten(1).sum(1)) for z in zs[:-1])
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_want.cpu().numpy(), rtol=1e-5)
+    pl = prior.compute_log_prob(zs[-1])
+    pl_want = -0.5 * zs[-1][0].numel() * np.log(2 * np.pi) - 0.5 * (zs[-1].double() ** 2).flatten(1).sum(1)
+    np.testing.assert_allclose(pl.cpu().numpy(), pl_want.cpu().numpy(), rtol=1e-5)
+    # (c) perturb the ZeroConvs so the coupling nets matter, then compare a 4-image subset with the oracle
+    g = torch.Generator().manual_seed(1)
+    for k in list(sd):
+        if k.endswith("net.4.weight") or k.endswith("net.4.bias") or k.endswith("net.4.logs") or ".split.conv." in k:
+            sd[k] = sd[k] + 0.01 * torch.randn(sd[k].shape, generator=g)
+    flow.load_state_dict(sd)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, lp = flow.transform(x, ld, lp)
+    idx = [0, 1, B // 2, B - 1]
+    xs = x.cpu()[idx]
+    ld_o, lp_o = torch.zeros(4, dtype=torch.float64), torch.zeros(4, dtype=torch.float64)
+    zo, ld_o, lp_o = O.glow_transform(sd, xs, L, K, ld_o, lp_o)
+    for a, b in zip(zs, zo):
+        assert relerr(a[idx], b) < 1e-4
+    np.testing.assert_allclose(ld.cpu().numpy()[idx], ld_o.numpy(), rtol=1e-5)
+    np.testing.assert_allclose(lp.cpu().numpy()[idx], lp_o.numpy(), rtol=1e-5)
+    assert (flow.invert(zs) - x).abs().max() < 1e-4
+
+
+def test_error_behaviour():
+    flow, _, _, _ = build(1, 2, 1, 5)
+    x = torch.zeros(2, 1, 8, 8, device=DEV)
+    with pytest.raises(ValueError):
+        flow.transform(torch.zeros(2, 1, 6, 6, device=DEV), torch.zeros(2, device=DEV), None)      # not divisible
+    with pytest.raises(ValueError):
+        flow.transform(torch.zeros(2, 3, 8, 8, device=DEV), torch.zeros(2, device=DEV), None)      # wrong channels
+    with pytest.raises(ValueError):
+        flow.transform(x, torch.zeros(3, device=DEV), None)                                         # wrong acc length
+    with pytest.raises(TypeError):
+        flow.transform(x.double(), torch.zeros(2, device=DEV), None)
+    with pytest.raises(ValueError):
+        nf.Squeeze().transform(torch.zeros(1, 1, 3, 4, device=DEV), None, None)
+    torch.set_grad_enabled(True)
+    with pytest.raises(NotImplementedError):
+        flow.transform(x, torch.zeros(2, device=DEV), None)           # trainable flow under autograd: not yet
+    torch.set_grad_enabled(False)
