@@ -29,7 +29,10 @@ int fail(const char* fmt, ...);
 #define NFDPM_CUDA(call)                                                                  \
   do {                                                                                    \
     cudaError_t e__ = (call);                                                             \
-    if (e__ != cudaSuccess) return nfdpm::fail("%s: %s", #call, cudaGetErrorString(e__)); \
+    if (e__ != cudaSuccess) {                                                             \
+      (void)cudaGetLastError(); /* do not leave a sticky error for the next call */       \
+      return nfdpm::fail("%s: %s", #call, cudaGetErrorString(e__));                       \
+    }                                                                                     \
   } while (0)
 
 static inline cudaStream_t as_stream(nfdpm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

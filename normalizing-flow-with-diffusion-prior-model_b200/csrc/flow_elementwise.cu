@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(256) chanmix_small_kernel(const float* __restr
   }
 }
 
-// K-A generic path: any C (<= 192).  CTA = 256 threads = 64 pixel groups x 4 output quarters; the x tile
-// [C][64*V] and the CxC matrix live in shared memory; each thread produces 4 output channels x V pixels at a
-// time.  V = 4 (128-bit access) when P % 4 == 0, else V = 1.
-template <int V>
+// K-A generic path: any C (<= 192).  CTA = 256 threads = TPG pixel groups x (256/TPG) output slices; the x tile
+// [C][TPG*V] and the CxC matrix live in shared memory; each thread produces 4 output channels x V pixels at a
+// time.  V = 4 (128-bit access) when P % 4 == 0, else V = 1.  TPG = 64 normally, 16 for wide C (smem budget).
+template <int V, int TPG>
 __global__ void __launch_bounds__(256) chanmix_generic_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                               const float* __restrict__ mt,
                                                               const float* __restrict__ beta, int C, int P,
@@ -64,15 +64,15 @@ __global__ void __launch_bounds__(256) chanmix_generic_kernel(const float* __res
   const int Cp = (C + 3) & ~3;
   float* s_m = sm;                 // [C][Cp]  (row = input channel, col = output channel, zero padded)
   float* s_b = s_m + C * Cp;       // [Cp]
-  float* s_x = s_b + Cp;           // [C][64*V]
-  constexpr int TPG = 64;          // pixel groups per tile
+  float* s_x = s_b + Cp;           // [C][TPG*V]
+  constexpr int NQ = 256 / TPG;    // output slices
   for (int i = threadIdx.x; i < C * Cp; i += 256) {
     const int r = i / Cp, c = i - r * Cp;
     s_m[i] = (c < C) ? mt[r * C + c] : 0.f;
   }
   for (int i = threadIdx.x; i < Cp; i += 256) s_b[i] = (i < C) ? beta[i] : 0.f;
-  const int pg = (threadIdx.x & 31) + ((threadIdx.x >> 5) & 1) * 32;  // pixel group within tile
-  const int q = threadIdx.x >> 6;                                      // output quarter
+  const int pg = threadIdx.x % TPG;   // pixel group within tile (consecutive lanes -> consecutive pixels)
+  const int q = threadIdx.x / TPG;    // output slice
   const int PV = P / V;
   for (int64_t tile = blockIdx.x; tile * TPG < n_groups; tile += gridDim.x) {
     __syncthreads();  // s_m ready (first iteration) / previous tile consumed
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) chanmix_generic_kernel(const float* __res
       b = g / PV;
       p = (int)(g - b * PV) * V;
     }
-    for (int o0 = q * 4; o0 < C; o0 += 16) {
+    for (int o0 = q * 4; o0 < C; o0 += 4 * NQ) {
       float acc[4][V];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -341,16 +341,20 @@ extern "C" int nfdpm_channel_mix(const float* x, float* y, const float* mt, cons
   }
   const int V = vec ? 4 : 1;
   const int Cp = (C + 3) & ~3;
-  const size_t smem = sizeof(float) * ((size_t)C * Cp + Cp + (size_t)C * 64 * V);
+  const int TPG = (C > 64) ? 16 : 64;
+  const size_t smem = sizeof(float) * ((size_t)C * Cp + Cp + (size_t)C * TPG * V);
+  NFDPM_REQUIRE(smem <= 227 * 1024, "nfdpm_channel_mix: C=%d needs %zu bytes of shared memory", C, smem);
   const int64_t ng = (int64_t)B * P / V;
-  const int grid = grid_for(cdiv64(ng, 64), 1, 148 * 4);
-  if (V == 4) {
-    NFDPM_CUDA(cudaFuncSetAttribute(chanmix_generic_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chanmix_generic_kernel<4><<<grid, 256, smem, st>>>(x, y, mt, beta, C, P, ng, xbs, ybs);
-  } else {
-    NFDPM_CUDA(cudaFuncSetAttribute(chanmix_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chanmix_generic_kernel<1><<<grid, 256, smem, st>>>(x, y, mt, beta, C, P, ng, xbs, ybs);
-  }
+  const int grid = grid_for(cdiv64(ng, TPG), 1, 148 * 4);
+#define LAUNCH(VV, TT)                                                                                           \
+  do {                                                                                                           \
+    NFDPM_CUDA(cudaFuncSetAttribute(chanmix_generic_kernel<VV, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                 \
+    chanmix_generic_kernel<VV, TT><<<grid, 256, smem, st>>>(x, y, mt, beta, C, P, ng, xbs, ybs);                 \
+  } while (0)
+  if (V == 4) { if (TPG == 64) LAUNCH(4, 64); else LAUNCH(4, 16); }
+  else { if (TPG == 64) LAUNCH(1, 64); else LAUNCH(1, 16); }
+#undef LAUNCH
   NFDPM_CHECK_LAUNCH("chanmix_generic_kernel");
   return 0;
 }

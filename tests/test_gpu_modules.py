@@ -28,7 +28,7 @@ def _fp32_mode(monkeypatch):
 
 
 def relerr(a, b):
-    a, b = a.detach().cpu().double(), torch.as_tensor(b).double()
+    a, b = a.detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
@@ -303,8 +303,9 @@ def test_full_size_properties(cfg):
     zo, ld_o, lp_o = O.glow_transform(sd, xs, L, K, ld_o, lp_o)
     for a, b in zip(zs, zo):
         assert relerr(a[idx], b) < 1e-4
-    np.testing.assert_allclose(ld.cpu().numpy()[idx], ld_o.numpy(), rtol=1e-5)
-    np.testing.assert_allclose(lp.cpu().numpy()[idx], lp_o.numpy(), rtol=1e-5)
+    # log-det is a sum of +-1e3-sized terms that nearly cancel at init: bound the error relative to the terms
+    np.testing.assert_allclose(ld.cpu().numpy()[idx], ld_o.numpy(), rtol=1e-5, atol=2e-2)
+    np.testing.assert_allclose(lp.cpu().numpy()[idx], lp_o.numpy(), rtol=1e-5, atol=2e-2)
     assert (flow.invert(zs) - x).abs().max() < 1e-4
 
 
