@@ -1,8 +1,367 @@
-// tcgen05 / TMEM bf16 GEMM (placeholder until the tensor-core kernel lands in this file).
+// tcgen05 / TMEM / TMA bf16 GEMM for the coupling networks:  D[M,N] = epilogue(A[M,K] * Bw[N,K]^T)
+//   A  [M,K] bf16 row-major (pixel-major activations), Bw [N,K] bf16 row-major (packed conv weights),
+//   fp32 accumulation in tensor memory, output bf16 or fp32.
+//
+// Persistent, warp-specialised CTA (one per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A box and a BNx64 B box (128B swizzle)
+//               into a 4-stage shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage,
+//               tcgen05.commit releases the smem stage / publishes the accumulator; also owns TMEM alloc/dealloc
+//   warps 2..5  epilogue: tcgen05.ld (32x32b.x16) of the accumulator quadrant, fused ActNorm+ReLU
+//               (utils.py:69,84-87), convert, 16-byte global stores.  Two TMEM accumulator stages (2 x 256 columns)
+//               let the epilogue of tile i overlap the main loop of tile i+1.
+// BN (<= 256, multiple of 16) is a runtime value: it only enters through the B tensor map box, the expected
+// transaction bytes and the instruction descriptor.
+//
+// Every mbarrier wait is bounded (2 s on %globaltimer) and traps instead of hanging the GPU.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace nfdpm {
-int gemm_nt_tc(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, int, int, const float*,
-               const float*, cudaStream_t) {
-  return fail("nfdpm_gemm_nt: bf16 tensor-core path not built in this version");
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
+constexpr int TC_B_BYTES_MAX = 256 * TC_BK * 2;        // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
+constexpr int TC_THREADS = 192;
+constexpr int TC_ACC_COLS = 256;     // TMEM columns per accumulator stage
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch failure), never hang the box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, single CTA, bf16 inputs / fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, dense [rows][64] bf16 tile:
+//   start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B (8 rows x 128 B) >> 4 = 64 |
+//   descriptor version 1 (Blackwell) | layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (kind::f16): D=F32 (bit 4), A=BF16 (bits 7..9 = 1), B=BF16 (bits 10..12 = 1),
+// both K-major (bits 15,16 = 0), N>>3 at bits 17..22, M>>4 at bits 24..28
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <typename OutT> struct TcStore;
+template <> struct TcStore<float> {
+  static __device__ __forceinline__ void vec16(float* p, const float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  static __device__ __forceinline__ void one(float* p, float a) { *p = a; }
+};
+template <> struct TcStore<__nv_bfloat16> {
+  static __device__ __forceinline__ void vec16(__nv_bfloat16* p, const float (&v)[16]) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(p + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+  static __device__ __forceinline__ void one(__nv_bfloat16* p, float a) { *p = __float2bfloat16_rn(a); }
+};
+
+template <int EPI, typename OutT>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   OutT* __restrict__ D, int64_t ldd, int M, int N, int K,
+                                                                   int BN, const float* __restrict__ ep_scale,
+                                                                   const float* __restrict__ ep_bias) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 4];
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1024-byte aligned tile ring (swizzle-128B requirement), then the epilogue parameters
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  float* s_ep = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[TC_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * TC_STAGES]), bar_tempty = smem_u32(&bars[2 * TC_STAGES + 2]);
+
+  const int num_n = (N + BN - 1) / BN;
+  const int num_m = (M + TC_BM - 1) / TC_BM;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / TC_BK;
+
+  if (EPI == NFDPM_EPI_ACTNORM_RELU) {
+    for (int i = threadIdx.x; i < N; i += TC_THREADS) {
+      s_ep[i] = expf(ep_scale[i]);
+      s_ep[N + i] = ep_bias[i];
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + BN * TC_BK * 2);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (lane == 0) {
+          const uint32_t sa = ring + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+          mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
+          tma_load_2d(sa, &tmA, kb * TC_BK, m_blk * TC_BM, bar_full + 8 * stage);
+          tma_load_2d(sb, &tmB, kb * TC_BK, n_blk * BN, bar_full + 8 * stage);
+        }
+        __syncwarp();
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t idesc = make_idesc(TC_BM, BN);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * TC_ACC_COLS;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);           // TMA bytes have landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ring + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)              // +32 bytes (= 2 x 16 B) per K=16 slice inside the swizzle row
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * stage);             // smem stage reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                               // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int row = m_blk * TC_BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_ACC_COLS;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c0;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = __uint_as_float(r[j]);
+          if (EPI == NFDPM_EPI_ACTNORM_RELU) {
+            const int n = min(n0 + j, N - 1);
+            v[j] = fmaxf(0.f, s_ep[n] * (v[j] + s_ep[N + n]));
+          }
+        }
+        if (row < M) {
+          OutT* dp = D + (int64_t)row * ldd + n0;
+          if (n0 + 15 < N) {
+            TcStore<OutT>::vec16(dp, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + j < N) TcStore<OutT>::one(dp + j, v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  NFDPM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NFDPM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%d)",
+                (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows);
+  return 0;
+}
+
+template <int EPI, typename OutT>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* D, int64_t ldd, int M, int N, int K, int BN,
+                     const float* es, const float* eb, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NFDPM_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    220 * 1024));
+    attr_set = true;
+  }
+  gemm_nt_tc_kernel<EPI, OutT><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, (OutT*)D, ldd, M, N, K, BN, es, eb);
+  NFDPM_CHECK_LAUNCH("gemm_nt_tc_kernel");
+  return 0;
+}
+
+int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
+               int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st) {
+  NFDPM_REQUIRE(N % 16 == 0, "nfdpm_gemm_nt(bf16): N=%d must be a multiple of 16", N);
+  NFDPM_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)D % 16 == 0),
+                "nfdpm_gemm_nt(bf16): operands must be 16-byte aligned");
+  NFDPM_REQUIRE(epilogue == NFDPM_EPI_RAW || N <= 2048, "nfdpm_gemm_nt(bf16): fused ActNorm epilogue supports N <= 2048");
+  // N tile: the largest multiple of 16 that is <= 256 and splits N evenly enough
+  const int nblk = (N + 255) / 256;
+  int BN = ((N + nblk - 1) / nblk + 15) / 16 * 16;
+  CUtensorMap tmA, tmB;
+  if (make_map(&tmA, A, M, K, lda, TC_BM)) return 1;
+  if (make_map(&tmB, Bw, N, K, ldb, BN)) return 1;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    NFDPM_CUDA(cudaGetDevice(&dev));
+    NFDPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sms ? tiles : sms;
+  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (epilogue == NFDPM_EPI_ACTNORM_RELU ? 2 * (size_t)N * 4 : 0);
+#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, D, ldd, M, N, K, BN, ep_scale, ep_bias, grid, smem, st)
+  if (out_dtype == NFDPM_F32) {
+    if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, float); else GO(NFDPM_EPI_ACTNORM_RELU, float);
+  } else {
+    if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, __nv_bfloat16); else GO(NFDPM_EPI_ACTNORM_RELU, __nv_bfloat16);
+  }
+#undef GO
+}
+
 }  // namespace nfdpm

@@ -324,3 +324,27 @@ def test_layout_converters_and_actnorm_apply():
     ref = O.actnorm_fwd(x, s.reshape(C, 1, 1), b.reshape(C, 1, 1))[0]
     assert torch.allclose(y.cpu(), ref, rtol=1e-6, atol=1e-6) and torch.allclose(back.cpu(), ref, rtol=1e-6, atol=1e-6)
     assert torch.allclose(inv.cpu(), x, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ tcgen05 / TMEM / TMA bf16 GEMM
+@pytest.mark.parametrize("M,N_,K", [(128, 256, 64), (300, 512, 64), (77, 112, 512), (4096, 224, 512), (2048, 432, 512),
+                                    (129, 16, 128), (32768, 512, 512), (1000, 512, 256), (50000, 48, 64)])
+@pytest.mark.parametrize("epi", [N.EPI_RAW, N.EPI_ACTNORM_RELU])
+@pytest.mark.parametrize("out_dt", [torch.bfloat16, torch.float32])
+def test_gemm_nt_bf16_tensor_core(M, N_, K, epi, out_dt):
+    """bf16 operands, fp32 TMEM accumulation.  Reference = fp64 product of the SAME bf16-rounded operands, so the
+    only error left is fp32 accumulation order (+ output rounding for bf16 stores: 2^-9 relative)."""
+    a = rnd(M, K, seed=M % 97).bfloat16()
+    b = (rnd(N_, K, seed=N_ + 1) * 0.1).bfloat16()
+    d = torch.full((M, N_), 3.0, dtype=out_dt, device=DEV)
+    es, eb = rnd(N_, seed=3, scale=0.2), rnd(N_, seed=4)
+    N.gemm_nt(a.cuda(), K, b.cuda(), K, d, N_, M, N_, K, epi, es.cuda(), eb.cuda())
+    sync()
+    ref = a.double() @ b.double().T
+    if epi == N.EPI_ACTNORM_RELU:
+        ref = torch.relu(torch.exp(es.double()) * (ref + eb.double()))
+    got = d.cpu().double()
+    if out_dt == torch.float32:
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+    else:
+        assert torch.allclose(got, ref, rtol=6e-3, atol=6e-3)
