@@ -292,7 +292,7 @@ def test_full_size_properties(cfg):
     g = torch.Generator().manual_seed(1)
     for k in list(sd):
         if k.endswith("net.4.weight") or k.endswith("net.4.bias") or k.endswith("net.4.logs") or ".split.conv." in k:
-            sd[k] = sd[k] + 0.01 * torch.randn(sd[k].shape, generator=g)
+            sd[k] = sd[k] + 0.003 * torch.randn(sd[k].shape, generator=g)   # 0.01 makes the fp32 reference itself diverge at K=16
     flow.load_state_dict(sd)
     ld = torch.zeros(B, dtype=torch.float64, device=DEV)
     lp = torch.zeros(B, dtype=torch.float64, device=DEV)
@@ -326,3 +326,36 @@ def test_error_behaviour():
     with pytest.raises(NotImplementedError):
         flow.transform(x, torch.zeros(2, device=DEV), None)           # trainable flow under autograd: not yet
     torch.set_grad_enabled(False)
+
+
+# ------------------------------------------------------------------ bf16 tensor-core mode (tcgen05 coupling nets)
+BF16_TOL = dict(z_rel=5e-3, ld_rel=2e-4, bpd_abs=1e-3)   # stated bf16 tolerance; measured:
+#   z relL2 <= 1.6e-3, log-det rel <= 4e-5, bpd abs <= 1.7e-4 on the cases below (tools/measure_bf16.py)
+
+
+@pytest.mark.parametrize("cfg", [(1, 3, 2, 3, 32, 11), (3, 3, 4, 16, 32, 13), (3, 3, 16, 16, 32, 14)])
+def test_glow_bf16_mode_within_stated_tolerance(cfg, monkeypatch):
+    c, L, K, B, S, seed = cfg
+    monkeypatch.setenv("NFDPM_PRECISION", "bf16")
+    flow, prior, sd, psd = build(c, L, K, seed)
+    x = O.seeded_input((B, c, S, S), seed + 1)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, lp = flow.transform(x.to(DEV), ld, lp)
+    pl = prior.compute_log_prob(zs[-1])
+    ld_o, lp_o = torch.zeros(B, dtype=torch.float64), torch.zeros(B, dtype=torch.float64)
+    zo, ld_o, lp_o = O.glow_transform(sd, x, L, K, ld_o, lp_o)
+    pl_o = O.gaussian_prior_logp(psd, zo[-1])
+    for a, b in zip(zs, zo):
+        assert relerr(a, b) < BF16_TOL["z_rel"]
+    assert float(((ld.cpu() - ld_o).abs() / ld_o.abs()).max()) < BF16_TOL["ld_rel"]
+    n_pix = float(c * S * S)
+    bpd = O.bpd_loss(ld.cpu() + lp.cpu() + pl.cpu().double(), 32.0, n_pix)
+    bpd_o = O.bpd_loss(ld_o + lp_o + pl_o.double(), 32.0, n_pix)
+    assert abs(float(bpd - bpd_o)) < BF16_TOL["bpd_abs"]
+    # the inverse runs and is finite; its accuracy is conditioning-limited in bf16 (SURVEY §7 hard part 2), so the
+    # < 1e-4 reconstruction bar is asserted in fp32 mode only (tests above); here: shallow flows stay within 5e-3
+    xr = flow.invert(zs)
+    assert torch.isfinite(xr).all()
+    if K <= 4:
+        assert (xr.cpu() - x).abs().max() < 5e-3
