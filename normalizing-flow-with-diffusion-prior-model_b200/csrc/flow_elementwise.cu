@@ -346,10 +346,15 @@ extern "C" int nfdpm_channel_mix(const float* x, float* y, const float* mt, cons
   NFDPM_REQUIRE(smem <= 227 * 1024, "nfdpm_channel_mix: C=%d needs %zu bytes of shared memory", C, smem);
   const int64_t ng = (int64_t)B * P / V;
   const int grid = grid_for(cdiv64(ng, TPG), 1, 148 * 4);
+  // the opt-in shared-memory limit is raised once per instantiation (never during a stream capture)
 #define LAUNCH(VV, TT)                                                                                           \
   do {                                                                                                           \
-    NFDPM_CUDA(cudaFuncSetAttribute(chanmix_generic_kernel<VV, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)smem));                                                                 \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      NFDPM_CUDA(cudaFuncSetAttribute(chanmix_generic_kernel<VV, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      227 * 1024));                                                              \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
     chanmix_generic_kernel<VV, TT><<<grid, 256, smem, st>>>(x, y, mt, beta, C, P, ng, xbs, ybs);                 \
   } while (0)
   if (V == 4) { if (TPG == 64) LAUNCH(4, 64); else LAUNCH(4, 16); }

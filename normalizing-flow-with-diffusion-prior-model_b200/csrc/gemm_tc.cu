@@ -2,14 +2,16 @@
 //   A  [M,K] bf16 row-major (pixel-major activations), Bw [N,K] bf16 row-major (packed conv weights),
 //   fp32 accumulation in tensor memory, output bf16 or fp32.
 //
-// Persistent, warp-specialised CTA (one per SM, 192 threads):
+// Persistent, warp-specialised CTA (one per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A box and a BNx64 B box (128B swizzle)
 //               into a 4-stage shared-memory ring, completion on mbarriers
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator; also owns TMEM alloc/dealloc
-//   warps 2..5  epilogue: tcgen05.ld (32x32b.x16) of the accumulator quadrant, fused ActNorm+ReLU
-//               (utils.py:69,84-87), convert, 16-byte global stores.  Two TMEM accumulator stages (2 x 256 columns)
-//               let the epilogue of tile i overlap the main loop of tile i+1.
+//   warps 2..9  epilogue: software-pipelined tcgen05.ld (32x32b.x16) of the accumulator quadrant, fused
+//               ActNorm+ReLU as one FMA + max per element (utils.py:69,84-87), convert, 16-byte global stores.
+//               Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the main loop of
+//               tile i+1.  (r1 profile: with 4 epilogue warps and scalar parameter loads the kernel was
+//               issue-bound in the epilogue at 30% tensor-pipe activity.)
 // BN (<= 256, multiple of 16) is a runtime value: it only enters through the B tensor map box, the expected
 // transaction bytes and the instruction descriptor.
 //
@@ -26,7 +28,8 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_B_BYTES_MAX = 256 * TC_BK * 2;        // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quadrant, alternating 16-column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_ACC_COLS = 256;     // TMEM columns per accumulator stage
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -167,10 +170,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
   const int num_tiles = num_m * num_n;
   const int num_kb = K / TC_BK;
 
+  const int n_pad = num_n * BN;        // columns covered by the tiles (>= N); parameters are zero beyond N
   if (EPI == NFDPM_EPI_ACTNORM_RELU) {
-    for (int i = threadIdx.x; i < N; i += TC_THREADS) {
-      s_ep[i] = expf(ep_scale[i]);
-      s_ep[N + i] = ep_bias[i];
+    for (int i = threadIdx.x; i < n_pad; i += TC_THREADS) {
+      const float e = (i < N) ? expf(ep_scale[i]) : 0.f;
+      s_ep[i] = e;                                   // y = max(0, e*acc + e*b)
+      s_ep[n_pad + i] = (i < N) ? e * ep_bias[i] : 0.f;
     }
   }
   if (warp == 0 && lane == 0) {
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128);
+      mbar_init(bar_tempty + 8 * a, 32 * TC_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -239,8 +244,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                               // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                     // which of the two warps of the quadrant
+    const int n_chunks = BN >> 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -249,30 +256,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       tc_fence_after();
       const int row = m_blk * TC_BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_ACC_COLS;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
+      OutT* drow = D + (int64_t)row * ldd;
+      auto process = [&](const uint32_t (&r)[16], int c0) {
         const int n0 = n_blk * BN + c0;
         float v[16];
+        if (EPI == NFDPM_EPI_ACTNORM_RELU) {
+          const float4* pe = reinterpret_cast<const float4*>(s_ep + n0);
+          const float4* pb = reinterpret_cast<const float4*>(s_ep + n_pad + n0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[j] = __uint_as_float(r[j]);
-          if (EPI == NFDPM_EPI_ACTNORM_RELU) {
-            const int n = min(n0 + j, N - 1);
-            v[j] = fmaxf(0.f, s_ep[n] * (v[j] + s_ep[N + n]));
+          for (int j = 0; j < 4; ++j) {
+            const float4 e = pe[j], b = pb[j];
+            v[4 * j + 0] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 0]), e.x, b.x));
+            v[4 * j + 1] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 1]), e.y, b.y));
+            v[4 * j + 2] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 2]), e.z, b.z));
+            v[4 * j + 3] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 3]), e.w, b.w));
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
         if (row < M) {
-          OutT* dp = D + (int64_t)row * ldd + n0;
           if (n0 + 15 < N) {
-            TcStore<OutT>::vec16(dp, v);
+            TcStore<OutT>::vec16(drow + n0, v);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (n0 + j < N) TcStore<OutT>::one(dp + j, v[j]);
+              if (n0 + j < N) TcStore<OutT>::one(drow + n0 + j, v[j]);
           }
         }
+      };
+      // chunks half, half+2, half+4, ... ; the load of the next chunk is in flight while this one is processed
+      uint32_t ra[16], rb[16];
+      int ch = half;
+      if (ch < n_chunks) tmem_ld16(taddr + ch * 16, ra);
+      while (ch < n_chunks) {
+        tmem_ld_wait();
+        if (ch + 2 < n_chunks) tmem_ld16(taddr + (ch + 2) * 16, rb);
+        process(ra, ch * 16);
+        ch += 2;
+        if (ch >= n_chunks) break;
+        tmem_ld_wait();
+        if (ch + 2 < n_chunks) tmem_ld16(taddr + (ch + 2) * 16, ra);
+        process(rb, ch * 16);
+        ch += 2;
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
@@ -354,7 +380,8 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   }
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sms ? tiles : sms;
-  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (epilogue == NFDPM_EPI_ACTNORM_RELU ? 2 * (size_t)N * 4 : 0);
+  const size_t n_pad = (size_t)((N + BN - 1) / BN) * BN;
+  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (epilogue == NFDPM_EPI_ACTNORM_RELU ? 2 * n_pad * 4 : 0);
 #define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, D, ldd, M, N, K, BN, ep_scale, ep_bias, grid, smem, st)
   if (out_dtype == NFDPM_F32) {
     if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, float); else GO(NFDPM_EPI_ACTNORM_RELU, float);

@@ -125,8 +125,11 @@ extern "C" int nfdpm_mix_prepare(const nfdpm_mix_item* items, int n, nfdpm_strea
   int smem_doubles = 2 * maxC * maxC;
   if ((size_t)smem_doubles * sizeof(double) > 96 * 1024) smem_doubles = 0;  // large C: work in lu_ws (global)
   const size_t smem = (size_t)smem_doubles * sizeof(double);
-  if (smem > 48 * 1024)
+  static bool attr_set = false;
+  if (!attr_set) {
     NFDPM_CUDA(cudaFuncSetAttribute(mix_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
   for (int base = 0; base < n; base += kPrepBatch) {
     PrepBatch pb;
     const int cnt = (n - base < kPrepBatch) ? n - base : kPrepBatch;

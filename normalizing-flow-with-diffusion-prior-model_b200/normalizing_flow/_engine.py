@@ -30,14 +30,20 @@ def round_up(a: int, b: int) -> int:
 
 
 class _Workspace:
-    """Grow-only scratch buffers keyed by (tag, dtype, device, stream).  Kernels of one flow run in stream
-    order and each buffer is consumed before it is overwritten, so one set per stream is enough."""
+    """Grow-only scratch buffers keyed by (scope, tag, dtype, device, stream).  Kernels of one flow run in stream
+    order and each buffer is consumed before it is overwritten, so one set per stream is enough.  A CUDA-graph
+    capture runs under its own ``scope`` so that the buffers baked into the graph are never re-allocated."""
 
     def __init__(self):
         self._bufs = {}
+        self.scope = None
+
+    def drop_scope(self, scope) -> None:
+        for k in [k for k in self._bufs if k[0] == scope]:
+            del self._bufs[k]
 
     def get(self, tag: str, numel: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
-        key = (tag, dtype, device.index, torch.cuda.current_stream(device).cuda_stream)
+        key = (self.scope, tag, dtype, device.index, torch.cuda.current_stream(device).cuda_stream)
         t = self._bufs.get(key)
         if t is None or t.numel() < numel:
             t = torch.empty(max(numel, 1), dtype=dtype, device=device)
@@ -50,6 +56,18 @@ class _Workspace:
 
 WS = _Workspace()
 _SCALARS = {}
+#: bumped whenever a parameter-derived cache buffer is (re)allocated; CUDA graphs that baked the old pointers
+#: compare it with the value at capture time and re-capture
+alloc_epoch = 0
+
+
+def _bump_epoch() -> None:
+    global alloc_epoch
+    alloc_epoch += 1
+
+
+def graphs_enabled() -> bool:
+    return os.environ.get("NFDPM_GRAPHS", "1") != "0"
 
 
 def scalar_f32(device: torch.device, value: float) -> torch.Tensor:
@@ -109,8 +127,10 @@ class MixCache:
             if logdet_slot is not None and (self.logdet is None or self.logdet.data_ptr() != logdet_slot.data_ptr()):
                 self.logdet = logdet_slot
                 self.key = None
+                _bump_epoch()
             return
         f = dict(dtype=torch.float32, device=device)
+        _bump_epoch()
         self.C = C
         self.fwd_mt = torch.empty(C * C, **f)
         self.fwd_beta = torch.empty(C, **f)
@@ -164,6 +184,7 @@ def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3:
     K1p = round_up(K1, 64)
     ldp = round_up(9 * C, 16)
     if cache.w1 is None or cache.w1.dtype != dt or cache.w1.numel() != F * K1p:
+        _bump_epoch()
         cache.w1 = torch.empty(F * K1p, dtype=dt, device=dev)
         cache.w3 = torch.empty(ldp * F, dtype=dt, device=dev)
         cache.w2 = torch.empty(F * F, dtype=dt, device=dev) if dt != torch.float32 else None
@@ -222,27 +243,36 @@ class SplitCache:
         self.Kp = self.ldh = 0
 
 
-def split_rows(sp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int) -> Tuple[Optional[torch.Tensor], int]:
-    """Raw ZeroConv3x3 (C/2 -> C) rows of the Split prior, always exact fp32 (the conv is tiny).
-    Returns (h, ldh) or (None, 0) when the prior is not learned."""
+def refresh_split(sp, C: int) -> None:
+    """(Re)pack the Split prior's ZeroConv weight if it changed."""
     conv = sp.conv
     if conv is None:
-        return None, 0
+        return
     cache = sp._cache
     w = conv.weight
-    Ch = C // 2
-    K = Ch * 9
+    K = (C // 2) * 9
     Kp = round_up(K, 16)
     ldh = round_up(C, 8)
     key = _vkey(w)
     if cache.key != key:
         if cache.w is None or cache.w.numel() != ldh * Kp:
+            _bump_epoch()
             cache.w = torch.empty(ldh * Kp, dtype=torch.float32, device=w.device)
         N.pack_matrix(w, cache.w, 1, C, K, 0, K, 1, Kp, ldh)
         cache.key, cache.Kp, cache.ldh = key, Kp, ldh
+
+
+def split_rows(sp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int) -> Tuple[Optional[torch.Tensor], int]:
+    """Raw ZeroConv3x3 (C/2 -> C) rows of the Split prior, always exact fp32 (the conv is tiny).
+    Returns (h, ldh) or (None, 0) when the prior is not learned."""
+    if sp.conv is None:
+        return None, 0
+    refresh_split(sp, C)
+    cache = sp._cache
+    Kp, ldh = cache.Kp, cache.ldh
     M = B * H * W
     A = WS.get("As", M * Kp, torch.float32, y.device)
-    N.im2col3x3(y, A, B, Ch, H, W, ybs, Kp)
+    N.im2col3x3(y, A, B, C // 2, H, W, ybs, Kp)
     h = WS.get("hs", M * ldh, torch.float32, y.device)
     N.gemm_nt(A, Kp, cache.w, Kp, h, ldh, M, C, Kp)
     return h, ldh

@@ -128,11 +128,77 @@ class Glow(Transform):
         self.final_flows = nn.ModuleList(StepFlow(in_channels=(2 ** (L + 1) * in_channel)) for _ in range(K))
         self._logdet_all: Optional[Tensor] = None
         self._cmul = {}
+        self._graphs = {}
+        self._plist = None
+        self._pver = None
 
     def _apply(self, fn, *a, **k):
         self._logdet_all = None
         self._cmul = {}
+        self._drop_graphs()
+        self._plist = None
         return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._pver = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    # ---- CUDA graphs: the ~300-kernel chain of one call is captured once per (direction, shape, precision) and
+    # replayed; only the parameter-version check and the final accumulate into the caller's tensors stay outside.
+    def _drop_graphs(self) -> None:
+        for key in list(self._graphs):
+            E.WS.drop_scope(("glow", id(self), key))
+        self._graphs = {}
+
+    def _params_changed(self) -> bool:
+        if self._plist is None:
+            self._plist = list(self.parameters())
+            self._pver = None
+        ver = [p._version for p in self._plist]
+        if ver != self._pver:
+            self._pver = ver
+            return True
+        return False
+
+    def _refresh_caches(self, steps, slots) -> None:
+        """Re-run LU/fold and weight packing for parameters that changed (outside any graph)."""
+        E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
+        dt = torch.float32 if E.precision() == "fp32" else torch.bfloat16
+        for s in steps:
+            conv1, _, conv2, _, zc = s.affcoupling._parts()
+            E._pack_coupling(s.affcoupling._cache, conv1.weight, conv2.weight, zc.weight, dt)
+        for blk in self.blocks:
+            E.refresh_split(blk.split, blk.flows[0]._C)
+
+    def _use_graph(self, ready: bool) -> bool:
+        return ready and E.graphs_enabled() and not torch.cuda.is_current_stream_capturing()
+
+    def _graph_entry(self, key, build):
+        """build() -> dict of static tensors; called once eagerly (warm-up) and once under capture."""
+        ent = self._graphs.get(key)
+        if ent is not None and ent["epoch"] == E.alloc_epoch:
+            return ent
+        scope = ("glow", id(self), key)
+        E.WS.drop_scope(scope)
+        prev = E.WS.scope
+        try:
+            E.WS.scope = ("warm", id(self))
+            build()                                   # eager warm-up: parameter caches, one-time kernel attributes
+            torch.cuda.current_stream().synchronize()
+            E.WS.drop_scope(("warm", id(self)))
+            E.WS.scope = scope                        # buffers baked into the graph live (only) under this scope
+            g = torch.cuda.CUDAGraph()
+            n0 = N.launch_count
+            with torch.cuda.graph(g):
+                out = build()
+            n_launch = N.launch_count - n0
+        finally:
+            E.WS.scope = prev
+        N.launch_count -= n_launch                    # counted per replay instead
+        ent = dict(out)
+        ent["graph"], ent["epoch"], ent["n_launch"] = g, E.alloc_epoch, n_launch
+        self._graphs[key] = ent
+        return ent
 
     # ---- helpers
     def _levels(self) -> List[Tuple[nn.ModuleList, Optional[Split]]]:
@@ -180,7 +246,37 @@ class Glow(Transform):
         levels = self._levels()
         slots = self._slots(dev)
         steps = [s for flows, _ in levels for s in flows]
-        if all(s._ready() for s in steps):
+        ready = all(s._ready() for s in steps)
+        if self._use_graph(ready):
+            if self._params_changed():
+                self._refresh_caches(steps, slots)
+            key = ("fwd", B, H, W, logp is not None, E.precision(), dev.index)
+            x_static = self._graphs.get(key, {}).get("x")
+            if x_static is None:
+                x_static = torch.empty_like(x)
+            x_static.copy_(x)
+
+            def build():
+                lat, ld_part, R_ld, lp_part, R_lp = self._transform_core(x_static, logp is not None, levels, slots, steps, True)
+                return {"x": x_static, "lat": lat, "ld_part": ld_part, "R_ld": R_ld, "lp_part": lp_part, "R_lp": R_lp}
+            ent = self._graph_entry(key, build)
+            if ent["x"] is not x_static:              # entry was (re)built around another buffer
+                ent["x"].copy_(x)
+            ent["graph"].replay()
+            N.launch_count += ent["n_launch"]
+            latents = [t.clone() for t in ent["lat"]]
+            ld_part, R_ld, lp_part, R_lp = ent["ld_part"], ent["R_ld"], ent["lp_part"], ent["R_lp"]
+        else:
+            latents, ld_part, R_ld, lp_part, R_lp = self._transform_core(x, logp is not None, levels, slots, steps, ready)
+        N.accumulate(log_det_jac, ld_part, R_ld, B, slots, self._multipliers(H, W, dev), self.L * self.K)
+        if logp is not None and R_lp > 0:
+            N.accumulate(logp, lp_part, R_lp, B)
+        return latents, log_det_jac, logp
+
+    def _transform_core(self, x: Tensor, with_logp: bool, levels, slots, steps, ready: bool):
+        B, c, H, W = x.shape
+        dev = x.device
+        if ready:
             # one batched LU/fold launch for every StepFlow whose parameters changed since the last call
             E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
         # partial-sum rows: per step T_l rows of B
@@ -194,7 +290,7 @@ class Glow(Transform):
         R_ld = sum(g[3] for g in geo) * self.K
         R_lp = sum(g[3] for g in geo[:-1])
         ld_part = E.WS.get("ld_part", max(R_ld, 1) * B, torch.float32, dev)
-        lp_part = E.WS.get("lp_part", max(R_lp, 1) * B, torch.float32, dev) if logp is not None else None
+        lp_part = E.WS.get("lp_part", max(R_lp, 1) * B, torch.float32, dev) if with_logp else None
         latents: List[Tensor] = []
         cur, cur_bs, cur_c, cur_h, cur_w = x, c * H * W, c, H, W
         row = lrow = si = 0
@@ -217,10 +313,7 @@ class Glow(Transform):
             lrow += T
             latents.append(z)
             cur, cur_bs, cur_c, cur_h, cur_w = a, C * P, C // 2, h, w
-        N.accumulate(log_det_jac, ld_part, R_ld, B, slots, self._multipliers(H, W, dev), self.L * self.K)
-        if logp is not None and R_lp > 0:
-            N.accumulate(logp, lp_part, R_lp, B)
-        return latents, log_det_jac, logp
+        return latents, ld_part, R_ld, lp_part, R_lp
 
     # ---- inverse: latents -> x
     def invert(self, latents: list, temperature: float = 1.0) -> Tensor:
@@ -233,7 +326,35 @@ class Glow(Transform):
         levels = self._levels()
         slots = self._slots(dev)
         steps = [s for flows, _ in levels for s in flows]
-        if all(s._ready() for s in steps):
+        ready = all(s._ready() for s in steps)
+        if self._use_graph(ready) and len(latents) == self.L:
+            lat_in = [E.check_input(t, "latent") for t in latents]
+            if self._params_changed():
+                self._refresh_caches(steps, slots)
+            key = ("inv", B, h, w, E.precision(), dev.index)
+            ent = self._graphs.get(key)
+            statics = ent["lat"] if ent is not None else [torch.empty_like(t) for t in lat_in]
+            for s_, t in zip(statics, lat_in):
+                if s_.shape != t.shape:
+                    raise ValueError(f"latent has shape {tuple(t.shape)}, expected {tuple(s_.shape)}")
+                s_.copy_(t)
+
+            def build():
+                return {"lat": statics, "out": self._invert_core(statics, temperature, levels, slots, steps, True)}
+            ent = self._graph_entry(key, build)
+            if ent["lat"] is not statics:
+                for s_, t in zip(ent["lat"], lat_in):
+                    s_.copy_(t)
+            ent["graph"].replay()
+            N.launch_count += ent["n_launch"]
+            return ent["out"].clone()
+        return self._invert_core(latents, temperature, levels, slots, steps, ready)
+
+    def _invert_core(self, latents, temperature, levels, slots, steps, ready: bool) -> Tensor:
+        z_last = E.check_input(latents[-1], "latents[-1]")
+        B, Cf, h, w = z_last.shape
+        dev = z_last.device
+        if ready:
             E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
         C, P = Cf, h * w
         cur = z_last

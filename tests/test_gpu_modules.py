@@ -359,3 +359,43 @@ def test_glow_bf16_mode_within_stated_tolerance(cfg, monkeypatch):
     assert torch.isfinite(xr).all()
     if K <= 4:
         assert (xr.cpu() - x).abs().max() < 5e-3
+
+
+def test_cuda_graph_path_equals_eager(monkeypatch):
+    """Glow.transform / invert replay a captured CUDA graph; results must equal the eager kernel chain bit for bit,
+    follow parameter updates, and keep earlier results intact (outputs are copies, not graph-owned buffers)."""
+    c, L, K, B, S = 3, 3, 2, 5, 32
+    flow, _, sd, _ = build(c, L, K, 33)
+    x1 = O.seeded_input((B, c, S, S), 34).to(DEV)
+    x2 = O.seeded_input((B, c, S, S), 35).to(DEV)
+
+    def run(x):
+        ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+        lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+        zs, ld, lp = flow.transform(x, ld, lp)
+        return zs, ld, lp, flow.invert(zs)
+    monkeypatch.setenv("NFDPM_GRAPHS", "0")
+    e1, e2 = run(x1), run(x2)
+    monkeypatch.setenv("NFDPM_GRAPHS", "1")
+    g1 = run(x1)
+    g2 = run(x2)
+    g1b = run(x1)
+    for e, g in ((e1, g1), (e2, g2), (e1, g1b)):
+        for a, b in zip(e[0], g[0]):
+            assert torch.equal(a, b)
+        assert torch.equal(e[1], g[1]) and torch.equal(e[2], g[2]) and torch.equal(e[3], g[3])
+    assert len(flow._graphs) == 2 and all(v["n_launch"] > 50 for v in flow._graphs.values())
+    # parameters change (as an optimiser step would): the replay must see the new weights
+    with torch.no_grad():
+        for p in flow.parameters():
+            p.mul_(1.01)
+    g3 = run(x1)
+    monkeypatch.setenv("NFDPM_GRAPHS", "0")
+    e3 = run(x1)
+    for a, b in zip(e3[0], g3[0]):
+        assert torch.equal(a, b)
+    assert torch.equal(e3[1], g3[1]) and torch.equal(e3[2], g3[2]) and torch.equal(e3[3], g3[3])
+    assert not torch.equal(g3[0][-1], g1[0][-1])
+    # earlier outputs were not overwritten by later replays
+    for a, b in zip(e1[0], g1[0]):
+        assert torch.equal(a, b)
