@@ -384,7 +384,7 @@ def test_cuda_graph_path_equals_eager(monkeypatch):
         for a, b in zip(e[0], g[0]):
             assert torch.equal(a, b)
         assert torch.equal(e[1], g[1]) and torch.equal(e[2], g[2]) and torch.equal(e[3], g[3])
-    assert len(flow._graphs) == 2 and all(v["n_launch"] > 50 for v in flow._graphs.values())
+    assert len(flow._graphs) == 2 and all(v["n_launch"] > 20 for v in flow._graphs.values())
     # parameters change (as an optimiser step would): the replay must see the new weights
     with torch.no_grad():
         for p in flow.parameters():
