@@ -156,6 +156,19 @@ int nfdpm_gauss_logp_const(const float* z, const float* bias, const float* logs,
 int nfdpm_gauss_sample_const(const float* eps, const float* bias, const float* logs, float temperature, float* out,
                              int B, int C, int P, nfdpm_stream_t stream);
 
+/* Fused step boundary (one CTA per image; P = H*W <= 256 and the image must fit in shared memory, see
+ * nfdpm_flow_boundary_smem): source -> [affine coupling with pm] -> [channel mix] -> NCHW state and/or im2col rows.
+ * Equivalent to nfdpm_coupling_apply + nfdpm_channel_mix + nfdpm_im2col3x3 (+ nfdpm_squeeze when squeeze_in) in ONE
+ * launch with coalesced traffic; replaces the same reference lines (transforms.py:80,132,144,93,179-184,196-200,226).
+ *   in  [B,C,P] (batch stride in_bs) or, with squeeze_in, [B,C/4,2H,2W];  pm == NULL: no coupling;
+ *   mt == NULL: no mix;  y == NULL / a1 == NULL: sink disabled;  ld_part [B] (forward coupling only, may be NULL);
+ *   a1: rows [B*P, lda1] of dtype a1_dtype (F32/BF16), column = c*9 + ky*3 + kx over the first C/2 channels. */
+size_t nfdpm_flow_boundary_smem(int C, int H, int W, int coupling, int mix);
+int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
+                        const float* bias3, const float* logs3, float* ld_part, const float* mt, const float* beta,
+                        float* y, int64_t y_bs, void* a1, int a1_dtype, int64_t lda1, int B, int C, int H, int W,
+                        int inverse, nfdpm_stream_t stream);
+
 /* Layout converters for stand-alone ZeroConv2d / Conv2dActNorm module calls (normalizing_flow/utils.py:43-44, :68-69).
  *   rows_to_nchw: out[b,n,p] = f(h[(b*P+p)*ldh + n]); mode 0: identity; 1: (v+p1[n])*exp(3*p2[n]) (ZeroConv2d gain);
  *                 2: exp(p1[n])*(v+p2[n]) (ActNorm).   nchw_to_rows: rows[m, c] = x[b,c,p], columns Cc..ld-1 zero. */

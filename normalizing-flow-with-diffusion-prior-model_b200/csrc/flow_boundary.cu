@@ -1,0 +1,245 @@
+// Fused "step boundary" kernel: everything that happens to the flow state between the last GEMM of one StepFlow
+// and the first GEMM of the next one, in ONE launch, one CTA per image:
+//
+//   source   SRC_PLAIN     x = in[b]                       (optionally with squeeze addressing, transforms.py:226)
+//            SRC_COUPLING  x = affine coupling of in[b] with the taps-as-N ZeroConv rows pm (forward:
+//                          transforms.py:179-184 incl. the per-image log-det partial; inverse: :196-200)
+//   mix      u = Mt^T x + beta     fused ActNorm + invertible 1x1 conv of the NEXT step (forward, transforms.py:80,132)
+//                                  or of THIS step (inverse, :144,:93); optional
+//   sinks    y[b]  <- u            NCHW fp32 flow state (optional)
+//            a1    <- im2col3x3(u[:C/2])  pixel-major rows for the next coupling network's first GEMM (optional)
+//
+// All global traffic is coalesced: the image is staged channel-major in shared memory, pm rows are read with the
+// channel index fastest across lanes (each pm element is consumed exactly once), im2col rows are written as 16-byte
+// (bf16) / 32-byte (fp32) pieces with the column group fastest across lanes.
+// Replaces, per StepFlow: nfdpm_coupling_apply + nfdpm_channel_mix + nfdpm_im2col3x3 (+ nfdpm_squeeze at level entry).
+#include "common.cuh"
+
+namespace nfdpm {
+
+struct BoundaryArgs {
+  const float* in; int64_t in_bs;       // source state [B,C,P] (or [B,C/4,2H,2W] when squeeze_in)
+  const float* pm; int64_t ldp;         // SRC_COUPLING: taps-as-N rows [B*P, ldp]
+  const float* bias3; const float* logs3;
+  float* ld_part;                       // forward coupling: [B] per-image log-det partial (may be null)
+  const float* mt; const float* beta;   // mix (null = identity)
+  float* y; int64_t y_bs;               // NCHW sink (may be null)
+  void* a1; int64_t lda1;               // im2col sink (may be null)
+  int B, C, H, W;
+  int squeeze_in, inverse;
+};
+
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool COUPLING, typename A1T>
+__global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
+  const int PS = P + 1;                       // padded pixel stride: conflict-free for lanes over channels
+  const int Cp = (C + 3) & ~3;
+  float* x_s = sm;                            // [C][PS]  source / coupling result
+  float* u_s = x_s + C * PS;                  // [C][PS]  mixed result (aliases x_s when there is no mix)
+  float* m_s = (a.mt != nullptr) ? u_s + C * PS : u_s;      // [C][Cp] + beta [Cp]
+  float* par_s = m_s + ((a.mt != nullptr) ? (C * Cp + Cp) : 0);   // [2C] bias3, exp(3 logs3)
+  float* ls_s = par_s + (COUPLING ? 2 * C : 0);                   // [P*Ch] log-det terms
+  if (a.mt == nullptr) u_s = x_s;
+  const int b = blockIdx.x, tid = threadIdx.x;
+
+  // ---- parameters
+  if (a.mt != nullptr) {
+    for (int i = tid; i < C * Cp; i += 256) {
+      const int r = i / Cp, c = i - r * Cp;
+      m_s[i] = (c < C) ? a.mt[r * C + c] : 0.f;
+    }
+    for (int i = tid; i < Cp; i += 256) m_s[C * Cp + i] = (i < C) ? a.beta[i] : 0.f;
+  }
+  if (COUPLING) {
+    for (int i = tid; i < C; i += 256) {
+      par_s[i] = a.bias3[i];
+      par_s[C + i] = expf(3.f * a.logs3[i]);
+    }
+  }
+  // ---- phase 0: stage the image channel-major (lanes over pixels -> coalesced)
+  const float* inb = a.in + (int64_t)b * a.in_bs;
+  if (a.squeeze_in) {
+    // in is [C/4, 2H, 2W]; channel c = cc*4 + h1*2 + w1 reads in[cc, 2y+h1, 2x+w1]
+    const int W2 = 2 * W;
+    for (int i = tid; i < (C >> 2) * P; i += 256) {
+      const int cc = i / P, p = i - cc * P;
+      const int py = p / W, px = p - py * W;
+      const float* s = inb + ((int64_t)cc * 2 * H + 2 * py) * W2 + 2 * px;
+      const float2 t0 = *reinterpret_cast<const float2*>(s), t1 = *reinterpret_cast<const float2*>(s + W2);
+      x_s[(cc * 4 + 0) * PS + p] = t0.x;
+      x_s[(cc * 4 + 1) * PS + p] = t0.y;
+      x_s[(cc * 4 + 2) * PS + p] = t1.x;
+      x_s[(cc * 4 + 3) * PS + p] = t1.y;
+    }
+  } else {
+    for (int i = tid; i < C * P; i += 256) {
+      const int c = i / P, p = i - c * P;
+      x_s[c * PS + p] = inb[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: affine coupling, item = (pixel, j) with j fastest (pm rows read contiguously)
+  if (COUPLING) {
+    const float* pmb = a.pm + (int64_t)b * P * a.ldp;
+    for (int it = tid; it < P * Ch; it += 256) {
+      const int p = it / Ch, j = it - p * Ch;
+      const int py = p / W, px = p - py * W;
+      float ls = 0.f, tt = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = py + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = px + kx - 1;
+          if (xx < 0 || xx >= W) continue;
+          const float* r = pmb + (int64_t)(yy * W + xx) * a.ldp + (ky * 3 + kx) * C + j;
+          ls += __ldg(r);
+          tt += __ldg(r + Ch);
+        }
+      }
+      const float log_s = (ls + par_s[j]) * par_s[C + j];
+      const float sh_t = (tt + par_s[Ch + j]) * par_s[C + Ch + j];
+      const float s = 1.f / (1.f + expf(-(log_s + 2.f)));
+      const float xb = x_s[(Ch + j) * PS + p];
+      if (a.inverse) {
+        x_s[(Ch + j) * PS + p] = xb / (s + 1e-6f) - sh_t;
+      } else {
+        x_s[(Ch + j) * PS + p] = (xb + sh_t) * s;
+        ls_s[it] = logf(s + 1e-6f);
+      }
+    }
+    __syncthreads();
+    if (!a.inverse && a.ld_part != nullptr && tid < 32) {
+      // deterministic per-image sum: fixed lane-strided order + shuffle tree
+      float acc = 0.f;
+      for (int i = tid; i < P * Ch; i += 32) acc += ls_s[i];
+      acc = warp_sum(acc);
+      if (tid == 0) a.ld_part[b] = acc;
+    }
+  }
+
+  // ---- phase 2: channel mix, item = (group of 4 outputs, pixel), lanes over pixels
+  if (a.mt != nullptr) {
+    const int n_og = Cp >> 2;
+    for (int it = tid; it < n_og * P; it += 256) {
+      const int og = it / P, p = it - og * P;
+      const float4 b4 = *reinterpret_cast<const float4*>(m_s + C * Cp + og * 4);
+      float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
+      for (int c = 0; c < C; ++c) {
+        const float xv = x_s[c * PS + p];
+        const float4 w = *reinterpret_cast<const float4*>(m_s + c * Cp + og * 4);
+        a0 = fmaf(w.x, xv, a0);
+        a1 = fmaf(w.y, xv, a1);
+        a2 = fmaf(w.z, xv, a2);
+        a3 = fmaf(w.w, xv, a3);
+      }
+      const int o = og * 4;
+      u_s[o * PS + p] = a0;
+      if (o + 1 < C) u_s[(o + 1) * PS + p] = a1;
+      if (o + 2 < C) u_s[(o + 2) * PS + p] = a2;
+      if (o + 3 < C) u_s[(o + 3) * PS + p] = a3;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 3a: NCHW sink (lanes over pixels)
+  if (a.y != nullptr) {
+    float* yb = a.y + (int64_t)b * a.y_bs;
+    for (int i = tid; i < C * P; i += 256) {
+      const int c = i / P, p = i - c * P;
+      yb[i] = u_s[c * PS + p];
+    }
+  }
+  // ---- phase 3b: im2col sink, item = (pixel, 8-column group), group fastest -> 128-byte runs per row
+  if (a.a1 != nullptr) {
+    const int K = Ch * 9;
+    const int n_g = (int)(a.lda1 >> 3);
+    A1T* a1b = reinterpret_cast<A1T*>(a.a1) + (int64_t)b * P * a.lda1;
+    for (int it = tid; it < P * n_g; it += 256) {
+      const int p = it / n_g, g = it - p * n_g;
+      const int py = p / W, px = p - py * W;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = g * 8 + e;
+        float val = 0.f;
+        if (k < K) {
+          const int c = k / 9, tap = k - c * 9;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const int yy = py + ky - 1, xx = px + kx - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = u_s[c * PS + yy * W + xx];
+        }
+        v[e] = val;
+      }
+      store8<A1T>(a1b + (int64_t)p * a.lda1 + g * 8, v);
+    }
+  }
+}
+
+}  // namespace nfdpm
+
+using namespace nfdpm;
+
+extern "C" size_t nfdpm_flow_boundary_smem(int C, int H, int W, int coupling, int mix) {
+  const size_t P = (size_t)H * W, PS = P + 1, Cp = (C + 3) & ~3;
+  size_t fl = (size_t)C * PS * (mix ? 2 : 1);
+  if (mix) fl += (size_t)C * Cp + Cp;
+  if (coupling) fl += 2 * (size_t)C + P * (C / 2);
+  return fl * sizeof(float);
+}
+
+extern "C" int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
+                                   const float* bias3, const float* logs3, float* ld_part, const float* mt,
+                                   const float* beta, float* y, int64_t y_bs, void* a1, int a1_dtype, int64_t lda1,
+                                   int B, int C, int H, int W, int inverse, nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(in != nullptr, "nfdpm_flow_boundary: null input");
+  NFDPM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && C % 2 == 0, "nfdpm_flow_boundary: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  NFDPM_REQUIRE((mt == nullptr) == (beta == nullptr), "nfdpm_flow_boundary: mt/beta must both be set or both NULL");
+  NFDPM_REQUIRE(pm == nullptr || (bias3 && logs3 && ldp >= 9 * (int64_t)C), "nfdpm_flow_boundary: coupling source needs bias3/logs3/ldp");
+  NFDPM_REQUIRE(!squeeze_in || (C % 4 == 0 && in_bs % 2 == 0 && ((uintptr_t)in % 8) == 0), "nfdpm_flow_boundary: squeeze source needs C %% 4 == 0 and 8-byte alignment");
+  NFDPM_REQUIRE(a1 == nullptr || (lda1 % 8 == 0 && lda1 >= 9 * (int64_t)(C / 2) && ((uintptr_t)a1 % 16) == 0), "nfdpm_flow_boundary: bad im2col sink");
+  NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16, "nfdpm_flow_boundary: bad a1 dtype");
+  NFDPM_REQUIRE(y != nullptr || a1 != nullptr, "nfdpm_flow_boundary: no sink");
+  const size_t smem = nfdpm_flow_boundary_smem(C, H, W, pm != nullptr, mt != nullptr);
+  NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_flow_boundary: image too large for the fused path (%zu bytes of shared memory); "
+                "use the unfused kernels", smem);
+  BoundaryArgs a;
+  a.in = in; a.in_bs = in_bs; a.pm = pm; a.ldp = ldp; a.bias3 = bias3; a.logs3 = logs3; a.ld_part = ld_part;
+  a.mt = mt; a.beta = beta; a.y = y; a.y_bs = y_bs; a.a1 = a1; a.lda1 = lda1;
+  a.B = B; a.C = C; a.H = H; a.W = W; a.squeeze_in = squeeze_in; a.inverse = inverse;
+  cudaStream_t st = as_stream(stream);
+  const bool bf = (a1 != nullptr && a1_dtype == NFDPM_BF16);
+#define LAUNCH(CP, T)                                                                                              \
+  do {                                                                                                             \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      NFDPM_CUDA(cudaFuncSetAttribute(flow_boundary_kernel<CP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                      200 * 1024));                                                                \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    flow_boundary_kernel<CP, T><<<B, 256, smem, st>>>(a);                                                          \
+  } while (0)
+  if (pm != nullptr) { if (bf) LAUNCH(true, __nv_bfloat16); else LAUNCH(true, float); }
+  else { if (bf) LAUNCH(false, __nv_bfloat16); else LAUNCH(false, float); }
+#undef LAUNCH
+  NFDPM_CHECK_LAUNCH("flow_boundary_kernel");
+  return 0;
+}

@@ -198,6 +198,39 @@ def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3:
     cache.key = key
 
 
+def coupling_dtype() -> torch.dtype:
+    return torch.float32 if precision() == "fp32" else torch.bfloat16
+
+
+def coupling_a1(cp, B: int, C: int, H: int, W: int, dev: torch.device) -> Tuple[torch.Tensor, int]:
+    """The im2col operand buffer of coupling network ``cp`` (filled by nfdpm_flow_boundary / nfdpm_im2col3x3)."""
+    conv1, _, conv2, _, zc = cp._parts()
+    dt = coupling_dtype()
+    _pack_coupling(cp._cache, conv1.weight, conv2.weight, zc.weight, dt)
+    K1p = cp._cache.K1p
+    return WS.get("A1", B * H * W * K1p, dt, dev), K1p
+
+
+def coupling_gemms(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int) -> Tuple[torch.Tensor, int]:
+    """GEMM1 -> GEMM2 -> GEMM3 of an initialised coupling network from its im2col rows ``A1``.
+    Returns the taps-as-N rows (pm, ldp)."""
+    conv1, an1, conv2, an2, zc = cp._parts()
+    F = conv1.weight.shape[0]
+    dt = A1.dtype
+    cache = cp._cache
+    dev = A1.device
+    M = B * H * W
+    K1p, ldp = cache.K1p, cache.ldp
+    h1 = WS.get("h1", M * F, dt, dev)
+    N.gemm_nt(A1, K1p, cache.w1, K1p, h1, F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
+    w2 = cache.w2 if dt != torch.float32 else conv2.weight
+    h2 = WS.get("h2", M * F, dt, dev)
+    N.gemm_nt(h1, F, w2, F, h2, F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
+    pm = WS.get("pm", M * ldp, torch.float32, dev)
+    N.gemm_nt(h2, F, cache.w3, F, pm, ldp, M, ldp, F)
+    return pm, ldp
+
+
 def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int, init: bool = False) -> Tuple[torch.Tensor, int]:
     """Run the coupling network of AffineCoupling ``cp`` on the first C/2 channels of ``y`` ([B,C,P], batch
     stride ``ybs``).  Returns (pm, ldp): the taps-as-N ZeroConv rows consumed by nfdpm_coupling_apply.

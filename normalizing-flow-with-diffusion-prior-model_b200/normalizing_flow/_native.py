@@ -55,6 +55,9 @@ def _load() -> C.CDLL:
         "nfdpm_gauss_sample_const": ([vp, vp, vp, f32, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_rows_to_nchw": ([vp, i64, i32, vp, vp, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_nchw_to_rows": ([vp, vp, i32, i32, i32, i32, i64, i64, vp], C.c_int),
+        "nfdpm_flow_boundary_smem": ([i32, i32, i32, i32, i32], C.c_size_t),
+        "nfdpm_flow_boundary": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i32, i64, i32, i32, i32, i32,
+                                 i32, vp], C.c_int),
         "nfdpm_accumulate": ([vp, i32, vp, i32, i32, vp, vp, i32, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
@@ -69,7 +72,8 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_channel_mix", "nfdpm_actnorm_apply", "nfdpm_channel_stats", "nfdpm_squeeze", "nfdpm_unsqueeze",
            "nfdpm_copy_channels", "nfdpm_im2col3x3", "nfdpm_pack_matrix", "nfdpm_gemm_nt", "nfdpm_coupling_apply",
            "nfdpm_split_prior_logp", "nfdpm_split_prior_sample", "nfdpm_gauss_logp_const",
-           "nfdpm_gauss_sample_const", "nfdpm_accumulate", "nfdpm_rows_to_nchw", "nfdpm_nchw_to_rows"]
+           "nfdpm_gauss_sample_const", "nfdpm_accumulate", "nfdpm_rows_to_nchw", "nfdpm_nchw_to_rows",
+           "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -185,3 +189,14 @@ def rows_to_nchw(h, ldh, mode, p1, p2, out, B, Nc, P) -> None:
 
 def nchw_to_rows(x, out, B, Cc, P, xbs, ld) -> None:
     _ok(lib.nfdpm_nchw_to_rows(_p(x), _p(out), _dt(out), B, Cc, P, xbs, ld, _st()))
+
+
+def flow_boundary_smem(Cc, H, W, coupling, mix) -> int:
+    return int(lib.nfdpm_flow_boundary_smem(Cc, H, W, int(coupling), int(mix)))
+
+
+def flow_boundary(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, a1, lda1, B, Cc, H, W,
+                  inverse) -> None:
+    _ok(lib.nfdpm_flow_boundary(_p(src), src_bs, int(squeeze_in), _p(pm), ldp, _p(bias3), _p(logs3), _p(ld_part),
+                                _p(mt), _p(beta), _p(y), y_bs, _p(a1), _dt(a1) if a1 is not None else F32, lda1, B, Cc,
+                                H, W, int(inverse), _st()))

@@ -11,6 +11,7 @@ parameter names (reference normalizing_flow/glow.py:12-246), scheduled as one ke
 ``Glow.transform`` / ``Glow.invert`` never copy activations for chunk/concat: halves are addressed through batch
 strides.
 """
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -273,9 +274,24 @@ class Glow(Transform):
             N.accumulate(logp, lp_part, R_lp, B)
         return latents, log_det_jac, logp
 
+    def _fast_ok(self, H: int, W: int) -> bool:
+        """The fused step-boundary kernel needs every level's image to fit one CTA (P <= 256 + smem budget)."""
+        if os.environ.get("NFDPM_FUSED_BOUNDARY", "1") == "0":
+            return False
+        h, w, ch = H, W, self.in_channel
+        for _ in range(self.L):
+            h, w = h // 2, w // 2
+            C = ch * 4
+            if h * w > 256 or N.flow_boundary_smem(C, h, w, 1, 1) > 200 * 1024:
+                return False
+            ch = C // 2
+        return True
+
     def _transform_core(self, x: Tensor, with_logp: bool, levels, slots, steps, ready: bool):
         B, c, H, W = x.shape
         dev = x.device
+        if ready and self._fast_ok(H, W):
+            return self._transform_fast(x, with_logp, levels, slots, steps)
         if ready:
             # one batched LU/fold launch for every StepFlow whose parameters changed since the last call
             E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
@@ -350,10 +366,96 @@ class Glow(Transform):
             return ent["out"].clone()
         return self._invert_core(latents, temperature, levels, slots, steps, ready)
 
+    def _transform_fast(self, x: Tensor, with_logp: bool, levels, slots, steps):
+        """Forward with the fused step-boundary kernel: 4 launches per StepFlow (boundary + 3 GEMMs)."""
+        B, c, H, W = x.shape
+        dev = x.device
+        E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
+        R_ld = self.L * self.K
+        R_lp = self.L - 1
+        ld_part = E.WS.get("ld_part", R_ld * B, torch.float32, dev)
+        lp_part = E.WS.get("lp_part", max(R_lp, 1) * B, torch.float32, dev) if with_logp else None
+        latents: List[Tensor] = []
+        cur, cur_bs = x, c * H * W
+        h, w, ch = H, W, c
+        row = 0
+        for li, (flows, split) in enumerate(levels):
+            h, w, C = h // 2, w // 2, ch * 4
+            P = h * w
+            st = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)     # flow state of this level (in place)
+            first = flows[0]
+            A1, K1p = E.coupling_a1(first.affcoupling, B, C, h, w, dev)
+            # level entry: squeeze + K-A of step 0 + im2col
+            N.flow_boundary(cur, cur_bs, True, None, 0, None, None, None, first._mix.fwd_mt, first._mix.fwd_beta,
+                            st, C * P, A1, K1p, B, C, h, w, False)
+            for k, step in enumerate(flows):
+                cp = step.affcoupling
+                zc = cp.net[4]
+                pm, ldp = E.coupling_gemms(cp, A1, B, C, h, w)
+                nxt = flows[k + 1] if k + 1 < len(flows) else None
+                if nxt is not None:
+                    A1, K1p = E.coupling_a1(nxt.affcoupling, B, C, h, w, dev)
+                    N.flow_boundary(st, C * P, False, pm, ldp, zc.bias, zc.logs, ld_part[row * B:], nxt._mix.fwd_mt,
+                                    nxt._mix.fwd_beta, st, C * P, A1, K1p, B, C, h, w, False)
+                else:
+                    N.flow_boundary(st, C * P, False, pm, ldp, zc.bias, zc.logs, ld_part[row * B:], None, None,
+                                    st, C * P, None, 0, B, C, h, w, False)
+                row += 1
+            if split is None:
+                latents.append(st)
+                break
+            z = torch.empty(B, C // 2, h, w, dtype=torch.float32, device=dev)
+            split._forward_views(st, C * P, B, C, h, w, z, lp_part[li * B:] if lp_part is not None else None)
+            latents.append(z)
+            cur, cur_bs, ch = st, C * P, C // 2
+        return latents, ld_part, R_ld, lp_part, (R_lp if with_logp else 0)
+
+    def _invert_fast(self, latents, temperature, levels, slots, steps) -> Tensor:
+        """Inverse with the fused step-boundary kernel."""
+        z_last = latents[-1]
+        B, C, h, w = z_last.shape
+        dev = z_last.device
+        E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
+        src = z_last                                   # caller memory: read only
+        for li in range(self.L - 1, -1, -1):
+            flows, _ = levels[li]
+            P = h * w
+            st = src if li < self.L - 1 else torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+            last = flows[-1]
+            A1, K1p = E.coupling_a1(last.affcoupling, B, C, h, w, dev)
+            N.flow_boundary(src, C * P, False, None, 0, None, None, None, None, None, None, 0, A1, K1p, B, C, h, w,
+                            False)                     # im2col of the level's entry state
+            for k in range(len(flows) - 1, -1, -1):
+                step = flows[k]
+                cp = step.affcoupling
+                zc = cp.net[4]
+                pm, ldp = E.coupling_gemms(cp, A1, B, C, h, w)
+                if k > 0:
+                    A1, K1p = E.coupling_a1(flows[k - 1].affcoupling, B, C, h, w, dev)
+                    N.flow_boundary(src, C * P, False, pm, ldp, zc.bias, zc.logs, None, step._mix.inv_mt,
+                                    step._mix.inv_beta, st, C * P, A1, K1p, B, C, h, w, True)
+                else:
+                    N.flow_boundary(src, C * P, False, pm, ldp, zc.bias, zc.logs, None, step._mix.inv_mt,
+                                    step._mix.inv_beta, st, C * P, None, 0, B, C, h, w, True)
+                src = st
+            if li == 0:
+                out = torch.empty(B, C // 4, h * 2, w * 2, dtype=torch.float32, device=dev)
+                N.unsqueeze(st, out, B, C, h, w, C * P, (C // 4) * P * 4)
+                return out
+            Cn, hn, wn = 2 * (C // 4), h * 2, w * 2
+            nxt = torch.empty(B, Cn, hn, wn, dtype=torch.float32, device=dev)
+            N.unsqueeze(st, nxt, B, C, h, w, C * P, Cn * hn * wn)
+            latent = get_item(latents, -(self.L - li + 1))
+            levels[li - 1][1]._fill_second_half(nxt, Cn * hn * wn, B, Cn, hn, wn, latent, temperature)
+            src, C, h, w = nxt, Cn, hn, wn
+        raise AssertionError("unreachable")
+
     def _invert_core(self, latents, temperature, levels, slots, steps, ready: bool) -> Tensor:
         z_last = E.check_input(latents[-1], "latents[-1]")
         B, Cf, h, w = z_last.shape
         dev = z_last.device
+        if ready and self._fast_ok(h * 2 ** self.L, w * 2 ** self.L):
+            return self._invert_fast([z_last] if len(latents) == 1 else list(latents), temperature, levels, slots, steps)
         if ready:
             E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
         C, P = Cf, h * w

@@ -348,3 +348,72 @@ def test_gemm_nt_bf16_tensor_core(M, N_, K, epi, out_dt):
         assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
     else:
         assert torch.allclose(got, ref, rtol=6e-3, atol=6e-3)
+
+
+# ------------------------------------------------------------------ fused step-boundary kernel
+@pytest.mark.parametrize("B,C,H,W", [(3, 4, 16, 16), (5, 12, 16, 16), (4, 24, 8, 8), (7, 48, 4, 4), (2, 6, 5, 7), (2, 16, 2, 2)])
+@pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16])
+def test_flow_boundary_equals_unfused_chain(B, C, H, W, a1_dt):
+    """nfdpm_flow_boundary == coupling_apply -> channel_mix -> im2col3x3 (forward and inverse), and
+    squeeze -> channel_mix -> im2col3x3 at a level entry."""
+    P, Ch = H * W, C // 2
+    ldp = (9 * C + 15) // 16 * 16
+    lda = (9 * Ch + 63) // 64 * 64
+    x = rnd(B, C, H, W, seed=1).cuda()
+    pm = (rnd(B * P, ldp, seed=2) * 0.1).cuda()
+    bias3, logs3 = rnd(C, seed=3, scale=0.1).cuda(), rnd(C, seed=4, scale=0.1).cuda()
+    mt, beta = rnd(C, C, seed=5, scale=0.4).cuda(), rnd(C, seed=6).cuda()
+    for inverse in (False, True):
+        # unfused chain
+        y_ref = torch.empty_like(x)
+        part_ref = torch.zeros(N.ld_tiles(P) * B, device=DEV)
+        N.coupling_apply(pm, ldp, bias3, logs3, x, y_ref, None if inverse else part_ref, B, C, H, W, C * P, C * P, inverse)
+        u_ref = torch.empty_like(x)
+        N.channel_mix(y_ref, u_ref, mt, beta, B, C, P, C * P, C * P)
+        a_ref = torch.full((B * P, lda), 9.0, dtype=a1_dt, device=DEV)
+        N.im2col3x3(u_ref, a_ref, B, Ch, H, W, C * P, lda)
+        # fused
+        u = torch.empty_like(x)
+        part = torch.zeros(B, device=DEV)
+        a1 = torch.full((B * P, lda), 7.0, dtype=a1_dt, device=DEV)
+        N.flow_boundary(x, C * P, False, pm, ldp, bias3, logs3, None if inverse else part, mt, beta, u, C * P, a1, lda,
+                        B, C, H, W, inverse)
+        sync()
+        assert torch.allclose(u, u_ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(a1.float(), a_ref.float(), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-5, atol=1e-5)
+        if not inverse:
+            assert torch.allclose(part, part_ref.reshape(-1, B).sum(0), rtol=1e-5, atol=1e-4)
+        # coupling only, in place, no mix / no im2col (last step of a level)
+        xin = x.clone()
+        N.flow_boundary(xin, C * P, False, pm, ldp, bias3, logs3, None, None, None, xin, C * P, None, 0, B, C, H, W, inverse)
+        sync()
+        assert torch.allclose(xin, y_ref, rtol=1e-6, atol=1e-6)
+    # im2col only (entry of an inverse level)
+    a_ref = torch.empty(B * P, lda, dtype=a1_dt, device=DEV)
+    N.im2col3x3(x, a_ref, B, Ch, H, W, C * P, lda)
+    a1 = torch.empty(B * P, lda, dtype=a1_dt, device=DEV)
+    N.flow_boundary(x, C * P, False, None, 0, None, None, None, None, None, None, 0, a1, lda, B, C, H, W, False)
+    sync()
+    assert torch.equal(a1, a_ref)
+    # level entry: squeeze the first C/4 channels of a wider, larger tensor, then mix + im2col
+    if C % 4 == 0:
+        src = rnd(B, C // 2, 2 * H, 2 * W, seed=7).cuda()                  # use its first C/4 channels
+        sq = torch.empty(B, C, H, W, device=DEV)
+        N.squeeze(src, sq, B, C // 4, 2 * H, 2 * W, (C // 2) * 4 * P, C * P)
+        u_ref = torch.empty_like(sq)
+        N.channel_mix(sq, u_ref, mt, beta, B, C, P, C * P, C * P)
+        a_ref = torch.empty(B * P, lda, dtype=a1_dt, device=DEV)
+        N.im2col3x3(u_ref, a_ref, B, Ch, H, W, C * P, lda)
+        u = torch.empty_like(sq)
+        a1 = torch.empty(B * P, lda, dtype=a1_dt, device=DEV)
+        N.flow_boundary(src, (C // 2) * 4 * P, True, None, 0, None, None, None, mt, beta, u, C * P, a1, lda, B, C, H, W, False)
+        sync()
+        assert torch.allclose(u, u_ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(a1.float(), a_ref.float(), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-5, atol=1e-5)
+
+
+def test_flow_boundary_rejects_large_images():
+    assert N.flow_boundary_smem(12, 64, 64, 1, 1) > 200 * 1024
+    x = torch.zeros(1, 12, 64, 64, device=DEV)
+    with pytest.raises(RuntimeError, match="too large"):
+        N.flow_boundary(x, 12 * 4096, False, None, 0, None, None, None, None, None, x, 12 * 4096, None, 0, 1, 12, 64, 64, False)

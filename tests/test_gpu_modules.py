@@ -43,9 +43,17 @@ def build(c, L, K, seed, learn_prior=True, initialized=True):
     return flow, prior, sd, psd
 
 
+PATHS = {"unfused-eager": ("0", "0"), "fused-eager": ("1", "0"), "fused-graph": ("1", "1")}
+
+
 @pytest.mark.parametrize("name", CASES)
 @pytest.mark.parametrize("acc_dtype", [torch.float64, torch.float32])
-def test_glow_against_reference_golden(golden_dir, name, acc_dtype):
+@pytest.mark.parametrize("path", list(PATHS))
+def test_glow_against_reference_golden(golden_dir, name, acc_dtype, path, monkeypatch):
+    """Every execution path (unfused kernels / fused step-boundary kernel / CUDA-graph replay) against the outputs
+    of the unmodified reference."""
+    monkeypatch.setenv("NFDPM_FUSED_BOUNDARY", PATHS[path][0])
+    monkeypatch.setenv("NFDPM_GRAPHS", PATHS[path][1])
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     c, L, K, B, S, seed, lp = [int(v) for v in g["cfg"]]
     flow, prior, sd, psd = build(c, L, K, seed, learn_prior=bool(lp))
