@@ -4,11 +4,13 @@
 //
 // Persistent, warp-specialised CTA (one per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A box and a BNx64 B box (128B swizzle)
-//               into a 4-stage shared-memory ring, completion on mbarriers
+//               into a 3-stage shared-memory ring, completion on mbarriers
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator; also owns TMEM alloc/dealloc
 //   warps 2..9  epilogue: software-pipelined tcgen05.ld (32x32b.x16) of the accumulator quadrant, fused
-//               ActNorm+ReLU as one FMA + max per element (utils.py:69,84-87), convert, 16-byte global stores.
+//               ActNorm+ReLU as one FMA + max per element (utils.py:69,84-87), convert, conflict-free 16-byte
+//               stores into a 128B-swizzled staging tile, then ONE thread issues cp.async.bulk.tensor stores
+//               (full 128-byte lines; r1 profile: per-thread row-strided global stores capped output at 2.3 TB/s).
 //               Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the main loop of
 //               tile i+1.  (r1 profile: with 4 epilogue warps and scalar parameter loads the kernel was
 //               issue-bound in the epilogue at 30% tensor-pipe activity.)
@@ -24,13 +26,14 @@ namespace nfdpm {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_B_BYTES_MAX = 256 * TC_BK * 2;        // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
 constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quadrant, alternating 16-column chunks
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_ACC_COLS = 256;     // TMEM columns per accumulator stage
+constexpr int TC_CSTAGE_BYTES = 64 * 1024;   // output staging: 128 rows x 256 bf16 / 128 fp32, as 16 KB swizzled boxes
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +83,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -126,32 +141,41 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <typename OutT> struct TcStore;
-template <> struct TcStore<float> {
-  static __device__ __forceinline__ void vec16(float* p, const float (&v)[16]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
-  static __device__ __forceinline__ void one(float* p, float a) { *p = a; }
-};
-template <> struct TcStore<__nv_bfloat16> {
-  static __device__ __forceinline__ void vec16(__nv_bfloat16* p, const float (&v)[16]) {
+// Staging-tile writers.  The tile is a sequence of 16 KB boxes [128 rows][128 bytes] in the TMA 128B-swizzle layout:
+// the 16-byte unit u of row r lives at r*128 + ((u ^ (r & 7)) * 16).  One thread owns one row, so the 8 rows of a
+// quarter-warp hit 8 different units: conflict-free st.shared.v4.
+template <typename OutT> struct TcStage;
+template <> struct TcStage<__nv_bfloat16> {
+  static constexpr int kColsPerBox = 64;
+  static __device__ __forceinline__ void put16(uint32_t cbase, int row, int c0, const float (&v)[16]) {
     uint32_t w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t*>(&t);
     }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(p + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    const uint32_t box = cbase + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)row * 128u;
+    const int u0 = (c0 & 63) >> 3;
+    st_shared_v4(box + (uint32_t)(((u0 + 0) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+    st_shared_v4(box + (uint32_t)(((u0 + 1) ^ (row & 7)) << 4), w[4], w[5], w[6], w[7]);
   }
-  static __device__ __forceinline__ void one(__nv_bfloat16* p, float a) { *p = __float2bfloat16_rn(a); }
+};
+template <> struct TcStage<float> {
+  static constexpr int kColsPerBox = 32;
+  static __device__ __forceinline__ void put16(uint32_t cbase, int row, int c0, const float (&v)[16]) {
+    const uint32_t box = cbase + (uint32_t)(c0 >> 5) * 16384u + (uint32_t)row * 128u;
+    const int u0 = (c0 & 31) >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      st_shared_v4(box + (uint32_t)(((u0 + i) ^ (row & 7)) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                   __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+  }
 };
 
 template <int EPI, typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
-                                                                   OutT* __restrict__ D, int64_t ldd, int M, int N, int K,
+                                                                   const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
                                                                    int BN, const float* __restrict__ ep_scale,
                                                                    const float* __restrict__ ep_bias) {
   extern __shared__ uint8_t smem_raw[];
@@ -161,7 +185,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1024-byte aligned tile ring (swizzle-128B requirement), then the epilogue parameters
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  float* s_ep = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t cstage = ring + TC_STAGES * TC_STAGE_BYTES;          // 1024-aligned output staging tile
+  float* s_ep = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + TC_STAGES * TC_STAGE_BYTES + TC_CSTAGE_BYTES);
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[TC_STAGES]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * TC_STAGES]), bar_tempty = smem_u32(&bars[2 * TC_STAGES + 2]);
 
@@ -181,6 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -254,9 +280,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const int row = m_blk * TC_BM + q * 32 + lane;
+      const int trow = q * 32 + lane;                      // row inside the tile == TMEM lane
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_ACC_COLS;
-      OutT* drow = D + (int64_t)row * ldd;
+      // the previous tile's TMA stores must have finished READING the staging tile before it is overwritten
+      if (warp == 2 && lane == 0) tma_store_wait_read();
+      epi_barrier();
       auto process = [&](const uint32_t (&r)[16], int c0) {
         const int n0 = n_blk * BN + c0;
         float v[16];
@@ -275,15 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
-        if (row < M) {
-          if (n0 + 15 < N) {
-            TcStore<OutT>::vec16(drow + n0, v);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + j < N) TcStore<OutT>::one(drow + n0 + j, v[j]);
-          }
-        }
+        TcStage<OutT>::put16(cstage, trow, c0, v);
       };
       // chunks half, half+2, half+4, ... ; the load of the next chunk is in flight while this one is processed
       uint32_t ra[16], rb[16];
@@ -300,11 +320,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
         process(rb, ch * 16);
         ch += 2;
       }
+      // accumulator drained: hand the TMEM stage back to the MMA warp before doing the stores
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
+      fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA engine
+      epi_barrier();
+      if (warp == 2 && lane == 0) {
+        constexpr int CPB = TcStage<OutT>::kColsPerBox;
+        const int n_boxes = (BN + CPB - 1) / CPB;
+        for (int j = 0; j < n_boxes; ++j)                  // rows >= M and columns >= N are clipped by the tensor map
+          tma_store_2d(&tmD, cstage + (uint32_t)j * 16384u, n_blk * BN + j * CPB, m_blk * TC_BM);
+        tma_store_commit();
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (warp == 2 && lane == 0) tma_store_wait_all();      // global writes complete before the kernel exits
   }
   tc_fence_before();
   __syncthreads();
@@ -330,15 +361,17 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 128 bytes of columns], 128B swizzle
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    bool f32 = false) {
   EncodeTiledFn enc = encode_fn();
   NFDPM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const int esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NFDPM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%d)",
@@ -347,7 +380,7 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
 }
 
 template <int EPI, typename OutT>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* D, int64_t ldd, int M, int N, int K, int BN,
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, int M, int N, int K, int BN,
                      const float* es, const float* eb, int grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -355,7 +388,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* D, in
                                     220 * 1024));
     attr_set = true;
   }
-  gemm_nt_tc_kernel<EPI, OutT><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, (OutT*)D, ldd, M, N, K, BN, es, eb);
+  gemm_nt_tc_kernel<EPI, OutT><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmD, M, N, K, BN, es, eb);
   NFDPM_CHECK_LAUNCH("gemm_nt_tc_kernel");
   return 0;
 }
@@ -366,12 +399,18 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   NFDPM_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)D % 16 == 0),
                 "nfdpm_gemm_nt(bf16): operands must be 16-byte aligned");
   NFDPM_REQUIRE(epilogue == NFDPM_EPI_RAW || N <= 2048, "nfdpm_gemm_nt(bf16): fused ActNorm epilogue supports N <= 2048");
-  // N tile: the largest multiple of 16 that is <= 256 and splits N evenly enough
-  const int nblk = (N + 255) / 256;
-  int BN = ((N + nblk - 1) / nblk + 15) / 16 * 16;
-  CUtensorMap tmA, tmB;
+  // N tile: multiple of 16 that splits N evenly; <= 256 columns for bf16 output, <= 128 for fp32 output (the staging
+  // tile holds 128 x 256 bf16 or 128 x 128 fp32)
+  const int bn_max = (out_dtype == NFDPM_F32) ? 128 : 256;
+  const int cpb = (out_dtype == NFDPM_F32) ? 32 : 64;     // columns per 128-byte TMA store box
+  const int nblk = (N + bn_max - 1) / bn_max;
+  // one N block: any multiple of 16 (columns >= N are clipped by the D tensor map); several N blocks: BN must be a
+  // whole number of store boxes, otherwise a tile's last box would spill into its neighbour's columns
+  const int BN = (nblk == 1) ? (N + 15) / 16 * 16 : ((N + nblk - 1) / nblk + cpb - 1) / cpb * cpb;
+  CUtensorMap tmA, tmB, tmD;
   if (make_map(&tmA, A, M, K, lda, TC_BM)) return 1;
   if (make_map(&tmB, Bw, N, K, ldb, BN)) return 1;
+  if (make_map(&tmD, D, M, N, ldd, TC_BM, out_dtype == NFDPM_F32)) return 1;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -381,8 +420,8 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sms ? tiles : sms;
   const size_t n_pad = (size_t)((N + BN - 1) / BN) * BN;
-  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (epilogue == NFDPM_EPI_ACTNORM_RELU ? 2 * n_pad * 4 : 0);
-#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, D, ldd, M, N, K, BN, ep_scale, ep_bias, grid, smem, st)
+  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_CSTAGE_BYTES + (epilogue == NFDPM_EPI_ACTNORM_RELU ? 2 * n_pad * 4 : 0);
+#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, tmD, M, N, K, BN, ep_scale, ep_bias, grid, smem, st)
   if (out_dtype == NFDPM_F32) {
     if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, float); else GO(NFDPM_EPI_ACTNORM_RELU, float);
   } else {

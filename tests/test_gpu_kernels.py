@@ -413,7 +413,7 @@ def test_flow_boundary_equals_unfused_chain(B, C, H, W, a1_dt):
 
 
 def test_flow_boundary_rejects_large_images():
-    assert N.flow_boundary_smem(12, 64, 64, 1, 1) > 200 * 1024
-    x = torch.zeros(1, 12, 64, 64, device=DEV)
+    assert N.flow_boundary_smem(24, 64, 64, 0, 0) > 200 * 1024
+    x = torch.zeros(1, 24, 64, 64, device=DEV)
     with pytest.raises(RuntimeError, match="too large"):
-        N.flow_boundary(x, 12 * 4096, False, None, 0, None, None, None, None, None, x, 12 * 4096, None, 0, 1, 12, 64, 64, False)
+        N.flow_boundary(x, 24 * 4096, False, None, 0, None, None, None, None, None, x, 24 * 4096, None, 0, 1, 24, 64, 64, False)
