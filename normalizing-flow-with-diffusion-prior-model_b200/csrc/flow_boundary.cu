@@ -45,7 +45,7 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
 }
 
 template <bool COUPLING, typename A1T>
-__global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a) {
+__global__ void __launch_bounds__(1024) flow_boundary_kernel(const BoundaryArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
   const int PS = P + 1;                       // padded pixel stride: conflict-free for lanes over channels
@@ -56,18 +56,18 @@ __global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a
   float* par_s = m_s + ((a.mt != nullptr) ? (C * Cp + Cp) : 0);   // [2C] bias3, exp(3 logs3)
   float* ls_s = par_s + (COUPLING ? 2 * C : 0);                   // [P*Ch] log-det terms
   if (a.mt == nullptr) u_s = x_s;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
   // ---- parameters
   if (a.mt != nullptr) {
-    for (int i = tid; i < C * Cp; i += 256) {
+    for (int i = tid; i < C * Cp; i += nt) {
       const int r = i / Cp, c = i - r * Cp;
       m_s[i] = (c < C) ? a.mt[r * C + c] : 0.f;
     }
-    for (int i = tid; i < Cp; i += 256) m_s[C * Cp + i] = (i < C) ? a.beta[i] : 0.f;
+    for (int i = tid; i < Cp; i += nt) m_s[C * Cp + i] = (i < C) ? a.beta[i] : 0.f;
   }
   if (COUPLING) {
-    for (int i = tid; i < C; i += 256) {
+    for (int i = tid; i < C; i += nt) {
       par_s[i] = a.bias3[i];
       par_s[C + i] = expf(3.f * a.logs3[i]);
     }
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a
   if (a.squeeze_in) {
     // in is [C/4, 2H, 2W]; channel c = cc*4 + h1*2 + w1 reads in[cc, 2y+h1, 2x+w1]
     const int W2 = 2 * W;
-    for (int i = tid; i < (C >> 2) * P; i += 256) {
+    for (int i = tid; i < (C >> 2) * P; i += nt) {
       const int cc = i / P, p = i - cc * P;
       const int py = p / W, px = p - py * W;
       const float* s = inb + ((int64_t)cc * 2 * H + 2 * py) * W2 + 2 * px;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a
       x_s[(cc * 4 + 3) * PS + p] = t1.y;
     }
   } else {
-    for (int i = tid; i < C * P; i += 256) {
+    for (int i = tid; i < C * P; i += nt) {
       const int c = i / P, p = i - c * P;
       x_s[c * PS + p] = inb[i];
     }
@@ -98,22 +98,25 @@ __global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a
   // ---- phase 1: affine coupling, item = (pixel, j) with j fastest (pm rows read contiguously)
   if (COUPLING) {
     const float* pmb = a.pm + (int64_t)b * P * a.ldp;
-    for (int it = tid; it < P * Ch; it += 256) {
+    for (int it = tid; it < P * Ch; it += nt) {
       const int p = it / Ch, j = it - p * Ch;
       const int py = p / W, px = p - py * W;
+      // all 18 loads are issued before the first use (each pm element is consumed exactly once: plain streaming reads)
+      float lv[9], tv[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+        const float* r = pmb + (int64_t)(ok ? yy * W + xx : p) * a.ldp + tap * C + j;
+        const float l0 = __ldg(r), t0 = __ldg(r + Ch);
+        lv[tap] = ok ? l0 : 0.f;
+        tv[tap] = ok ? t0 : 0.f;
+      }
       float ls = 0.f, tt = 0.f;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = py + ky - 1;
-        if (yy < 0 || yy >= H) continue;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xx = px + kx - 1;
-          if (xx < 0 || xx >= W) continue;
-          const float* r = pmb + (int64_t)(yy * W + xx) * a.ldp + (ky * 3 + kx) * C + j;
-          ls += __ldg(r);
-          tt += __ldg(r + Ch);
-        }
+      for (int tap = 0; tap < 9; ++tap) {
+        ls += lv[tap];
+        tt += tv[tap];
       }
       const float log_s = (ls + par_s[j]) * par_s[C + j];
       const float sh_t = (tt + par_s[Ch + j]) * par_s[C + Ch + j];
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a
   // ---- phase 2: channel mix, item = (group of 4 outputs, pixel), lanes over pixels
   if (a.mt != nullptr) {
     const int n_og = Cp >> 2;
-    for (int it = tid; it < n_og * P; it += 256) {
+    for (int it = tid; it < n_og * P; it += nt) {
       const int og = it / P, p = it - og * P;
       const float4 b4 = *reinterpret_cast<const float4*>(m_s + C * Cp + og * 4);
       float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a
   // ---- phase 3a: NCHW sink (lanes over pixels)
   if (a.y != nullptr) {
     float* yb = a.y + (int64_t)b * a.y_bs;
-    for (int i = tid; i < C * P; i += 256) {
+    for (int i = tid; i < C * P; i += nt) {
       const int c = i / P, p = i - c * P;
       yb[i] = u_s[c * PS + p];
     }
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(256) flow_boundary_kernel(const BoundaryArgs a
     const int K = Ch * 9;
     const int n_g = (int)(a.lda1 >> 3);
     A1T* a1b = reinterpret_cast<A1T*>(a.a1) + (int64_t)b * P * a.lda1;
-    for (int it = tid; it < P * n_g; it += 256) {
+    for (int it = tid; it < P * n_g; it += nt) {
       const int p = it / n_g, g = it - p * n_g;
       const int py = p / W, px = p - py * W;
       float v[8];
@@ -227,6 +230,12 @@ extern "C" int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_i
   a.B = B; a.C = C; a.H = H; a.W = W; a.squeeze_in = squeeze_in; a.inverse = inverse;
   cudaStream_t st = as_stream(stream);
   const bool bf = (a1 != nullptr && a1_dtype == NFDPM_BF16);
+  // one CTA per image: give it as many warps as its largest phase has work items (latency hiding), up to 1024 threads
+  int64_t items = (int64_t)H * W * (C / 2);
+  if (a1 != nullptr && (int64_t)H * W * (lda1 / 8) > items) items = (int64_t)H * W * (lda1 / 8);
+  int threads = (int)((items + 31) / 32 * 32);
+  if (threads > 1024) threads = 1024;
+  if (threads < 128) threads = 128;
 #define LAUNCH(CP, T)                                                                                              \
   do {                                                                                                             \
     static bool attr_set = false;                                                                                  \
@@ -235,7 +244,7 @@ extern "C" int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_i
                                       200 * 1024));                                                                \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    flow_boundary_kernel<CP, T><<<B, 256, smem, st>>>(a);                                                          \
+    flow_boundary_kernel<CP, T><<<B, threads, smem, st>>>(a);                                                      \
   } while (0)
   if (pm != nullptr) { if (bf) LAUNCH(true, __nv_bfloat16); else LAUNCH(true, float); }
   else { if (bf) LAUNCH(false, __nv_bfloat16); else LAUNCH(false, float); }
