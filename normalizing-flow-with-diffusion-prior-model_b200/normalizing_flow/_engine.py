@@ -3,10 +3,10 @@ launch sequences of one StepFlow / coupling network.  No arithmetic happens here
 produced by a kernel of the C-ABI library; torch supplies device memory and the current stream.
 
 Precision modes (env ``NFDPM_PRECISION``):
+  * ``bf16`` (default) — coupling-network GEMMs on tcgen05 tensor cores, bf16 operands, fp32 TMEM accumulators
+    (parity bar stated in DESIGN.md / tests).  Everything outside the coupling nets is fp32 in both modes.
   * ``fp32`` — coupling-network GEMMs on CUDA cores with exact fp32 FMA accumulation
     (parity bar: z / log-det within 1e-4 relative of the reference).
-  * ``bf16`` — coupling-network GEMMs on tcgen05 tensor cores, bf16 operands, fp32 TMEM accumulators
-    (parity bar stated in DESIGN.md / tests).  Everything outside the coupling nets is fp32 in both modes.
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ from . import _native as N
 
 
 def precision() -> str:
-    p = os.environ.get("NFDPM_PRECISION", "fp32").lower()
+    p = os.environ.get("NFDPM_PRECISION", "bf16").lower()
     if p not in ("fp32", "bf16"):
         raise ValueError(f"NFDPM_PRECISION must be 'fp32' or 'bf16', got {p!r}")
     return p
