@@ -122,6 +122,17 @@ int nfdpm_gemm_nt(const void* A, int64_t lda, const void* Bw, int64_t ldb, void*
                   int K, int in_dtype, int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias,
                   nfdpm_stream_t stream);
 
+/* Fused coupling network on tcgen05 (bf16 operands, fp32 TMEM accumulation): the three convolutions of
+ * utils.py:83-89 in ONE kernel per 128-row tile; h1/h2 stay in shared memory, only a1 is read and pm written.
+ *   a1 [M,lda1] bf16 im2col rows (K1p = padded 9*C/2, multiple of 64, <= 512); w1 [512,K1p], w2 [512,512],
+ *   w3 [ldp,512] bf16 (nfdpm_pack_matrix layouts); pm [M,ldp] fp32, ldp = 9C rounded up to 16, <= 512;
+ *   ep [4][512] fp32 = exp(s1), exp(s1)*b1, exp(s2), exp(s2)*b2 of the two inner ActNorms (nfdpm_fold_actnorm).
+ * Equivalent to three nfdpm_gemm_nt calls (ACTNORM_RELU, ACTNORM_RELU, RAW). */
+int nfdpm_coupling_fused(const void* a1, int64_t lda1, const void* w1, const void* w2, const void* w3, float* pm,
+                         int64_t ldp, int M, int K1p, const float* ep, nfdpm_stream_t stream);
+/* e_out[i] = exp(scale[i]), eb_out[i] = exp(scale[i])*bias[i]  (ActNorm folded to one FMA: y = e*x + e*b). */
+int nfdpm_fold_actnorm(const float* scale, const float* bias, float* e_out, float* eb_out, int n, nfdpm_stream_t stream);
+
 /* Affine-coupling epilogue (transforms.py:179-184 forward, :196-200 inverse).
  *   pm   [M, ldp]: taps-as-N output of the ZeroConv GEMM (column = tap*C + co, tap = ky*3+kx)
  *   net[co] = (sum_tap pm[m + (ky-1)*W + (kx-1), tap*C+co] (zero outside the image) + bias3[co]) * exp(3*logs3[co])

@@ -171,6 +171,8 @@ class CouplingCache:
         self.key = None
         self.w1 = self.w2 = self.w3 = None
         self.K1 = self.K1p = self.ldp = 0
+        self.ep = None            # [4, F] folded inner-ActNorm parameters for the fused tensor-core kernel
+        self.ep_key = None
 
 
 def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, dt: torch.dtype):
@@ -211,9 +213,30 @@ def coupling_a1(cp, B: int, C: int, H: int, W: int, dev: torch.device) -> Tuple[
     return WS.get("A1", B * H * W * K1p, dt, dev), K1p
 
 
+def fused_coupling_enabled() -> bool:
+    return os.environ.get("NFDPM_FUSED_COUPLING", "1") != "0"
+
+
+def refresh_folded(cp) -> None:
+    """(Re)compute the folded inner-ActNorm parameters of coupling network ``cp`` if they changed."""
+    _, an1, _, an2, _ = cp._parts()
+    cache = cp._cache
+    key = _vkey(an1.scale, an1.bias, an2.scale, an2.bias)
+    if cache.ep_key == key:
+        return
+    F = an1.scale.shape[0]
+    if cache.ep is None or cache.ep.numel() != 4 * F:
+        _bump_epoch()
+        cache.ep = torch.empty(4 * F, dtype=torch.float32, device=an1.scale.device)
+    N.fold_actnorm(an1.scale, an1.bias, cache.ep, cache.ep[F:], F)
+    N.fold_actnorm(an2.scale, an2.bias, cache.ep[2 * F:], cache.ep[3 * F:], F)
+    cache.ep_key = key
+
+
 def coupling_gemms(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int) -> Tuple[torch.Tensor, int]:
     """GEMM1 -> GEMM2 -> GEMM3 of an initialised coupling network from its im2col rows ``A1``.
-    Returns the taps-as-N rows (pm, ldp)."""
+    Returns the taps-as-N rows (pm, ldp).  bf16 mode with F = 512 and 9C <= 512 runs them as ONE fused
+    tcgen05 kernel (h1 / h2 stay in shared memory)."""
     conv1, an1, conv2, an2, zc = cp._parts()
     F = conv1.weight.shape[0]
     dt = A1.dtype
@@ -221,6 +244,11 @@ def coupling_gemms(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int) -> Tupl
     dev = A1.device
     M = B * H * W
     K1p, ldp = cache.K1p, cache.ldp
+    if dt == torch.bfloat16 and F == 512 and ldp <= 512 and K1p <= 512 and fused_coupling_enabled():
+        refresh_folded(cp)
+        pm = WS.get("pm", M * ldp, torch.float32, dev)
+        N.coupling_fused(A1, K1p, cache.w1, cache.w2, cache.w3, pm, ldp, M, K1p, cache.ep)
+        return pm, ldp
     h1 = WS.get("h1", M * F, dt, dev)
     N.gemm_nt(A1, K1p, cache.w1, K1p, h1, F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
     w2 = cache.w2 if dt != torch.float32 else conv2.weight

@@ -58,6 +58,8 @@ def _load() -> C.CDLL:
         "nfdpm_flow_boundary_smem": ([i32, i32, i32, i32, i32], C.c_size_t),
         "nfdpm_flow_boundary": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i32, i64, i32, i32, i32, i32,
                                  i32, vp], C.c_int),
+        "nfdpm_coupling_fused": ([vp, i64, vp, vp, vp, vp, i64, i32, i32, vp, vp], C.c_int),
+        "nfdpm_fold_actnorm": ([vp, vp, vp, vp, i32, vp], C.c_int),
         "nfdpm_accumulate": ([vp, i32, vp, i32, i32, vp, vp, i32, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
@@ -73,7 +75,7 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_copy_channels", "nfdpm_im2col3x3", "nfdpm_pack_matrix", "nfdpm_gemm_nt", "nfdpm_coupling_apply",
            "nfdpm_split_prior_logp", "nfdpm_split_prior_sample", "nfdpm_gauss_logp_const",
            "nfdpm_gauss_sample_const", "nfdpm_accumulate", "nfdpm_rows_to_nchw", "nfdpm_nchw_to_rows",
-           "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary"]
+           "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary", "nfdpm_coupling_fused", "nfdpm_fold_actnorm"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -200,3 +202,11 @@ def flow_boundary(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, b
     _ok(lib.nfdpm_flow_boundary(_p(src), src_bs, int(squeeze_in), _p(pm), ldp, _p(bias3), _p(logs3), _p(ld_part),
                                 _p(mt), _p(beta), _p(y), y_bs, _p(a1), _dt(a1) if a1 is not None else F32, lda1, B, Cc,
                                 H, W, int(inverse), _st()))
+
+
+def coupling_fused(a1, lda1, w1, w2, w3, pm, ldp, M, K1p, ep) -> None:
+    _ok(lib.nfdpm_coupling_fused(_p(a1), lda1, _p(w1), _p(w2), _p(w3), _p(pm), ldp, M, K1p, _p(ep), _st()))
+
+
+def fold_actnorm(scale, bias, e_out, eb_out, n) -> None:
+    _ok(lib.nfdpm_fold_actnorm(_p(scale), _p(bias), _p(e_out), _p(eb_out), n, _st()))

@@ -168,6 +168,8 @@ class Glow(Transform):
         for s in steps:
             conv1, _, conv2, _, zc = s.affcoupling._parts()
             E._pack_coupling(s.affcoupling._cache, conv1.weight, conv2.weight, zc.weight, dt)
+            if dt == torch.bfloat16:
+                E.refresh_folded(s.affcoupling)
         for blk in self.blocks:
             E.refresh_split(blk.split, blk.flows[0]._C)
 

@@ -417,3 +417,39 @@ def test_flow_boundary_rejects_large_images():
     x = torch.zeros(1, 24, 64, 64, device=DEV)
     with pytest.raises(RuntimeError, match="too large"):
         N.flow_boundary(x, 24 * 4096, False, None, 0, None, None, None, None, None, x, 24 * 4096, None, 0, 1, 24, 64, 64, False)
+
+
+# ------------------------------------------------------------------ fused coupling network (tcgen05)
+@pytest.mark.parametrize("M,K1p,ldp", [(300, 64, 112), (128, 64, 48), (8192, 128, 224), (2048, 256, 432),
+                                       (32768, 64, 112), (5000, 128, 224), (77, 192, 160)])
+def test_coupling_fused_equals_three_gemms(M, K1p, ldp):
+    """nfdpm_coupling_fused == gemm_nt(ACTNORM_RELU) -> gemm_nt(ACTNORM_RELU) -> gemm_nt(RAW) on the tensor-core path
+    (same bf16 roundings of h1/h2, same K order), and both agree with an fp64 reference of the bf16 pipeline."""
+    Fh = 512
+    a1 = rnd(M, K1p, seed=1).bfloat16().cuda()
+    w1 = (rnd(Fh, K1p, seed=2) * (1.0 / math.sqrt(K1p))).bfloat16().cuda()
+    w2 = (rnd(Fh, Fh, seed=3) * (1.0 / math.sqrt(Fh))).bfloat16().cuda()
+    w3 = (rnd(ldp, Fh, seed=4) * 0.05).bfloat16().cuda()
+    s1, b1 = rnd(Fh, seed=5, scale=0.2).cuda(), rnd(Fh, seed=6, scale=0.5).cuda()
+    s2, b2 = rnd(Fh, seed=7, scale=0.2).cuda(), rnd(Fh, seed=8, scale=0.5).cuda()
+    h1 = torch.empty(M, Fh, dtype=torch.bfloat16, device=DEV)
+    h2 = torch.empty(M, Fh, dtype=torch.bfloat16, device=DEV)
+    pm_ref = torch.empty(M, ldp, device=DEV)
+    N.gemm_nt(a1, K1p, w1, K1p, h1, Fh, M, Fh, K1p, N.EPI_ACTNORM_RELU, s1, b1)
+    N.gemm_nt(h1, Fh, w2, Fh, h2, Fh, M, Fh, Fh, N.EPI_ACTNORM_RELU, s2, b2)
+    N.gemm_nt(h2, Fh, w3, Fh, pm_ref, ldp, M, ldp, Fh)
+    ep = torch.empty(4 * Fh, device=DEV)
+    N.fold_actnorm(s1, b1, ep, ep[Fh:], Fh)
+    N.fold_actnorm(s2, b2, ep[2 * Fh:], ep[3 * Fh:], Fh)
+    pm = torch.full((M, ldp), 123.0, device=DEV)
+    N.coupling_fused(a1, K1p, w1, w2, w3, pm, ldp, M, K1p, ep)
+    sync()
+    assert torch.isfinite(pm).all()
+    assert torch.allclose(pm, pm_ref, rtol=1e-5, atol=1e-5), float((pm - pm_ref).abs().max())
+    # fp64 reference of the same bf16 pipeline (first 256 rows)
+    n = min(M, 256)
+    H1 = torch.relu(torch.exp(s1.double().cpu()) * (a1[:n].double().cpu() @ w1.double().cpu().T + b1.double().cpu()))
+    H1 = H1.float().bfloat16().double()
+    H2 = torch.relu(torch.exp(s2.double().cpu()) * (H1 @ w2.double().cpu().T + b2.double().cpu())).float().bfloat16().double()
+    ref = H2 @ w3.double().cpu().T
+    assert torch.allclose(pm[:n].cpu().double(), ref, rtol=2e-2, atol=2e-2)
