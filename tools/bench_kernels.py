@@ -50,19 +50,25 @@ for lvl, (C, hw) in enumerate([(12, 16), (24, 8), (48, 4)]):
     b3, l3 = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     part = torch.empty(B, device=dev)
     tb = timeit(lambda: N.flow_boundary(x, C * P, False, pm, ldp, b3, l3, part, mt, beta, x, C * P, a1, K1p, B, C, hw, hw, False))
+    tf = float("nan")
+    if dt == torch.bfloat16:
+        ep = torch.zeros(4 * F, device=dev); ep[:F] = 1; ep[2 * F:3 * F] = 1
+        tf = timeit(lambda: N.coupling_fused(a1, K1p, w1, w2, w3, pm, ldp, M, K1p, ep))
     fl = lambda k, n: 2.0 * M * n * k
     rows.append(dict(level=lvl, C=C, P=P, M=M, K1p=K1p, ldp=ldp,
                      gemm1_us=t1, gemm1_tflops=fl(K1p, F) / t1 / 1e6,
                      gemm2_us=t2, gemm2_tflops=fl(F, F) / t2 / 1e6,
                      gemm3_us=t3, gemm3_tflops=fl(F, ldp) / t3 / 1e6,
+                     fused_us=tf, fused_tflops=(fl(K1p, F) + fl(F, F) + fl(F, ldp)) / tf / 1e6,
                      boundary_us=tb,
                      boundary_gbs=(M * ldp * 4 + 2 * B * C * P * 4 + M * K1p * a1.element_size()) / tb / 1e3))
 print(f"# B={B} mode={mode} warm={WARM}")
-print(f"{'lvl':>3} {'M':>6} {'gemm1':>8} {'TF':>6} {'gemm2':>8} {'TF':>6} {'gemm3':>8} {'TF':>6} {'bound':>8} {'GB/s':>6}  (us)")
+print(f"{'lvl':>3} {'M':>6} {'gemm1':>8} {'TF':>6} {'gemm2':>8} {'TF':>6} {'gemm3':>8} {'TF':>6} {'fused':>8} {'TF':>6} {'bound':>8} {'GB/s':>6}  (us)")
 tot = 0
 for r in rows:
     print(f"{r['level']:>3} {r['M']:>6} {r['gemm1_us']:8.1f} {r['gemm1_tflops']:6.0f} {r['gemm2_us']:8.1f} {r['gemm2_tflops']:6.0f} "
-          f"{r['gemm3_us']:8.1f} {r['gemm3_tflops']:6.0f} {r['boundary_us']:8.1f} {r['boundary_gbs']:6.0f}")
-    tot += r['gemm1_us'] + r['gemm2_us'] + r['gemm3_us'] + r['boundary_us']
+          f"{r['gemm3_us']:8.1f} {r['gemm3_tflops']:6.0f} {r['fused_us']:8.1f} {r['fused_tflops']:6.0f} "
+          f"{r['boundary_us']:8.1f} {r['boundary_gbs']:6.0f}")
+    tot += (r['fused_us'] if r['fused_us'] == r['fused_us'] else r['gemm1_us'] + r['gemm2_us'] + r['gemm3_us']) + r['boundary_us']
 print(f"# sum per StepFlow over levels = {tot:.1f} us  ->  x16 steps x2 directions = {tot * 32 / 1e3:.2f} ms")
 print(json.dumps(rows))
