@@ -267,7 +267,9 @@ def main():
             "roofline": {"bound": "tensor", "kernel": ("gemm_nt_f32_kernel (CUDA-core fp32)" if mode == "fp32" else
                                                         "gemm_nt_tc_kernel (tcgen05 bf16)") + f" M={M} N=512 K=512",
                          "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
-                         "traffic": None, "peak_source": f"{src} bf16 burst (kernel timed alone)", "kernel_ms": k_ms},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture
+                         # profiles/r01_ncu_full_summary.md (34.10 MB read + 0.61 MB written back within the launch)
+                         "traffic": (34.71e6 if (mode == "bf16" and B == 128) else None), "peak_source": f"{src} bf16 burst (kernel timed alone)", "kernel_ms": k_ms},
             "clocks": clocks,
             "checks": {"recon_max_abs_err": recon, "step_tflops": 2 * FLOP_PER_IMG_FWD * B / (ms / args.steps * 1e-3) / 1e12},
         }

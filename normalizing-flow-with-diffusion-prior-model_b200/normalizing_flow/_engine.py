@@ -214,7 +214,10 @@ def coupling_a1(cp, B: int, C: int, H: int, W: int, dev: torch.device) -> Tuple[
 
 
 def fused_coupling_enabled() -> bool:
-    return os.environ.get("NFDPM_FUSED_COUPLING", "1") != "0"
+    # Opt-in: the single-kernel coupling network keeps h1/h2 on chip but (round-1 measurement, profiles/) is still
+    # slower than the three pipelined GEMMs: both are L2->SM operand-bandwidth bound and the fused kernel cannot
+    # overlap its epilogues with MMAs.  It becomes the default once weights are multicast across a CTA cluster.
+    return os.environ.get("NFDPM_FUSED_COUPLING", "0") == "1"
 
 
 def refresh_folded(cp) -> None:
