@@ -188,6 +188,53 @@ int nfdpm_rows_to_nchw(const float* h, int64_t ldh, int mode, const float* p1, c
 int nfdpm_nchw_to_rows(const float* x, void* out, int out_dtype, int B, int Cc, int P, int64_t x_bstride, int64_t ld,
                        nfdpm_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward (training) — what autograd computes for the reference lines cited at each forward entry point.
+ * All reductions are two-stage in a fixed order (deterministic).
+ */
+/* Affine coupling + log-det backward (transforms.py:179-184).  dy [B,C,P] grad of the coupling output, dld [B] grad of
+ * log_det_jac (may be NULL), u [B,C,P] coupling input, pm as in the forward.  Outputs: du [B,C,P] (first half = dy_a;
+ * the coupling-net part is added by nfdpm_mix_bwd), dpm [B*P, ldp], dpar [B][2C] per-image partials (dbias3[C], dlogs3[C]). */
+int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs, const float* pm,
+                       int64_t ldp, const float* bias3, const float* logs3, float* du, int64_t du_bs, float* dpm,
+                       float* dpar, int B, int C, int H, int W, nfdpm_stream_t stream);
+/* ActNorm+ReLU backward on rows (utils.py:69,84-87): dpre = dh*(h>0)*exp(scale); part[cta][2N] partial d(scale), d(bias);
+ * ctas = ceil(M/rows_per_cta). */
+int nfdpm_actnorm_relu_bwd(const float* dh, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h, const float* scale,
+                           void* dpre, int o_dtype, int64_t ld_o, float* part, int M, int N, int rows_per_cta,
+                           nfdpm_stream_t stream);
+/* out[i] (+)= sum_{r<R} part[r*stride + i], i < n */
+int nfdpm_reduce_rows(const float* part, float* out, int R, int n, int64_t stride, int accumulate, nfdpm_stream_t stream);
+/* Fused ActNorm + 1x1 conv backward (transforms.py:80,132) incl. col2im of the im2col-row gradient da1 (may be NULL):
+ * dx = W^T du; part [B][C*C + C]: per-image sum_p du[o]x[i] and sum_p du[o]. */
+int nfdpm_mix_bwd(const float* du, int64_t du_bs, const float* da1, int64_t lda1, const float* x, int64_t x_bs,
+                  const float* mt, float* dx, int64_t dx_bs, float* part, int B, int C, int H, int W,
+                  nfdpm_stream_t stream);
+/* d(InvConv2d.weight), d(ActNorm.scale), d(ActNorm.bias) of n StepFlows from the nfdpm_mix_bwd partials plus the
+ * log-det terms  P*sum(dld)*W^-T  and  P*sum(dld)  (transforms.py:81,131). */
+typedef struct {
+  const float* part; int32_t B; int32_t C;
+  const float* weight; const float* scale; const float* bias; const float* winv;
+  const float* dld_sum; float P; int32_t pad_;
+  float* d_weight; float* d_scale; float* d_bias; float* scratch; /* scratch: C*C + C floats */
+} nfdpm_mix_grad_item;
+int nfdpm_mix_param_grad(const nfdpm_mix_grad_item* items_host, int n, nfdpm_stream_t stream);
+/* Weight gradients: D[N1,N2] (+)= sum_m A[m,N1]*B[m,N2] (A, B row-major, F32 or BF16; D fp32 with ldd == N2).
+ * ws: nfdpm_gemm_tn_workspace(M,N1,N2,NULL) floats. */
+int64_t nfdpm_gemm_tn_workspace(int M, int N1, int N2, int* splits_out);
+int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void* Bm, int b_dtype, int64_t ldb, float* D, int64_t ldd,
+                  int M, int N1, int N2, float* ws, int accumulate, nfdpm_stream_t stream);
+/* Split prior backward (transforms.py:286-289, prior.py:36-37): dstate[:, C/2:] += dz; dh rows [M, ldh]; dpar [B][2C]. */
+int nfdpm_split_prior_bwd(const float* dlp, const float* h, int64_t ldh, const float* bias, const float* logs,
+                          const float* x, int64_t xbs, float* dstate, int64_t dbs, float* dh, float* dpar, int B, int C,
+                          int H, int W, nfdpm_stream_t stream);
+/* GaussianPrior backward (prior.py:79-83): dz [B,C,P]; dpar [B][4C] per-image partials: d(bias)[2C], d(logs)[2C]. */
+int nfdpm_gauss_const_bwd(const float* dl, const float* z, const float* bias, const float* logs, float* dz, float* dpar,
+                          int B, int C, int P, nfdpm_stream_t stream);
+/* dstate[b,c,p] += col2im(da)[b,c,p] for c < Cin (input gradient of a 3x3 "same" conv expressed as im2col rows). */
+int nfdpm_col2im_add(const float* da, int64_t lda, float* dstate, int64_t dbs, int B, int Cin, int H, int W,
+                     nfdpm_stream_t stream);
+
 /* acc[b] += sum_{r<R} part[r*B+b] + sum_{j<nc} cmul[j]*cval[j]   (fixed order -> deterministic).
  * acc is the caller's running log_det_jac / logp (`+=` in place, transforms.py:81,131,184,288), fp32 or fp64.
  * cval/cmul: device fp32 arrays (e.g. logdet constants and their H*W multipliers); may be NULL with nc=0. */

@@ -1,0 +1,615 @@
+// Backward kernels of the Glow flow path (training): what autograd would compute for
+// normalizing_flow/transforms.py:80-81,131-132,179-184,286-289, utils.py:43-44,68-69, prior.py:36-37,79-83.
+//   coupling_bwd_kernel        affine coupling + log-det: d(out), d(ld) -> d(K-A output), d(pm), d(bias3), d(logs3)
+//   actnorm_relu_bwd_kernel    rows: dpre = dh*(h>0)*exp(s); per-channel ds, db partials
+//   mix_bwd_kernel             fused ActNorm+1x1 conv backward (+ col2im of the im2col-row gradient): dx, dW^, db^ partials
+//   mix_param_grad_kernel      folds dW^, db^ and the log-det terms into d(weight), d(scale), d(bias)
+//   gemm_tn_kernel             weight gradients: D[N1,N2] = sum_m A[m,N1]*B[m,N2] (split over M, deterministic partials)
+//   split_prior_bwd_kernel / gauss_const_bwd_kernel / col2im_add_kernel / reduce_rows_kernel
+// All reductions are two-stage with a fixed order (no float atomics): bitwise reproducible.
+#include "common.cuh"
+
+namespace nfdpm {
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------ coupling backward
+struct CouplingBwdArgs {
+  const float* dy; int64_t dy_bs;      // grad wrt coupling output [B,C,P]
+  const float* dld;                    // grad wrt log_det_jac [B] (may be null)
+  const float* u; int64_t u_bs;        // coupling input (K-A output) [B,C,P]
+  const float* pm; int64_t ldp;        // taps-as-N rows [B*P, ldp]
+  const float* bias3; const float* logs3;
+  float* du; int64_t du_bs;            // out: grad wrt coupling input (first half = dy_a, im2col part added by mix_bwd)
+  float* dpm;                          // out: [B*P, ldp]
+  float* dpar;                         // out: [B][2C] per-image partials: dbias3[C], dlogs3[C]
+  int B, C, H, W;
+};
+
+__global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1, PS = P + 1;
+  float* g_s = sm;                  // [C][PS] dy, second half becomes du_b
+  float* ub_s = g_s + C * PS;       // [Ch][PS] u_b
+  float* dP_s = ub_s + Ch * PS;     // [C][PS] grad wrt gathered conv output
+  float* r_s = dP_s + C * PS;       // [4][P*Ch] reduction terms
+  float* par_s = r_s + 4 * P * Ch;  // [2C]
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < C; i += nt) {
+    par_s[i] = a.bias3[i];
+    par_s[C + i] = expf(3.f * a.logs3[i]);
+  }
+  const float* dyb = a.dy + (int64_t)b * a.dy_bs;
+  const float* ub = a.u + (int64_t)b * a.u_bs;
+  for (int i = tid; i < C * P; i += nt) {
+    const int c = i / P, p = i - c * P;
+    g_s[c * PS + p] = dyb[i];
+    if (c >= Ch) ub_s[(c - Ch) * PS + p] = ub[i];
+  }
+  __syncthreads();
+  const float gld = (a.dld != nullptr) ? a.dld[b] : 0.f;
+  const float* pmb = a.pm + (int64_t)b * P * a.ldp;
+  for (int it = tid; it < P * Ch; it += nt) {
+    const int p = it / Ch, j = it - p * Ch;
+    const int py = p / W, px = p - py * W;
+    float ls = 0.f, tt = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      const float* r = pmb + (int64_t)(ok ? yy * W + xx : p) * a.ldp + tap * C + j;
+      const float l0 = __ldg(r), t0 = __ldg(r + Ch);
+      ls += ok ? l0 : 0.f;
+      tt += ok ? t0 : 0.f;
+    }
+    const float g_l = par_s[C + j], g_t = par_s[C + Ch + j];
+    const float log_s = (ls + par_s[j]) * g_l;
+    const float t = (tt + par_s[Ch + j]) * g_t;
+    const float s = 1.f / (1.f + expf(-(log_s + 2.f)));
+    const float dyv = g_s[(Ch + j) * PS + p];
+    const float ds = dyv * (ub_s[j * PS + p] + t) + gld / (s + 1e-6f);
+    const float dt = dyv * s;
+    const float dls = ds * s * (1.f - s);
+    g_s[(Ch + j) * PS + p] = dyv * s;            // du_b
+    dP_s[j * PS + p] = dls * g_l;
+    dP_s[(Ch + j) * PS + p] = dt * g_t;
+    r_s[0 * P * Ch + j * P + p] = dls * g_l;         // -> dbias3[j]
+    r_s[1 * P * Ch + j * P + p] = dt * g_t;          // -> dbias3[Ch+j]
+    r_s[2 * P * Ch + j * P + p] = 3.f * dls * log_s; // -> dlogs3[j]
+    r_s[3 * P * Ch + j * P + p] = 3.f * dt * t;      // -> dlogs3[Ch+j]
+  }
+  __syncthreads();
+  // outputs: du (coalesced over pixels)
+  float* dub = a.du + (int64_t)b * a.du_bs;
+  for (int i = tid; i < C * P; i += nt) {
+    const int c = i / P, p = i - c * P;
+    dub[i] = g_s[c * PS + p];
+  }
+  // dpm rows: dpm[p', tap*C+co] = dP[co][p' - shift(tap)]  (zero outside the image / in the padding columns)
+  float* dpmb = a.dpm + (int64_t)b * P * a.ldp;
+  const int ldp = (int)a.ldp;
+  for (int i = tid; i < P * ldp; i += nt) {
+    const int pp = i / ldp, col = i - pp * ldp;
+    float v = 0.f;
+    if (col < 9 * C) {
+      const int tap = col / C, co = col - tap * C;
+      const int py = pp / W, px = pp - py * W;
+      // pm row pp at tap feeds output pixel (py - (ky-1), px - (kx-1))
+      const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = dP_s[co * PS + yy * W + xx];
+    }
+    dpmb[i] = v;
+  }
+  // per-image parameter partials: one warp per (kind, j) row of r_s, fixed order
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int row = warp; row < 4 * Ch; row += nw) {
+    float acc = 0.f;
+    const float* rp = r_s + row * P;      // row = kind*Ch + j  (r_s laid out [kind][j][p])
+    for (int p = lane; p < P; p += 32) acc += rp[p];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const int kind = row / Ch, j = row - kind * Ch;
+      // kind 0: dbias[j], 1: dbias[Ch+j], 2: dlogs[j], 3: dlogs[Ch+j]
+      const int dst = (kind < 2 ? 0 : C) + ((kind & 1) ? Ch : 0) + j;
+      a.dpar[(int64_t)b * 2 * C + dst] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ActNorm+ReLU backward
+// rows [M, ld]; CTA = 64 rows x all N columns; threads walk columns (coalesced), loop over rows.
+template <typename TH, typename TO>
+__global__ void __launch_bounds__(256) actnorm_relu_bwd_kernel(const float* __restrict__ dh, const TH* __restrict__ h,
+                                                               const float* __restrict__ scale, TO* __restrict__ dpre,
+                                                               float* __restrict__ part, int M, int N, int64_t ld_dh,
+                                                               int64_t ld_h, int64_t ld_o, int rows_per_cta) {
+  const int m0 = blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  for (int n = threadIdx.x; n < N; n += 256) {
+    const float e = expf(__ldg(scale + n));
+    float ds = 0.f, db = 0.f;
+    for (int m = m0; m < m1; ++m) {
+      const float hv = ldf<TH>(h + (int64_t)m * ld_h + n);
+      const float g = (hv > 0.f) ? dh[(int64_t)m * ld_dh + n] : 0.f;
+      ds += g * hv;
+      db += g * e;
+      stf<TO>(dpre + (int64_t)m * ld_o + n, g * e);
+    }
+    part[(int64_t)blockIdx.x * 2 * N + n] = ds;
+    part[(int64_t)blockIdx.x * 2 * N + N + n] = db;
+  }
+}
+
+// out[n] (+)= sum_r part[r*stride + n]
+__global__ void reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int R, int n, int64_t stride,
+                                   int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += part[(int64_t)r * stride + i];
+  out[i] = accumulate ? out[i] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------ K-A backward
+struct MixBwdArgs {
+  const float* du; int64_t du_bs;     // grad wrt K-A output [B,C,P] (first half still lacks the im2col part)
+  const float* da1; int64_t lda1;     // grad wrt im2col rows [B*P, lda1] (may be null)
+  const float* x; int64_t x_bs;       // K-A input [B,C,P]
+  const float* mt;                    // fwd_mt[i*C+o] = W^[o][i]
+  float* dx; int64_t dx_bs;           // out
+  float* part;                        // out: [B][C*C + C]: dW^x[o*C+i] = sum_p du[o]x[i];  db^[o] = sum_p du[o]
+  int B, C, H, W;
+};
+
+__global__ void __launch_bounds__(1024) mix_bwd_kernel(const MixBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1, PS = P + 1;
+  float* d_s = sm;                 // [C][PS] du (complete)
+  float* x_s = d_s + C * PS;       // [C][PS]
+  float* w_s = x_s + C * PS;       // [C][C]  w_s[o*C+i] = W^[o][i]
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < C * C; i += nt) {
+    const int o = i / C, ii = i - o * C;
+    w_s[i] = a.mt[ii * C + o];
+  }
+  const float* dub = a.du + (int64_t)b * a.du_bs;
+  const float* xb = a.x + (int64_t)b * a.x_bs;
+  for (int i = tid; i < C * P; i += nt) {
+    const int c = i / P, p = i - c * P;
+    d_s[c * PS + p] = dub[i];
+    x_s[c * PS + p] = xb[i];
+  }
+  __syncthreads();
+  if (a.da1 != nullptr) {
+    // col2im: A1[m, c*9+tap] = u[c][m + shift(tap)]  =>  du[c][p] += sum_tap dA1[p - shift(tap), c*9+tap]
+    const float* dab = a.da1 + (int64_t)b * P * a.lda1;
+    for (int it = tid; it < P * Ch; it += nt) {
+      const int p = it / Ch, c = it - p * Ch;
+      const int py = p / W, px = p - py * W;
+      float acc = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += __ldg(dab + (int64_t)(yy * W + xx) * a.lda1 + c * 9 + tap);
+      }
+      d_s[c * PS + p] += acc;
+    }
+    __syncthreads();
+  }
+  // dx[i][p] = sum_o W^[o][i] du[o][p]
+  float* dxb = a.dx + (int64_t)b * a.dx_bs;
+  for (int it = tid; it < C * P; it += nt) {
+    const int i = it / P, p = it - i * P;
+    float acc = 0.f;
+    for (int o = 0; o < C; ++o) acc = fmaf(w_s[o * C + i], d_s[o * PS + p], acc);
+    dxb[it] = acc;
+  }
+  // partials: one warp per output element (o, i) / o, fixed order
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  float* pb = a.part + (int64_t)b * (C * C + C);
+  for (int e = warp; e < C * C + C; e += nw) {
+    float acc = 0.f;
+    if (e < C * C) {
+      const int o = e / C, i = e - o * C;
+      for (int p = lane; p < P; p += 32) acc = fmaf(d_s[o * PS + p], x_s[i * PS + p], acc);
+    } else {
+      const int o = e - C * C;
+      for (int p = lane; p < P; p += 32) acc += d_s[o * PS + p];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) pb[e] = acc;
+  }
+}
+
+// dW, ds, db of one StepFlow from the per-image partials and the log-det terms.  One CTA per StepFlow.
+struct MixParamItem {
+  const float* part; int B;        // [B][C*C + C]
+  const float* W; const float* s; const float* bv; const float* winv;
+  const float* dld_sum;            // [1] sum_b d(ld)[b]
+  float P;                         // H*W multiplier of the log-det constants
+  float* dW; float* ds; float* db; // out (overwritten)
+  float* scratch;                  // [C*C + C] reduced partials
+  int C;
+};
+constexpr int kParamBatch = 16;
+struct MixParamBatch { MixParamItem it[kParamBatch]; };
+
+__global__ void __launch_bounds__(256) mix_param_grad_kernel(const MixParamBatch batch) {
+  const MixParamItem it = batch.it[blockIdx.x];
+  const int C = it.C, n = C * C + C, tid = threadIdx.x;
+  for (int e = tid; e < n; e += 256) {
+    float acc = 0.f;
+    for (int b = 0; b < it.B; ++b) acc += it.part[(int64_t)b * n + e];
+    it.scratch[e] = acc;
+  }
+  __syncthreads();
+  const float G = it.dld_sum[0] * it.P;
+  // dW^_total[o][i] = dW^x[o][i] + db^[o]*b[i];  W^[o][i] = W[o][i]*exp(s[i])
+  for (int e = tid; e < C * C; e += 256) {
+    const int o = e / C, i = e - o * C;
+    const float bi = it.bv ? it.bv[i] : 0.f, es = expf(it.s ? it.s[i] : 0.f);
+    const float dwh = it.scratch[e] + it.scratch[C * C + o] * bi;
+    if (it.dW) it.dW[e] = dwh * es + G * it.winv[i * C + o];
+  }
+  for (int i = tid; i < C; i += 256) {
+    const float bi = it.bv ? it.bv[i] : 0.f, es = expf(it.s ? it.s[i] : 0.f);
+    float ds = 0.f, db = 0.f;
+    for (int o = 0; o < C; ++o) {
+      const float wh = it.W[o * C + i] * es;
+      const float dwh = it.scratch[o * C + i] + it.scratch[C * C + o] * bi;
+      ds = fmaf(dwh, wh, ds);
+      db = fmaf(wh, it.scratch[C * C + o], db);
+    }
+    if (it.ds) it.ds[i] = ds + G;
+    if (it.db) it.db[i] = db;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad GEMM (TN)
+// D[N1, N2] = sum_m A[m, N1] * B[m, N2];  tile 128 x 128, 256 threads, 8x8 per thread; grid.z splits M, each split
+// writes its own partial slab (reduced by reduce_rows_kernel) -> deterministic.
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ Bm,
+                                                      int64_t ldb, float* __restrict__ part, int M, int N1, int N2,
+                                                      int rows_per_split) {
+  constexpr int BT = 128, BKm = 16;
+  __shared__ __align__(16) float As[BKm][BT + 4];
+  __shared__ __align__(16) float Bs[BKm][BT + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n1_0 = blockIdx.y * BT, n2_0 = blockIdx.x * BT;
+  const int m_lo = blockIdx.z * rows_per_split, m_hi = min(M, m_lo + rows_per_split);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int m0 = m_lo; m0 < m_hi; m0 += BKm) {
+    // 16 rows x 128 cols per operand = 2048 elements, 8 per thread; column fastest -> coalesced
+    for (int e = tid; e < BKm * BT; e += 256) {
+      const int r = e >> 7, c = e & 127;
+      const int m = m0 + r;
+      As[r][c] = (m < m_hi && n1_0 + c < N1) ? ldf<TA>(A + (int64_t)m * lda + n1_0 + c) : 0.f;
+      Bs[r][c] = (m < m_hi && n2_0 + c < N2) ? ldf<TB>(Bm + (int64_t)m * ldb + n2_0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BKm; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* pz = part + (int64_t)blockIdx.z * N1 * N2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = n1_0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (r >= N1) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = n2_0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (c < N2) pz[(int64_t)r * N2 + c] = acc[i][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ priors
+// Split prior backward, one thread per pixel (same tiling as the forward kernel): writes dz into channels C/2..C of
+// dstate, dh rows [M, ldh] (columns C..ldh zero) and per-image partials [B][2C] (dbias[C], dlogs[C]).
+__global__ void __launch_bounds__(256) split_prior_bwd_kernel(const float* __restrict__ dlp, const float* __restrict__ h,
+                                                              int64_t ldh, const float* __restrict__ bias,
+                                                              const float* __restrict__ logs, const float* __restrict__ x,
+                                                              int64_t xbs, float* __restrict__ dstate, int64_t dbs,
+                                                              float* __restrict__ dh, float* __restrict__ dpar, int B,
+                                                              int C, int P) {
+  extern __shared__ __align__(16) float s_par[];   // [2C]
+  __shared__ float red[256];
+  const int Ch = C >> 1, b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < C; i += 256) {
+    s_par[i] = (h != nullptr) ? bias[i] : 0.f;
+    s_par[C + i] = (h != nullptr) ? expf(3.f * logs[i]) : 1.f;
+  }
+  __syncthreads();
+  const float g = dlp[b];
+  // per-channel partial sums are accumulated channel by channel (fixed order) to stay deterministic
+  for (int j = 0; j < Ch; ++j) {
+    float s_bm = 0.f, s_bl = 0.f, s_lm = 0.f, s_ll = 0.f;
+    for (int p = tid; p < P; p += 256) {
+      const int64_t m = (int64_t)b * P + p;
+      float mean = 0.f, lg = 0.f;
+      if (h != nullptr) {
+        mean = (h[m * ldh + j] + s_par[j]) * s_par[C + j];
+        lg = (h[m * ldh + Ch + j] + s_par[Ch + j]) * s_par[C + Ch + j];
+      }
+      const float z = x[b * xbs + (int64_t)(Ch + j) * P + p];
+      const float d = z - mean, iv = expf(-2.f * lg);
+      const float dz = -d * iv * g, dmean = d * iv * g, dlg = (-1.f + d * d * iv) * g;
+      dstate[b * dbs + (int64_t)(Ch + j) * P + p] += dz;
+      if (h != nullptr) {
+        const float dhm = dmean * s_par[C + j], dhl = dlg * s_par[C + Ch + j];
+        dh[m * ldh + j] = dhm;
+        dh[m * ldh + Ch + j] = dhl;
+        s_bm += dhm; s_bl += dhl;
+        s_lm += 3.f * dmean * mean; s_ll += 3.f * dlg * lg;
+      }
+    }
+    if (h != nullptr) {
+      float* vals[4] = {&s_bm, &s_bl, &s_lm, &s_ll};
+      const int dst[4] = {j, Ch + j, C + j, C + Ch + j};
+      for (int k = 0; k < 4; ++k) {
+        red[tid] = *vals[k];
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+          if (tid < s) red[tid] += red[tid + s];
+          __syncthreads();
+        }
+        if (tid == 0) dpar[(int64_t)b * 2 * C + dst[k]] = red[0];
+        __syncthreads();
+      }
+    }
+  }
+  if (h != nullptr) {
+    for (int i = tid; i < P * (int)(ldh - C); i += 256) {
+      const int p = i / (int)(ldh - C), c = C + i % (int)(ldh - C);
+      dh[((int64_t)b * P + p) * ldh + c] = 0.f;
+    }
+  }
+}
+
+// Gaussian prior with per-channel constants: dz and per-image partials [B][4C]: dbias[2C], dlogs[2C] of the 2C-channel conv
+__global__ void __launch_bounds__(256) gauss_const_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ z,
+                                                              const float* __restrict__ bias, const float* __restrict__ logs,
+                                                              float* __restrict__ dz, float* __restrict__ dpar, int C, int P) {
+  __shared__ float red[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float g = dl[b];
+  for (int c = 0; c < C; ++c) {
+    float mean = 0.f, lg = 0.f, em = 1.f, el = 1.f;
+    if (bias != nullptr) {
+      em = expf(3.f * logs[c]); el = expf(3.f * logs[C + c]);
+      mean = bias[c] * em; lg = bias[C + c] * el;
+    }
+    const float iv = expf(-2.f * lg);
+    float sm_ = 0.f, sl_ = 0.f;
+    for (int p = tid; p < P; p += 256) {
+      const int64_t i = ((int64_t)b * C + c) * P + p;
+      const float d = z[i] - mean;
+      dz[i] = -d * iv * g;
+      sm_ += d * iv * g;
+      sl_ += (-1.f + d * d * iv) * g;
+    }
+    if (bias != nullptr) {
+      float v[2] = {sm_, sl_};
+      for (int k = 0; k < 2; ++k) {
+        red[tid] = v[k];
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+          if (tid < s) red[tid] += red[tid + s];
+          __syncthreads();
+        }
+        if (tid == 0) {
+          const float tot = red[0];
+          // mean_c = bias_c*em: dbias_c = tot*em, dlogs_c = 3*tot*mean ; same for the log-sd half
+          const int cc = k == 0 ? c : C + c;
+          const float e = k == 0 ? em : el, val = k == 0 ? mean : lg;
+          dpar[(int64_t)b * 4 * C + cc] = tot * e;
+          dpar[(int64_t)b * 4 * C + 2 * C + cc] = 3.f * tot * val;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// dstate[b, c, p] += sum_tap dA[(b,p - shift(tap)), c*9+tap]   for c < Cin  (col2im of a 3x3 "same" conv input gradient)
+__global__ void col2im_add_kernel(const float* __restrict__ da, int64_t lda, float* __restrict__ dstate, int64_t dbs, int Cin,
+                                  int H, int W, int64_t n) {
+  const int P = H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % P);
+    int64_t r = i / P;
+    const int c = (int)(r % Cin);
+    const int64_t b = r / Cin;
+    const int py = p / W, px = p - py * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += da[(b * P + yy * W + xx) * lda + c * 9 + tap];
+    }
+    dstate[b * dbs + (int64_t)c * P + p] += acc;
+  }
+}
+
+}  // namespace nfdpm
+
+using namespace nfdpm;
+
+extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs,
+                                  const float* pm, int64_t ldp, const float* bias3, const float* logs3, float* du,
+                                  int64_t du_bs, float* dpm, float* dpar, int B, int C, int H, int W,
+                                  nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(dy && u && pm && bias3 && logs3 && du && dpm && dpar, "nfdpm_coupling_bwd: null pointer");
+  NFDPM_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0 && ldp >= 9 * (int64_t)C, "nfdpm_coupling_bwd: bad shape");
+  const size_t P = (size_t)H * W, PS = P + 1, Ch = C / 2;
+  const size_t smem = sizeof(float) * (2 * C * PS + Ch * PS + 4 * P * Ch + 2 * C);
+  NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_coupling_bwd: image too large (%zu bytes of shared memory)", smem);
+  CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, dpar, B, C, H, W};
+  static bool attr_set = false;
+  if (!attr_set) {
+    NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int threads = (int)((P * Ch + 31) / 32 * 32);
+  threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
+  coupling_bwd_kernel<<<B, threads, smem, as_stream(stream)>>>(a);
+  NFDPM_CHECK_LAUNCH("coupling_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_actnorm_relu_bwd(const float* dh, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
+                                      const float* scale, void* dpre, int o_dtype, int64_t ld_o, float* part, int M,
+                                      int N, int rows_per_cta, nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(dh && h && scale && dpre && part, "nfdpm_actnorm_relu_bwd: null pointer");
+  NFDPM_REQUIRE(M > 0 && N > 0 && rows_per_cta > 0, "nfdpm_actnorm_relu_bwd: bad shape");
+  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  cudaStream_t st = as_stream(stream);
+#define GO(TH, TO) actnorm_relu_bwd_kernel<TH, TO><<<grid, 256, 0, st>>>(dh, (const TH*)h, scale, (TO*)dpre, part, M, N, ld_dh, ld_h, ld_o, rows_per_cta)
+  if (h_dtype == NFDPM_F32 && o_dtype == NFDPM_F32) GO(float, float);
+  else if (h_dtype == NFDPM_BF16 && o_dtype == NFDPM_F32) GO(__nv_bfloat16, float);
+  else if (h_dtype == NFDPM_BF16 && o_dtype == NFDPM_BF16) GO(__nv_bfloat16, __nv_bfloat16);
+  else if (h_dtype == NFDPM_F32 && o_dtype == NFDPM_BF16) GO(float, __nv_bfloat16);
+  else return fail("nfdpm_actnorm_relu_bwd: bad dtypes");
+#undef GO
+  NFDPM_CHECK_LAUNCH("actnorm_relu_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_reduce_rows(const float* part, float* out, int R, int n, int64_t stride, int accumulate,
+                                 nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(part && out && R > 0 && n > 0 && stride >= n, "nfdpm_reduce_rows: bad arguments");
+  reduce_rows_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(part, out, R, n, stride, accumulate);
+  NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_mix_bwd(const float* du, int64_t du_bs, const float* da1, int64_t lda1, const float* x, int64_t x_bs,
+                             const float* mt, float* dx, int64_t dx_bs, float* part, int B, int C, int H, int W,
+                             nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(du && x && mt && dx && part, "nfdpm_mix_bwd: null pointer");
+  NFDPM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "nfdpm_mix_bwd: bad shape");
+  NFDPM_REQUIRE(da1 == nullptr || (C % 2 == 0 && lda1 >= 9 * (int64_t)(C / 2)), "nfdpm_mix_bwd: bad im2col gradient");
+  const size_t P = (size_t)H * W, PS = P + 1;
+  const size_t smem = sizeof(float) * (2 * C * PS + (size_t)C * C);
+  NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_mix_bwd: image too large (%zu bytes of shared memory)", smem);
+  MixBwdArgs a{du, du_bs, da1, lda1, x, x_bs, mt, dx, dx_bs, part, B, C, H, W};
+  static bool attr_set = false;
+  if (!attr_set) {
+    NFDPM_CUDA(cudaFuncSetAttribute(mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int threads = (int)((P * C + 31) / 32 * 32);
+  threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
+  mix_bwd_kernel<<<B, threads, smem, as_stream(stream)>>>(a);
+  NFDPM_CHECK_LAUNCH("mix_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_mix_param_grad(const nfdpm_mix_grad_item* items, int n, nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(items && n > 0, "nfdpm_mix_param_grad: no items");
+  for (int base = 0; base < n; base += kParamBatch) {
+    MixParamBatch pb;
+    const int cnt = (n - base < kParamBatch) ? n - base : kParamBatch;
+    for (int i = 0; i < cnt; ++i) {
+      const nfdpm_mix_grad_item& s = items[base + i];
+      NFDPM_REQUIRE(s.part && s.weight && s.winv && s.dld_sum && s.scratch && s.C > 0 && s.B > 0,
+                    "nfdpm_mix_param_grad: item %d incomplete", base + i);
+      pb.it[i] = MixParamItem{s.part, s.B, s.weight, s.scale, s.bias, s.winv, s.dld_sum, s.P, s.d_weight, s.d_scale,
+                              s.d_bias, s.scratch, s.C};
+    }
+    mix_param_grad_kernel<<<cnt, 256, 0, as_stream(stream)>>>(pb);
+    NFDPM_CHECK_LAUNCH("mix_param_grad_kernel");
+  }
+  return 0;
+}
+
+extern "C" int64_t nfdpm_gemm_tn_workspace(int M, int N1, int N2, int* splits_out) {
+  // enough splits to fill the GPU (~296 CTAs) but at least 256 rows per split
+  const int tiles = ((N1 + 127) / 128) * ((N2 + 127) / 128);
+  int splits = (296 + tiles - 1) / tiles;
+  const int max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits_out) *splits_out = splits;
+  return (int64_t)splits * N1 * N2;
+}
+
+extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void* Bm, int b_dtype, int64_t ldb, float* D,
+                             int64_t ldd, int M, int N1, int N2, float* ws, int accumulate, nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(A && Bm && D && ws, "nfdpm_gemm_tn: null pointer");
+  NFDPM_REQUIRE(M > 0 && N1 > 0 && N2 > 0 && lda >= N1 && ldb >= N2 && ldd == N2, "nfdpm_gemm_tn: bad shape (ldd must equal N2)");
+  int splits = 1;
+  nfdpm_gemm_tn_workspace(M, N1, N2, &splits);
+  int rows = (M + splits - 1) / splits;
+  rows = (rows + 15) / 16 * 16;
+  splits = (M + rows - 1) / rows;
+  dim3 grid((N2 + 127) / 128, (N1 + 127) / 128, splits);
+  cudaStream_t st = as_stream(stream);
+#define GO(TA, TB) gemm_tn_kernel<TA, TB><<<grid, 256, 0, st>>>((const TA*)A, lda, (const TB*)Bm, ldb, ws, M, N1, N2, rows)
+  if (a_dtype == NFDPM_F32 && b_dtype == NFDPM_F32) GO(float, float);
+  else if (a_dtype == NFDPM_F32 && b_dtype == NFDPM_BF16) GO(float, __nv_bfloat16);
+  else if (a_dtype == NFDPM_BF16 && b_dtype == NFDPM_BF16) GO(__nv_bfloat16, __nv_bfloat16);
+  else if (a_dtype == NFDPM_BF16 && b_dtype == NFDPM_F32) GO(__nv_bfloat16, float);
+  else return fail("nfdpm_gemm_tn: bad dtypes");
+#undef GO
+  NFDPM_CHECK_LAUNCH("gemm_tn_kernel");
+  const int n = N1 * N2;
+  reduce_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, D, splits, n, n, accumulate);
+  NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_split_prior_bwd(const float* dlp, const float* h, int64_t ldh, const float* bias, const float* logs,
+                                     const float* x, int64_t xbs, float* dstate, int64_t dbs, float* dh, float* dpar,
+                                     int B, int C, int H, int W, nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(dlp && x && dstate, "nfdpm_split_prior_bwd: null pointer");
+  NFDPM_REQUIRE(h == nullptr || (bias && logs && dh && dpar && ldh >= C), "nfdpm_split_prior_bwd: learned prior needs bias/logs/dh/dpar");
+  NFDPM_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0, "nfdpm_split_prior_bwd: bad shape");
+  split_prior_bwd_kernel<<<B, 256, sizeof(float) * 2 * C, as_stream(stream)>>>(dlp, h, ldh, bias, logs, x, xbs, dstate, dbs,
+                                                                                dh, dpar, B, C, H * W);
+  NFDPM_CHECK_LAUNCH("split_prior_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_gauss_const_bwd(const float* dl, const float* z, const float* bias, const float* logs, float* dz,
+                                     float* dpar, int B, int C, int P, nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(dl && z && dz, "nfdpm_gauss_const_bwd: null pointer");
+  NFDPM_REQUIRE((bias == nullptr) == (logs == nullptr) && (bias == nullptr || dpar), "nfdpm_gauss_const_bwd: bias/logs/dpar mismatch");
+  NFDPM_REQUIRE(B > 0 && C > 0 && P > 0, "nfdpm_gauss_const_bwd: bad shape");
+  gauss_const_bwd_kernel<<<B, 256, 0, as_stream(stream)>>>(dl, z, bias, logs, dz, dpar, C, P);
+  NFDPM_CHECK_LAUNCH("gauss_const_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_col2im_add(const float* da, int64_t lda, float* dstate, int64_t dbs, int B, int Cin, int H, int W,
+                                nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(da && dstate, "nfdpm_col2im_add: null pointer");
+  NFDPM_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && lda >= 9 * (int64_t)Cin, "nfdpm_col2im_add: bad shape");
+  const int64_t n = (int64_t)B * Cin * H * W;
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  col2im_add_kernel<<<(int)g, 256, 0, as_stream(stream)>>>(da, lda, dstate, dbs, Cin, H, W, n);
+  NFDPM_CHECK_LAUNCH("col2im_add_kernel");
+  return 0;
+}

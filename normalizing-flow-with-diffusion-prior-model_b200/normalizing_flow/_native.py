@@ -26,6 +26,13 @@ class MixItem(C.Structure):
                 ("inv_beta", C.c_void_p), ("winv", C.c_void_p), ("logdet", C.c_void_p), ("lu_ws", C.c_void_p)]
 
 
+class MixGradItem(C.Structure):
+    """struct nfdpm_mix_grad_item (include/nfdpm_b200.h)."""
+    _fields_ = [("part", C.c_void_p), ("B", C.c_int32), ("C", C.c_int32), ("weight", C.c_void_p), ("scale", C.c_void_p),
+                ("bias", C.c_void_p), ("winv", C.c_void_p), ("dld_sum", C.c_void_p), ("P", C.c_float), ("pad_", C.c_int32),
+                ("d_weight", C.c_void_p), ("d_scale", C.c_void_p), ("d_bias", C.c_void_p), ("scratch", C.c_void_p)]
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -60,6 +67,16 @@ def _load() -> C.CDLL:
                                  i32, vp], C.c_int),
         "nfdpm_coupling_fused": ([vp, i64, vp, vp, vp, vp, i64, i32, i32, vp, vp], C.c_int),
         "nfdpm_fold_actnorm": ([vp, vp, vp, vp, i32, vp], C.c_int),
+        "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_actnorm_relu_bwd": ([vp, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
+        "nfdpm_reduce_rows": ([vp, vp, i32, i32, i64, i32, vp], C.c_int),
+        "nfdpm_mix_bwd": ([vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_mix_param_grad": ([C.POINTER(MixGradItem), i32, vp], C.c_int),
+        "nfdpm_gemm_tn_workspace": ([i32, i32, i32, C.POINTER(C.c_int)], C.c_int64),
+        "nfdpm_gemm_tn": ([vp, i32, i64, vp, i32, i64, vp, i64, i32, i32, i32, vp, i32, vp], C.c_int),
+        "nfdpm_split_prior_bwd": ([vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_gauss_const_bwd": ([vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], C.c_int),
+        "nfdpm_col2im_add": ([vp, i64, vp, i64, i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_accumulate": ([vp, i32, vp, i32, i32, vp, vp, i32, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
@@ -75,7 +92,10 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_copy_channels", "nfdpm_im2col3x3", "nfdpm_pack_matrix", "nfdpm_gemm_nt", "nfdpm_coupling_apply",
            "nfdpm_split_prior_logp", "nfdpm_split_prior_sample", "nfdpm_gauss_logp_const",
            "nfdpm_gauss_sample_const", "nfdpm_accumulate", "nfdpm_rows_to_nchw", "nfdpm_nchw_to_rows",
-           "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary", "nfdpm_coupling_fused", "nfdpm_fold_actnorm"]
+           "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary", "nfdpm_coupling_fused", "nfdpm_fold_actnorm",
+           "nfdpm_coupling_bwd", "nfdpm_actnorm_relu_bwd", "nfdpm_reduce_rows", "nfdpm_mix_bwd", "nfdpm_mix_param_grad",
+           "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
+           "nfdpm_col2im_add"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -210,3 +230,48 @@ def coupling_fused(a1, lda1, w1, w2, w3, pm, ldp, M, K1p, ep) -> None:
 
 def fold_actnorm(scale, bias, e_out, eb_out, n) -> None:
     _ok(lib.nfdpm_fold_actnorm(_p(scale), _p(bias), _p(e_out), _p(eb_out), n, _st()))
+
+
+# ---------------------------------------------------------------------------------------------- backward
+def coupling_bwd(dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, dpar, B, Cc, H, W) -> None:
+    _ok(lib.nfdpm_coupling_bwd(_p(dy), dy_bs, _p(dld), _p(u), u_bs, _p(pm), ldp, _p(bias3), _p(logs3), _p(du), du_bs,
+                               _p(dpm), _p(dpar), B, Cc, H, W, _st()))
+
+
+def actnorm_relu_bwd(dh, ld_dh, h, ld_h, scale, dpre, ld_o, part, M, Nn, rows_per_cta) -> None:
+    _ok(lib.nfdpm_actnorm_relu_bwd(_p(dh), ld_dh, _p(h), _dt(h), ld_h, _p(scale), _p(dpre), _dt(dpre), ld_o, _p(part), M,
+                                   Nn, rows_per_cta, _st()))
+
+
+def reduce_rows(part, out, R, n, stride, accumulate=False) -> None:
+    _ok(lib.nfdpm_reduce_rows(_p(part), _p(out), R, n, stride, int(accumulate), _st()))
+
+
+def mix_bwd(du, du_bs, da1, lda1, x, x_bs, mt, dx, dx_bs, part, B, Cc, H, W) -> None:
+    _ok(lib.nfdpm_mix_bwd(_p(du), du_bs, _p(da1), lda1, _p(x), x_bs, _p(mt), _p(dx), dx_bs, _p(part), B, Cc, H, W, _st()))
+
+
+def mix_param_grad(items) -> None:
+    arr = (MixGradItem * len(items))(*items)
+    _ok(lib.nfdpm_mix_param_grad(arr, len(items), _st()), (len(items) + 15) // 16)
+
+
+def gemm_tn_workspace(M, N1, N2) -> int:
+    return int(lib.nfdpm_gemm_tn_workspace(M, N1, N2, None))
+
+
+def gemm_tn(A, lda, Bm, ldb, D, M, N1, N2, ws, accumulate=False) -> None:
+    _ok(lib.nfdpm_gemm_tn(_p(A), _dt(A), lda, _p(Bm), _dt(Bm), ldb, _p(D), N2, M, N1, N2, _p(ws), int(accumulate), _st()), 2)
+
+
+def split_prior_bwd(dlp, h, ldh, bias, logs, x, xbs, dstate, dbs, dh, dpar, B, Cc, H, W) -> None:
+    _ok(lib.nfdpm_split_prior_bwd(_p(dlp), _p(h), ldh, _p(bias), _p(logs), _p(x), xbs, _p(dstate), dbs, _p(dh), _p(dpar),
+                                  B, Cc, H, W, _st()))
+
+
+def gauss_const_bwd(dl, z, bias, logs, dz, dpar, B, Cc, P) -> None:
+    _ok(lib.nfdpm_gauss_const_bwd(_p(dl), _p(z), _p(bias), _p(logs), _p(dz), _p(dpar), B, Cc, P, _st()))
+
+
+def col2im_add(da, lda, dstate, dbs, B, Cin, H, W) -> None:
+    _ok(lib.nfdpm_col2im_add(_p(da), lda, _p(dstate), dbs, B, Cin, H, W, _st()))
