@@ -180,6 +180,13 @@ int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_in, const fl
                         float* y, int64_t y_bs, void* a1, int a1_dtype, int64_t lda1, int B, int C, int H, int W,
                         int inverse, nfdpm_stream_t stream);
 
+/* Forward-only nfdpm_flow_boundary with one more sink for training: xs [B,C,P] receives the PRE-mix state (the
+ * coupling output == the next StepFlow's input x, which its backward needs for d(weight) = du x^T). */
+int nfdpm_flow_boundary_stash(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
+                              const float* bias3, const float* logs3, float* ld_part, const float* mt, const float* beta,
+                              float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype, int64_t lda1,
+                              int B, int C, int H, int W, nfdpm_stream_t stream);
+
 /* Layout converters for stand-alone ZeroConv2d / Conv2dActNorm module calls (normalizing_flow/utils.py:43-44, :68-69).
  *   rows_to_nchw: out[b,n,p] = f(h[(b*P+p)*ldh + n]); mode 0: identity; 1: (v+p1[n])*exp(3*p2[n]) (ZeroConv2d gain);
  *                 2: exp(p1[n])*(v+p2[n]) (ActNorm).   nchw_to_rows: rows[m, c] = x[b,c,p], columns Cc..ld-1 zero. */
@@ -194,10 +201,11 @@ int nfdpm_nchw_to_rows(const float* x, void* out, int out_dtype, int B, int Cc, 
  */
 /* Affine coupling + log-det backward (transforms.py:179-184).  dy [B,C,P] grad of the coupling output, dld [B] grad of
  * log_det_jac (may be NULL), u [B,C,P] coupling input, pm as in the forward.  Outputs: du [B,C,P] (first half = dy_a;
- * the coupling-net part is added by nfdpm_mix_bwd), dpm [B*P, ldp], dpar [B][2C] per-image partials (dbias3[C], dlogs3[C]). */
+ * the coupling-net part is added by nfdpm_mix_bwd), dpm [B*P, ld_dpm] (F32 or BF16, columns >= 9C zero-filled: the
+ * K operand of the ZeroConv dgrad GEMM), dpar [B][2C] per-image partials (dbias3[C], dlogs3[C]). */
 int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs, const float* pm,
-                       int64_t ldp, const float* bias3, const float* logs3, float* du, int64_t du_bs, float* dpm,
-                       float* dpar, int B, int C, int H, int W, nfdpm_stream_t stream);
+                       int64_t ldp, const float* bias3, const float* logs3, float* du, int64_t du_bs, void* dpm,
+                       int dpm_dtype, int64_t ld_dpm, float* dpar, int B, int C, int H, int W, nfdpm_stream_t stream);
 /* ActNorm+ReLU backward on rows (utils.py:69,84-87): dpre = dh*(h>0)*exp(scale); part[cta][2N] partial d(scale), d(bias);
  * ctas = ceil(M/rows_per_cta). */
 int nfdpm_actnorm_relu_bwd(const float* dh, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h, const float* scale,

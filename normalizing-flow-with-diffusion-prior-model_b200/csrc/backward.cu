@@ -26,11 +26,12 @@ struct CouplingBwdArgs {
   const float* pm; int64_t ldp;        // taps-as-N rows [B*P, ldp]
   const float* bias3; const float* logs3;
   float* du; int64_t du_bs;            // out: grad wrt coupling input (first half = dy_a, im2col part added by mix_bwd)
-  float* dpm;                          // out: [B*P, ldp]
+  void* dpm; int64_t ld_dpm;           // out: [B*P, ld_dpm] (fp32 or bf16; columns >= 9C are zero)
   float* dpar;                         // out: [B][2C] per-image partials: dbias3[C], dlogs3[C]
   int B, C, H, W;
 };
 
+template <typename TD>
 __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1, PS = P + 1;
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
     dub[i] = g_s[c * PS + p];
   }
   // dpm rows: dpm[p', tap*C+co] = dP[co][p' - shift(tap)]  (zero outside the image / in the padding columns)
-  float* dpmb = a.dpm + (int64_t)b * P * a.ldp;
-  const int ldp = (int)a.ldp;
+  const int ldp = (int)a.ld_dpm;
+  TD* dpmb = reinterpret_cast<TD*>(a.dpm) + (int64_t)b * P * ldp;
   for (int i = tid; i < P * ldp; i += nt) {
     const int pp = i / ldp, col = i - pp * ldp;
     float v = 0.f;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
       const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = dP_s[co * PS + yy * W + xx];
     }
-    dpmb[i] = v;
+    stf<TD>(dpmb + i, v);
   }
   // per-image parameter partials: one warp per (kind, j) row of r_s, fixed order
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
@@ -458,22 +459,26 @@ using namespace nfdpm;
 
 extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs,
                                   const float* pm, int64_t ldp, const float* bias3, const float* logs3, float* du,
-                                  int64_t du_bs, float* dpm, float* dpar, int B, int C, int H, int W,
-                                  nfdpm_stream_t stream) {
+                                  int64_t du_bs, void* dpm, int dpm_dtype, int64_t ld_dpm, float* dpar, int B, int C,
+                                  int H, int W, nfdpm_stream_t stream) {
   NFDPM_REQUIRE(dy && u && pm && bias3 && logs3 && du && dpm && dpar, "nfdpm_coupling_bwd: null pointer");
-  NFDPM_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0 && ldp >= 9 * (int64_t)C, "nfdpm_coupling_bwd: bad shape");
+  NFDPM_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0 && ldp >= 9 * (int64_t)C && ld_dpm >= 9 * (int64_t)C,
+                "nfdpm_coupling_bwd: bad shape");
+  NFDPM_REQUIRE(dpm_dtype == NFDPM_F32 || dpm_dtype == NFDPM_BF16, "nfdpm_coupling_bwd: bad dpm dtype");
   const size_t P = (size_t)H * W, PS = P + 1, Ch = C / 2;
   const size_t smem = sizeof(float) * (2 * C * PS + Ch * PS + 4 * P * Ch + 2 * C);
   NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_coupling_bwd: image too large (%zu bytes of shared memory)", smem);
-  CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, dpar, B, C, H, W};
+  CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W};
   static bool attr_set = false;
   if (!attr_set) {
-    NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   int threads = (int)((P * Ch + 31) / 32 * 32);
   threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
-  coupling_bwd_kernel<<<B, threads, smem, as_stream(stream)>>>(a);
+  if (dpm_dtype == NFDPM_F32) coupling_bwd_kernel<float><<<B, threads, smem, as_stream(stream)>>>(a);
+  else coupling_bwd_kernel<__nv_bfloat16><<<B, threads, smem, as_stream(stream)>>>(a);
   NFDPM_CHECK_LAUNCH("coupling_bwd_kernel");
   return 0;
 }

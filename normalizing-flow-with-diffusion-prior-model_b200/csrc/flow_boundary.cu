@@ -24,6 +24,7 @@ struct BoundaryArgs {
   float* ld_part;                       // forward coupling: [B] per-image log-det partial (may be null)
   const float* mt; const float* beta;   // mix (null = identity)
   float* y; int64_t y_bs;               // NCHW sink (may be null)
+  float* xs; int64_t xs_bs;             // NCHW sink of the PRE-mix state (training stash of the next step's input; may be null)
   void* a1; int64_t lda1;               // im2col sink (may be null)
   int B, C, H, W;
   int squeeze_in, inverse;
@@ -139,6 +140,15 @@ __global__ void __launch_bounds__(1024) flow_boundary_kernel(const BoundaryArgs 
     }
   }
 
+  // ---- phase 1b: stash the pre-mix state (the next StepFlow's input, needed by its backward)
+  if (a.xs != nullptr) {
+    float* xb = a.xs + (int64_t)b * a.xs_bs;
+    for (int i = tid; i < C * P; i += nt) {
+      const int c = i / P, p = i - c * P;
+      xb[i] = x_s[c * PS + p];
+    }
+  }
+
   // ---- phase 2: channel mix, item = (group of 4 outputs, pixel), lanes over pixels
   if (a.mt != nullptr) {
     const int n_og = Cp >> 2;
@@ -209,10 +219,10 @@ extern "C" size_t nfdpm_flow_boundary_smem(int C, int H, int W, int coupling, in
   return fl * sizeof(float);
 }
 
-extern "C" int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
-                                   const float* bias3, const float* logs3, float* ld_part, const float* mt,
-                                   const float* beta, float* y, int64_t y_bs, void* a1, int a1_dtype, int64_t lda1,
-                                   int B, int C, int H, int W, int inverse, nfdpm_stream_t stream) {
+static int flow_boundary_impl(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
+                              const float* bias3, const float* logs3, float* ld_part, const float* mt,
+                              const float* beta, float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype,
+                              int64_t lda1, int B, int C, int H, int W, int inverse, nfdpm_stream_t stream) {
   NFDPM_REQUIRE(in != nullptr, "nfdpm_flow_boundary: null input");
   NFDPM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && C % 2 == 0, "nfdpm_flow_boundary: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   NFDPM_REQUIRE((mt == nullptr) == (beta == nullptr), "nfdpm_flow_boundary: mt/beta must both be set or both NULL");
@@ -220,13 +230,13 @@ extern "C" int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_i
   NFDPM_REQUIRE(!squeeze_in || (C % 4 == 0 && in_bs % 2 == 0 && ((uintptr_t)in % 8) == 0), "nfdpm_flow_boundary: squeeze source needs C %% 4 == 0 and 8-byte alignment");
   NFDPM_REQUIRE(a1 == nullptr || (lda1 % 8 == 0 && lda1 >= 9 * (int64_t)(C / 2) && ((uintptr_t)a1 % 16) == 0), "nfdpm_flow_boundary: bad im2col sink");
   NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16, "nfdpm_flow_boundary: bad a1 dtype");
-  NFDPM_REQUIRE(y != nullptr || a1 != nullptr, "nfdpm_flow_boundary: no sink");
+  NFDPM_REQUIRE(y != nullptr || a1 != nullptr || xs != nullptr, "nfdpm_flow_boundary: no sink");
   const size_t smem = nfdpm_flow_boundary_smem(C, H, W, pm != nullptr, mt != nullptr);
   NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_flow_boundary: image too large for the fused path (%zu bytes of shared memory); "
                 "use the unfused kernels", smem);
   BoundaryArgs a;
   a.in = in; a.in_bs = in_bs; a.pm = pm; a.ldp = ldp; a.bias3 = bias3; a.logs3 = logs3; a.ld_part = ld_part;
-  a.mt = mt; a.beta = beta; a.y = y; a.y_bs = y_bs; a.a1 = a1; a.lda1 = lda1;
+  a.mt = mt; a.beta = beta; a.y = y; a.y_bs = y_bs; a.xs = xs; a.xs_bs = xs_bs; a.a1 = a1; a.lda1 = lda1;
   a.B = B; a.C = C; a.H = H; a.W = W; a.squeeze_in = squeeze_in; a.inverse = inverse;
   cudaStream_t st = as_stream(stream);
   const bool bf = (a1 != nullptr && a1_dtype == NFDPM_BF16);
@@ -251,4 +261,20 @@ extern "C" int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_i
 #undef LAUNCH
   NFDPM_CHECK_LAUNCH("flow_boundary_kernel");
   return 0;
+}
+
+extern "C" int nfdpm_flow_boundary(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
+                                   const float* bias3, const float* logs3, float* ld_part, const float* mt,
+                                   const float* beta, float* y, int64_t y_bs, void* a1, int a1_dtype, int64_t lda1,
+                                   int B, int C, int H, int W, int inverse, nfdpm_stream_t stream) {
+  return flow_boundary_impl(in, in_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, nullptr, 0, a1,
+                            a1_dtype, lda1, B, C, H, W, inverse, stream);
+}
+
+extern "C" int nfdpm_flow_boundary_stash(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
+                                         const float* bias3, const float* logs3, float* ld_part, const float* mt,
+                                         const float* beta, float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1,
+                                         int a1_dtype, int64_t lda1, int B, int C, int H, int W, nfdpm_stream_t stream) {
+  return flow_boundary_impl(in, in_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1,
+                            a1_dtype, lda1, B, C, H, W, 0, stream);
 }

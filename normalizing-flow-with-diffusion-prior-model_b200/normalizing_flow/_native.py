@@ -67,7 +67,10 @@ def _load() -> C.CDLL:
                                  i32, vp], C.c_int),
         "nfdpm_coupling_fused": ([vp, i64, vp, vp, vp, vp, i64, i32, i32, vp, vp], C.c_int),
         "nfdpm_fold_actnorm": ([vp, vp, vp, vp, i32, vp], C.c_int),
-        "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i64, vp, i32, i32, i32, i32, vp],
+                               C.c_int),
+        "nfdpm_flow_boundary_stash": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
+                                       i32, i32, vp], C.c_int),
         "nfdpm_actnorm_relu_bwd": ([vp, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_reduce_rows": ([vp, vp, i32, i32, i64, i32, vp], C.c_int),
         "nfdpm_mix_bwd": ([vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp], C.c_int),
@@ -95,7 +98,7 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary", "nfdpm_coupling_fused", "nfdpm_fold_actnorm",
            "nfdpm_coupling_bwd", "nfdpm_actnorm_relu_bwd", "nfdpm_reduce_rows", "nfdpm_mix_bwd", "nfdpm_mix_param_grad",
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
-           "nfdpm_col2im_add"]
+           "nfdpm_col2im_add", "nfdpm_flow_boundary_stash"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -233,9 +236,16 @@ def fold_actnorm(scale, bias, e_out, eb_out, n) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- backward
-def coupling_bwd(dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, dpar, B, Cc, H, W) -> None:
+def coupling_bwd(dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, Cc, H, W) -> None:
     _ok(lib.nfdpm_coupling_bwd(_p(dy), dy_bs, _p(dld), _p(u), u_bs, _p(pm), ldp, _p(bias3), _p(logs3), _p(du), du_bs,
-                               _p(dpm), _p(dpar), B, Cc, H, W, _st()))
+                               _p(dpm), _dt(dpm), ld_dpm, _p(dpar), B, Cc, H, W, _st()))
+
+
+def flow_boundary_stash(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1, lda1,
+                        B, Cc, H, W) -> None:
+    _ok(lib.nfdpm_flow_boundary_stash(_p(src), src_bs, int(squeeze_in), _p(pm), ldp, _p(bias3), _p(logs3), _p(ld_part),
+                                      _p(mt), _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1),
+                                      _dt(a1) if a1 is not None else F32, lda1, B, Cc, H, W, _st()))
 
 
 def actnorm_relu_bwd(dh, ld_dh, h, ld_h, scale, dpre, ld_o, part, M, Nn, rows_per_cta) -> None:

@@ -1,0 +1,392 @@
+"""Training path of the Glow flow: forward with activation stash + hand-written backward kernel chain, exposed to
+autograd as ONE ``torch.autograd.Function`` per ``Glow.transform`` call (and one per ``GaussianPrior.compute_log_prob``).
+
+What autograd computes for the reference module (normalizing_flow/trainer.py:155-164 drives
+glow.py:172-201 -> transforms.py:56-82, 116-133, 166-185, 270-290 and utils.py:43-44, 68-69) is reproduced by the
+kernel sequence below; no torch arithmetic is involved (torch supplies memory, dtype casts of the incoming [B]
+gradient vectors and the autograd plumbing).
+
+Per StepFlow, backward order (k = K-1 .. 0), with M = B*P rows:
+    coupling_bwd      dy, d(ld)            -> du (partial), dpm, d(bias3), d(logs3)
+    dgrad3  (NT GEMM) dpm  x W3p           -> dh2           wgrad3 (TN GEMM) dpm^T h2  -> d(W3)
+    actnorm_relu_bwd  dh2, h2              -> dpre2, d(scale2), d(bias2)
+    wgrad2  (TN GEMM) dpre2^T h1 -> d(W2)  dgrad2 (NT GEMM) dpre2 x W2 -> dh1
+    actnorm_relu_bwd  dh1, h1              -> dpre1, d(scale1), d(bias1)
+    wgrad1  (TN GEMM) dpre1^T A1 -> d(W1)  dgrad1 (NT GEMM) dpre1 x W1 -> dA1
+    mix_bwd           du + col2im(dA1), x  -> dx, per-image partials of d(W^), d(b^)
+and per level one mix_param_grad launch folding those partials and the log-det terms P*sum(d ld)*W^-T, P*sum(d ld)
+into d(InvConv2d.weight), d(ActNorm.scale), d(ActNorm.bias).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _engine as E
+from . import _native as N
+
+ROWS_PER_CTA = 64          # rows of one actnorm_relu_bwd CTA
+
+
+def _f32(t: Optional[Tensor], B: int, dev) -> Tensor:
+    """[B] gradient vector as contiguous fp32 (zeros when autograd passed None)."""
+    if t is None:
+        return torch.zeros(B, dtype=torch.float32, device=dev)
+    return t.to(torch.float32).contiguous()
+
+
+class _BwdCache:
+    """Transposed (dgrad) copies of the three conv weights of one coupling network, per parameter version."""
+
+    def __init__(self):
+        self.key = None
+        self.w1t = self.w2t = self.w3t = self.w3p32 = None
+        self.Kp3 = 0
+
+
+def _pack_bwd(cp, dt: torch.dtype) -> _BwdCache:
+    conv1, _, conv2, _, zc = cp._parts()
+    cache = getattr(cp, "_bwd_cache", None)
+    if cache is None:
+        cache = cp._bwd_cache = _BwdCache()
+    w1, w2, w3 = conv1.weight, conv2.weight, zc.weight
+    key = (E._vkey(w1, w2, w3), dt)
+    if cache.key == key:
+        return cache
+    F, Ch = w1.shape[0], w1.shape[1]
+    C = w3.shape[0]
+    dev = w1.device
+    K1, K1p = Ch * 9, E.round_up(Ch * 9, 64)
+    ldp = E.round_up(9 * C, 16)
+    Kp3 = E.round_up(9 * C, 64)
+    if cache.w1t is None or cache.w1t.dtype != dt:
+        cache.w1t = torch.empty(K1p * F, dtype=dt, device=dev)
+        cache.w2t = torch.empty(F * F, dtype=dt, device=dev)
+        cache.w3t = torch.empty(F * Kp3, dtype=dt, device=dev)
+        cache.w3p32 = torch.empty(ldp * F, dtype=torch.float32, device=dev)
+    # w1t[k, o] = W1[o, k]           (rows K1..K1p zero)      -> dgrad1: dA1[M,K1p] = dpre1[M,F] x w1t[K1p,F]^T
+    N.pack_matrix(w1, cache.w1t, K1, 1, F, 1, 0, K1, F, K1p)
+    # w2t[i, o] = W2[o, i]                                     -> dgrad2: dh1[M,F] = dpre2[M,F] x w2t[F,F]^T
+    N.pack_matrix(w2, cache.w2t, F, 1, F, 1, 0, F, F, F)
+    # w3p32[tap*C+co, ci] = W3[co, ci, tap] (fp32), then w3t[ci, tap*C+co] (columns 9C..Kp3 zero)
+    N.pack_matrix(w3, cache.w3p32, 9, C, F, 1, F * 9, 9, F, ldp)
+    N.pack_matrix(cache.w3p32, cache.w3t, F, 1, ldp, 1, 0, F, Kp3, F)
+    cache.Kp3 = Kp3
+    cache.key = key
+    return cache
+
+
+class _LevelStash:
+    __slots__ = ("C", "h", "w", "u", "x", "A1", "h1", "h2", "pm", "K1p", "ldp", "state_out")
+
+
+class Stash:
+    def __init__(self):
+        self.levels: List[_LevelStash] = []
+        self.B = 0
+        self.with_logp = False
+        self.in_shape = None
+        self.dt = torch.bfloat16
+
+
+def supported(glow, H: int, W: int) -> bool:
+    return glow._fast_ok(H, W)
+
+
+def forward_train(glow, x: Tensor, with_logp: bool):
+    """Glow.transform with every tensor the backward needs kept alive: per StepFlow the K-A input x_k, the K-A output
+    u_k (= coupling input), the im2col rows A1_k, the hidden maps h1_k / h2_k and the taps-as-N rows pm_k."""
+    B, c, H, W = x.shape
+    dev = x.device
+    levels = glow._levels()
+    slots = glow._slots(dev)
+    steps = [s for flows, _ in levels for s in flows]
+    E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
+    K = glow.K
+    dt = E.coupling_dtype()
+    st = Stash()
+    st.B, st.with_logp, st.in_shape, st.dt = B, with_logp, (B, c, H, W), dt
+    R_ld, R_lp = glow.L * K, glow.L - 1
+    ld_part = torch.empty(R_ld * B, dtype=torch.float32, device=dev)
+    lp_part = torch.empty(max(R_lp, 1) * B, dtype=torch.float32, device=dev) if with_logp else None
+    latents: List[Tensor] = []
+    cur, cur_bs = x, c * H * W
+    h, w, ch = H, W, c
+    row = 0
+    for li, (flows, split) in enumerate(levels):
+        h, w, C = h // 2, w // 2, ch * 4
+        P, M = h * w, B * h * w
+        first = flows[0].affcoupling
+        conv1 = first._parts()[0]
+        F = conv1.weight.shape[0]
+        E._pack_coupling(first._cache, *[m.weight for m in (first._parts()[0], first._parts()[2], first._parts()[4])], dt)
+        K1p, ldp = first._cache.K1p, first._cache.ldp
+        lv = _LevelStash()
+        lv.C, lv.h, lv.w, lv.K1p, lv.ldp = C, h, w, K1p, ldp
+        f32 = dict(dtype=torch.float32, device=dev)
+        lv.u = torch.empty(K, B, C, P, **f32)
+        lv.x = torch.empty(K, B, C, P, **f32)
+        lv.A1 = torch.empty(K, M, K1p, dtype=dt, device=dev)
+        lv.h1 = torch.empty(K, M, F, dtype=dt, device=dev)
+        lv.h2 = torch.empty(K, M, F, dtype=dt, device=dev)
+        lv.pm = torch.empty(K, M, ldp, **f32)
+        lv.state_out = torch.empty(B, C, h, w, **f32)
+        # level entry: squeeze + stash x_0 + K-A of step 0 + im2col
+        N.flow_boundary_stash(cur, cur_bs, True, None, 0, None, None, None, flows[0]._mix.fwd_mt, flows[0]._mix.fwd_beta,
+                              lv.u[0], C * P, lv.x[0], C * P, lv.A1[0], K1p, B, C, h, w)
+        for k, step in enumerate(flows):
+            cp = step.affcoupling
+            conv1, an1, conv2, an2, zc = cp._parts()
+            E._pack_coupling(cp._cache, conv1.weight, conv2.weight, zc.weight, dt)
+            cache = cp._cache
+            N.gemm_nt(lv.A1[k], K1p, cache.w1, K1p, lv.h1[k], F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
+            w2 = cache.w2 if dt != torch.float32 else conv2.weight
+            N.gemm_nt(lv.h1[k], F, w2, F, lv.h2[k], F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
+            N.gemm_nt(lv.h2[k], F, cache.w3, F, lv.pm[k], ldp, M, ldp, F)
+            if k + 1 < K:
+                nxt = flows[k + 1]
+                N.flow_boundary_stash(lv.u[k], C * P, False, lv.pm[k], ldp, zc.bias, zc.logs, ld_part[row * B:],
+                                      nxt._mix.fwd_mt, nxt._mix.fwd_beta, lv.u[k + 1], C * P, lv.x[k + 1], C * P,
+                                      lv.A1[k + 1], K1p, B, C, h, w)
+            else:
+                N.flow_boundary_stash(lv.u[k], C * P, False, lv.pm[k], ldp, zc.bias, zc.logs, ld_part[row * B:],
+                                      None, None, lv.state_out, C * P, None, 0, None, 0, B, C, h, w)
+            row += 1
+        st.levels.append(lv)
+        if split is None:
+            latents.append(lv.state_out)
+            break
+        z = torch.empty(B, C // 2, h, w, **f32)
+        split._forward_views(lv.state_out, C * P, B, C, h, w, z, lp_part[li * B:] if lp_part is not None else None)
+        latents.append(z)
+        cur, cur_bs, ch = lv.state_out, C * P, C // 2
+    return latents, ld_part, R_ld, lp_part, (R_lp if with_logp else 0), st
+
+
+def _strip_cols(src: Tensor, rows: int, ld: int, cols: int) -> Tensor:
+    """[rows, ld] -> contiguous [rows, cols] (drops the GEMM padding columns)."""
+    if ld == cols:
+        return src[:rows * cols]
+    out = torch.empty(rows * cols, dtype=torch.float32, device=src.device)
+    N.pack_matrix(src, out, rows, 1, cols, ld, 0, 1, cols, rows)
+    return out
+
+
+def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional[Tensor], dlp: Optional[Tensor],
+                   need_dx: bool) -> Tuple[Optional[Tensor], Dict[int, Tensor]]:
+    """Returns (d x or None, {id(parameter): gradient})."""
+    B = st.B
+    levels = glow._levels()
+    dev = st.levels[0].u.device
+    dt = st.dt
+    K = glow.K
+    f32 = dict(dtype=torch.float32, device=dev)
+    dld32 = _f32(dld, B, dev)
+    dlp32 = _f32(dlp, B, dev) if st.with_logp else None
+    dld_sum = torch.empty(1, **f32)
+    N.reduce_rows(dld32, dld_sum, B, 1, 1)
+    grads: Dict[int, Tensor] = {}
+    dx_next: Optional[Tensor] = None     # grad wrt the squeezed input of the level processed last
+    for li in range(glow.L - 1, -1, -1):
+        lv = st.levels[li]
+        flows, split = levels[li]
+        C, h, w = lv.C, lv.h, lv.w
+        Ch, P, M = C // 2, h * w, B * h * w
+        K1p, ldp = lv.K1p, lv.ldp
+        F = lv.h1.shape[-1]
+        # ---- gradient wrt the level's final state
+        if split is None:
+            g = d_lat[li]
+            dy = g.to(torch.float32).contiguous() if g is not None else torch.zeros(B, C, h, w, **f32)
+        else:
+            dy = torch.empty(B, C, h, w, **f32)
+            # first half <- squeeze backward of the next level's input gradient
+            N.unsqueeze(dx_next, dy, B, 2 * C, h // 2, w // 2, 2 * C * (P // 4), C * P)
+            second = dy.view(-1)[Ch * P:]
+            g = d_lat[li]
+            if g is not None:
+                N.copy_channels(g.to(torch.float32).contiguous(), second, B, Ch, P, Ch * P, C * P)
+            else:
+                dy[:, Ch:].zero_()
+            if st.with_logp:
+                conv = split.conv
+                if conv is None:
+                    N.split_prior_bwd(dlp32, None, 0, None, None, lv.state_out, C * P, dy, C * P, None, None, B, C, h, w)
+                else:
+                    Ks, Kp, ldh = Ch * 9, E.round_up(Ch * 9, 16), E.round_up(C, 16)
+                    wp = torch.empty(ldh * Kp, **f32)
+                    N.pack_matrix(conv.weight, wp, 1, C, Ks, 0, Ks, 1, Kp, ldh)
+                    wst = torch.empty(Kp * ldh, **f32)
+                    N.pack_matrix(conv.weight, wst, Ks, 1, C, 1, 0, Ks, ldh, Kp)
+                    As = torch.empty(M * Kp, **f32)
+                    N.im2col3x3(lv.state_out, As, B, Ch, h, w, C * P, Kp)
+                    hs = torch.empty(M * ldh, **f32)
+                    N.gemm_nt(As, Kp, wp, Kp, hs, ldh, M, C, Kp)
+                    dh = torch.empty(M * ldh, **f32)
+                    dpar = torch.empty(B * 2 * C, **f32)
+                    N.split_prior_bwd(dlp32, hs, ldh, conv.bias, conv.logs, lv.state_out, C * P, dy, C * P, dh, dpar,
+                                      B, C, h, w)
+                    gpar = torch.empty(2 * C, **f32)
+                    N.reduce_rows(dpar, gpar, B, 2 * C, 2 * C)
+                    grads[id(conv.bias)] = gpar[:C]
+                    grads[id(conv.logs)] = gpar[C:].view(1, C, 1, 1)
+                    dws = torch.empty(C * Kp, **f32)
+                    ws = torch.empty(N.gemm_tn_workspace(M, C, Kp), **f32)
+                    N.gemm_tn(dh, ldh, As, Kp, dws, M, C, Kp, ws)
+                    grads[id(conv.weight)] = _strip_cols(dws, C, Kp, Ks).view(C, Ch, 3, 3)
+                    dAs = torch.empty(M * Kp, **f32)
+                    N.gemm_nt(dh, ldh, wst, ldh, dAs, Kp, M, Kp, ldh)
+                    N.col2im_add(dAs, Kp, dy, C * P, B, Ch, h, w)
+            elif split.conv is not None:
+                for p_ in (split.conv.weight, split.conv.bias, split.conv.logs):
+                    grads[id(p_)] = torch.zeros_like(p_)
+        # ---- K StepFlows in reverse
+        n_cta = (M + ROWS_PER_CTA - 1) // ROWS_PER_CTA
+        du = torch.empty(B, C, P, **f32)
+        pong = (torch.empty(B, C, P, **f32), torch.empty(B, C, P, **f32))   # dx of successive steps alternate
+        Kp3 = E.round_up(9 * C, 64)
+        dpm = torch.empty(M * Kp3, dtype=dt, device=dev)
+        dh = torch.empty(M * F, **f32)
+        dpre = torch.empty(M * F, dtype=dt, device=dev)
+        dA1 = torch.empty(M * K1p, **f32)
+        an_part = torch.empty(n_cta * 2 * F, **f32)
+        dpar3 = torch.empty(B * 2 * C, **f32)
+        mix_part = torch.empty(K, B * (C * C + C), **f32)
+        ws = torch.empty(max(N.gemm_tn_workspace(M, F, F), N.gemm_tn_workspace(M, ldp, F),
+                             N.gemm_tn_workspace(M, F, K1p)), **f32)
+        for k in range(K - 1, -1, -1):
+            step = flows[k]
+            cp = step.affcoupling
+            conv1, an1, conv2, an2, zc = cp._parts()
+            bc = _pack_bwd(cp, dt)
+            N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3, dpar3,
+                           B, C, h, w)
+            g3 = torch.empty(2 * C, **f32)
+            N.reduce_rows(dpar3, g3, B, 2 * C, 2 * C)
+            grads[id(zc.bias)] = g3[:C]
+            grads[id(zc.logs)] = g3[C:].view(1, C, 1, 1)
+            # ZeroConv 3x3: weight gradient in the taps-as-N layout, then back to [C, F, 3, 3]
+            d3 = torch.empty(ldp * F, **f32)
+            N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws)
+            dw3 = torch.empty(C, F, 3, 3, **f32)
+            N.pack_matrix(d3, dw3, C, F, 9, F, 1, C * F, 9, C * F)
+            grads[id(zc.weight)] = dw3
+            N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
+            # second Conv2dActNorm (1x1)
+            N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
+            g2 = torch.empty(2 * F, **f32)
+            N.reduce_rows(an_part, g2, n_cta, 2 * F, 2 * F)
+            grads[id(an2.scale)] = g2[:F].view(F, 1, 1)
+            grads[id(an2.bias)] = g2[F:].view(F, 1, 1)
+            dw2 = torch.empty(F, F, 1, 1, **f32)
+            N.gemm_tn(dpre, F, lv.h1[k], F, dw2, M, F, F, ws)
+            grads[id(conv2.weight)] = dw2
+            N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
+            # first Conv2dActNorm (3x3)
+            N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
+            g1 = torch.empty(2 * F, **f32)
+            N.reduce_rows(an_part, g1, n_cta, 2 * F, 2 * F)
+            grads[id(an1.scale)] = g1[:F].view(F, 1, 1)
+            grads[id(an1.bias)] = g1[F:].view(F, 1, 1)
+            d1 = torch.empty(F * K1p, **f32)
+            N.gemm_tn(dpre, F, lv.A1[k], K1p, d1, M, F, K1p, ws)
+            grads[id(conv1.weight)] = _strip_cols(d1, F, K1p, Ch * 9).view(F, Ch, 3, 3)
+            N.gemm_nt(dpre, F, bc.w1t, F, dA1, K1p, M, K1p, F)
+            # fused ActNorm + 1x1 conv
+            dxb = pong[k & 1]
+            N.mix_bwd(du, C * P, dA1, K1p, lv.x[k], C * P, step._mix.fwd_mt, dxb, C * P, mix_part[k], B, C, h, w)
+            dy = dxb
+        items = []
+        keep = []
+        for k, step in enumerate(flows):
+            wgt, sc, bi = step.invconv2d.weight, step.actnorm.scale, step.actnorm.bias
+            dW, dS, dB = torch.empty_like(wgt), torch.empty_like(sc), torch.empty_like(bi)
+            scratch = torch.empty(C * C + C, **f32)
+            keep.append(scratch)
+            grads[id(wgt)], grads[id(sc)], grads[id(bi)] = dW, dS, dB
+            items.append(N.MixGradItem(part=mix_part[k].data_ptr(), B=B, C=C, weight=wgt.data_ptr(), scale=sc.data_ptr(),
+                                       bias=bi.data_ptr(), winv=step._mix.winv.data_ptr(), dld_sum=dld_sum.data_ptr(),
+                                       P=float(P), pad_=0, d_weight=dW.data_ptr(), d_scale=dS.data_ptr(),
+                                       d_bias=dB.data_ptr(), scratch=scratch.data_ptr()))
+        N.mix_param_grad(items)
+        dx_next = dy
+    dx = None
+    if need_dx:
+        Bc, c, H, W = st.in_shape
+        lv = st.levels[0]
+        dx = torch.empty(B, c, H, W, **f32)
+        N.unsqueeze(dx_next, dx, B, lv.C, lv.h, lv.w, lv.C * lv.h * lv.w, c * H * W)
+    return dx, grads
+
+
+class GlowTransformFn(torch.autograd.Function):
+    """(x, log_det_jac, logp, *parameters) -> (log_det_jac, logp, *latents); both accumulators are updated in place
+    like the reference (`+=`, transforms.py:81,131,184,288) and marked dirty."""
+
+    @staticmethod
+    def forward(ctx, glow, x, ld, lp, *params):
+        with_logp = lp is not None
+        B, c, H, W = x.shape
+        latents, ld_part, R_ld, lp_part, R_lp, st = forward_train(glow, x, with_logp)
+        dev = x.device
+        N.accumulate(ld, ld_part, R_ld, B, glow._slots(dev), glow._multipliers(H, W, dev), glow.L * glow.K)
+        dirty = [ld]
+        if with_logp:
+            if R_lp > 0:
+                N.accumulate(lp, lp_part, R_lp, B)
+            dirty.append(lp)
+        ctx.mark_dirty(*dirty)
+        ctx.glow, ctx.stash, ctx.n_params, ctx.with_logp = glow, st, len(params), with_logp
+        ctx.param_ids = [id(p) for p in params]
+        ctx.param_meta = [(p.shape, p.dtype, p.device) for p in params]
+        if with_logp:
+            return (ld, lp) + tuple(latents)
+        return (ld,) + tuple(latents)
+
+    @staticmethod
+    def backward(ctx, *gout):
+        st = ctx.stash
+        if st is None:
+            raise RuntimeError("Glow.transform: backward called twice (the activation stash was released)")
+        if ctx.with_logp:
+            g_ld, g_lp, g_lat = gout[0], gout[1], list(gout[2:])
+        else:
+            g_ld, g_lp, g_lat = gout[0], None, list(gout[1:])
+        dx, grads = backward_train(ctx.glow, st, g_lat, g_ld, g_lp, ctx.needs_input_grad[1])
+        ctx.stash = None
+        pg = []
+        for pid, (shape, dtype, dev) in zip(ctx.param_ids, ctx.param_meta):
+            g = grads.get(pid)
+            pg.append(g if g is not None else torch.zeros(shape, dtype=dtype, device=dev))
+        return (None, dx, g_ld, g_lp) + tuple(pg)
+
+
+class GaussianPriorFn(torch.autograd.Function):
+    """(z, weight, bias, logs) -> log p(z) [B] for the per-channel-constant prior (prior.py:79-83)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, bias, logs):
+        B, C, H, W = z.shape
+        out = torch.empty(B, dtype=torch.float32, device=z.device)
+        N.gauss_logp_const(z, bias, logs, out, B, C, H * W)
+        ctx.save_for_backward(z, weight, bias, logs)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        z, weight, bias, logs = ctx.saved_tensors
+        B, C, H, W = z.shape
+        f32 = dict(dtype=torch.float32, device=z.device)
+        g32 = g.to(torch.float32).contiguous()
+        dz = torch.empty_like(z)
+        if bias is None:
+            N.gauss_const_bwd(g32, z, None, None, dz, None, B, C, H * W)
+            return dz, None, None, None
+        dpar = torch.empty(B * 4 * C, **f32)
+        N.gauss_const_bwd(g32, z, bias, logs, dz, dpar, B, C, H * W)
+        gp = torch.empty(4 * C, **f32)
+        N.reduce_rows(dpar, gp, B, 4 * C, 4 * C)
+        # the reference convolves an all-zero map: the weight receives an exactly-zero gradient
+        return dz, torch.zeros_like(weight), gp[:2 * C].view_as(bias), gp[2 * C:].view_as(logs)

@@ -238,7 +238,6 @@ class Glow(Transform):
 
     # ---- forward: x -> ([z_0..z_{L-1}], log_det_jac, logp)
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[list, Tensor, Tensor]:
-        _no_autograd(x, self, "Glow.transform")
         x = E.check_input(x)
         B, c, H, W = self._check_image(x)
         if log_det_jac is None:
@@ -250,6 +249,8 @@ class Glow(Transform):
         slots = self._slots(dev)
         steps = [s for flows, _ in levels for s in flows]
         ready = all(s._ready() for s in steps)
+        if E.autograd_needed(x, self):
+            return self._transform_autograd(x, log_det_jac, logp, levels, slots, steps, ready)
         if self._use_graph(ready):
             if self._params_changed():
                 self._refresh_caches(steps, slots)
@@ -275,6 +276,27 @@ class Glow(Transform):
         if logp is not None and R_lp > 0:
             N.accumulate(logp, lp_part, R_lp, B)
         return latents, log_det_jac, logp
+
+    def _transform_autograd(self, x, log_det_jac, logp, levels, slots, steps, ready):
+        """Training path (reference trainer.py:155-164): forward with activation stash, hand-written backward kernels
+        behind one autograd Function (normalizing_flow/_train.py)."""
+        from . import _train as T
+        B, c, H, W = x.shape
+        if not T.supported(self, H, W):
+            raise NotImplementedError(
+                f"Glow.transform under autograd: the training kernels need every level's image to fit one CTA "
+                f"(H*W/4 <= 256 at level 0); got {H}x{W}.  Use torch.no_grad() for likelihood evaluation.")
+        if not ready:
+            # data-dependent ActNorm initialisation happens inside the first transform (transforms.py:74-78), without
+            # gradient; run it once on this batch, then take the training path
+            with torch.no_grad():
+                self._transform_core(x.detach(), logp is not None, levels, slots, steps, False)
+        if torch.is_grad_enabled() and (log_det_jac.requires_grad or (logp is not None and logp.requires_grad)):
+            raise RuntimeError("log_det_jac / logp are updated in place and must not require grad on entry")
+        out = T.GlowTransformFn.apply(self, x, log_det_jac, logp, *list(self.parameters()))
+        if logp is not None:
+            return list(out[2:]), out[0], out[1]
+        return list(out[1:]), out[0], None
 
     def _fast_ok(self, H: int, W: int) -> bool:
         """The fused step-boundary kernel needs every level's image to fit one CTA (P <= 256 + smem budget)."""

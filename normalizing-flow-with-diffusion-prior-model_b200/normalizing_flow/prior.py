@@ -80,14 +80,15 @@ class GaussianPrior(Prior):
         return (c.bias, c.logs) if c is not None else (None, None)
 
     def compute_log_prob(self, x: Tensor) -> Tensor:
-        if E.autograd_needed(x, self):
-            raise NotImplementedError("GaussianPrior.compute_log_prob: backward kernels are not part of this build "
-                                      "yet; call under torch.no_grad()")
         x = E.check_input(x)
         B, C, H, W = x.shape
         if C != self._C:
             raise ValueError(f"GaussianPrior built for {self._C} channels got {C}")
         bias, logs = self._params()
+        if E.autograd_needed(x, self):
+            from ._train import GaussianPriorFn
+            weight = self.__conv.weight if self.__conv is not None else None
+            return GaussianPriorFn.apply(x, weight, bias, logs)
         out = torch.empty(B, dtype=torch.float32, device=x.device)
         N.gauss_logp_const(x, bias, logs, out, B, C, H * W)
         return out

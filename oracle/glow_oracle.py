@@ -275,6 +275,30 @@ def nll_bpd(sd: Dict[str, Tensor], psd: Dict[str, Tensor], x: Tensor, L: int, K:
     return bpd_loss(ld + lp, n_bins, n_pixel)
 
 
+def train_grads(sd: Dict[str, Tensor], psd: Dict[str, Tensor], x: Tensor, L: int, K: int, n_bins: float,
+                n_pixel: float) -> Tuple[Tensor, Dict[str, Tensor], Dict[str, Tensor]]:
+    """Loss and parameter gradients of one training step as normalizing_flow/trainer.py:154-164 computes them
+    (fp64 accumulators, transform, prior log-prob, bits-per-dim loss, backward).  Returns
+    (loss, {flow key: grad}, {prior key: grad}); parameters without a gradient path are reported as zeros,
+    the way torch leaves the all-zero-input GaussianPrior conv weight."""
+    sd_g = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    psd_g = {k: v.clone().requires_grad_(True) for k, v in psd.items()}
+    with torch.enable_grad():
+        loss = nll_bpd(sd_g, psd_g, x, L, K, n_bins, n_pixel)
+        loss.backward()
+    g = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd_g.items() if v.dtype.is_floating_point}
+    pg = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in psd_g.items()}
+    return loss.detach(), g, pg
+
+
+def grad_signature(g: Tensor, seed: int) -> Tuple[float, float]:
+    """(L2 norm, projection on a PCG64 standard-normal vector) of a gradient tensor in fp64: a compact fingerprint
+    that pins large gradients in the golden fixtures without storing them."""
+    v = g.detach().double().reshape(-1)
+    r = torch.from_numpy(np.random.default_rng(seed).standard_normal(v.numel()))
+    return float(v.norm()), float((v * r).sum())
+
+
 def output_shapes(L: int, in_channels: int, size: int) -> List[Tuple[int, int, int]]:
     """Latent shapes (normalizing_flow/utils.py:93-117)."""
     out = []

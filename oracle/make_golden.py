@@ -94,6 +94,42 @@ def main():
     glow_case("glow_c3_L2_K1_b5_s16", 3, 2, 1, 5, 16, 13)
     glow_case("glow_c1_L2_K1_b2_s8_noprior", 1, 2, 1, 2, 8, 14, learn_prior=False)
 
+    # ---- one training step's loss and gradients (trainer.py:154-164) from the reference's own autograd
+    def grad_case(name, c, L, K, B, S, seed):
+        sd, psd = O.seeded_state(c, L, K, seed)
+        ref = nf.Glow(in_channel=c, L=L, K=K)
+        ref.load_state_dict(sd, strict=True)
+        gp = nf.GaussianPrior(in_channels=2 ** (L + 1) * c)
+        gp.load_state_dict(psd, strict=True)
+        x = O.seeded_input((B, c, S, S), seed + 1000)
+        from normalizing_flow.utils import calculate_loss, initialize_with_zeros
+        n_bins, n_pixel = 32.0, S * S * 3.0
+        with torch.enable_grad():
+            ld, lp = initialize_with_zeros(2, B, torch.device("cpu"))
+            zs, ld, lp = ref.transform(x, ld, lp)
+            lp += gp.compute_log_prob(zs[-1])
+            loss = calculate_loss(ld + lp, n_bins, n_pixel)
+            loss.backward()
+        rec = {"x": np_(x), "loss": np_(loss), "cfg": np.array([c, L, K, B, S, seed, 1]),
+               "checksum": np.array(O.state_checksum(sd))}
+        lo, g_o, pg_o = O.train_grads(sd, psd, x, L, K, n_bins, n_pixel)
+        assert torch.allclose(lo, loss.detach(), rtol=1e-9), name
+        names = []
+        for i, (k, p) in enumerate(list(ref.named_parameters()) + [("prior/" + k, p) for k, p in gp.named_parameters()]):
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            rec["sig/" + k] = np.array(O.grad_signature(g, 5000 + i))
+            if g.numel() <= 4096:
+                rec["grad/" + k] = np_(g)
+            go = pg_o[k[len("prior/"):]] if k.startswith("prior/") else g_o[k]
+            assert torch.allclose(go, g, rtol=1e-4, atol=1e-7), (name, k, float((go - g).abs().max()))
+            names.append(k)
+        rec["names"] = np.array(names)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **rec)
+        print(name, "ok", float(loss), len(names), "parameters")
+
+    grad_case("glow_grad_c3_L2_K2_b3_s16", 3, 2, 2, 3, 16, 51)
+    grad_case("glow_grad_c1_L3_K1_b2_s32", 1, 3, 1, 2, 32, 52)
+
     # ---- data-dependent initialisation (transforms.py:74-78 through the whole model)
     c, L, K, B, S, seed = 1, 2, 1, 6, 16, 21
     sd, _ = O.seeded_state(c, L, K, seed, initialized=False)

@@ -332,7 +332,9 @@ def test_error_behaviour():
         nf.Squeeze().transform(torch.zeros(1, 1, 3, 4, device=DEV), None, None)
     torch.set_grad_enabled(True)
     with pytest.raises(NotImplementedError):
-        flow.transform(x, torch.zeros(2, device=DEV), None)           # trainable flow under autograd: not yet
+        flow.blocks[0].flows[0].transform(torch.zeros(2, 4, 4, 4, device=DEV), torch.zeros(2, device=DEV), None)
+    with pytest.raises(RuntimeError):                                 # accumulators are updated in place
+        flow.transform(x, torch.zeros(2, device=DEV, requires_grad=True), None)
     torch.set_grad_enabled(False)
 
 

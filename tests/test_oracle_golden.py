@@ -138,3 +138,28 @@ def test_closed_form_kats():
     np.testing.assert_allclose(O.gaussian_logp(z, torch.zeros_like(z), torch.zeros_like(z)).numpy(),
                                (-0.5 * z.numel() / 2 * np.log(2 * np.pi) - 0.5 * (z ** 2).reshape(2, -1).sum(1)).numpy(),
                                rtol=1e-6)
+
+
+GRAD_CASES = ["glow_grad_c3_L2_K2_b3_s16", "glow_grad_c1_L3_K1_b2_s32"]
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_train_gradients(golden_dir, name):
+    """Oracle loss and parameter gradients of one training step (trainer.py:154-164) against the unmodified
+    reference's autograd: full tensors for small parameters, (norm, seeded projection) signatures for large ones."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    c, L, K, B, S, seed, _ = [int(v) for v in g["cfg"]]
+    sd, psd = O.seeded_state(c, L, K, seed)
+    assert np.allclose(np.array(O.state_checksum(sd)), g["checksum"], atol=1e-9)
+    x = torch.from_numpy(g["x"])
+    loss, gr, pgr = O.train_grads(sd, psd, x, L, K, 32.0, S * S * 3.0)
+    assert abs(float(loss) - float(g["loss"])) < 1e-9
+    for i, k in enumerate(g["names"]):
+        k = str(k)
+        t = pgr[k[len("prior/"):]] if k.startswith("prior/") else gr[k]
+        nrm, proj = O.grad_signature(t, 5000 + i)
+        ref_n, ref_p = g["sig/" + k]
+        assert abs(nrm - ref_n) <= 1e-4 * ref_n + 1e-9, k
+        assert abs(proj - ref_p) <= 1e-4 * max(ref_n, abs(ref_p)) * np.sqrt(t.numel()) ** 0 + 1e-6 * ref_n + 1e-9, k
+        if ("grad/" + k) in g.files:
+            assert np.allclose(t.numpy(), g["grad/" + k], rtol=1e-4, atol=1e-7), k
