@@ -135,6 +135,99 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bench_train(args, torch, dist, nf, N, O, dev, world, rank, B, x_host, timed, flush_buf):
+    """Full training step of the reference recipe (normalizing_flow/trainer.py:150-167): dequantisation noise,
+    transform, prior log-prob, bits/dim loss, backward, [gradient all-reduce over NCCL when N > 1], clip value 1,
+    clip norm 1, Adam(1e-4).  The whole step is captured once in a CUDA graph and replayed (host launch overhead of
+    the ~1100 kernels would otherwise dominate); `e2e` adds the H2D copy of the batch and the D2H read of the loss."""
+    c, L, K, S = CFG["in_channel"], CFG["L"], CFG["K"], CFG["S"]
+    n_bins, n_pixel = 32.0, S * S * 3.0
+    sd, psd = O.seeded_state(c, L, K, 0)
+    flow = nf.Glow(c, L, K).to(dev)
+    flow.load_state_dict(sd)
+    prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
+    prior.load_state_dict(psd)
+    params = list(flow.parameters()) + list(prior.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4, capturable=True, foreach=True)
+    dp = None
+    if world > 1:
+        dp = nf.GradAllReduce(flow, prior)
+        dp.broadcast_parameters(src=0)
+    x_static = x_host.to(dev)
+    loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        ld, lp = nf.initialize_with_zeros(2, B, dev)
+        zs, ld, lp = flow.transform(x_static + torch.rand_like(x_static) / n_bins, ld, lp)
+        lp += prior.compute_log_prob(zs[-1])
+        loss = nf.calculate_loss(ld + lp, n_bins, n_pixel)
+        loss.backward()
+        if dp is not None:
+            dp.finish()
+        torch.nn.utils.clip_grad_value_(params, 1.0)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            loss0 = step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    first_loss = float(loss0)
+    graph, n_launch = None, None
+    if not args.train_eager:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            l0 = N.launch_count
+            with torch.cuda.graph(graph):
+                loss_static = step()
+            n_launch = N.launch_count - l0
+        except Exception as e:                      # pragma: no cover - reported, eager numbers follow
+            graph = None
+            if rank == 0:
+                print(f"# train-step graph capture failed ({type(e).__name__}: {e}); timing eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+    if graph is not None:
+        def run_dev():
+            graph.replay()
+            return loss_static
+
+        def run_e2e():
+            x_static.copy_(x_host, non_blocking=True)
+            graph.replay()
+            loss_host.copy_(loss_static, non_blocking=True)
+    else:
+        def run_dev():
+            return step()
+
+        def run_e2e():
+            x_static.copy_(x_host, non_blocking=True)
+            loss_host.copy_(step().detach(), non_blocking=True)
+    for _ in range(max(args.warmup, 3)):
+        run_dev()
+    torch.cuda.synchronize()
+    steps = args.steps
+    l0 = N.launch_count
+    ms = timed(run_dev, steps)
+    launches = (n_launch * steps) if graph is not None else (N.launch_count - l0)
+    ms_e2e = timed(run_e2e, steps)
+    torch.cuda.synchronize()
+    last_loss = float(loss_host)
+    imgs = B * world * steps
+    return {"metric": "Glow L3/K16 32x32 full train step imgs/sec (fwd + bwd + clip + Adam)", "value": imgs / (ms * 1e-3),
+            "unit": "img/s", "ms_per_step": ms / steps,
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 8},
+            "gpu_launches": launches, "cuda_graph": graph is not None,
+            "grad_allreduce": (f"NCCL AVG, {len(flow.blocks) + 1} level buckets overlapped with backward" if dp else None),
+            "step_tflops": 3 * FLOP_PER_IMG_FWD * B / (ms / steps * 1e-3) / 1e12,
+            "loss_first": first_loss, "loss_last": last_loss}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +236,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the full-train-step measurement")
+    ap.add_argument("--train-eager", action="store_true", help="do not capture the train step in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -250,6 +345,10 @@ def main():
         k_ms = sum(s.elapsed_time(e) for s, e in evs) / reps
         achieved = 2.0 * M * F * F / (k_ms * 1e-3) / 1e12
 
+    train = None
+    if not args.no_train:
+        train = bench_train(args, torch, dist, nf, N, O, dev, world, rank, B, x_host, timed, flush_buf)
+
     if rank == 0:
         imgs = B * world * args.steps
         value = imgs / (ms * 1e-3)
@@ -273,6 +372,8 @@ def main():
             "clocks": clocks,
             "checks": {"recon_max_abs_err": recon, "step_tflops": 2 * FLOP_PER_IMG_FWD * B / (ms / args.steps * 1e-3) / 1e12},
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             Bs = 32
             st = oracle_step_fn(Bs)

@@ -1,0 +1,114 @@
+"""Data-parallel training of the Glow flow on the GPUs of one box: one process per GPU, full parameter
+replica, the batch sharded by images.  Forward, likelihood evaluation, inverse and sampling need no communication.
+Training has ONE exchange step per iteration: the gradient all-reduce (NCCL over NVLink/NVSwitch, fp32, average —
+the loss is a batch mean, normalizing_flow/utils.py:256, so equal shards + AVG reproduce the single-GPU gradient),
+after which every rank applies the identical clip + Adam update (trainer.py:165-167).
+
+The backward kernels write all gradients of a step into one flat buffer in ``parameters()`` order
+(_train.GradSink); levels finish deepest-first, so each level's slice is all-reduced on a communication stream as
+soon as its last gradient kernel has been enqueued, overlapping with the backward of the shallower levels.
+
+The reference has no distributed code; a trainer adopts this with three lines:
+
+    dp = GradAllReduce(flow, prior)          # after torch.distributed.init_process_group("nccl")
+    dp.broadcast_parameters()                # once, after the data-dependent initialisation on rank 0's first batch
+    loss.backward(); dp.finish()             # every step, before clip_grad_* / optimizer.step()
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard(n: int, rank: int, world: int) -> slice:
+    """Contiguous, equal shard of a global batch of n images (n must be divisible by world: the gradient average
+    over ranks equals the global batch mean only for equal shards)."""
+    if n % world != 0:
+        raise ValueError(f"global batch {n} is not divisible by the world size {world}")
+    per = n // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+class GradAllReduce:
+    def __init__(self, flow, prior: Optional[torch.nn.Module] = None, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("GradAllReduce needs torch.distributed.init_process_group(...) first")
+        self.flow, self.prior, self.group = flow, prior, group
+        self.world = dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+        self.cuda = next(flow.parameters()).is_cuda
+        self.stream = torch.cuda.Stream() if self.cuda else None
+        self.sink = None
+        self.ranges: List = []
+        self.launched = 0
+        flow._grad_hook = self
+
+    def detach(self) -> None:
+        if getattr(self.flow, "_grad_hook", None) is self:
+            self.flow._grad_hook = None
+
+    # ---- collectives
+    def _avg(self, t: torch.Tensor) -> None:
+        if self.backend == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:                                   # gloo (CPU tests) has no AVG
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Parameters and buffers (incl. the uint8 ``is_initialized`` flags) of rank ``src`` to every rank: run once
+        after the data-dependent ActNorm initialisation (normalizing_flow/utils.py:275-292) so replicas start equal."""
+        mods = [self.flow] + ([self.prior] if self.prior is not None else [])
+        with torch.no_grad():
+            for m in mods:
+                ts = [p.data for p in m.parameters()] + [b for b in m.buffers()]
+                for dt in sorted({t.dtype for t in ts}, key=str):
+                    grp = [t for t in ts if t.dtype == dt]
+                    flat = torch.cat([t.reshape(-1) for t in grp])
+                    dist.broadcast(flat, src=src, group=self.group)
+                    off = 0
+                    for t in grp:
+                        t.copy_(flat[off:off + t.numel()].view_as(t))
+                        off += t.numel()
+        for m in self.flow.modules():                  # host-side caches of the flags / prepared matrices
+            if hasattr(m, "_init_known"):
+                m._init_known = None
+
+    # ---- hooks called by _train.GlowTransformFn.backward
+    def begin(self, glow, sink) -> None:
+        self.sink = sink
+        self.ranges = sink.level_ranges(glow)
+        self.launched = 0
+        if self.cuda:
+            sink.flat.record_stream(self.stream)
+
+    def level_done(self, li: int) -> None:
+        lo, hi = self.ranges[li]
+        buf = self.sink.flat[lo:hi]
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self._avg(buf)
+        else:
+            self._avg(buf)
+        self.launched += 1
+
+    def finish(self) -> None:
+        """Join the communication stream and average the (few, small) GaussianPrior gradients.  Call after
+        ``loss.backward()`` and before clipping / the optimizer step."""
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        if self.sink is not None and self.launched != len(self.ranges):
+            raise RuntimeError("gradient all-reduce incomplete: backward did not visit every level")
+        self.sink = None
+        if self.prior is not None:
+            gs = [p.grad for p in self.prior.parameters() if p.grad is not None]
+            if gs:
+                flat = torch.cat([g.reshape(-1) for g in gs])
+                self._avg(flat)
+                off = 0
+                for g in gs:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()

@@ -110,6 +110,19 @@ def _vkey(*tensors) -> tuple:
     return tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
 
 
+#: True while Glow captures its own inference graph (parameter caches are refreshed OUTSIDE that graph)
+own_capture = False
+
+
+def cache_hit(cached_key, key) -> bool:
+    """Parameter-derived caches (LU/fold, packed weights) are keyed on tensor version counters.  Inside a CUDA-graph
+    capture started by the CALLER (e.g. a whole training step: forward, backward, optimizer) the refresh kernels
+    must be part of the graph, because the parameters change between replays without the host noticing."""
+    if cached_key != key:
+        return False
+    return own_capture or not torch.cuda.is_current_stream_capturing()
+
+
 # ------------------------------------------------------------------------------------------- mix cache
 class MixCache:
     """Prepared mixing matrices of one (ActNorm, InvConv2d) pair: see nfdpm_mix_prepare."""
@@ -151,7 +164,7 @@ def prepare_mix(entries: Sequence[Tuple[MixCache, Optional[torch.Tensor], Option
         dev = (w if w is not None else s).device
         cache._alloc(C, dev, slot)
         key = _vkey(w, s, b)
-        if cache.key == key:
+        if cache_hit(cache.key, key):
             continue
         cache.key = key
         items.append(N.MixItem(weight=N._p(w), scale=N._p(s), bias=N._p(b), C=C, pad_=0,
@@ -177,7 +190,7 @@ class CouplingCache:
 
 def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, dt: torch.dtype):
     key = (_vkey(w1, w2, w3), dt)
-    if cache.key == key:
+    if cache_hit(cache.key, key):
         return
     F, Ch = w1.shape[0], w1.shape[1]
     C = w3.shape[0]
@@ -225,7 +238,7 @@ def refresh_folded(cp) -> None:
     _, an1, _, an2, _ = cp._parts()
     cache = cp._cache
     key = _vkey(an1.scale, an1.bias, an2.scale, an2.bias)
-    if cache.ep_key == key:
+    if cache_hit(cache.ep_key, key):
         return
     F = an1.scale.shape[0]
     if cache.ep is None or cache.ep.numel() != 4 * F:
@@ -318,7 +331,7 @@ def refresh_split(sp, C: int) -> None:
     Kp = round_up(K, 16)
     ldh = round_up(C, 8)
     key = _vkey(w)
-    if cache.key != key:
+    if not cache_hit(cache.key, key):
         if cache.w is None or cache.w.numel() != ldh * Kp:
             _bump_epoch()
             cache.w = torch.empty(ldh * Kp, dtype=torch.float32, device=w.device)

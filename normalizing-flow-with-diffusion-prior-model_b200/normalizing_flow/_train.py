@@ -53,7 +53,7 @@ def _pack_bwd(cp, dt: torch.dtype) -> _BwdCache:
         cache = cp._bwd_cache = _BwdCache()
     w1, w2, w3 = conv1.weight, conv2.weight, zc.weight
     key = (E._vkey(w1, w2, w3), dt)
-    if cache.key == key:
+    if E.cache_hit(cache.key, key):
         return cache
     F, Ch = w1.shape[0], w1.shape[1]
     C = w3.shape[0]
@@ -165,18 +165,51 @@ def forward_train(glow, x: Tensor, with_logp: bool):
     return latents, ld_part, R_ld, lp_part, (R_lp if with_logp else 0), st
 
 
-def _strip_cols(src: Tensor, rows: int, ld: int, cols: int) -> Tensor:
+class GradSink:
+    """Destination of every parameter gradient of one backward pass: ONE flat fp32 buffer in ``parameters()`` order
+    (each tensor padded to 64 floats), so that the data-parallel all-reduce (normalizing_flow/_dp.py) and the
+    optimizer work on contiguous memory and the backward kernels write their results in place (no per-parameter
+    copies).  ``flat`` is allocated per backward: gradients of an earlier step that the caller still holds stay valid."""
+    ALIGN = 64
+
+    def __init__(self, params: List[Tensor]):
+        self.offsets: Dict[int, Tuple[int, torch.Size]] = {}
+        off = 0
+        for p in params:
+            self.offsets[id(p)] = (off, p.shape)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        dev = params[0].device
+        self.flat = torch.empty(off, dtype=torch.float32, device=dev)
+        self.written = set()
+
+    def get(self, p: Tensor) -> Tensor:
+        off, shape = self.offsets[id(p)]
+        self.written.add(id(p))
+        return self.flat[off:off + p.numel()].view(shape)
+
+    def level_ranges(self, glow) -> List[Tuple[int, int]]:
+        """[start, end) element range of every level's parameters (levels are contiguous in parameters() order)."""
+        out = []
+        for blk in list(glow.blocks) + [glow.final_flows]:
+            ps = list(blk.parameters())
+            lo = self.offsets[id(ps[0])][0]
+            o, shp = self.offsets[id(ps[-1])]
+            hi = o + (ps[-1].numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            out.append((lo, hi))
+        return out
+
+
+def _strip_cols(src: Tensor, out: Tensor, rows: int, ld: int, cols: int) -> None:
     """[rows, ld] -> contiguous [rows, cols] (drops the GEMM padding columns)."""
-    if ld == cols:
-        return src[:rows * cols]
-    out = torch.empty(rows * cols, dtype=torch.float32, device=src.device)
     N.pack_matrix(src, out, rows, 1, cols, ld, 0, 1, cols, rows)
-    return out
 
 
 def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional[Tensor], dlp: Optional[Tensor],
-                   need_dx: bool) -> Tuple[Optional[Tensor], Dict[int, Tensor]]:
-    """Returns (d x or None, {id(parameter): gradient})."""
+                   need_dx: bool, sink: GradSink, level_done=None) -> Optional[Tensor]:
+    """Writes every parameter gradient into ``sink`` and returns d x (or None).  ``level_done(li)`` is called after
+    the last kernel that writes level li's gradients has been enqueued (deepest level first): the hook the
+    data-parallel gradient all-reduce uses to overlap communication with the rest of the backward."""
     B = st.B
     levels = glow._levels()
     dev = st.levels[0].u.device
@@ -187,7 +220,6 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
     dlp32 = _f32(dlp, B, dev) if st.with_logp else None
     dld_sum = torch.empty(1, **f32)
     N.reduce_rows(dld32, dld_sum, B, 1, 1)
-    grads: Dict[int, Tensor] = {}
     dx_next: Optional[Tensor] = None     # grad wrt the squeezed input of the level processed last
     for li in range(glow.L - 1, -1, -1):
         lv = st.levels[li]
@@ -228,20 +260,18 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
                     dpar = torch.empty(B * 2 * C, **f32)
                     N.split_prior_bwd(dlp32, hs, ldh, conv.bias, conv.logs, lv.state_out, C * P, dy, C * P, dh, dpar,
                                       B, C, h, w)
-                    gpar = torch.empty(2 * C, **f32)
-                    N.reduce_rows(dpar, gpar, B, 2 * C, 2 * C)
-                    grads[id(conv.bias)] = gpar[:C]
-                    grads[id(conv.logs)] = gpar[C:].view(1, C, 1, 1)
+                    N.reduce_rows(dpar, sink.get(conv.bias), B, C, 2 * C)
+                    N.reduce_rows(dpar[C:], sink.get(conv.logs), B, C, 2 * C)
                     dws = torch.empty(C * Kp, **f32)
                     ws = torch.empty(N.gemm_tn_workspace(M, C, Kp), **f32)
                     N.gemm_tn(dh, ldh, As, Kp, dws, M, C, Kp, ws)
-                    grads[id(conv.weight)] = _strip_cols(dws, C, Kp, Ks).view(C, Ch, 3, 3)
+                    _strip_cols(dws, sink.get(conv.weight), C, Kp, Ks)
                     dAs = torch.empty(M * Kp, **f32)
                     N.gemm_nt(dh, ldh, wst, ldh, dAs, Kp, M, Kp, ldh)
                     N.col2im_add(dAs, Kp, dy, C * P, B, Ch, h, w)
             elif split.conv is not None:
                 for p_ in (split.conv.weight, split.conv.bias, split.conv.logs):
-                    grads[id(p_)] = torch.zeros_like(p_)
+                    sink.get(p_).zero_()
         # ---- K StepFlows in reverse
         n_cta = (M + ROWS_PER_CTA - 1) // ROWS_PER_CTA
         du = torch.empty(B, C, P, **f32)
@@ -254,6 +284,8 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         an_part = torch.empty(n_cta * 2 * F, **f32)
         dpar3 = torch.empty(B * 2 * C, **f32)
         mix_part = torch.empty(K, B * (C * C + C), **f32)
+        d1 = torch.empty(F * K1p, **f32)
+        d3 = torch.empty(ldp * F, **f32)
         ws = torch.empty(max(N.gemm_tn_workspace(M, F, F), N.gemm_tn_workspace(M, ldp, F),
                              N.gemm_tn_workspace(M, F, K1p)), **f32)
         for k in range(K - 1, -1, -1):
@@ -263,36 +295,24 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             bc = _pack_bwd(cp, dt)
             N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3, dpar3,
                            B, C, h, w)
-            g3 = torch.empty(2 * C, **f32)
-            N.reduce_rows(dpar3, g3, B, 2 * C, 2 * C)
-            grads[id(zc.bias)] = g3[:C]
-            grads[id(zc.logs)] = g3[C:].view(1, C, 1, 1)
+            N.reduce_rows(dpar3, sink.get(zc.bias), B, C, 2 * C)
+            N.reduce_rows(dpar3[C:], sink.get(zc.logs), B, C, 2 * C)
             # ZeroConv 3x3: weight gradient in the taps-as-N layout, then back to [C, F, 3, 3]
-            d3 = torch.empty(ldp * F, **f32)
             N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws)
-            dw3 = torch.empty(C, F, 3, 3, **f32)
-            N.pack_matrix(d3, dw3, C, F, 9, F, 1, C * F, 9, C * F)
-            grads[id(zc.weight)] = dw3
+            N.pack_matrix(d3, sink.get(zc.weight), C, F, 9, F, 1, C * F, 9, C * F)
             N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
             # second Conv2dActNorm (1x1)
             N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
-            g2 = torch.empty(2 * F, **f32)
-            N.reduce_rows(an_part, g2, n_cta, 2 * F, 2 * F)
-            grads[id(an2.scale)] = g2[:F].view(F, 1, 1)
-            grads[id(an2.bias)] = g2[F:].view(F, 1, 1)
-            dw2 = torch.empty(F, F, 1, 1, **f32)
-            N.gemm_tn(dpre, F, lv.h1[k], F, dw2, M, F, F, ws)
-            grads[id(conv2.weight)] = dw2
+            N.reduce_rows(an_part, sink.get(an2.scale), n_cta, F, 2 * F)
+            N.reduce_rows(an_part[F:], sink.get(an2.bias), n_cta, F, 2 * F)
+            N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws)
             N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
             # first Conv2dActNorm (3x3)
             N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
-            g1 = torch.empty(2 * F, **f32)
-            N.reduce_rows(an_part, g1, n_cta, 2 * F, 2 * F)
-            grads[id(an1.scale)] = g1[:F].view(F, 1, 1)
-            grads[id(an1.bias)] = g1[F:].view(F, 1, 1)
-            d1 = torch.empty(F * K1p, **f32)
+            N.reduce_rows(an_part, sink.get(an1.scale), n_cta, F, 2 * F)
+            N.reduce_rows(an_part[F:], sink.get(an1.bias), n_cta, F, 2 * F)
             N.gemm_tn(dpre, F, lv.A1[k], K1p, d1, M, F, K1p, ws)
-            grads[id(conv1.weight)] = _strip_cols(d1, F, K1p, Ch * 9).view(F, Ch, 3, 3)
+            _strip_cols(d1, sink.get(conv1.weight), F, K1p, Ch * 9)
             N.gemm_nt(dpre, F, bc.w1t, F, dA1, K1p, M, K1p, F)
             # fused ActNorm + 1x1 conv
             dxb = pong[k & 1]
@@ -302,15 +322,16 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         keep = []
         for k, step in enumerate(flows):
             wgt, sc, bi = step.invconv2d.weight, step.actnorm.scale, step.actnorm.bias
-            dW, dS, dB = torch.empty_like(wgt), torch.empty_like(sc), torch.empty_like(bi)
+            dW, dS, dB = sink.get(wgt), sink.get(sc), sink.get(bi)
             scratch = torch.empty(C * C + C, **f32)
             keep.append(scratch)
-            grads[id(wgt)], grads[id(sc)], grads[id(bi)] = dW, dS, dB
             items.append(N.MixGradItem(part=mix_part[k].data_ptr(), B=B, C=C, weight=wgt.data_ptr(), scale=sc.data_ptr(),
                                        bias=bi.data_ptr(), winv=step._mix.winv.data_ptr(), dld_sum=dld_sum.data_ptr(),
                                        P=float(P), pad_=0, d_weight=dW.data_ptr(), d_scale=dS.data_ptr(),
                                        d_bias=dB.data_ptr(), scratch=scratch.data_ptr()))
         N.mix_param_grad(items)
+        if level_done is not None:
+            level_done(li)
         dx_next = dy
     dx = None
     if need_dx:
@@ -318,7 +339,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         lv = st.levels[0]
         dx = torch.empty(B, c, H, W, **f32)
         N.unsqueeze(dx_next, dx, B, lv.C, lv.h, lv.w, lv.C * lv.h * lv.w, c * H * W)
-    return dx, grads
+    return dx
 
 
 class GlowTransformFn(torch.autograd.Function):
@@ -338,9 +359,8 @@ class GlowTransformFn(torch.autograd.Function):
                 N.accumulate(lp, lp_part, R_lp, B)
             dirty.append(lp)
         ctx.mark_dirty(*dirty)
-        ctx.glow, ctx.stash, ctx.n_params, ctx.with_logp = glow, st, len(params), with_logp
-        ctx.param_ids = [id(p) for p in params]
-        ctx.param_meta = [(p.shape, p.dtype, p.device) for p in params]
+        ctx.glow, ctx.stash, ctx.with_logp = glow, st, with_logp
+        ctx.params = params
         if with_logp:
             return (ld, lp) + tuple(latents)
         return (ld,) + tuple(latents)
@@ -354,12 +374,24 @@ class GlowTransformFn(torch.autograd.Function):
             g_ld, g_lp, g_lat = gout[0], gout[1], list(gout[2:])
         else:
             g_ld, g_lp, g_lat = gout[0], None, list(gout[1:])
-        dx, grads = backward_train(ctx.glow, st, g_lat, g_ld, g_lp, ctx.needs_input_grad[1])
+        glow, params = ctx.glow, list(ctx.params)
+        sink = GradSink(params)
+        hook = getattr(glow, "_grad_hook", None)           # data-parallel all-reduce (normalizing_flow/_dp.py)
+        if hook is not None:
+            hook.begin(glow, sink)
+        dx = backward_train(glow, st, g_lat, g_ld, g_lp, ctx.needs_input_grad[1], sink,
+                            hook.level_done if hook is not None else None)
         ctx.stash = None
+        ctx.params = None
+        glow._last_grad_flat = sink.flat                   # contiguous view of all gradients of this step
         pg = []
-        for pid, (shape, dtype, dev) in zip(ctx.param_ids, ctx.param_meta):
-            g = grads.get(pid)
-            pg.append(g if g is not None else torch.zeros(shape, dtype=dtype, device=dev))
+        for p in params:
+            untouched = id(p) not in sink.written
+            g = sink.get(p)
+            if untouched:
+                g.zero_()
+            pg.append(g)
+        del sink
         return (None, dx, g_ld, g_lp) + tuple(pg)
 
 

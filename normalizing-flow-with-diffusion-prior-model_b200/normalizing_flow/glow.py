@@ -192,10 +192,12 @@ class Glow(Transform):
             E.WS.scope = scope                        # buffers baked into the graph live (only) under this scope
             g = torch.cuda.CUDAGraph()
             n0 = N.launch_count
+            E.own_capture = True                      # parameter caches were refreshed above, outside the graph
             with torch.cuda.graph(g):
                 out = build()
             n_launch = N.launch_count - n0
         finally:
+            E.own_capture = False
             E.WS.scope = prev
         N.launch_count -= n_launch                    # counted per replay instead
         ent = dict(out)

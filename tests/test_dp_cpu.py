@@ -1,0 +1,97 @@
+"""Host logic of the data-parallel path on CPU: world_size-2 ``gloo`` processes exercise the bucketed gradient
+all-reduce (per-level slices of the flat gradient buffer, deepest level first), the parameter/buffer broadcast and the
+batch sharding.  No kernels run here; the NCCL path is the same code with backend "nccl" (bench.py --gpus N)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import normalizing_flow as nf
+        from normalizing_flow._train import GradSink
+        torch.manual_seed(100 + rank)                      # replicas start DIFFERENT on purpose
+        flow = nf.Glow(1, 3, 2)
+        prior = nf.GaussianPrior(16)
+        dp = nf.GradAllReduce(flow, prior)
+        # --- broadcast: every rank ends with rank 0's parameters and flags
+        if rank == 0:
+            for m in flow.modules():
+                if hasattr(m, "is_initialized"):
+                    m.is_initialized.fill_(1)
+        dp.broadcast_parameters(src=0)
+        chk = torch.stack([p.detach().double().sum() for p in flow.parameters()]).sum()
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        assert all(float(c) == float(allc[0]) for c in allc), "parameters differ after broadcast"
+        assert all(int(m.is_initialized) == 1 for m in flow.modules() if hasattr(m, "is_initialized"))
+        # --- bucketed gradient average in the order the backward reports the levels
+        params = list(flow.parameters())
+        sink = GradSink(params)
+        for i, p in enumerate(params):
+            sink.get(p).fill_(float(rank + 1) * (i + 1))
+        ranges = sink.level_ranges(flow)
+        assert len(ranges) == 3 and ranges[0][0] == 0 and ranges[-1][1] == sink.numel
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(2)), "levels must tile the flat buffer"
+        dp.begin(flow, sink)
+        for li in (2, 1, 0):
+            dp.level_done(li)
+        for p, v in zip(prior.parameters(), (1.0, 2.0, 3.0)):
+            p.grad = torch.full_like(p, v * (rank + 1))
+        dp.finish()
+        mean_rank = sum(r + 1 for r in range(world)) / world
+        for i, p in enumerate(params):
+            assert torch.allclose(sink.get(p), torch.full_like(p, mean_rank * (i + 1))), i
+        for p, v in zip(prior.parameters(), (1.0, 2.0, 3.0)):
+            assert torch.allclose(p.grad, torch.full_like(p, v * mean_rank))
+        # --- an incomplete backward is an error, not a silent partial average
+        dp.begin(flow, sink)
+        dp.level_done(2)
+        try:
+            dp.finish()
+            raise AssertionError("finish() accepted an incomplete all-reduce")
+        except RuntimeError:
+            pass
+        # --- sharding
+        sl = nf.shard(8, rank, world)
+        assert (sl.start, sl.stop) == (rank * 4, rank * 4 + 4)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
+def test_gradient_allreduce_and_broadcast_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def test_shard_rejects_ragged_batches():
+    import normalizing_flow as nf
+    with pytest.raises(ValueError):
+        nf.shard(10, 0, 4)
