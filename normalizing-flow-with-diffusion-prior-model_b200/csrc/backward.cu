@@ -453,6 +453,12 @@ __global__ void col2im_add_kernel(const float* __restrict__ da, int64_t lda, flo
   }
 }
 
+// tcgen05 path (gemm_tn_tc.cu)
+void gemm_tn_tc_plan(int M, int N1, int N2, int* BN, int* tiles, int* splits, int* kb_per_split);
+bool gemm_tn_tc_ok(const void* A, int64_t lda, const void* Bm, int64_t ldb, int N1, int N2);
+int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* ws, int M, int N1, int N2, int* splits_out,
+               cudaStream_t st);
+
 }  // namespace nfdpm
 
 using namespace nfdpm;
@@ -557,20 +563,32 @@ extern "C" int64_t nfdpm_gemm_tn_workspace(int M, int N1, int N2, int* splits_ou
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   if (splits_out) *splits_out = splits;
-  return (int64_t)splits * N1 * N2;
+  // the tensor-core path (bf16 operands) splits M differently: size the workspace for whichever is larger
+  int bn, t, s_tc, per;
+  gemm_tn_tc_plan(M, N1, N2, &bn, &t, &s_tc, &per);
+  const int smax = splits > s_tc ? splits : s_tc;
+  return (int64_t)smax * N1 * N2;
 }
 
 extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void* Bm, int b_dtype, int64_t ldb, float* D,
                              int64_t ldd, int M, int N1, int N2, float* ws, int accumulate, nfdpm_stream_t stream) {
   NFDPM_REQUIRE(A && Bm && D && ws, "nfdpm_gemm_tn: null pointer");
   NFDPM_REQUIRE(M > 0 && N1 > 0 && N2 > 0 && lda >= N1 && ldb >= N2 && ldd == N2, "nfdpm_gemm_tn: bad shape (ldd must equal N2)");
+  cudaStream_t st = as_stream(stream);
+  const int n = N1 * N2;
+  if (a_dtype == NFDPM_BF16 && b_dtype == NFDPM_BF16 && gemm_tn_tc_ok(A, lda, Bm, ldb, N1, N2)) {
+    int s_tc = 1;
+    if (gemm_tn_tc(A, lda, Bm, ldb, ws, M, N1, N2, &s_tc, st)) return 1;
+    reduce_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, D, s_tc, n, n, accumulate);
+    NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
+    return 0;
+  }
   int splits = 1;
   nfdpm_gemm_tn_workspace(M, N1, N2, &splits);
   int rows = (M + splits - 1) / splits;
   rows = (rows + 15) / 16 * 16;
   splits = (M + rows - 1) / rows;
   dim3 grid((N2 + 127) / 128, (N1 + 127) / 128, splits);
-  cudaStream_t st = as_stream(stream);
 #define GO(TA, TB) gemm_tn_kernel<TA, TB><<<grid, 256, 0, st>>>((const TA*)A, lda, (const TB*)Bm, ldb, ws, M, N1, N2, rows)
   if (a_dtype == NFDPM_F32 && b_dtype == NFDPM_F32) GO(float, float);
   else if (a_dtype == NFDPM_F32 && b_dtype == NFDPM_BF16) GO(float, __nv_bfloat16);
@@ -579,7 +597,6 @@ extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void
   else return fail("nfdpm_gemm_tn: bad dtypes");
 #undef GO
   NFDPM_CHECK_LAUNCH("gemm_tn_kernel");
-  const int n = N1 * N2;
   reduce_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, D, splits, n, n, accumulate);
   NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;

@@ -1,0 +1,193 @@
+// tcgen05 / TMEM / TMA weight-gradient GEMM:  D[N1,N2] (+)= sum_m A[m,N1] * B[m,N2]   (bf16 in, fp32 out)
+//
+// Both operands are read straight from their row-major activation layouts ([M, ld], channel fastest): the reduction
+// index m is the STRIDED dimension, i.e. both UMMA operands are "MN-major".  No transposed copies are made:
+//   TMA     box = 64 columns (128 bytes) x 64 rows of m, 128B swizzle -> smem rows of 128 bytes, one per m
+//   UMMA    shared-memory descriptors in MN-major SWIZZLE_128B form: 64 contiguous MN elements per row,
+//           8-row (K) groups 1024 bytes apart (SBO), 64-column MN chunks one TMA box apart (LBO);
+//           instruction descriptor with the A/B "major" bits set (transpose), M=128, N=BN<=256, K=16
+// Output tile 128 (N1) x BN (N2); the M reduction is split across CTAs (tiles x splits <= #SMs) and every CTA writes
+// its fp32 partial tile to a workspace slab; reduce_rows_kernel sums the slabs in a fixed order (deterministic, no
+// float atomics — `torch.use_deterministic_algorithms(True)` stays honest, reference utils.py:45-60).
+//   warp 0: TMA producer (4-stage ring) | warp 1: MMA issuer, TMEM owner | warps 2..5: epilogue (TMEM -> global)
+#include "tc_common.cuh"
+
+namespace nfdpm {
+
+constexpr int TN_BK = 64;                       // rows of m per pipeline stage
+constexpr int TN_STAGES = 4;
+constexpr int TN_A_BYTES = 2 * TN_BK * 128;     // two 64-column boxes (N1 tile = 128)
+constexpr int TN_B_BYTES_MAX = 4 * TN_BK * 128; // up to four 64-column boxes (BN <= 256)
+constexpr int TN_STAGE_BYTES = TN_A_BYTES + TN_B_BYTES_MAX;
+constexpr int TN_THREADS = 64 + 128;
+
+// MN-major, SWIZZLE_128B: LBO = bytes between 64-element MN chunks (one TMA box), SBO = 1024 (8 k-rows of 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((TN_BK * 128) >> 4) << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   float* __restrict__ ws, int M, int N1, int N2, int BN,
+                                                                   int num_n2, int splits, int kb_per_split) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TN_STAGES + 1];
+  __shared__ uint32_t s_tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[TN_STAGES]);
+  const uint32_t bar_done = smem_u32(&bars[2 * TN_STAGES]);
+
+  const int tile = blockIdx.x / splits, split = blockIdx.x - tile * splits;
+  const int t1 = tile / num_n2, t2 = tile - t1 * num_n2;
+  const int num_kb = (M + TN_BK - 1) / TN_BK;
+  const int kb0 = split * kb_per_split;
+  const int kb1 = min(num_kb, kb0 + kb_per_split);
+  const int nb_boxes = BN >> 6;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < TN_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = (uint32_t)(TN_A_BYTES + nb_boxes * TN_BK * 128);
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+      if (lane == 0) {
+        const uint32_t sa = ring + stage * TN_STAGE_BYTES, sb = sa + TN_A_BYTES;
+        mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d(sa + j * (TN_BK * 128), &tmA, t1 * 128 + j * 64, kb * TN_BK, bar_full + 8 * stage);
+        for (int j = 0; j < nb_boxes; ++j)
+          tma_load_2d(sb + j * (TN_BK * 128), &tmB, t2 * BN + j * 64, kb * TN_BK, bar_full + 8 * stage);
+      }
+      __syncwarp();
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t idesc = make_idesc_mn(128, BN);
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(bar_full + 8 * stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = ring + stage * TN_STAGE_BYTES, sb = sa + TN_A_BYTES;
+        const uint64_t adesc = make_smem_desc_mn(sa), bdesc = make_smem_desc_mn(sb);
+#pragma unroll
+        for (int k = 0; k < TN_BK / 16; ++k)            // 16 k-rows = 2048 bytes = 128 descriptor units
+          umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_empty + 8 * stage);
+        if (kb == kb1 - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // epilogue: TMEM lane = row of the tile = n1 index
+    const int q = warp & 3;
+    const int n1 = t1 * 128 + q * 32 + lane;
+    float* dst = ws + ((int64_t)split * N1 + n1) * N2 + t2 * BN;
+    const bool have = kb1 > kb0;                           // an empty split (tail) contributes zeros
+    if (have) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      if (have) {
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      if (n1 < N1 && t2 * BN + c0 < N2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(dst + c0 + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+// tiling shared by the launcher and the workspace query
+void gemm_tn_tc_plan(int M, int N1, int N2, int* BN, int* tiles, int* splits, int* kb_per_split) {
+  const int bn = N2 >= 256 ? 256 : (N2 + 63) / 64 * 64;
+  const int n2t = (N2 + bn - 1) / bn, n1t = (N1 + 127) / 128;
+  const int t = n1t * n2t;
+  const int num_kb = (M + TN_BK - 1) / TN_BK;
+  int s = sm_count() / t;
+  if (s < 1) s = 1;
+  if (s > num_kb) s = num_kb;
+  const int per = (num_kb + s - 1) / s;
+  s = (num_kb + per - 1) / per;
+  *BN = bn; *tiles = t; *splits = s; *kb_per_split = per;
+}
+
+bool gemm_tn_tc_ok(const void* A, int64_t lda, const void* Bm, int64_t ldb, int N1, int N2) {
+  return (lda % 8 == 0) && (ldb % 8 == 0) && (N2 % 16 == 0) && (N2 % 4 == 0) && ((uintptr_t)A % 16 == 0) &&
+         ((uintptr_t)Bm % 16 == 0) && N1 > 0;
+}
+
+int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* ws, int M, int N1, int N2, int* splits_out,
+               cudaStream_t st) {
+  int BN, tiles, splits, per;
+  gemm_tn_tc_plan(M, N1, N2, &BN, &tiles, &splits, &per);
+  const int num_n2 = (N2 + BN - 1) / BN;
+  // the tensor maps cover the physical row width (lda / ldb): padding columns inside it are real memory, columns
+  // beyond it and rows >= M are zero-filled by TMA
+  CUtensorMap tmA, tmB;
+  if (make_map(&tmA, A, M, lda, lda, TN_BK)) return 1;
+  if (make_map(&tmB, Bm, M, ldb, ldb, TN_BK)) return 1;
+  static bool attr_set = false;
+  const size_t smem = 1024 + (size_t)TN_STAGES * TN_STAGE_BYTES;
+  if (!attr_set) {
+    NFDPM_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  gemm_tn_tc_kernel<<<tiles * splits, TN_THREADS, smem, st>>>(tmA, tmB, ws, M, N1, N2, BN, num_n2, splits, per);
+  NFDPM_CHECK_LAUNCH("gemm_tn_tc_kernel");
+  *splits_out = splits;
+  return 0;
+}
+
+}  // namespace nfdpm

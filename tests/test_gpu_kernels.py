@@ -453,3 +453,43 @@ def test_coupling_fused_equals_three_gemms(M, K1p, ldp):
     H2 = torch.relu(torch.exp(s2.double().cpu()) * (H1 @ w2.double().cpu().T + b2.double().cpu())).float().bfloat16().double()
     ref = H2 @ w3.double().cpu().T
     assert torch.allclose(pm[:n].cpu().double(), ref, rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------ weight-gradient GEMM (TN)
+@pytest.mark.parametrize("M,N1,lda,N2,ldb", [(32768, 512, 512, 512, 512), (8192, 224, 256, 512, 512),
+                                             (2048, 432, 448, 512, 512), (4096, 512, 512, 64, 64),
+                                             (300, 112, 128, 512, 512), (64, 512, 512, 128, 128),
+                                             (1000, 512, 512, 256, 256)])
+def test_gemm_tn_bf16_tensor_core(M, N1, lda, N2, ldb):
+    """D[N1,N2] = A[:, :N1]^T B[:, :N2] on tcgen05 with MN-major (transposed) operands read in place, split over M."""
+    A = rnd(M, lda, seed=1).to(DEV).to(torch.bfloat16)
+    B = rnd(M, ldb, seed=2).to(DEV).to(torch.bfloat16)
+    D = torch.full((N1 * N2,), float("nan"), device=DEV)
+    ws = torch.empty(N.gemm_tn_workspace(M, N1, N2), device=DEV)
+    N.gemm_tn(A, lda, B, ldb, D, M, N1, N2, ws)
+    sync()
+    ref = A[:, :N1].double().T @ B[:, :N2].double()
+    got = D.view(N1, N2).double()
+    assert torch.isfinite(got).all()
+    assert float((got - ref).norm() / ref.norm()) < 1e-5
+    # accumulate=1 adds into D; the result is bitwise reproducible (fixed-order split reduction)
+    D2 = D.clone()
+    N.gemm_tn(A, lda, B, ldb, D2, M, N1, N2, ws, accumulate=True)
+    D3 = D.clone()
+    N.gemm_tn(A, lda, B, ldb, D3, M, N1, N2, ws, accumulate=True)
+    sync()
+    assert torch.equal(D2, D3)
+    assert float((D2.view(N1, N2).double() - 2 * ref).norm() / ref.norm()) < 2e-5
+
+
+@pytest.mark.parametrize("dta,dtb", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
+def test_gemm_tn_cuda_core(dta, dtb):
+    M, N1, N2 = 1500, 24, 112
+    A = rnd(M, 32, seed=3).to(DEV).to(dta)
+    B = rnd(M, 112, seed=4).to(DEV).to(dtb)
+    D = torch.empty(N1 * N2, device=DEV)
+    ws = torch.empty(N.gemm_tn_workspace(M, N1, N2), device=DEV)
+    N.gemm_tn(A, 32, B, 112, D, M, N1, N2, ws)
+    sync()
+    ref = A[:, :N1].double().T @ B.double()
+    assert float((D.view(N1, N2).double() - ref).norm() / ref.norm()) < 1e-5
