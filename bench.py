@@ -148,7 +148,10 @@ def bench_train(args, torch, dist, nf, N, O, dev, world, rank, B, x_host, timed,
     prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
     prior.load_state_dict(psd)
     params = list(flow.parameters()) + list(prior.parameters())
-    opt = torch.optim.Adam(params, lr=1e-4, capturable=True, foreach=True)
+    if args.torch_optimizer:
+        opt = torch.optim.Adam(params, lr=1e-4, capturable=True, foreach=True)
+    else:       # clip value 1 + clip norm 1 (flow parameters, trainer.py:165-166) + Adam in three fused launches
+        opt = nf.FusedClipAdam(params, lr=1e-4, clip_params=list(flow.parameters()), clip_value=1.0, max_norm=1.0)
     dp = None
     if world > 1:
         dp = nf.GradAllReduce(flow, prior)
@@ -165,8 +168,9 @@ def bench_train(args, torch, dist, nf, N, O, dev, world, rank, B, x_host, timed,
         loss.backward()
         if dp is not None:
             dp.finish()
-        torch.nn.utils.clip_grad_value_(params, 1.0)
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        if args.torch_optimizer:
+            torch.nn.utils.clip_grad_value_(list(flow.parameters()), 1.0)
+            torch.nn.utils.clip_grad_norm_(list(flow.parameters()), 1.0)
         opt.step()
         return loss
 
@@ -223,6 +227,8 @@ def bench_train(args, torch, dist, nf, N, O, dev, world, rank, B, x_host, timed,
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": launches, "cuda_graph": graph is not None,
+            "optimizer": "torch clip_grad_value_/clip_grad_norm_/Adam(foreach)" if args.torch_optimizer else
+                         "FusedClipAdam (clip value + clip norm + Adam, 3 launches)",
             "grad_allreduce": (f"NCCL AVG, {len(flow.blocks) + 1} level buckets overlapped with backward" if dp else None),
             "step_tflops": 3 * FLOP_PER_IMG_FWD * B / (ms / steps * 1e-3) / 1e12,
             "loss_first": first_loss, "loss_last": last_loss}
@@ -238,6 +244,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the full-train-step measurement")
     ap.add_argument("--train-eager", action="store_true", help="do not capture the train step in a CUDA graph")
+    ap.add_argument("--torch-optimizer", action="store_true",
+                    help="train arm: torch clip_grad_value_/clip_grad_norm_/Adam instead of the fused optimiser step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

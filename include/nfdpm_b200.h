@@ -208,11 +208,14 @@ int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const f
                        int dpm_dtype, int64_t ld_dpm, float* dpar, int B, int C, int H, int W, nfdpm_stream_t stream);
 /* ActNorm+ReLU backward on rows (utils.py:69,84-87): dpre = dh*(h>0)*exp(scale); part[cta][2N] partial d(scale), d(bias);
  * ctas = ceil(M/rows_per_cta). */
-int nfdpm_actnorm_relu_bwd(const float* dh, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h, const float* scale,
-                           void* dpre, int o_dtype, int64_t ld_o, float* part, int M, int N, int rows_per_cta,
-                           nfdpm_stream_t stream);
+int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
+                           const float* scale, void* dpre, int o_dtype, int64_t ld_o, float* part, int M, int N,
+                           int rows_per_cta, nfdpm_stream_t stream);
 /* out[i] (+)= sum_{r<R} part[r*stride + i], i < n */
 int nfdpm_reduce_rows(const float* part, float* out, int R, int n, int64_t stride, int accumulate, nfdpm_stream_t stream);
+/* out0[i] = sum_r part[r*stride + i] for i < n0, out1[i-n0] likewise for n0 <= i < n0+n1 (a parameter pair in one launch) */
+int nfdpm_reduce_rows2(const float* part, float* out0, float* out1, int R, int n0, int n1, int64_t stride,
+                       nfdpm_stream_t stream);
 /* Fused ActNorm + 1x1 conv backward (transforms.py:80,132) incl. col2im of the im2col-row gradient da1 (may be NULL):
  * dx = W^T du; part [B][C*C + C]: per-image sum_p du[o]x[i] and sum_p du[o]. */
 int nfdpm_mix_bwd(const float* du, int64_t du_bs, const float* da1, int64_t lda1, const float* x, int64_t x_bs,
@@ -242,6 +245,20 @@ int nfdpm_gauss_const_bwd(const float* dl, const float* z, const float* bias, co
 /* dstate[b,c,p] += col2im(da)[b,c,p] for c < Cin (input gradient of a 3x3 "same" conv expressed as im2col rows). */
 int nfdpm_col2im_add(const float* da, int64_t lda, float* dstate, int64_t dbs, int B, int Cin, int H, int W,
                      nfdpm_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused optimiser step = trainer.py:165-167 (clip_grad_value_, clip_grad_norm_, Adam/AdamW step; utils.py:120-137) in
+ * three launches over all parameter tensors.
+ *   refs    device table, one 32-byte record per tensor: { float* param; float* grad (NULL = skip); int64 state_off;
+ *           int32 numel; int32 clip (member of the clip group) }
+ *   chunks  device table of n_chunks int32 pairs { tensor index, element offset }, one per nfdpm_opt_chunk() elements
+ *   exp_avg / exp_avg_sq  flat fp32 state (indexed by state_off), partial [n_chunks] scratch,
+ *   scal    [3] device floats: clip coefficient (out), gradient norm of the clip group (out), step count (in/out, += 1)
+ * Gradients of the clip group are modified in place (clamped, then scaled) exactly like the two torch utilities. */
+int nfdpm_opt_chunk(void);
+int nfdpm_fused_clip_adam(const void* refs, const int32_t* chunks, int n_chunks, float* exp_avg, float* exp_avg_sq,
+                          float* partial, float* scal, float clip_value, float max_norm, double lr, double beta1,
+                          double beta2, double eps, double weight_decay, int decoupled, nfdpm_stream_t stream);
 
 /* acc[b] += sum_{r<R} part[r*B+b] + sum_{j<nc} cmul[j]*cval[j]   (fixed order -> deterministic).
  * acc is the caller's running log_det_jac / logp (`+=` in place, transforms.py:81,131,184,288), fp32 or fp64.

@@ -123,36 +123,123 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
 }
 
 // ------------------------------------------------------------------------------------------------ ActNorm+ReLU backward
-// rows [M, ld]; CTA = 64 rows x all N columns; threads walk columns (coalesced), loop over rows.
-template <typename TH, typename TO>
-__global__ void __launch_bounds__(256) actnorm_relu_bwd_kernel(const float* __restrict__ dh, const TH* __restrict__ h,
+// rows [M, ld], channel fastest.  CTA = `rows_per_cta` rows x all N columns; a thread owns 8 consecutive columns
+// (16-byte bf16 / 32-byte fp32 vectors, fully coalesced rows), the CTA's 256 threads cover 256/(N/8) rows at a time and
+// loop over the rest; per-column partial sums are combined across the row groups in shared memory in a fixed order.
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename TD, typename TH, typename TO>
+__global__ void __launch_bounds__(256) actnorm_relu_bwd_kernel(const TD* __restrict__ dh, const TH* __restrict__ h,
                                                                const float* __restrict__ scale, TO* __restrict__ dpre,
                                                                float* __restrict__ part, int M, int N, int64_t ld_dh,
                                                                int64_t ld_h, int64_t ld_o, int rows_per_cta) {
+  extern __shared__ __align__(16) float red[];           // [row groups][2][N]
+  const int cg = N >> 3;                                  // column groups of 8 (N % 8 == 0, cg <= 256)
+  const int rg = 256 / cg;                                // row groups processed concurrently
+  const int tid = threadIdx.x;
+  const int g = tid % cg, r0 = tid / cg;
   const int m0 = blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
-  for (int n = threadIdx.x; n < N; n += 256) {
-    const float e = expf(__ldg(scale + n));
-    float ds = 0.f, db = 0.f;
-    for (int m = m0; m < m1; ++m) {
-      const float hv = ldf<TH>(h + (int64_t)m * ld_h + n);
-      const float g = (hv > 0.f) ? dh[(int64_t)m * ld_dh + n] : 0.f;
-      ds += g * hv;
-      db += g * e;
-      stf<TO>(dpre + (int64_t)m * ld_o + n, g * e);
+  float ds[8], db[8], e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ds[j] = 0.f; db[j] = 0.f; }
+  if (r0 < rg) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = expf(__ldg(scale + g * 8 + j));
+#pragma unroll 4
+    for (int m = m0 + r0; m < m1; m += rg) {
+      float gv[8], hv[8], o[8];
+      Vec8<TD>::load(dh + (int64_t)m * ld_dh + g * 8, gv);
+      Vec8<TH>::load(h + (int64_t)m * ld_h + g * 8, hv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = (hv[j] > 0.f) ? gv[j] : 0.f;
+        ds[j] = fmaf(gg, hv[j], ds[j]);
+        o[j] = gg * e[j];
+        db[j] += o[j];
+      }
+      Vec8<TO>::store(dpre + (int64_t)m * ld_o + g * 8, o);
     }
-    part[(int64_t)blockIdx.x * 2 * N + n] = ds;
-    part[(int64_t)blockIdx.x * 2 * N + N + n] = db;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[(r0 * 2 + 0) * N + g * 8 + j] = ds[j];
+      red[(r0 * 2 + 1) * N + g * 8 + j] = db[j];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * N; i += 256) {
+    float acc = 0.f;
+    for (int r = 0; r < rg; ++r) acc += red[r * 2 * N + i];
+    part[(int64_t)blockIdx.x * 2 * N + i] = acc;
   }
 }
 
 // out[n] (+)= sum_r part[r*stride + n]
-__global__ void reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int R, int n, int64_t stride,
-                                   int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// Column sums of a [R, stride] partial matrix in a fixed order: CTA = 32 columns x 8 row lanes; lane ry sums rows
+// ry, ry+8, ... and the 8 lane sums are added in order (deterministic; coalesced 128-byte row segments).
+__device__ __forceinline__ float colsum_32x8(const float* __restrict__ part, int R, int64_t stride, int col, bool valid,
+                                             float (*sh)[33]) {
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   float s = 0.f;
-  for (int r = 0; r < R; ++r) s += part[(int64_t)r * stride + i];
-  out[i] = accumulate ? out[i] + s : s;
+  if (valid)
+    for (int r = ry; r < R; r += 8) s += part[(int64_t)r * stride + col];
+  sh[ry][cx] = s;
+  __syncthreads();
+  float t = 0.f;
+  if (ry == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][cx];
+  }
+  return t;   // valid for ry == 0
+}
+
+// out0[i] = sum_r part[r*stride + i] (i < n0);  out1[i - n0] = ... (n0 <= i < n0 + n1): one launch for a (scale, bias) or
+// (bias, logs) pair whose partials sit side by side
+__global__ void __launch_bounds__(256) reduce_rows2_kernel(const float* __restrict__ part, float* __restrict__ out0,
+                                                           float* __restrict__ out1, int R, int n0, int n1, int64_t stride) {
+  __shared__ float sh[8][33];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float s = colsum_32x8(part, R, stride, i, i < n0 + n1, sh);
+  if ((threadIdx.x >> 5) == 0 && i < n0 + n1) {
+    if (i < n0) out0[i] = s; else out1[i - n0] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int R,
+                                                          int n, int64_t stride, int accumulate) {
+  __shared__ float sh[8][33];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float s = colsum_32x8(part, R, stride, i, i < n, sh);
+  if ((threadIdx.x >> 5) == 0 && i < n) out[i] = accumulate ? out[i] + s : s;
 }
 
 // ------------------------------------------------------------------------------------------------ K-A backward
@@ -489,28 +576,52 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
   return 0;
 }
 
-extern "C" int nfdpm_actnorm_relu_bwd(const float* dh, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
+extern "C" int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
                                       const float* scale, void* dpre, int o_dtype, int64_t ld_o, float* part, int M,
                                       int N, int rows_per_cta, nfdpm_stream_t stream) {
   NFDPM_REQUIRE(dh && h && scale && dpre && part, "nfdpm_actnorm_relu_bwd: null pointer");
   NFDPM_REQUIRE(M > 0 && N > 0 && rows_per_cta > 0, "nfdpm_actnorm_relu_bwd: bad shape");
+  NFDPM_REQUIRE(N % 8 == 0 && N <= 2048 && ld_dh % 8 == 0 && ld_h % 8 == 0 && ld_o % 8 == 0,
+                "nfdpm_actnorm_relu_bwd: N and the leading dimensions must be multiples of 8 (N <= 2048)");
+  NFDPM_REQUIRE(((uintptr_t)dh % 16 == 0) && ((uintptr_t)h % 16 == 0) && ((uintptr_t)dpre % 16 == 0),
+                "nfdpm_actnorm_relu_bwd: operands must be 16-byte aligned");
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  const int cg = N / 8;
+  NFDPM_REQUIRE(cg <= 256, "nfdpm_actnorm_relu_bwd: N too large");
+  const int rg = 256 / cg;
+  const size_t smem = sizeof(float) * (size_t)rg * 2 * N;
   cudaStream_t st = as_stream(stream);
-#define GO(TH, TO) actnorm_relu_bwd_kernel<TH, TO><<<grid, 256, 0, st>>>(dh, (const TH*)h, scale, (TO*)dpre, part, M, N, ld_dh, ld_h, ld_o, rows_per_cta)
-  if (h_dtype == NFDPM_F32 && o_dtype == NFDPM_F32) GO(float, float);
-  else if (h_dtype == NFDPM_BF16 && o_dtype == NFDPM_F32) GO(__nv_bfloat16, float);
-  else if (h_dtype == NFDPM_BF16 && o_dtype == NFDPM_BF16) GO(__nv_bfloat16, __nv_bfloat16);
-  else if (h_dtype == NFDPM_F32 && o_dtype == NFDPM_BF16) GO(float, __nv_bfloat16);
-  else return fail("nfdpm_actnorm_relu_bwd: bad dtypes");
+#define GO(TD, TH, TO) actnorm_relu_bwd_kernel<TD, TH, TO><<<grid, 256, smem, st>>>((const TD*)dh, (const TH*)h, scale, (TO*)dpre, part, M, N, ld_dh, ld_h, ld_o, rows_per_cta)
+  const int key = (dh_dtype == NFDPM_BF16 ? 4 : 0) | (h_dtype == NFDPM_BF16 ? 2 : 0) | (o_dtype == NFDPM_BF16 ? 1 : 0);
+  NFDPM_REQUIRE((dh_dtype == NFDPM_F32 || dh_dtype == NFDPM_BF16) && (h_dtype == NFDPM_F32 || h_dtype == NFDPM_BF16) &&
+                (o_dtype == NFDPM_F32 || o_dtype == NFDPM_BF16), "nfdpm_actnorm_relu_bwd: bad dtypes");
+  switch (key) {
+    case 0: GO(float, float, float); break;
+    case 1: GO(float, float, __nv_bfloat16); break;
+    case 2: GO(float, __nv_bfloat16, float); break;
+    case 3: GO(float, __nv_bfloat16, __nv_bfloat16); break;
+    case 4: GO(__nv_bfloat16, float, float); break;
+    case 5: GO(__nv_bfloat16, float, __nv_bfloat16); break;
+    case 6: GO(__nv_bfloat16, __nv_bfloat16, float); break;
+    default: GO(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
+  }
 #undef GO
   NFDPM_CHECK_LAUNCH("actnorm_relu_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_reduce_rows2(const float* part, float* out0, float* out1, int R, int n0, int n1, int64_t stride,
+                                  nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(part && out0 && out1 && R > 0 && n0 > 0 && n1 > 0 && stride >= n0 + n1, "nfdpm_reduce_rows2: bad arguments");
+  reduce_rows2_kernel<<<(n0 + n1 + 31) / 32, 256, 0, as_stream(stream)>>>(part, out0, out1, R, n0, n1, stride);
+  NFDPM_CHECK_LAUNCH("reduce_rows2_kernel");
   return 0;
 }
 
 extern "C" int nfdpm_reduce_rows(const float* part, float* out, int R, int n, int64_t stride, int accumulate,
                                  nfdpm_stream_t stream) {
   NFDPM_REQUIRE(part && out && R > 0 && n > 0 && stride >= n, "nfdpm_reduce_rows: bad arguments");
-  reduce_rows_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(part, out, R, n, stride, accumulate);
+  reduce_rows_kernel<<<(n + 31) / 32, 256, 0, as_stream(stream)>>>(part, out, R, n, stride, accumulate);
   NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;
 }
@@ -579,7 +690,7 @@ extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void
   if (a_dtype == NFDPM_BF16 && b_dtype == NFDPM_BF16 && gemm_tn_tc_ok(A, lda, Bm, ldb, N1, N2)) {
     int s_tc = 1;
     if (gemm_tn_tc(A, lda, Bm, ldb, ws, M, N1, N2, &s_tc, st)) return 1;
-    reduce_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, D, s_tc, n, n, accumulate);
+    reduce_rows_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, D, s_tc, n, n, accumulate);
     NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
     return 0;
   }
@@ -597,7 +708,7 @@ extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void
   else return fail("nfdpm_gemm_tn: bad dtypes");
 #undef GO
   NFDPM_CHECK_LAUNCH("gemm_tn_kernel");
-  reduce_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, D, splits, n, n, accumulate);
+  reduce_rows_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, D, splits, n, n, accumulate);
   NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
   return 0;
 }

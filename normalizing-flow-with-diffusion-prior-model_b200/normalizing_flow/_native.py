@@ -71,7 +71,11 @@ def _load() -> C.CDLL:
                                C.c_int),
         "nfdpm_flow_boundary_stash": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
                                        i32, i32, vp], C.c_int),
-        "nfdpm_actnorm_relu_bwd": ([vp, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
+        "nfdpm_actnorm_relu_bwd": ([vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
+        "nfdpm_reduce_rows2": ([vp, vp, vp, i32, i32, i32, i64, vp], C.c_int),
+        "nfdpm_opt_chunk": ([], C.c_int),
+        "nfdpm_fused_clip_adam": ([vp, vp, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double,
+                                   C.c_double, C.c_double, i32, vp], C.c_int),
         "nfdpm_reduce_rows": ([vp, vp, i32, i32, i64, i32, vp], C.c_int),
         "nfdpm_mix_bwd": ([vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_mix_param_grad": ([C.POINTER(MixGradItem), i32, vp], C.c_int),
@@ -98,7 +102,8 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary", "nfdpm_coupling_fused", "nfdpm_fold_actnorm",
            "nfdpm_coupling_bwd", "nfdpm_actnorm_relu_bwd", "nfdpm_reduce_rows", "nfdpm_mix_bwd", "nfdpm_mix_param_grad",
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
-           "nfdpm_col2im_add", "nfdpm_flow_boundary_stash"]
+           "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
+           "nfdpm_opt_chunk", "nfdpm_fused_clip_adam"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -249,12 +254,16 @@ def flow_boundary_stash(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part,
 
 
 def actnorm_relu_bwd(dh, ld_dh, h, ld_h, scale, dpre, ld_o, part, M, Nn, rows_per_cta) -> None:
-    _ok(lib.nfdpm_actnorm_relu_bwd(_p(dh), ld_dh, _p(h), _dt(h), ld_h, _p(scale), _p(dpre), _dt(dpre), ld_o, _p(part), M,
-                                   Nn, rows_per_cta, _st()))
+    _ok(lib.nfdpm_actnorm_relu_bwd(_p(dh), _dt(dh), ld_dh, _p(h), _dt(h), ld_h, _p(scale), _p(dpre), _dt(dpre), ld_o,
+                                   _p(part), M, Nn, rows_per_cta, _st()))
 
 
 def reduce_rows(part, out, R, n, stride, accumulate=False) -> None:
     _ok(lib.nfdpm_reduce_rows(_p(part), _p(out), R, n, stride, int(accumulate), _st()))
+
+
+def reduce_rows2(part, out0, out1, R, n0, n1, stride) -> None:
+    _ok(lib.nfdpm_reduce_rows2(_p(part), _p(out0), _p(out1), R, n0, n1, stride, _st()))
 
 
 def mix_bwd(du, du_bs, da1, lda1, x, x_bs, mt, dx, dx_bs, part, B, Cc, H, W) -> None:
@@ -285,3 +294,13 @@ def gauss_const_bwd(dl, z, bias, logs, dz, dpar, B, Cc, P) -> None:
 
 def col2im_add(da, lda, dstate, dbs, B, Cin, H, W) -> None:
     _ok(lib.nfdpm_col2im_add(_p(da), lda, _p(dstate), dbs, B, Cin, H, W, _st()))
+
+
+def opt_chunk() -> int:
+    return int(lib.nfdpm_opt_chunk())
+
+
+def fused_clip_adam(refs, chunks, n_chunks, exp_avg, exp_avg_sq, partial, scal, clip_value, max_norm, lr, beta1, beta2, eps,
+                    weight_decay, decoupled) -> None:
+    _ok(lib.nfdpm_fused_clip_adam(_p(refs), _p(chunks), n_chunks, _p(exp_avg), _p(exp_avg_sq), _p(partial), _p(scal),
+                                  clip_value, max_norm, lr, beta1, beta2, eps, weight_decay, int(decoupled), _st()), 3)

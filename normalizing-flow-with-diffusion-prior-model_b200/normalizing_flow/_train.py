@@ -27,6 +27,9 @@ from torch import Tensor
 from . import _engine as E
 from . import _native as N
 
+#: write parameter gradients straight into ``p.grad`` (views of one flat buffer) when it is empty; set to False to
+#: hand every gradient to autograd instead (needed for torch.autograd.grad(), which must not touch ``.grad``)
+DIRECT_GRADS = True
 ROWS_PER_CTA = 64          # rows of one actnorm_relu_bwd CTA
 
 
@@ -260,8 +263,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
                     dpar = torch.empty(B * 2 * C, **f32)
                     N.split_prior_bwd(dlp32, hs, ldh, conv.bias, conv.logs, lv.state_out, C * P, dy, C * P, dh, dpar,
                                       B, C, h, w)
-                    N.reduce_rows(dpar, sink.get(conv.bias), B, C, 2 * C)
-                    N.reduce_rows(dpar[C:], sink.get(conv.logs), B, C, 2 * C)
+                    N.reduce_rows2(dpar, sink.get(conv.bias), sink.get(conv.logs), B, C, C, 2 * C)
                     dws = torch.empty(C * Kp, **f32)
                     ws = torch.empty(N.gemm_tn_workspace(M, C, Kp), **f32)
                     N.gemm_tn(dh, ldh, As, Kp, dws, M, C, Kp, ws)
@@ -278,7 +280,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         pong = (torch.empty(B, C, P, **f32), torch.empty(B, C, P, **f32))   # dx of successive steps alternate
         Kp3 = E.round_up(9 * C, 64)
         dpm = torch.empty(M * Kp3, dtype=dt, device=dev)
-        dh = torch.empty(M * F, **f32)
+        dh = torch.empty(M * F, dtype=dt, device=dev)
         dpre = torch.empty(M * F, dtype=dt, device=dev)
         dA1 = torch.empty(M * K1p, **f32)
         an_part = torch.empty(n_cta * 2 * F, **f32)
@@ -295,22 +297,19 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             bc = _pack_bwd(cp, dt)
             N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3, dpar3,
                            B, C, h, w)
-            N.reduce_rows(dpar3, sink.get(zc.bias), B, C, 2 * C)
-            N.reduce_rows(dpar3[C:], sink.get(zc.logs), B, C, 2 * C)
+            N.reduce_rows2(dpar3, sink.get(zc.bias), sink.get(zc.logs), B, C, C, 2 * C)
             # ZeroConv 3x3: weight gradient in the taps-as-N layout, then back to [C, F, 3, 3]
             N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws)
             N.pack_matrix(d3, sink.get(zc.weight), C, F, 9, F, 1, C * F, 9, C * F)
             N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
             # second Conv2dActNorm (1x1)
             N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
-            N.reduce_rows(an_part, sink.get(an2.scale), n_cta, F, 2 * F)
-            N.reduce_rows(an_part[F:], sink.get(an2.bias), n_cta, F, 2 * F)
+            N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_cta, F, F, 2 * F)
             N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws)
             N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
             # first Conv2dActNorm (3x3)
             N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
-            N.reduce_rows(an_part, sink.get(an1.scale), n_cta, F, 2 * F)
-            N.reduce_rows(an_part[F:], sink.get(an1.bias), n_cta, F, 2 * F)
+            N.reduce_rows2(an_part, sink.get(an1.scale), sink.get(an1.bias), n_cta, F, F, 2 * F)
             N.gemm_tn(dpre, F, lv.A1[k], K1p, d1, M, F, K1p, ws)
             _strip_cols(d1, sink.get(conv1.weight), F, K1p, Ch * 9)
             N.gemm_nt(dpre, F, bc.w1t, F, dA1, K1p, M, K1p, F)
@@ -384,13 +383,22 @@ class GlowTransformFn(torch.autograd.Function):
         ctx.stash = None
         ctx.params = None
         glow._last_grad_flat = sink.flat                   # contiguous view of all gradients of this step
+        # Parameters whose .grad is empty receive their slice of the flat buffer DIRECTLY (no AccumulateGrad copy: 700+
+        # small kernels per step otherwise); a parameter that already holds a gradient gets the usual accumulation.
         pg = []
         for p in params:
+            if not p.requires_grad:
+                pg.append(None)
+                continue
             untouched = id(p) not in sink.written
             g = sink.get(p)
             if untouched:
                 g.zero_()
-            pg.append(g)
+            if p.grad is None and DIRECT_GRADS:
+                p.grad = g
+                pg.append(None)
+            else:
+                pg.append(g)
         del sink
         return (None, dx, g_ld, g_lp) + tuple(pg)
 

@@ -163,3 +163,38 @@ def test_adam_steps_track_the_oracle(monkeypatch):
         opt_o.step()
         assert abs(float(loss) - float(lo)) < 2e-4, (it, float(loss), float(lo))
     assert float(loss) < 1e9
+
+
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (True, 1e-2)])
+def test_fused_clip_adam_matches_torch(decoupled, wd):
+    """FusedClipAdam.step() == clip_grad_value_(1) + clip_grad_norm_(1) + torch Adam/AdamW step (trainer.py:165-167,
+    utils.py:120-137) on identical gradients: parameters, moments and the in-place clipped gradients."""
+    rng = np.random.default_rng(3)
+    shapes = [(512, 6, 3, 3), (512, 1, 1), (12, 12, 1, 1), (5000,), (1, 7, 1, 1), (3,), (96, 96, 3, 3)]
+    ps = [torch.nn.Parameter(torch.from_numpy(rng.standard_normal(s).astype(np.float32)).to(DEV)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    n_clip = 5                                  # the last two tensors play the prior's parameters: not clipped
+    opt = nf.FusedClipAdam(ps, lr=1e-3, weight_decay=wd, decoupled_weight_decay=decoupled, clip_params=ps[:n_clip])
+    ref = (torch.optim.AdamW(qs, lr=1e-3, weight_decay=wd) if decoupled else torch.optim.Adam(qs, lr=1e-3))
+    for it in range(4):
+        scale = [5.0, 0.01, 1.0, 0.3][it]       # exercise both clips, then neither
+        for p, q in zip(ps, qs):
+            g = torch.from_numpy((scale * rng.standard_normal(tuple(p.shape))).astype(np.float32)).to(DEV)
+            p.grad, q.grad = g.clone(), g.clone()
+        v0 = ps[0]._version
+        opt.step()
+        assert ps[0]._version > v0
+        torch.nn.utils.clip_grad_value_(qs[:n_clip], 1.0)
+        total = torch.nn.utils.clip_grad_norm_(qs[:n_clip], 1.0)
+        ref.step()
+        assert abs(float(opt.grad_norm) - float(total)) <= 1e-5 * float(total)
+        for p, q in zip(ps, qs):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-8)
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), float((p - q).abs().max())
+            assert torch.allclose(opt.state[p]["exp_avg"], ref.state[q]["exp_avg"], rtol=1e-5, atol=1e-8)
+            assert torch.allclose(opt.state[p]["exp_avg_sq"], ref.state[q]["exp_avg_sq"], rtol=2e-5, atol=1e-10)
+    assert float(opt.state[ps[0]]["step"]) == 4.0
+    # a torch Adam state_dict loads into the fused optimiser
+    opt2 = nf.FusedClipAdam(ps, lr=1e-3)
+    opt2.load_state_dict(ref.state_dict())
+    assert torch.allclose(opt2.state[ps[3]]["exp_avg"], ref.state[qs[3]]["exp_avg"])
