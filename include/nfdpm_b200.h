@@ -114,6 +114,13 @@ int nfdpm_im2col3x3(const float* x, void* out, int out_dtype, int B, int Cin, in
 int nfdpm_pack_matrix(const float* in, void* out, int out_dtype, int na, int nb, int nk, int64_t sa, int64_t sb,
                       int64_t sk, int64_t ld_out, int rows_out, nfdpm_stream_t stream);
 
+/* nfdpm_pack_matrix for MANY matrices in one launch (all weight layouts of all StepFlows after an optimiser step).
+ * jobs_dev: device table of 10 x int64 per job: in, out, sa, sb, sk, ld_out, na|nb<<32, nk|rows_out<<32,
+ * out_dtype|first_block<<32, nk2|sk2<<32 (column k reads offset (k/nk2)*sk + (k%nk2)*sk2; nk2 = 1 is the plain form).
+ * Job i owns blocks [first_block_i, first_block_{i+1}), ceil(rows_out*ld_out / nfdpm_pack_elems()) of them. */
+int nfdpm_pack_elems(void);
+int nfdpm_pack_batch(const int64_t* jobs_dev, int n_jobs, int n_blocks, nfdpm_stream_t stream);
+
 /* D[M,N] = epilogue(A[M,K] * Bw[N,K]^T).  A, Bw: in_dtype (NFDPM_F32 -> CUDA-core fp32 kernel,
  * NFDPM_BF16 -> tcgen05/TMEM kernel, fp32 accumulate); D: out_dtype (F32 or BF16).  K must be a multiple
  * of 16 (F32) / 64 (BF16) and lda, ldb, ldd multiples of 8.  Replaces nn.Conv2d.forward at

@@ -64,6 +64,48 @@ __global__ void pack_matrix_kernel(const float* __restrict__ in, T* __restrict__
   }
 }
 
+// Batched pack: every weight layout of every StepFlow in ONE launch (the parameters change once per optimiser step; 7
+// separate packs per StepFlow were ~440 launches per training step).  jobs: device table, 10 x int64 per job:
+//   [0] in  [1] out  [2] sa  [3] sb  [4] sk  [5] ld_out  [6] na | nb<<32  [7] nk | rows_out<<32
+//   [8] out_dtype | first_block<<32  [9] nk2 | sk2<<32   (column k -> (k / nk2)*sk + (k % nk2)*sk2; nk2 = 1: plain)
+constexpr int PACK_ELEMS = 4096;
+__global__ void __launch_bounds__(256) pack_batch_kernel(const int64_t* __restrict__ jobs, int n_jobs) {
+  __shared__ int s_job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_jobs - 1;                       // last job whose first_block <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int)(jobs[mid * 10 + 8] >> 32) <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_job = lo;
+  }
+  __syncthreads();
+  const int64_t* j = jobs + (int64_t)s_job * 10;
+  const float* in = reinterpret_cast<const float*>(j[0]);
+  const int64_t sa = j[2], sb = j[3], sk = j[4], ld = j[5];
+  const int na = (int)(j[6] & 0xffffffff), nb = (int)(j[6] >> 32);
+  const int nk = (int)(j[7] & 0xffffffff), rows_out = (int)(j[7] >> 32);
+  const int dtype = (int)(j[8] & 0xffffffff), first = (int)(j[8] >> 32);
+  const int nk2 = (int)(j[9] & 0xffffffff);
+  const int64_t sk2 = j[9] >> 32;
+  const int64_t n = (int64_t)rows_out * ld;
+  const int64_t base = (int64_t)(blockIdx.x - first) * PACK_ELEMS;
+  for (int e = threadIdx.x; e < PACK_ELEMS; e += 256) {
+    const int64_t i = base + e;
+    if (i >= n) break;
+    const int64_t r = i / ld;
+    const int k = (int)(i - r * ld);
+    float v = 0.f;
+    if (r < (int64_t)na * nb && k < nk) {
+      const int a = (int)(r / nb), b = (int)(r - (int64_t)a * nb);
+      const int k1 = k / nk2, k2 = k - k1 * nk2;
+      v = __ldg(in + a * sa + b * sb + k1 * sk + k2 * sk2);
+    }
+    if (dtype == NFDPM_F32) reinterpret_cast<float*>(j[1])[i] = v;
+    else reinterpret_cast<__nv_bfloat16*>(j[1])[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // Tile geometry shared by the per-pixel kernels: CTA `blockIdx.x` owns up to TPB consecutive flattened pixels.
 //   P >  TPB: grid = B * T, T = ceil(P/TPB); CTA (b, t) owns pixels [t*TPB, min(P,(t+1)*TPB)) of image b
 //   P <= TPB: grid = ceil(B / ipc), ipc = TPB / P whole images per CTA
@@ -294,6 +336,15 @@ extern "C" int nfdpm_pack_matrix(const float* in, void* out, int out_dtype, int 
   else
     return fail("nfdpm_pack_matrix: out_dtype %d unsupported", out_dtype);
   NFDPM_CHECK_LAUNCH("pack_matrix_kernel");
+  return 0;
+}
+
+extern "C" int nfdpm_pack_elems(void) { return PACK_ELEMS; }
+
+extern "C" int nfdpm_pack_batch(const int64_t* jobs_dev, int n_jobs, int n_blocks, nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(jobs_dev && n_jobs > 0 && n_blocks > 0, "nfdpm_pack_batch: bad arguments");
+  pack_batch_kernel<<<n_blocks, 256, 0, as_stream(stream)>>>(jobs_dev, n_jobs);
+  NFDPM_CHECK_LAUNCH("pack_batch_kernel");
   return 0;
 }
 

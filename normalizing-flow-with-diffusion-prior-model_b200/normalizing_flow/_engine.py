@@ -213,6 +213,77 @@ def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3:
     cache.key = key
 
 
+class PackPlan:
+    """All weight layouts of all coupling networks of one Glow (forward operands, and the transposed dgrad operands
+    when ``train``) refreshed by ONE nfdpm_pack_batch launch whenever a parameter changed — instead of 3 (+4)
+    nfdpm_pack_matrix launches per StepFlow."""
+
+    def __init__(self, steps, dt: torch.dtype, train: bool):
+        import numpy as np
+        from . import _train as T
+        self.dt, self.train = dt, train
+        self.weights, self.marks, jobs = [], [], []
+        code = N.F32 if dt == torch.float32 else N.BF16
+        pe = N.pack_elems()
+        blocks = 0
+
+        def job(src, out, na, nb, nk, sa, sb, sk, ld, rows, nk2=1, sk2=0, out_code=code):
+            nonlocal blocks
+            jobs.append([src.data_ptr(), out.data_ptr(), sa, sb, sk, ld, na | (nb << 32), nk | (rows << 32),
+                         out_code | (blocks << 32), nk2 | (sk2 << 32)])
+            blocks += (rows * ld + pe - 1) // pe
+
+        for s in steps:
+            cp = s.affcoupling
+            conv1, _, conv2, _, zc = cp._parts()
+            w1, w2, w3 = conv1.weight, conv2.weight, zc.weight
+            F, Ch, C = w1.shape[0], w1.shape[1], w3.shape[0]
+            dev = w1.device
+            K1, K1p, ldp, Kp3 = Ch * 9, round_up(Ch * 9, 64), round_up(9 * C, 16), round_up(9 * C, 64)
+            c = cp._cache
+            if c.w1 is None or c.w1.dtype != dt or c.w1.numel() != F * K1p:
+                _bump_epoch()
+                c.w1 = torch.empty(F * K1p, dtype=dt, device=dev)
+                c.w3 = torch.empty(ldp * F, dtype=dt, device=dev)
+                c.w2 = torch.empty(F * F, dtype=dt, device=dev) if dt != torch.float32 else None
+            c.K1, c.K1p, c.ldp = K1, K1p, ldp
+            job(w1, c.w1, 1, F, K1, 0, K1, 1, K1p, F)
+            if dt != torch.float32:
+                job(w2, c.w2, 1, F, F, 0, F, 1, F, F)
+            job(w3, c.w3, 9, C, F, 1, F * 9, 9, F, ldp)
+            caches = [c]
+            if train:
+                b = getattr(cp, "_bwd_cache", None)
+                if b is None:
+                    b = cp._bwd_cache = T._BwdCache()
+                if b.w1t is None or b.w1t.dtype != dt:
+                    b.w1t = torch.empty(K1p * F, dtype=dt, device=dev)
+                    b.w2t = torch.empty(F * F, dtype=dt, device=dev)
+                    b.w3t = torch.empty(F * Kp3, dtype=dt, device=dev)
+                b.Kp3 = Kp3
+                job(w1, b.w1t, K1, 1, F, 1, 0, K1, F, K1p)
+                job(w2, b.w2t, F, 1, F, 1, 0, F, F, F)
+                # w3t[ci, tap*C + co] = W3[co, ci, tap]: two-level column index (tap, co)
+                job(w3, b.w3t, F, 1, 9 * C, 9, 0, 1, Kp3, F, nk2=C, sk2=F * 9)
+                caches.append(b)
+            self.weights += [w1, w2, w3]
+            self.marks.append((caches, (w1, w2, w3)))
+        self.n_jobs, self.n_blocks = len(jobs), blocks
+        self.table = torch.tensor(np.asarray(jobs, dtype=np.int64).reshape(-1), device=self.weights[0].device)
+        self.key = None
+
+    def refresh(self) -> None:
+        key = _vkey(*self.weights)
+        if cache_hit(self.key, key):
+            return
+        N.pack_batch(self.table, self.n_jobs, self.n_blocks)
+        self.key = key
+        for caches, ws in self.marks:
+            k = (_vkey(*ws), self.dt)
+            for c in caches:
+                c.key = k
+
+
 def coupling_dtype() -> torch.dtype:
     return torch.float32 if precision() == "fp32" else torch.bfloat16
 

@@ -74,6 +74,8 @@ def _load() -> C.CDLL:
         "nfdpm_actnorm_relu_bwd": ([vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_reduce_rows2": ([vp, vp, vp, i32, i32, i32, i64, vp], C.c_int),
         "nfdpm_opt_chunk": ([], C.c_int),
+        "nfdpm_pack_elems": ([], C.c_int),
+        "nfdpm_pack_batch": ([vp, i32, i32, vp], C.c_int),
         "nfdpm_fused_clip_adam": ([vp, vp, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double,
                                    C.c_double, C.c_double, i32, vp], C.c_int),
         "nfdpm_reduce_rows": ([vp, vp, i32, i32, i64, i32, vp], C.c_int),
@@ -103,7 +105,7 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_coupling_bwd", "nfdpm_actnorm_relu_bwd", "nfdpm_reduce_rows", "nfdpm_mix_bwd", "nfdpm_mix_param_grad",
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
-           "nfdpm_opt_chunk", "nfdpm_fused_clip_adam"]
+           "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -304,3 +306,11 @@ def fused_clip_adam(refs, chunks, n_chunks, exp_avg, exp_avg_sq, partial, scal, 
                     weight_decay, decoupled) -> None:
     _ok(lib.nfdpm_fused_clip_adam(_p(refs), _p(chunks), n_chunks, _p(exp_avg), _p(exp_avg_sq), _p(partial), _p(scal),
                                   clip_value, max_norm, lr, beta1, beta2, eps, weight_decay, int(decoupled), _st()), 3)
+
+
+def pack_elems() -> int:
+    return int(lib.nfdpm_pack_elems())
+
+
+def pack_batch(jobs_dev, n_jobs, n_blocks) -> None:
+    _ok(lib.nfdpm_pack_batch(_p(jobs_dev), n_jobs, n_blocks, _st()))

@@ -109,6 +109,7 @@ def forward_train(glow, x: Tensor, with_logp: bool):
     E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
     K = glow.K
     dt = E.coupling_dtype()
+    glow._pack_plan(steps, dt, True).refresh()      # every forward / transposed weight layout in one launch
     st = Stash()
     st.B, st.with_logp, st.in_shape, st.dt = B, with_logp, (B, c, H, W), dt
     R_ld, R_lp = glow.L * K, glow.L - 1
@@ -124,7 +125,6 @@ def forward_train(glow, x: Tensor, with_logp: bool):
         first = flows[0].affcoupling
         conv1 = first._parts()[0]
         F = conv1.weight.shape[0]
-        E._pack_coupling(first._cache, *[m.weight for m in (first._parts()[0], first._parts()[2], first._parts()[4])], dt)
         K1p, ldp = first._cache.K1p, first._cache.ldp
         lv = _LevelStash()
         lv.C, lv.h, lv.w, lv.K1p, lv.ldp = C, h, w, K1p, ldp
@@ -142,7 +142,6 @@ def forward_train(glow, x: Tensor, with_logp: bool):
         for k, step in enumerate(flows):
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
-            E._pack_coupling(cp._cache, conv1.weight, conv2.weight, zc.weight, dt)
             cache = cp._cache
             N.gemm_nt(lv.A1[k], K1p, cache.w1, K1p, lv.h1[k], F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
             w2 = cache.w2 if dt != torch.float32 else conv2.weight
@@ -294,7 +293,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             step = flows[k]
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
-            bc = _pack_bwd(cp, dt)
+            bc = cp._bwd_cache                   # refreshed by the forward's PackPlan
             N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3, dpar3,
                            B, C, h, w)
             N.reduce_rows2(dpar3, sink.get(zc.bias), sink.get(zc.logs), B, C, C, 2 * C)

@@ -132,8 +132,18 @@ class Glow(Transform):
         self._graphs = {}
         self._plist = None
         self._pver = None
+        self._plans = {}
+
+    def _pack_plan(self, steps, dt, train: bool) -> "E.PackPlan":
+        """The batched weight-packing job table for (dtype, train); built once, dropped when the module moves."""
+        key = (dt, train)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = E.PackPlan(steps, dt, train)
+        return plan
 
     def _apply(self, fn, *a, **k):
+        self._plans = {}
         self._logdet_all = None
         self._cmul = {}
         self._drop_graphs()
@@ -165,10 +175,9 @@ class Glow(Transform):
         """Re-run LU/fold and weight packing for parameters that changed (outside any graph)."""
         E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
         dt = torch.float32 if E.precision() == "fp32" else torch.bfloat16
-        for s in steps:
-            conv1, _, conv2, _, zc = s.affcoupling._parts()
-            E._pack_coupling(s.affcoupling._cache, conv1.weight, conv2.weight, zc.weight, dt)
-            if dt == torch.bfloat16:
+        self._pack_plan(steps, dt, False).refresh()
+        if dt == torch.bfloat16 and E.fused_coupling_enabled():
+            for s in steps:
                 E.refresh_folded(s.affcoupling)
         for blk in self.blocks:
             E.refresh_split(blk.split, blk.flows[0]._C)
