@@ -194,6 +194,18 @@ int nfdpm_flow_boundary_stash(const float* in, int64_t in_bs, int squeeze_in, co
                               float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype, int64_t lda1,
                               int B, int C, int H, int W, nfdpm_stream_t stream);
 
+/* ZeroConv GEMM + step boundary in ONE launch (tensor-core mode): pm = h2[M,K] * w3p[ldp,K]^T is accumulated in tensor
+ * memory, staged in shared memory and consumed by the arithmetic of nfdpm_flow_boundary (coupling source), so the
+ * taps-as-N rows never reach L2/HBM.  Same reference lines as nfdpm_gemm_nt (utils.py:44) + nfdpm_flow_boundary.
+ * h2, w3p bf16; CTAs own whole images: needs H*W == 256 or H*W dividing 128, ldp <= 512 (nfdpm_gemm3_boundary_ok).
+ * pm_out (optional, fp32 [M, ld_pm_out]): copy of pm for the training stash; xs: pre-mix stash as in ..._stash. */
+int nfdpm_gemm3_boundary_ok(int B, int C, int H, int W, int K, int64_t ldp);
+int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p, float* pm_out, int64_t ld_pm_out, const float* in,
+                         int64_t in_bs, const float* bias3, const float* logs3, float* ld_part, const float* mt,
+                         const float* beta, float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype,
+                         int64_t lda1, int B, int C, int H, int W, int K, int64_t ldp, int inverse,
+                         nfdpm_stream_t stream);
+
 /* Layout converters for stand-alone ZeroConv2d / Conv2dActNorm module calls (normalizing_flow/utils.py:43-44, :68-69).
  *   rows_to_nchw: out[b,n,p] = f(h[(b*P+p)*ldh + n]); mode 0: identity; 1: (v+p1[n])*exp(3*p2[n]) (ZeroConv2d gain);
  *                 2: exp(p1[n])*(v+p2[n]) (ActNorm).   nchw_to_rows: rows[m, c] = x[b,c,p], columns Cc..ld-1 zero. */

@@ -1,4 +1,6 @@
 // Error plumbing and misc entry points of the C ABI.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nfdpm {
@@ -10,6 +12,14 @@ int fail(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return 1;
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NFDPM_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 }  // namespace nfdpm
 

@@ -38,6 +38,24 @@ int fail(const char* fmt, ...);
 static inline cudaStream_t as_stream(nfdpm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+bool pdl_enabled();   // env NFDPM_PDL (default on)
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute (PDL) when enabled
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // streaming 128-bit access: read-once / write-once tensors should not pollute L1
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;
@@ -51,6 +69,12 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
                "f"(v.w)
                : "memory");
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining; it must call pdl_wait() before touching global memory the predecessor writes (the call
+// returns once the predecessor grid has completed and flushed), and pdl_trigger() lets ITS successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

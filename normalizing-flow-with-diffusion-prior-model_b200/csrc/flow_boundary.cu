@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(1024) flow_boundary_kernel(const BoundaryArgs 
   float* ls_s = par_s + (COUPLING ? 2 * C : 0);                   // [P*Ch] log-det terms
   if (a.mt == nullptr) u_s = x_s;
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  pdl_trigger();      // PDL: the next kernel of the chain may be scheduled as soon as SMs free up ...
+  pdl_wait();         // ... and this one reads nothing before its predecessor has completed
 
   // ---- parameters
   if (a.mt != nullptr) {
@@ -254,7 +256,7 @@ static int flow_boundary_impl(const float* in, int64_t in_bs, int squeeze_in, co
                                       200 * 1024));                                                                \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    flow_boundary_kernel<CP, T><<<B, threads, smem, st>>>(a);                                                      \
+    NFDPM_CUDA(launch_pdl(flow_boundary_kernel<CP, T>, dim3(B), dim3(threads), smem, st, a));                      \
   } while (0)
   if (pm != nullptr) { if (bf) LAUNCH(true, __nv_bfloat16); else LAUNCH(true, float); }
   else { if (bf) LAUNCH(false, __nv_bfloat16); else LAUNCH(false, float); }

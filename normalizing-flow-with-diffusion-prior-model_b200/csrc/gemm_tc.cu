@@ -56,13 +56,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
   const int num_kb = K / TC_BK;
 
   const int n_pad = num_n * BN;        // columns covered by the tiles (>= N); parameters are zero beyond N
-  if (EPI == NFDPM_EPI_ACTNORM_RELU) {
-    for (int i = threadIdx.x; i < n_pad; i += TC_THREADS) {
-      const float e = (i < N) ? expf(ep_scale[i]) : 0.f;
-      s_ep[i] = e;                                   // y = max(0, e*acc + e*b)
-      s_ep[n_pad + i] = (i < N) ? e * ep_bias[i] : 0.f;
-    }
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -78,6 +71,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), 512);
+  // everything above overlaps the tail of the previous kernel in the stream (PDL); global memory is touched below
+  pdl_trigger();
+  pdl_wait();
+  if (EPI == NFDPM_EPI_ACTNORM_RELU) {
+    for (int i = threadIdx.x; i < n_pad; i += TC_THREADS) {
+      const float e = (i < N) ? expf(ep_scale[i]) : 0.f;
+      s_ep[i] = e;                                   // y = max(0, e*acc + e*b)
+      s_ep[n_pad + i] = (i < N) ? e * ep_bias[i] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -215,8 +218,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                                     220 * 1024));
     attr_set = true;
   }
-  gemm_nt_tc_kernel<EPI, OutT><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmD, M, N, K, BN, es, eb);
-  NFDPM_CHECK_LAUNCH("gemm_nt_tc_kernel");
+  NFDPM_CUDA(launch_pdl(gemm_nt_tc_kernel<EPI, OutT>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, tmD, M, N, K, BN,
+                        es, eb));
   return 0;
 }
 

@@ -346,6 +346,53 @@ def coupling_gemms(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int) -> Tupl
     return pm, ldp
 
 
+def fused_g3_enabled() -> bool:
+    return os.environ.get("NFDPM_FUSED_G3", "1") != "0"
+
+
+def fused_g3_ok(B: int, C: int, H: int, W: int, F: int, ldp: int) -> bool:
+    """Use nfdpm_gemm3_boundary?  Measured in situ (tools/bench_levels.py, profiles/): with ONE image per CTA
+    (16x16 images: 128 CTAs) it beats GEMM3 + boundary (54.6 vs 61.4 us per StepFlow chain); at the deeper levels a
+    128-row tile holds 2..8 images, only 64 / 16 CTAs exist and the separate kernels win — so only H*W == 256 takes it
+    unless NFDPM_FUSED_G3=all."""
+    v = os.environ.get("NFDPM_FUSED_G3", "1")
+    if v == "0" or not N.gemm3_boundary_ok(B, C, H, W, F, ldp):
+        return False
+    return v == "all" or H * W == 256
+
+
+def coupling_boundary(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int, src, src_bs, ld_part, mt, beta, y, y_bs,
+                      a1_next, lda1_next, inverse: bool, pm_out=None, xs=None) -> None:
+    """One StepFlow's coupling network + everything up to the next network's first GEMM:
+    GEMM1 -> GEMM2 -> [GEMM3 + coupling + next mix + sinks].  In tensor-core mode the bracketed part is ONE kernel
+    (nfdpm_gemm3_boundary: the ZeroConv output stays in tensor/shared memory); otherwise GEMM3 and
+    nfdpm_flow_boundary run separately."""
+    conv1, an1, conv2, an2, zc = cp._parts()
+    F = conv1.weight.shape[0]
+    dt = A1.dtype
+    cache = cp._cache
+    dev = A1.device
+    M = B * H * W
+    K1p, ldp = cache.K1p, cache.ldp
+    fused = dt == torch.bfloat16 and not fused_coupling_enabled() and fused_g3_ok(B, C, H, W, F, ldp)
+    if not fused:
+        if pm_out is None:
+            pm, _ = coupling_gemms(cp, A1, B, C, H, W)
+        else:
+            raise RuntimeError("coupling_boundary: the training stash path needs the fused kernel or explicit GEMMs")
+        if xs is None:
+            N.flow_boundary(src, src_bs, False, pm, ldp, zc.bias, zc.logs, ld_part, mt, beta, y, y_bs, a1_next,
+                            lda1_next, B, C, H, W, inverse)
+        return
+    h1 = WS.get("h1", M * F, dt, dev)
+    N.gemm_nt(A1, K1p, cache.w1, K1p, h1, F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
+    h2 = WS.get("h2", M * F, dt, dev)
+    N.gemm_nt(h1, F, cache.w2, F, h2, F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
+    N.gemm3_boundary(h2, F, cache.w3, pm_out, ldp if pm_out is not None else 0, src, src_bs, zc.bias, zc.logs, ld_part,
+                     mt, beta, y, y_bs, xs, (C * H * W) if xs is not None else 0, a1_next, lda1_next, B, C, H, W, F, ldp,
+                     inverse)
+
+
 def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int, init: bool = False) -> Tuple[torch.Tensor, int]:
     """Run the coupling network of AffineCoupling ``cp`` on the first C/2 channels of ``y`` ([B,C,P], batch
     stride ``ybs``).  Returns (pm, ldp): the taps-as-N ZeroConv rows consumed by nfdpm_coupling_apply.

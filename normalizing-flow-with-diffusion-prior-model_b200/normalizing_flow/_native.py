@@ -73,6 +73,9 @@ def _load() -> C.CDLL:
                                        i32, i32, vp], C.c_int),
         "nfdpm_actnorm_relu_bwd": ([vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_reduce_rows2": ([vp, vp, vp, i32, i32, i32, i64, vp], C.c_int),
+        "nfdpm_gemm3_boundary_ok": ([i32, i32, i32, i32, i32, i64], C.c_int),
+        "nfdpm_gemm3_boundary": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
+                                  i32, i32, i32, i64, i32, vp], C.c_int),
         "nfdpm_opt_chunk": ([], C.c_int),
         "nfdpm_pack_elems": ([], C.c_int),
         "nfdpm_pack_batch": ([vp, i32, i32, vp], C.c_int),
@@ -105,7 +108,8 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_coupling_bwd", "nfdpm_actnorm_relu_bwd", "nfdpm_reduce_rows", "nfdpm_mix_bwd", "nfdpm_mix_param_grad",
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
-           "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch"]
+           "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch",
+           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -314,3 +318,14 @@ def pack_elems() -> int:
 
 def pack_batch(jobs_dev, n_jobs, n_blocks) -> None:
     _ok(lib.nfdpm_pack_batch(_p(jobs_dev), n_jobs, n_blocks, _st()))
+
+
+def gemm3_boundary_ok(B, Cc, H, W, K, ldp) -> bool:
+    return bool(lib.nfdpm_gemm3_boundary_ok(B, Cc, H, W, K, ldp))
+
+
+def gemm3_boundary(h2, ldh, w3p, pm_out, ld_pm_out, src, src_bs, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1,
+                   lda1, B, Cc, H, W, K, ldp, inverse) -> None:
+    _ok(lib.nfdpm_gemm3_boundary(_p(h2), ldh, _p(w3p), _p(pm_out), ld_pm_out, _p(src), src_bs, _p(bias3), _p(logs3),
+                                 _p(ld_part), _p(mt), _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1),
+                                 _dt(a1) if a1 is not None else F32, lda1, B, Cc, H, W, K, ldp, int(inverse), _st()))

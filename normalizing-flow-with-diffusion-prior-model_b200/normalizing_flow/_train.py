@@ -136,6 +136,7 @@ def forward_train(glow, x: Tensor, with_logp: bool):
         lv.h2 = torch.empty(K, M, F, dtype=dt, device=dev)
         lv.pm = torch.empty(K, M, ldp, **f32)
         lv.state_out = torch.empty(B, C, h, w, **f32)
+        fused_g3 = dt == torch.bfloat16 and E.fused_g3_ok(B, C, h, w, F, ldp)
         # level entry: squeeze + stash x_0 + K-A of step 0 + im2col
         N.flow_boundary_stash(cur, cur_bs, True, None, 0, None, None, None, flows[0]._mix.fwd_mt, flows[0]._mix.fwd_beta,
                               lv.u[0], C * P, lv.x[0], C * P, lv.A1[0], K1p, B, C, h, w)
@@ -146,15 +147,21 @@ def forward_train(glow, x: Tensor, with_logp: bool):
             N.gemm_nt(lv.A1[k], K1p, cache.w1, K1p, lv.h1[k], F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
             w2 = cache.w2 if dt != torch.float32 else conv2.weight
             N.gemm_nt(lv.h1[k], F, w2, F, lv.h2[k], F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
-            N.gemm_nt(lv.h2[k], F, cache.w3, F, lv.pm[k], ldp, M, ldp, F)
-            if k + 1 < K:
-                nxt = flows[k + 1]
-                N.flow_boundary_stash(lv.u[k], C * P, False, lv.pm[k], ldp, zc.bias, zc.logs, ld_part[row * B:],
-                                      nxt._mix.fwd_mt, nxt._mix.fwd_beta, lv.u[k + 1], C * P, lv.x[k + 1], C * P,
-                                      lv.A1[k + 1], K1p, B, C, h, w)
+            nxt = flows[k + 1] if k + 1 < K else None
+            mt, beta = (nxt._mix.fwd_mt, nxt._mix.fwd_beta) if nxt is not None else (None, None)
+            y = lv.u[k + 1] if nxt is not None else lv.state_out
+            xs = lv.x[k + 1] if nxt is not None else None
+            a1n = lv.A1[k + 1] if nxt is not None else None
+            if fused_g3:
+                # ZeroConv GEMM + coupling + next mix + sinks in one kernel; pm is also written out for the backward
+                N.gemm3_boundary(lv.h2[k], F, cache.w3, lv.pm[k], ldp, lv.u[k], C * P, zc.bias, zc.logs,
+                                 ld_part[row * B:], mt, beta, y, C * P, xs, C * P if xs is not None else 0, a1n,
+                                 K1p if a1n is not None else 0, B, C, h, w, F, ldp, False)
             else:
+                N.gemm_nt(lv.h2[k], F, cache.w3, F, lv.pm[k], ldp, M, ldp, F)
                 N.flow_boundary_stash(lv.u[k], C * P, False, lv.pm[k], ldp, zc.bias, zc.logs, ld_part[row * B:],
-                                      None, None, lv.state_out, C * P, None, 0, None, 0, B, C, h, w)
+                                      mt, beta, y, C * P, xs, C * P if xs is not None else 0, a1n,
+                                      K1p if a1n is not None else 0, B, C, h, w)
             row += 1
         st.levels.append(lv)
         if split is None:

@@ -271,22 +271,59 @@ class Glow(Transform):
                 x_static = torch.empty_like(x)
             x_static.copy_(x)
 
+            nsub = self._n_sub(B)
+            Bs = B // nsub
+
             def build():
-                lat, ld_part, R_ld, lp_part, R_lp = self._transform_core(x_static, logp is not None, levels, slots, steps, True)
-                return {"x": x_static, "lat": lat, "ld_part": ld_part, "R_ld": R_ld, "lp_part": lp_part, "R_lp": R_lp}
+                # images are independent: sub-batches run on concurrent streams inside the graph, so that the deep
+                # levels (few rows per kernel, < 148 CTAs) of one sub-batch overlap with kernels of the other
+                parts = self._fork_join(nsub, lambda i: self._transform_core(
+                    x_static[i * Bs:(i + 1) * Bs], logp is not None, levels, slots, steps, True))
+                return {"x": x_static, "parts": parts}
             ent = self._graph_entry(key, build)
             if ent["x"] is not x_static:              # entry was (re)built around another buffer
                 ent["x"].copy_(x)
             ent["graph"].replay()
             N.launch_count += ent["n_launch"]
-            latents = [t.clone() for t in ent["lat"]]
-            ld_part, R_ld, lp_part, R_lp = ent["ld_part"], ent["R_ld"], ent["lp_part"], ent["R_lp"]
-        else:
-            latents, ld_part, R_ld, lp_part, R_lp = self._transform_core(x, logp is not None, levels, slots, steps, ready)
+            parts = ent["parts"]
+            latents = [torch.cat([p[0][j] for p in parts]) if nsub > 1 else parts[0][0][j].clone()
+                       for j in range(len(parts[0][0]))]
+            cm = self._multipliers(H, W, dev)
+            for i, (_, ld_part, R_ld, lp_part, R_lp) in enumerate(parts):
+                N.accumulate(log_det_jac[i * Bs:(i + 1) * Bs], ld_part, R_ld, Bs, slots, cm, self.L * self.K)
+                if logp is not None and R_lp > 0:
+                    N.accumulate(logp[i * Bs:(i + 1) * Bs], lp_part, R_lp, Bs)
+            return latents, log_det_jac, logp
+        latents, ld_part, R_ld, lp_part, R_lp = self._transform_core(x, logp is not None, levels, slots, steps, ready)
         N.accumulate(log_det_jac, ld_part, R_ld, B, slots, self._multipliers(H, W, dev), self.L * self.K)
         if logp is not None and R_lp > 0:
             N.accumulate(logp, lp_part, R_lp, B)
         return latents, log_det_jac, logp
+
+    # ---- concurrent sub-batches inside a captured graph
+    def _n_sub(self, B: int) -> int:
+        # measured (profiles/): with batch 128 two concurrent sub-batches are 6% SLOWER than one stream (the deep-level
+        # kernels are latency-, not occupancy-bound), so the default is one stream; the knob stays for large batches
+        n = int(os.environ.get("NFDPM_STREAMS", "1"))
+        if n <= 1 or B % n != 0 or B // n < 16:
+            return 1
+        return n
+
+    def _fork_join(self, n: int, fn):
+        if n == 1:
+            return [fn(0)]
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_streams", None) is None or len(self._streams) < n:
+            self._streams = [torch.cuda.Stream() for _ in range(n)]
+        out = []
+        for i in range(n):
+            s = self._streams[i]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                out.append(fn(i))
+        for i in range(n):
+            cur.wait_stream(self._streams[i])
+        return out
 
     def _transform_autograd(self, x, log_det_jac, logp, levels, slots, steps, ready):
         """Training path (reference trainer.py:155-164): forward with activation stash, hand-written backward kernels
@@ -390,15 +427,20 @@ class Glow(Transform):
                     raise ValueError(f"latent has shape {tuple(t.shape)}, expected {tuple(s_.shape)}")
                 s_.copy_(t)
 
+            nsub = self._n_sub(B)
+            Bs = B // nsub
+
             def build():
-                return {"lat": statics, "out": self._invert_core(statics, temperature, levels, slots, steps, True)}
+                outs = self._fork_join(nsub, lambda i: self._invert_core(
+                    [t[i * Bs:(i + 1) * Bs] for t in statics], temperature, levels, slots, steps, True))
+                return {"lat": statics, "outs": outs}
             ent = self._graph_entry(key, build)
             if ent["lat"] is not statics:
                 for s_, t in zip(ent["lat"], lat_in):
                     s_.copy_(t)
             ent["graph"].replay()
             N.launch_count += ent["n_launch"]
-            return ent["out"].clone()
+            return torch.cat(ent["outs"]) if nsub > 1 else ent["outs"][0].clone()
         return self._invert_core(latents, temperature, levels, slots, steps, ready)
 
     def _transform_fast(self, x: Tensor, with_logp: bool, levels, slots, steps):
@@ -425,16 +467,15 @@ class Glow(Transform):
                             st, C * P, A1, K1p, B, C, h, w, False)
             for k, step in enumerate(flows):
                 cp = step.affcoupling
-                zc = cp.net[4]
-                pm, ldp = E.coupling_gemms(cp, A1, B, C, h, w)
                 nxt = flows[k + 1] if k + 1 < len(flows) else None
                 if nxt is not None:
-                    A1, K1p = E.coupling_a1(nxt.affcoupling, B, C, h, w, dev)
-                    N.flow_boundary(st, C * P, False, pm, ldp, zc.bias, zc.logs, ld_part[row * B:], nxt._mix.fwd_mt,
-                                    nxt._mix.fwd_beta, st, C * P, A1, K1p, B, C, h, w, False)
+                    A1n, K1p = E.coupling_a1(nxt.affcoupling, B, C, h, w, dev)     # same scratch buffer as A1
+                    E.coupling_boundary(cp, A1, B, C, h, w, st, C * P, ld_part[row * B:], nxt._mix.fwd_mt,
+                                        nxt._mix.fwd_beta, st, C * P, A1n, K1p, False)
+                    A1 = A1n
                 else:
-                    N.flow_boundary(st, C * P, False, pm, ldp, zc.bias, zc.logs, ld_part[row * B:], None, None,
-                                    st, C * P, None, 0, B, C, h, w, False)
+                    E.coupling_boundary(cp, A1, B, C, h, w, st, C * P, ld_part[row * B:], None, None, st, C * P,
+                                        None, 0, False)
                 row += 1
             if split is None:
                 latents.append(st)
@@ -463,15 +504,14 @@ class Glow(Transform):
             for k in range(len(flows) - 1, -1, -1):
                 step = flows[k]
                 cp = step.affcoupling
-                zc = cp.net[4]
-                pm, ldp = E.coupling_gemms(cp, A1, B, C, h, w)
                 if k > 0:
-                    A1, K1p = E.coupling_a1(flows[k - 1].affcoupling, B, C, h, w, dev)
-                    N.flow_boundary(src, C * P, False, pm, ldp, zc.bias, zc.logs, None, step._mix.inv_mt,
-                                    step._mix.inv_beta, st, C * P, A1, K1p, B, C, h, w, True)
+                    A1n, K1p = E.coupling_a1(flows[k - 1].affcoupling, B, C, h, w, dev)
+                    E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
+                                        st, C * P, A1n, K1p, True)
+                    A1 = A1n
                 else:
-                    N.flow_boundary(src, C * P, False, pm, ldp, zc.bias, zc.logs, None, step._mix.inv_mt,
-                                    step._mix.inv_beta, st, C * P, None, 0, B, C, h, w, True)
+                    E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
+                                        st, C * P, None, 0, True)
                 src = st
             if li == 0:
                 out = torch.empty(B, C // 4, h * 2, w * 2, dtype=torch.float32, device=dev)

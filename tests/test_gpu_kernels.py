@@ -493,3 +493,69 @@ def test_gemm_tn_cuda_core(dta, dtb):
     sync()
     ref = A[:, :N1].double().T @ B.double()
     assert float((D.view(N1, N2).double() - ref).norm() / ref.norm()) < 1e-5
+
+
+# ------------------------------------------------------------------ ZeroConv GEMM + step boundary in one kernel
+@pytest.mark.parametrize("B,C,H,W", [(5, 12, 16, 16), (3, 4, 16, 16), (5, 24, 8, 8), (4, 8, 8, 8), (11, 48, 4, 4),
+                                     (8, 16, 4, 4), (6, 32, 4, 2)])
+@pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16])
+def test_gemm3_boundary_equals_gemm_plus_boundary(B, C, H, W, a1_dt):
+    """nfdpm_gemm3_boundary == nfdpm_gemm_nt (bf16 tcgen05, fp32 out) -> nfdpm_flow_boundary_stash: every sink
+    (state, pre-mix stash, im2col rows, log-det partials, pm copy), forward and inverse, with and without the next mix;
+    B deliberately not a multiple of the images-per-CTA count."""
+    P, Ch, F = H * W, C // 2, 512
+    ldp = (9 * C + 15) // 16 * 16
+    lda = (9 * Ch + 63) // 64 * 64
+    M = B * P
+    assert N.gemm3_boundary_ok(B, C, H, W, F, ldp)
+    x = rnd(B, C, H, W, seed=1).cuda()
+    h2 = (rnd(M, F, seed=2).cuda().clamp_min(0) * 0.5).to(torch.bfloat16)
+    w3 = (rnd(ldp, F, seed=3, scale=0.02).cuda()).to(torch.bfloat16)
+    w3[9 * C:] = 0
+    bias3, logs3 = rnd(C, seed=4, scale=0.1).cuda(), rnd(C, seed=5, scale=0.1).cuda()
+    mt, beta = rnd(C, C, seed=6, scale=0.4).cuda(), rnd(C, seed=7).cuda()
+    pm_ref = torch.empty(M, ldp, device=DEV)
+    N.gemm_nt(h2, F, w3, F, pm_ref, ldp, M, ldp, F)
+    for inverse in (False, True):
+        for with_mix in (True, False):
+            m_, b_ = (mt, beta) if with_mix else (None, None)
+            y_ref, xs_ref = torch.empty_like(x), torch.empty_like(x)
+            a_ref = torch.full((M, lda), 3.0, dtype=a1_dt, device=DEV) if with_mix else None
+            part_ref = torch.zeros(B, device=DEV)
+            if inverse:
+                N.flow_boundary(x, C * P, False, pm_ref, ldp, bias3, logs3, None, m_, b_, y_ref, C * P, a_ref,
+                                lda if with_mix else 0, B, C, H, W, True)
+            else:
+                N.flow_boundary_stash(x, C * P, False, pm_ref, ldp, bias3, logs3, part_ref, m_, b_, y_ref, C * P, xs_ref,
+                                      C * P, a_ref, lda if with_mix else 0, B, C, H, W)
+            y, xs = torch.empty_like(x), torch.empty_like(x)
+            a1 = torch.full((M, lda), 5.0, dtype=a1_dt, device=DEV) if with_mix else None
+            part = torch.zeros(B, device=DEV)
+            pm_out = torch.full((M, ldp), float("nan"), device=DEV)
+            N.gemm3_boundary(h2, F, w3, pm_out, ldp, x, C * P, bias3, logs3, None if inverse else part, m_, b_, y, C * P,
+                             None if inverse else xs, 0 if inverse else C * P, a1, lda if with_mix else 0, B, C, H, W, F,
+                             ldp, inverse)
+            sync()
+            assert torch.equal(pm_out, pm_ref)
+            assert torch.allclose(y, y_ref, rtol=1e-6, atol=1e-6), float((y - y_ref).abs().max())
+            if with_mix:
+                assert torch.allclose(a1.float(), a_ref.float(), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-6, atol=1e-6)
+            if not inverse:
+                assert torch.allclose(xs, xs_ref, rtol=1e-6, atol=1e-6)
+                assert torch.allclose(part, part_ref, rtol=1e-6, atol=1e-5)
+    # in place (y aliases the source), as Glow.transform runs it
+    xin = x.clone()
+    N.gemm3_boundary(h2, F, w3, None, 0, xin, C * P, bias3, logs3, None, mt, beta, xin, C * P, None, 0, None, 0, B, C, H, W,
+                     F, ldp, False)
+    y_ref = torch.empty_like(x)
+    N.flow_boundary(x, C * P, False, pm_ref, ldp, bias3, logs3, None, mt, beta, y_ref, C * P, None, 0, B, C, H, W, False)
+    sync()
+    assert torch.allclose(xin, y_ref, rtol=1e-6, atol=1e-6)
+
+
+def test_gemm3_boundary_support_query():
+    assert not N.gemm3_boundary_ok(2, 12, 64, 64, 512, 112)      # image larger than a CTA tile
+    assert not N.gemm3_boundary_ok(2, 6, 14, 14, 512, 64)        # 196 pixels: neither 256 nor a divisor of 128
+    assert not N.gemm3_boundary_ok(2, 96, 8, 8, 512, 864)        # 9C > 512 TMEM columns
+    assert not N.gemm3_boundary_ok(3, 16, 2, 2, 512, 144)        # 32 images per tile: more than one per warp
+    assert N.gemm3_boundary_ok(128, 48, 4, 4, 512, 432)
