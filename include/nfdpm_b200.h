@@ -221,10 +221,13 @@ int nfdpm_nchw_to_rows(const float* x, void* out, int out_dtype, int B, int Cc, 
 /* Affine coupling + log-det backward (transforms.py:179-184).  dy [B,C,P] grad of the coupling output, dld [B] grad of
  * log_det_jac (may be NULL), u [B,C,P] coupling input, pm as in the forward.  Outputs: du [B,C,P] (first half = dy_a;
  * the coupling-net part is added by nfdpm_mix_bwd), dpm [B*P, ld_dpm] (F32 or BF16, columns >= 9C zero-filled: the
- * K operand of the ZeroConv dgrad GEMM), dpar [B][2C] per-image partials (dbias3[C], dlogs3[C]). */
+ * K operand of the ZeroConv dgrad GEMM), dpar [B][2C] per-image partials (dbias3[C], dlogs3[C]).  With `counter` (one
+ * zero-initialised int32, re-armed by the kernel) the last CTA sums dpar over the images in order into dbias[C] /
+ * dlogs[C]; with counter == NULL reduce dpar with nfdpm_reduce_rows2. */
 int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs, const float* pm,
                        int64_t ldp, const float* bias3, const float* logs3, float* du, int64_t du_bs, void* dpm,
-                       int dpm_dtype, int64_t ld_dpm, float* dpar, int B, int C, int H, int W, nfdpm_stream_t stream);
+                       int dpm_dtype, int64_t ld_dpm, float* dpar, float* dbias, float* dlogs, int32_t* counter, int B,
+                       int C, int H, int W, nfdpm_stream_t stream);
 /* ActNorm+ReLU backward on rows (utils.py:69,84-87): dpre = dh*(h>0)*exp(scale); part[cta][2N] partial d(scale), d(bias);
  * ctas = ceil(M/rows_per_cta). */
 int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
@@ -250,10 +253,18 @@ typedef struct {
 } nfdpm_mix_grad_item;
 int nfdpm_mix_param_grad(const nfdpm_mix_grad_item* items_host, int n, nfdpm_stream_t stream);
 /* Weight gradients: D[N1,N2] (+)= sum_m A[m,N1]*B[m,N2] (A, B row-major, F32 or BF16; D fp32 with ldd == N2).
- * ws: nfdpm_gemm_tn_workspace(M,N1,N2,NULL) floats. */
+ * ws: nfdpm_gemm_tn_workspace(M,N1,N2,NULL) floats.  counters (may be NULL): >= 1024 int32, ZERO before the first use
+ * and private to one stream; with it the bf16 tensor-core path sums its split-M partial slabs inside the GEMM kernel
+ * (the CTAs of an output tile wait for each other; fixed slab order, so the result stays bitwise reproducible) instead
+ * of in a second launch.  The kernel re-arms the counters itself.  out_mode != PLAIN (needs counters + bf16 operands)
+ * writes the sum directly in the weight tensor's own layout, saving the unpack launch. */
 int64_t nfdpm_gemm_tn_workspace(int M, int N1, int N2, int* splits_out);
+#define NFDPM_TN_OUT_PLAIN 0 /* D[n1*N2 + n2]                                                               */
+#define NFDPM_TN_OUT_TAPS 1  /* n1 = tap*out_c + co -> D[(co*N2 + n2)*9 + tap]: ZeroConv weight [out_c,N2,3,3] */
+#define NFDPM_TN_OUT_STRIP 2 /* D[n1*out_c + n2] for n2 < out_c: drops the K-padding columns of the im2col rows  */
 int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void* Bm, int b_dtype, int64_t ldb, float* D, int64_t ldd,
-                  int M, int N1, int N2, float* ws, int accumulate, nfdpm_stream_t stream);
+                  int M, int N1, int N2, float* ws, int accumulate, int32_t* counters, int out_mode, int out_c,
+                  nfdpm_stream_t stream);
 /* Split prior backward (transforms.py:286-289, prior.py:36-37): dstate[:, C/2:] += dz; dh rows [M, ldh]; dpar [B][2C]. */
 int nfdpm_split_prior_bwd(const float* dlp, const float* h, int64_t ldh, const float* bias, const float* logs,
                           const float* x, int64_t xbs, float* dstate, int64_t dbs, float* dh, float* dpar, int B, int C,

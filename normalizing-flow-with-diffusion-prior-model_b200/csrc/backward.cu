@@ -29,6 +29,7 @@ struct CouplingBwdArgs {
   void* dpm; int64_t ld_dpm;           // out: [B*P, ld_dpm] (fp32 or bf16; columns >= 9C are zero)
   float* dpar;                         // out: [B][2C] per-image partials: dbias3[C], dlogs3[C]
   int B, C, H, W;
+  float* dbias; float* dlogs; int* counter;   // optional: the last CTA sums the partials (image order) into these
 };
 
 template <typename TD>
@@ -118,6 +119,23 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
       // kind 0: dbias[j], 1: dbias[Ch+j], 2: dlogs[j], 3: dlogs[Ch+j]
       const int dst = (kind < 2 ? 0 : C) + ((kind & 1) ? Ch : 0) + j;
       a.dpar[(int64_t)b * 2 * C + dst] = acc;
+    }
+  }
+  if (a.counter != nullptr) {
+    // the CTA that finishes last reduces all per-image partials in image order (deterministic) and re-arms the counter
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.counter, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int i = tid; i < 2 * C; i += nt) {
+        float acc = 0.f;
+        for (int bb = 0; bb < a.B; ++bb) acc += __ldcg(a.dpar + (int64_t)bb * 2 * C + i);
+        if (i < C) a.dbias[i] = acc; else a.dlogs[i - C] = acc;
+      }
+      if (tid == 0) *a.counter = 0;
     }
   }
 }
@@ -296,20 +314,35 @@ __global__ void __launch_bounds__(1024) mix_bwd_kernel(const MixBwdArgs a) {
     for (int o = 0; o < C; ++o) acc = fmaf(w_s[o * C + i], d_s[o * PS + p], acc);
     dxb[it] = acc;
   }
-  // partials: one warp per output element (o, i) / o, fixed order
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  // partials of d(W^) and d(b^), fixed summation order.  Many pixels: one warp per element, lanes over pixels + shuffle
+  // tree.  Few pixels (deep levels, C up to 48..192 -> thousands of elements): one THREAD per element, sequential over p.
   float* pb = a.part + (int64_t)b * (C * C + C);
-  for (int e = warp; e < C * C + C; e += nw) {
-    float acc = 0.f;
-    if (e < C * C) {
-      const int o = e / C, i = e - o * C;
-      for (int p = lane; p < P; p += 32) acc = fmaf(d_s[o * PS + p], x_s[i * PS + p], acc);
-    } else {
-      const int o = e - C * C;
-      for (int p = lane; p < P; p += 32) acc += d_s[o * PS + p];
+  if (P >= 64) {
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int e = warp; e < C * C + C; e += nw) {
+      float acc = 0.f;
+      if (e < C * C) {
+        const int o = e / C, i = e - o * C;
+        for (int p = lane; p < P; p += 32) acc = fmaf(d_s[o * PS + p], x_s[i * PS + p], acc);
+      } else {
+        const int o = e - C * C;
+        for (int p = lane; p < P; p += 32) acc += d_s[o * PS + p];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) pb[e] = acc;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) pb[e] = acc;
+  } else {
+    for (int e = tid; e < C * C + C; e += nt) {
+      float acc = 0.f;
+      if (e < C * C) {
+        const int o = e / C, i = e - o * C;       // lanes share o (broadcast) and walk i: rows PS = P+1 apart -> no conflicts
+        for (int p = 0; p < P; ++p) acc = fmaf(d_s[o * PS + p], x_s[i * PS + p], acc);
+      } else {
+        const int o = e - C * C;
+        for (int p = 0; p < P; ++p) acc += d_s[o * PS + p];
+      }
+      pb[e] = acc;
+    }
   }
 }
 
@@ -544,7 +577,7 @@ __global__ void col2im_add_kernel(const float* __restrict__ da, int64_t lda, flo
 void gemm_tn_tc_plan(int M, int N1, int N2, int* BN, int* tiles, int* splits, int* kb_per_split);
 bool gemm_tn_tc_ok(const void* A, int64_t lda, const void* Bm, int64_t ldb, int N1, int N2);
 int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* ws, int M, int N1, int N2, int* splits_out,
-               cudaStream_t st);
+               float* D, int accumulate, int* counters, int out_mode, int out_c, cudaStream_t st);
 
 }  // namespace nfdpm
 
@@ -552,8 +585,8 @@ using namespace nfdpm;
 
 extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs,
                                   const float* pm, int64_t ldp, const float* bias3, const float* logs3, float* du,
-                                  int64_t du_bs, void* dpm, int dpm_dtype, int64_t ld_dpm, float* dpar, int B, int C,
-                                  int H, int W, nfdpm_stream_t stream) {
+                                  int64_t du_bs, void* dpm, int dpm_dtype, int64_t ld_dpm, float* dpar, float* dbias,
+                                  float* dlogs, int32_t* counter, int B, int C, int H, int W, nfdpm_stream_t stream) {
   NFDPM_REQUIRE(dy && u && pm && bias3 && logs3 && du && dpm && dpar, "nfdpm_coupling_bwd: null pointer");
   NFDPM_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0 && ldp >= 9 * (int64_t)C && ld_dpm >= 9 * (int64_t)C,
                 "nfdpm_coupling_bwd: bad shape");
@@ -561,7 +594,9 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
   const size_t P = (size_t)H * W, PS = P + 1, Ch = C / 2;
   const size_t smem = sizeof(float) * (2 * C * PS + Ch * PS + 4 * P * Ch + 2 * C);
   NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_coupling_bwd: image too large (%zu bytes of shared memory)", smem);
-  CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W};
+  NFDPM_REQUIRE(counter == nullptr || (dbias && dlogs), "nfdpm_coupling_bwd: the fused reduction needs dbias/dlogs");
+  CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W, dbias, dlogs,
+                    counter};
   static bool attr_set = false;
   if (!attr_set) {
     NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -642,6 +677,7 @@ extern "C" int nfdpm_mix_bwd(const float* du, int64_t du_bs, const float* da1, i
     attr_set = true;
   }
   int threads = (int)((P * C + 31) / 32 * 32);
+  if (P < 64 && threads < 512) threads = 512;        // per-element partial sums at deep levels
   threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
   mix_bwd_kernel<<<B, threads, smem, as_stream(stream)>>>(a);
   NFDPM_CHECK_LAUNCH("mix_bwd_kernel");
@@ -682,18 +718,24 @@ extern "C" int64_t nfdpm_gemm_tn_workspace(int M, int N1, int N2, int* splits_ou
 }
 
 extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void* Bm, int b_dtype, int64_t ldb, float* D,
-                             int64_t ldd, int M, int N1, int N2, float* ws, int accumulate, nfdpm_stream_t stream) {
+                             int64_t ldd, int M, int N1, int N2, float* ws, int accumulate, int32_t* counters,
+                             int out_mode, int out_c, nfdpm_stream_t stream) {
   NFDPM_REQUIRE(A && Bm && D && ws, "nfdpm_gemm_tn: null pointer");
   NFDPM_REQUIRE(M > 0 && N1 > 0 && N2 > 0 && lda >= N1 && ldb >= N2 && ldd == N2, "nfdpm_gemm_tn: bad shape (ldd must equal N2)");
+  NFDPM_REQUIRE(out_mode >= NFDPM_TN_OUT_PLAIN && out_mode <= NFDPM_TN_OUT_STRIP && (out_mode == NFDPM_TN_OUT_PLAIN || out_c > 0),
+                "nfdpm_gemm_tn: bad output mode");
   cudaStream_t st = as_stream(stream);
   const int n = N1 * N2;
   if (a_dtype == NFDPM_BF16 && b_dtype == NFDPM_BF16 && gemm_tn_tc_ok(A, lda, Bm, ldb, N1, N2)) {
     int s_tc = 1;
-    if (gemm_tn_tc(A, lda, Bm, ldb, ws, M, N1, N2, &s_tc, st)) return 1;
-    reduce_rows_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, D, s_tc, n, n, accumulate);
-    NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
+    if (gemm_tn_tc(A, lda, Bm, ldb, ws, M, N1, N2, &s_tc, D, accumulate, counters, out_mode, out_c, st)) return 1;
+    if (s_tc > 0) {                                     // not reduced in-kernel
+      reduce_rows_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, D, s_tc, n, n, accumulate);
+      NFDPM_CHECK_LAUNCH("reduce_rows_kernel");
+    }
     return 0;
   }
+  NFDPM_REQUIRE(out_mode == NFDPM_TN_OUT_PLAIN, "nfdpm_gemm_tn: layout-changing outputs need bf16 operands + counters");
   int splits = 1;
   nfdpm_gemm_tn_workspace(M, N1, N2, &splits);
   int rows = (M + splits - 1) / splits;

@@ -34,7 +34,9 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) {
 __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    float* __restrict__ ws, int M, int N1, int N2, int BN,
-                                                                   int num_n2, int splits, int kb_per_split) {
+                                                                   int num_n2, int splits, int kb_per_split,
+                                                                   float* __restrict__ D, int accumulate,
+                                                                   int* __restrict__ counters, int out_mode, int out_c) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TN_STAGES + 1];
   __shared__ uint32_t s_tmem_base;
@@ -137,6 +139,74 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(const __grid_
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+  if (counters == nullptr) return;          // the caller reduces the slabs with a separate kernel
+
+  // ---- in-kernel split reduction.  All CTAs of the grid are co-resident (grid <= #SMs, one CTA per SM), so the
+  // CTAs of a tile can wait for each other: publish the slab, wait until all `splits` slabs of the tile exist, then
+  // every CTA sums a band of the tile's rows over the slabs IN SLAB ORDER (deterministic) straight into D.
+  int* arrive = counters + 2 * tile;
+  int* done = arrive + 1;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(arrive, 1);
+    const uint64_t t0 = global_timer_ns();
+    while (atomicAdd(arrive, 0) < splits) {
+      __nanosleep(64);
+      if (global_timer_ns() - t0 > 2000000000ull) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const int band = (128 + splits - 1) / splits;
+  const int r_lo = split * band, r_hi = min(128, r_lo + band);
+  const int cols = min(BN, N2 - t2 * BN);
+  const int c4 = cols >> 2;
+  for (int r = r_lo; r < r_hi; ++r) {
+    const int n1 = t1 * 128 + r;
+    if (n1 >= N1) break;
+    const int64_t off = (int64_t)n1 * N2 + t2 * BN;
+    if (out_mode == NFDPM_TN_OUT_PLAIN) {
+      for (int c = threadIdx.x; c < c4; c += TN_THREADS) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s2 = 0; s2 < splits; ++s2) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (int64_t)s2 * N1 * N2 + off) + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float4* d = reinterpret_cast<float4*>(D + off) + c;
+        if (accumulate) {
+          const float4 o = *d;
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        *d = acc;
+      }
+    } else {
+      // layout-changing outputs (the weight tensors' own layouts), element-wise
+      for (int c = threadIdx.x; c < cols; c += TN_THREADS) {
+        const int n2 = t2 * BN + c;
+        int64_t o;
+        if (out_mode == NFDPM_TN_OUT_TAPS) {            // n1 = tap*out_c + co  ->  [co][n2][tap]  (ZeroConv weight)
+          const int tap = n1 / out_c, co = n1 - tap * out_c;
+          if (tap >= 9) continue;
+          o = ((int64_t)co * N2 + n2) * 9 + tap;
+        } else {                                         // NFDPM_TN_OUT_STRIP: keep the first out_c columns
+          if (n2 >= out_c) continue;
+          o = (int64_t)n1 * out_c + n2;
+        }
+        float acc = 0.f;
+        for (int s2 = 0; s2 < splits; ++s2) acc += __ldcg(ws + (int64_t)s2 * N1 * N2 + off + c);
+        D[o] = accumulate ? D[o] + acc : acc;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(done, 1) == splits - 1) {    // last CTA of the tile: re-arm the counters for the next launch
+      *arrive = 0;
+      *done = 0;
+      __threadfence();
+    }
+  }
 }
 
 static int sm_count() {
@@ -169,7 +239,7 @@ bool gemm_tn_tc_ok(const void* A, int64_t lda, const void* Bm, int64_t ldb, int 
 }
 
 int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* ws, int M, int N1, int N2, int* splits_out,
-               cudaStream_t st) {
+               float* D, int accumulate, int* counters, int out_mode, int out_c, cudaStream_t st) {
   int BN, tiles, splits, per;
   gemm_tn_tc_plan(M, N1, N2, &BN, &tiles, &splits, &per);
   const int num_n2 = (N2 + BN - 1) / BN;
@@ -184,9 +254,13 @@ int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* w
     NFDPM_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  gemm_tn_tc_kernel<<<tiles * splits, TN_THREADS, smem, st>>>(tmA, tmB, ws, M, N1, N2, BN, num_n2, splits, per);
+  if (tiles > 500 || tiles * splits > sm_count()) counters = nullptr;     // co-residency not guaranteed: reduce separately
+  NFDPM_REQUIRE(out_mode == NFDPM_TN_OUT_PLAIN || counters != nullptr,
+                "nfdpm_gemm_tn: a layout-changing output needs the in-kernel reduction (counters)");
+  gemm_tn_tc_kernel<<<tiles * splits, TN_THREADS, smem, st>>>(tmA, tmB, ws, M, N1, N2, BN, num_n2, splits, per, D,
+                                                             accumulate, counters, out_mode, out_c);
   NFDPM_CHECK_LAUNCH("gemm_tn_tc_kernel");
-  *splits_out = splits;
+  *splits_out = counters != nullptr ? 0 : splits;     // 0: already reduced into D
   return 0;
 }
 

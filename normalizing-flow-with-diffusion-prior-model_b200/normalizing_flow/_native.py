@@ -67,8 +67,8 @@ def _load() -> C.CDLL:
                                  i32, vp], C.c_int),
         "nfdpm_coupling_fused": ([vp, i64, vp, vp, vp, vp, i64, i32, i32, vp, vp], C.c_int),
         "nfdpm_fold_actnorm": ([vp, vp, vp, vp, i32, vp], C.c_int),
-        "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i64, vp, i32, i32, i32, i32, vp],
-                               C.c_int),
+        "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i64, vp, vp, vp, vp, i32, i32, i32,
+                                i32, vp], C.c_int),
         "nfdpm_flow_boundary_stash": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
                                        i32, i32, vp], C.c_int),
         "nfdpm_actnorm_relu_bwd": ([vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
@@ -85,7 +85,7 @@ def _load() -> C.CDLL:
         "nfdpm_mix_bwd": ([vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_mix_param_grad": ([C.POINTER(MixGradItem), i32, vp], C.c_int),
         "nfdpm_gemm_tn_workspace": ([i32, i32, i32, C.POINTER(C.c_int)], C.c_int64),
-        "nfdpm_gemm_tn": ([vp, i32, i64, vp, i32, i64, vp, i64, i32, i32, i32, vp, i32, vp], C.c_int),
+        "nfdpm_gemm_tn": ([vp, i32, i64, vp, i32, i64, vp, i64, i32, i32, i32, vp, i32, vp, i32, i32, vp], C.c_int),
         "nfdpm_split_prior_bwd": ([vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_gauss_const_bwd": ([vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_col2im_add": ([vp, i64, vp, i64, i32, i32, i32, i32, vp], C.c_int),
@@ -247,9 +247,12 @@ def fold_actnorm(scale, bias, e_out, eb_out, n) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- backward
-def coupling_bwd(dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, Cc, H, W) -> None:
+def coupling_bwd(dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, Cc, H, W, dbias=None,
+                 dlogs=None) -> None:
+    """With dbias/dlogs the kernel's last CTA reduces the per-image partials itself (no nfdpm_reduce_rows2 launch)."""
+    cnt = _tn_counters(dy.device)[1023:] if dbias is not None else None
     _ok(lib.nfdpm_coupling_bwd(_p(dy), dy_bs, _p(dld), _p(u), u_bs, _p(pm), ldp, _p(bias3), _p(logs3), _p(du), du_bs,
-                               _p(dpm), _dt(dpm), ld_dpm, _p(dpar), B, Cc, H, W, _st()))
+                               _p(dpm), _dt(dpm), ld_dpm, _p(dpar), _p(dbias), _p(dlogs), _p(cnt), B, Cc, H, W, _st()))
 
 
 def flow_boundary_stash(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1, lda1,
@@ -285,8 +288,25 @@ def gemm_tn_workspace(M, N1, N2) -> int:
     return int(lib.nfdpm_gemm_tn_workspace(M, N1, N2, None))
 
 
-def gemm_tn(A, lda, Bm, ldb, D, M, N1, N2, ws, accumulate=False) -> None:
-    _ok(lib.nfdpm_gemm_tn(_p(A), _dt(A), lda, _p(Bm), _dt(Bm), ldb, _p(D), N2, M, N1, N2, _p(ws), int(accumulate), _st()), 2)
+_TN_COUNTERS = {}
+
+
+def _tn_counters(dev: torch.device):
+    """Zero-initialised, self-re-arming tile counters of the in-kernel split reduction (one set per device+stream)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _TN_COUNTERS.get(key)
+    if t is None:
+        t = _TN_COUNTERS[key] = torch.zeros(1024, dtype=torch.int32, device=dev)
+    return t
+
+
+TN_OUT_PLAIN, TN_OUT_TAPS, TN_OUT_STRIP = 0, 1, 2
+
+
+def gemm_tn(A, lda, Bm, ldb, D, M, N1, N2, ws, accumulate=False, fused_reduce=True, out_mode=TN_OUT_PLAIN, out_c=0) -> None:
+    cnt = _tn_counters(A.device) if fused_reduce else None
+    _ok(lib.nfdpm_gemm_tn(_p(A), _dt(A), lda, _p(Bm), _dt(Bm), ldb, _p(D), N2, M, N1, N2, _p(ws), int(accumulate),
+                          _p(cnt), out_mode, out_c, _st()), 1 if fused_reduce else 2)
 
 
 def split_prior_bwd(dlp, h, ldh, bias, logs, x, xbs, dstate, dbs, dh, dpar, B, Cc, H, W) -> None:

@@ -30,7 +30,7 @@ from . import _native as N
 #: write parameter gradients straight into ``p.grad`` (views of one flat buffer) when it is empty; set to False to
 #: hand every gradient to autograd instead (needed for torch.autograd.grad(), which must not touch ``.grad``)
 DIRECT_GRADS = True
-ROWS_PER_CTA = 64          # rows of one actnorm_relu_bwd CTA
+ROWS_PER_CTA = 64          # rows of one actnorm_relu_bwd CTA at large M (fewer at deep levels: >= ~256 CTAs)
 
 
 def _f32(t: Optional[Tensor], B: int, dev) -> Tensor:
@@ -272,7 +272,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
                     N.reduce_rows2(dpar, sink.get(conv.bias), sink.get(conv.logs), B, C, C, 2 * C)
                     dws = torch.empty(C * Kp, **f32)
                     ws = torch.empty(N.gemm_tn_workspace(M, C, Kp), **f32)
-                    N.gemm_tn(dh, ldh, As, Kp, dws, M, C, Kp, ws)
+                    N.gemm_tn(dh, ldh, As, Kp, dws, M, C, Kp, ws, fused_reduce=False)
                     _strip_cols(dws, sink.get(conv.weight), C, Kp, Ks)
                     dAs = torch.empty(M * Kp, **f32)
                     N.gemm_nt(dh, ldh, wst, ldh, dAs, Kp, M, Kp, ldh)
@@ -281,7 +281,10 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
                 for p_ in (split.conv.weight, split.conv.bias, split.conv.logs):
                     sink.get(p_).zero_()
         # ---- K StepFlows in reverse
-        n_cta = (M + ROWS_PER_CTA - 1) // ROWS_PER_CTA
+        rows_cta = ROWS_PER_CTA
+        while rows_cta > 8 and (M + rows_cta - 1) // rows_cta < 256:
+            rows_cta //= 2
+        n_cta = (M + rows_cta - 1) // rows_cta
         du = torch.empty(B, C, P, **f32)
         pong = (torch.empty(B, C, P, **f32), torch.empty(B, C, P, **f32))   # dx of successive steps alternate
         Kp3 = E.round_up(9 * C, 64)
@@ -292,6 +295,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         an_part = torch.empty(n_cta * 2 * F, **f32)
         dpar3 = torch.empty(B * 2 * C, **f32)
         mix_part = torch.empty(K, B * (C * C + C), **f32)
+        tc = dt == torch.bfloat16            # tensor-core wgrad: in-kernel split reduction + direct weight layouts
         d1 = torch.empty(F * K1p, **f32)
         d3 = torch.empty(ldp * F, **f32)
         ws = torch.empty(max(N.gemm_tn_workspace(M, F, F), N.gemm_tn_workspace(M, ldp, F),
@@ -302,22 +306,28 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             conv1, an1, conv2, an2, zc = cp._parts()
             bc = cp._bwd_cache                   # refreshed by the forward's PackPlan
             N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3, dpar3,
-                           B, C, h, w)
-            N.reduce_rows2(dpar3, sink.get(zc.bias), sink.get(zc.logs), B, C, C, 2 * C)
+                           B, C, h, w, sink.get(zc.bias), sink.get(zc.logs))
             # ZeroConv 3x3: weight gradient in the taps-as-N layout, then back to [C, F, 3, 3]
-            N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws)
-            N.pack_matrix(d3, sink.get(zc.weight), C, F, 9, F, 1, C * F, 9, C * F)
+            if tc:      # the split reduction writes d(W3) straight in its [C, F, 3, 3] layout
+                N.gemm_tn(dpm, Kp3, lv.h2[k], F, sink.get(zc.weight), M, ldp, F, ws, out_mode=N.TN_OUT_TAPS, out_c=C)
+            else:
+                N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws, fused_reduce=False)
+                N.pack_matrix(d3, sink.get(zc.weight), C, F, 9, F, 1, C * F, 9, C * F)
             N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
             # second Conv2dActNorm (1x1)
-            N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
+            N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, rows_cta)
             N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_cta, F, F, 2 * F)
-            N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws)
+            N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws, fused_reduce=tc)
             N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
             # first Conv2dActNorm (3x3)
-            N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, ROWS_PER_CTA)
+            N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, rows_cta)
             N.reduce_rows2(an_part, sink.get(an1.scale), sink.get(an1.bias), n_cta, F, F, 2 * F)
-            N.gemm_tn(dpre, F, lv.A1[k], K1p, d1, M, F, K1p, ws)
-            _strip_cols(d1, sink.get(conv1.weight), F, K1p, Ch * 9)
+            if tc:
+                N.gemm_tn(dpre, F, lv.A1[k], K1p, sink.get(conv1.weight), M, F, K1p, ws, out_mode=N.TN_OUT_STRIP,
+                          out_c=Ch * 9)
+            else:
+                N.gemm_tn(dpre, F, lv.A1[k], K1p, d1, M, F, K1p, ws, fused_reduce=False)
+                _strip_cols(d1, sink.get(conv1.weight), F, K1p, Ch * 9)
             N.gemm_nt(dpre, F, bc.w1t, F, dA1, K1p, M, K1p, F)
             # fused ActNorm + 1x1 conv
             dxb = pong[k & 1]
