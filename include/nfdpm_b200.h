@@ -226,8 +226,11 @@ int nfdpm_nchw_to_rows(const float* x, void* out, int out_dtype, int B, int Cc, 
  * dlogs[C]; with counter == NULL reduce dpar with nfdpm_reduce_rows2. */
 int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs, const float* pm,
                        int64_t ldp, const float* bias3, const float* logs3, float* du, int64_t du_bs, void* dpm,
-                       int dpm_dtype, int64_t ld_dpm, float* dpar, float* dbias, float* dlogs, int32_t* counter, int B,
-                       int C, int H, int W, nfdpm_stream_t stream);
+                       int dpm_dtype, int64_t ld_dpm, float* dpar, float* dbias, float* dlogs, int32_t* counter,
+                       float* dp_scratch, int B, int C, int H, int W, nfdpm_stream_t stream);
+/* 1: one CTA per image (dp_scratch unused).  > 1: the image is processed in pixel tiles: dpar has B*tiles rows (reduce
+ * with nfdpm_reduce_rows2), dp_scratch [B*H*W*C] floats is required and counter must be NULL. */
+int nfdpm_coupling_bwd_tiles(int C, int H, int W);
 /* ActNorm+ReLU backward on rows (utils.py:69,84-87): dpre = dh*(h>0)*exp(scale); part[cta][2N] partial d(scale), d(bias);
  * ctas = ceil(M/rows_per_cta). */
 int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
@@ -240,6 +243,8 @@ int nfdpm_reduce_rows2(const float* part, float* out0, float* out1, int R, int n
                        nfdpm_stream_t stream);
 /* Fused ActNorm + 1x1 conv backward (transforms.py:80,132) incl. col2im of the im2col-row gradient da1 (may be NULL):
  * dx = W^T du; part [B][C*C + C]: per-image sum_p du[o]x[i] and sum_p du[o]. */
+/* pixel tiles per image of nfdpm_mix_bwd: `part` has B*tiles rows of C*C + C floats */
+int nfdpm_mix_bwd_tiles(int C, int H, int W);
 int nfdpm_mix_bwd(const float* du, int64_t du_bs, const float* da1, int64_t lda1, const float* x, int64_t x_bs,
                   const float* mt, float* dx, int64_t dx_bs, float* part, int B, int C, int H, int W,
                   nfdpm_stream_t stream);

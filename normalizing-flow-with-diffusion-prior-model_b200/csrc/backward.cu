@@ -140,6 +140,99 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
   }
 }
 
+// Tiled variant for images (or channel counts) that do not fit one CTA: CTA = (image, tile of TP pixels), direct global
+// access; the gradient wrt the gathered conv output goes to dP [M, C] and dpm_expand_kernel scatters it into the
+// taps-as-N rows afterwards (a pixel's dpm row needs dP of its 8 neighbours, which may live in other tiles).
+__global__ void __launch_bounds__(256) coupling_bwd_tiled_kernel(const CouplingBwdArgs a, float* __restrict__ dP, int TP) {
+  extern __shared__ __align__(16) float sm[];        // r_s [4][Ch][TP] + par_s [2C]
+  const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
+  const int T = (P + TP - 1) / TP;
+  const int b = blockIdx.x / T, t = blockIdx.x - b * T;
+  const int p0 = t * TP, np = min(TP, P - p0);
+  float* r_s = sm;
+  float* par_s = r_s + 4 * Ch * TP;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < C; i += nt) {
+    par_s[i] = a.bias3[i];
+    par_s[C + i] = expf(3.f * a.logs3[i]);
+  }
+  __syncthreads();
+  const float* dyb = a.dy + (int64_t)b * a.dy_bs;
+  const float* ub = a.u + (int64_t)b * a.u_bs;
+  float* dub = a.du + (int64_t)b * a.du_bs;
+  for (int i = tid; i < Ch * np; i += nt) {           // first half passes through
+    const int c = i / np, pl = i - c * np;
+    dub[(int64_t)c * P + p0 + pl] = dyb[(int64_t)c * P + p0 + pl];
+  }
+  const float gld = (a.dld != nullptr) ? a.dld[b] : 0.f;
+  const float* pmb = a.pm + (int64_t)b * P * a.ldp;
+  for (int it = tid; it < np * Ch; it += nt) {
+    const int pl = it / Ch, j = it - pl * Ch;
+    const int p = p0 + pl;
+    const int py = p / W, px = p - py * W;
+    float ls = 0.f, tt = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      const float* r = pmb + (int64_t)(ok ? yy * W + xx : p) * a.ldp + tap * C + j;
+      const float l0 = __ldg(r), t0 = __ldg(r + Ch);
+      ls += ok ? l0 : 0.f;
+      tt += ok ? t0 : 0.f;
+    }
+    const float g_l = par_s[C + j], g_t = par_s[C + Ch + j];
+    const float log_s = (ls + par_s[j]) * g_l;
+    const float tv = (tt + par_s[Ch + j]) * g_t;
+    const float s = 1.f / (1.f + expf(-(log_s + 2.f)));
+    const float dyv = dyb[(int64_t)(Ch + j) * P + p];
+    const float ds = dyv * (ub[(int64_t)(Ch + j) * P + p] + tv) + gld / (s + 1e-6f);
+    const float dt = dyv * s;
+    const float dls = ds * s * (1.f - s);
+    dub[(int64_t)(Ch + j) * P + p] = dyv * s;
+    float* dpr = dP + ((int64_t)b * P + p) * C;
+    dpr[j] = dls * g_l;
+    dpr[Ch + j] = dt * g_t;
+    r_s[(0 * Ch + j) * TP + pl] = dls * g_l;
+    r_s[(1 * Ch + j) * TP + pl] = dt * g_t;
+    r_s[(2 * Ch + j) * TP + pl] = 3.f * dls * log_s;
+    r_s[(3 * Ch + j) * TP + pl] = 3.f * dt * tv;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int row = warp; row < 4 * Ch; row += nw) {
+    float acc = 0.f;
+    const float* rp = r_s + row * TP;
+    for (int pl = lane; pl < np; pl += 32) acc += rp[pl];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const int kind = row / Ch, j = row - kind * Ch;
+      const int dst = (kind < 2 ? 0 : C) + ((kind & 1) ? Ch : 0) + j;
+      a.dpar[(int64_t)blockIdx.x * 2 * C + dst] = acc;
+    }
+  }
+}
+
+// dpm[m, tap*C+co] = dP[m - shift(tap), co] inside the image, 0 outside and in the padding columns
+template <typename TD>
+__global__ void dpm_expand_kernel(const float* __restrict__ dP, TD* __restrict__ dpm, int64_t ld, int C, int H, int W,
+                                  int64_t n) {
+  const int P = H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / ld;
+    const int col = (int)(i - m * ld);
+    float v = 0.f;
+    if (col < 9 * C) {
+      const int tap = col / C, co = col - tap * C;
+      const int64_t b = m / P;
+      const int p = (int)(m - b * P);
+      const int py = p / W, px = p - py * W;
+      const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(dP + (b * P + yy * W + xx) * C + co);
+    }
+    stf<TD>(dpm + i, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ ActNorm+ReLU backward
 // rows [M, ld], channel fastest.  CTA = `rows_per_cta` rows x all N columns; a thread owns 8 consecutive columns
 // (16-byte bf16 / 32-byte fp32 vectors, fully coalesced rows), the CTA's 256 threads cover 256/(N/8) rows at a time and
@@ -267,34 +360,40 @@ struct MixBwdArgs {
   const float* x; int64_t x_bs;       // K-A input [B,C,P]
   const float* mt;                    // fwd_mt[i*C+o] = W^[o][i]
   float* dx; int64_t dx_bs;           // out
-  float* part;                        // out: [B][C*C + C]: dW^x[o*C+i] = sum_p du[o]x[i];  db^[o] = sum_p du[o]
+  float* part;                        // out: [B*T][C*C + C]: dW^x[o*C+i] = sum_p du[o]x[i];  db^[o] = sum_p du[o]
   int B, C, H, W;
+  int TP;                             // pixels per CTA tile (T = ceil(P/TP) tiles per image)
 };
 
 __global__ void __launch_bounds__(1024) mix_bwd_kernel(const MixBwdArgs a) {
+  // CTA = (image b, pixel tile t): pixels [p0, p0 + np) of the image; images up to 256 pixels are one tile
   extern __shared__ __align__(16) float sm[];
-  const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1, PS = P + 1;
+  const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
+  const int T = (P + a.TP - 1) / a.TP;
+  const int b = blockIdx.x / T, t = blockIdx.x - b * T;
+  const int p0 = t * a.TP, np = min(a.TP, P - p0), PS = a.TP + 1;
   float* d_s = sm;                 // [C][PS] du (complete)
   float* x_s = d_s + C * PS;       // [C][PS]
   float* w_s = x_s + C * PS;       // [C][C]  w_s[o*C+i] = W^[o][i]
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < C * C; i += nt) {
     const int o = i / C, ii = i - o * C;
     w_s[i] = a.mt[ii * C + o];
   }
   const float* dub = a.du + (int64_t)b * a.du_bs;
   const float* xb = a.x + (int64_t)b * a.x_bs;
-  for (int i = tid; i < C * P; i += nt) {
-    const int c = i / P, p = i - c * P;
-    d_s[c * PS + p] = dub[i];
-    x_s[c * PS + p] = xb[i];
+  for (int i = tid; i < C * np; i += nt) {
+    const int c = i / np, pl = i - c * np;
+    d_s[c * PS + pl] = dub[(int64_t)c * P + p0 + pl];
+    x_s[c * PS + pl] = xb[(int64_t)c * P + p0 + pl];
   }
   __syncthreads();
   if (a.da1 != nullptr) {
     // col2im: A1[m, c*9+tap] = u[c][m + shift(tap)]  =>  du[c][p] += sum_tap dA1[p - shift(tap), c*9+tap]
     const float* dab = a.da1 + (int64_t)b * P * a.lda1;
-    for (int it = tid; it < P * Ch; it += nt) {
-      const int p = it / Ch, c = it - p * Ch;
+    for (int it = tid; it < np * Ch; it += nt) {
+      const int pl = it / Ch, c = it - pl * Ch;
+      const int p = p0 + pl;
       const int py = p / W, px = p - py * W;
       float acc = 0.f;
 #pragma unroll
@@ -302,31 +401,31 @@ __global__ void __launch_bounds__(1024) mix_bwd_kernel(const MixBwdArgs a) {
         const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += __ldg(dab + (int64_t)(yy * W + xx) * a.lda1 + c * 9 + tap);
       }
-      d_s[c * PS + p] += acc;
+      d_s[c * PS + pl] += acc;
     }
     __syncthreads();
   }
   // dx[i][p] = sum_o W^[o][i] du[o][p]
   float* dxb = a.dx + (int64_t)b * a.dx_bs;
-  for (int it = tid; it < C * P; it += nt) {
-    const int i = it / P, p = it - i * P;
+  for (int it = tid; it < C * np; it += nt) {
+    const int i = it / np, pl = it - i * np;
     float acc = 0.f;
-    for (int o = 0; o < C; ++o) acc = fmaf(w_s[o * C + i], d_s[o * PS + p], acc);
-    dxb[it] = acc;
+    for (int o = 0; o < C; ++o) acc = fmaf(w_s[o * C + i], d_s[o * PS + pl], acc);
+    dxb[(int64_t)i * P + p0 + pl] = acc;
   }
   // partials of d(W^) and d(b^), fixed summation order.  Many pixels: one warp per element, lanes over pixels + shuffle
   // tree.  Few pixels (deep levels, C up to 48..192 -> thousands of elements): one THREAD per element, sequential over p.
-  float* pb = a.part + (int64_t)b * (C * C + C);
-  if (P >= 64) {
+  float* pb = a.part + (int64_t)blockIdx.x * (C * C + C);
+  if (np >= 64) {
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     for (int e = warp; e < C * C + C; e += nw) {
       float acc = 0.f;
       if (e < C * C) {
         const int o = e / C, i = e - o * C;
-        for (int p = lane; p < P; p += 32) acc = fmaf(d_s[o * PS + p], x_s[i * PS + p], acc);
+        for (int pl = lane; pl < np; pl += 32) acc = fmaf(d_s[o * PS + pl], x_s[i * PS + pl], acc);
       } else {
         const int o = e - C * C;
-        for (int p = lane; p < P; p += 32) acc += d_s[o * PS + p];
+        for (int pl = lane; pl < np; pl += 32) acc += d_s[o * PS + pl];
       }
       acc = warp_sum(acc);
       if (lane == 0) pb[e] = acc;
@@ -335,11 +434,11 @@ __global__ void __launch_bounds__(1024) mix_bwd_kernel(const MixBwdArgs a) {
     for (int e = tid; e < C * C + C; e += nt) {
       float acc = 0.f;
       if (e < C * C) {
-        const int o = e / C, i = e - o * C;       // lanes share o (broadcast) and walk i: rows PS = P+1 apart -> no conflicts
-        for (int p = 0; p < P; ++p) acc = fmaf(d_s[o * PS + p], x_s[i * PS + p], acc);
+        const int o = e / C, i = e - o * C;       // lanes share o (broadcast) and walk i: rows PS apart -> no conflicts
+        for (int pl = 0; pl < np; ++pl) acc = fmaf(d_s[o * PS + pl], x_s[i * PS + pl], acc);
       } else {
         const int o = e - C * C;
-        for (int p = 0; p < P; ++p) acc += d_s[o * PS + p];
+        for (int pl = 0; pl < np; ++pl) acc += d_s[o * PS + pl];
       }
       pb[e] = acc;
     }
@@ -583,31 +682,69 @@ int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* w
 
 using namespace nfdpm;
 
+static size_t coupling_bwd_smem(int C, int P) {
+  const size_t PS = P + 1, Ch = C / 2;
+  return sizeof(float) * (2 * (size_t)C * PS + Ch * PS + 4 * (size_t)P * Ch + 2 * C);
+}
+static int coupling_bwd_tile(int C, int P) {
+  int tp = P < 128 ? P : 128;
+  while (tp > 8 && sizeof(float) * (4 * (size_t)(C / 2) * tp + 2 * C) > 96 * 1024) tp = (tp + 1) / 2;
+  if (tp >= P) tp = (P + 1) / 2;       // the tiled path always has >= 2 tiles (tiles == 1 means "single-kernel path")
+  return tp;
+}
+/* 1: the image fits one CTA (single kernel, dp_scratch unused); otherwise the number of pixel tiles per image: dpar has
+ * B*tiles rows, dp_scratch [B*H*W*C] floats is required and the last-CTA reduction (counter) is not used. */
+extern "C" int nfdpm_coupling_bwd_tiles(int C, int H, int W) {
+  const int P = H * W;
+  if (coupling_bwd_smem(C, P) <= 200 * 1024) return 1;
+  const int tp = coupling_bwd_tile(C, P);
+  return (P + tp - 1) / tp;
+}
+
 extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const float* u, int64_t u_bs,
                                   const float* pm, int64_t ldp, const float* bias3, const float* logs3, float* du,
                                   int64_t du_bs, void* dpm, int dpm_dtype, int64_t ld_dpm, float* dpar, float* dbias,
-                                  float* dlogs, int32_t* counter, int B, int C, int H, int W, nfdpm_stream_t stream) {
+                                  float* dlogs, int32_t* counter, float* dp_scratch, int B, int C, int H, int W,
+                                  nfdpm_stream_t stream) {
   NFDPM_REQUIRE(dy && u && pm && bias3 && logs3 && du && dpm && dpar, "nfdpm_coupling_bwd: null pointer");
   NFDPM_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0 && ldp >= 9 * (int64_t)C && ld_dpm >= 9 * (int64_t)C,
                 "nfdpm_coupling_bwd: bad shape");
   NFDPM_REQUIRE(dpm_dtype == NFDPM_F32 || dpm_dtype == NFDPM_BF16, "nfdpm_coupling_bwd: bad dpm dtype");
-  const size_t P = (size_t)H * W, PS = P + 1, Ch = C / 2;
-  const size_t smem = sizeof(float) * (2 * C * PS + Ch * PS + 4 * P * Ch + 2 * C);
-  NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_coupling_bwd: image too large (%zu bytes of shared memory)", smem);
   NFDPM_REQUIRE(counter == nullptr || (dbias && dlogs), "nfdpm_coupling_bwd: the fused reduction needs dbias/dlogs");
-  CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W, dbias, dlogs,
-                    counter};
+  const int P = H * W, Ch = C / 2;
+  cudaStream_t st = as_stream(stream);
   static bool attr_set = false;
   if (!attr_set) {
     NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
-  int threads = (int)((P * Ch + 31) / 32 * 32);
-  threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
-  if (dpm_dtype == NFDPM_F32) coupling_bwd_kernel<float><<<B, threads, smem, as_stream(stream)>>>(a);
-  else coupling_bwd_kernel<__nv_bfloat16><<<B, threads, smem, as_stream(stream)>>>(a);
-  NFDPM_CHECK_LAUNCH("coupling_bwd_kernel");
+  const size_t smem = coupling_bwd_smem(C, P);
+  if (smem <= 200 * 1024) {
+    CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W, dbias, dlogs,
+                      counter};
+    int threads = (P * Ch + 31) / 32 * 32;
+    threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
+    if (dpm_dtype == NFDPM_F32) coupling_bwd_kernel<float><<<B, threads, smem, st>>>(a);
+    else coupling_bwd_kernel<__nv_bfloat16><<<B, threads, smem, st>>>(a);
+    NFDPM_CHECK_LAUNCH("coupling_bwd_kernel");
+    return 0;
+  }
+  NFDPM_REQUIRE(dp_scratch != nullptr && counter == nullptr,
+                "nfdpm_coupling_bwd: this image needs the tiled path (dp_scratch, no fused reduction): see nfdpm_coupling_bwd_tiles");
+  const int TP = coupling_bwd_tile(C, P), T = (P + TP - 1) / TP;
+  CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W, nullptr,
+                    nullptr, nullptr};
+  const size_t smem_t = sizeof(float) * (4 * (size_t)Ch * TP + 2 * C);
+  coupling_bwd_tiled_kernel<<<B * T, 256, smem_t, st>>>(a, dp_scratch, TP);
+  NFDPM_CHECK_LAUNCH("coupling_bwd_tiled_kernel");
+  const int64_t n = (int64_t)B * P * ld_dpm;
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  if (dpm_dtype == NFDPM_F32) dpm_expand_kernel<float><<<(int)g, 256, 0, st>>>(dp_scratch, (float*)dpm, ld_dpm, C, H, W, n);
+  else dpm_expand_kernel<__nv_bfloat16><<<(int)g, 256, 0, st>>>(dp_scratch, (__nv_bfloat16*)dpm, ld_dpm, C, H, W, n);
+  NFDPM_CHECK_LAUNCH("dpm_expand_kernel");
   return 0;
 }
 
@@ -661,25 +798,36 @@ extern "C" int nfdpm_reduce_rows(const float* part, float* out, int R, int n, in
   return 0;
 }
 
+static int mix_bwd_tile(int C, int P) {
+  int tp = P < 256 ? P : 256;
+  while (tp > 8 && sizeof(float) * (2 * (size_t)C * (tp + 1) + (size_t)C * C) > 200 * 1024) tp = (tp + 1) / 2;
+  return tp;
+}
+/* number of pixel tiles per image of nfdpm_mix_bwd (rows of `part` per image) */
+extern "C" int nfdpm_mix_bwd_tiles(int C, int H, int W) {
+  const int P = H * W, tp = mix_bwd_tile(C, P);
+  return (P + tp - 1) / tp;
+}
+
 extern "C" int nfdpm_mix_bwd(const float* du, int64_t du_bs, const float* da1, int64_t lda1, const float* x, int64_t x_bs,
                              const float* mt, float* dx, int64_t dx_bs, float* part, int B, int C, int H, int W,
                              nfdpm_stream_t stream) {
   NFDPM_REQUIRE(du && x && mt && dx && part, "nfdpm_mix_bwd: null pointer");
   NFDPM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "nfdpm_mix_bwd: bad shape");
   NFDPM_REQUIRE(da1 == nullptr || (C % 2 == 0 && lda1 >= 9 * (int64_t)(C / 2)), "nfdpm_mix_bwd: bad im2col gradient");
-  const size_t P = (size_t)H * W, PS = P + 1;
-  const size_t smem = sizeof(float) * (2 * C * PS + (size_t)C * C);
-  NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_mix_bwd: image too large (%zu bytes of shared memory)", smem);
-  MixBwdArgs a{du, du_bs, da1, lda1, x, x_bs, mt, dx, dx_bs, part, B, C, H, W};
+  const int P = H * W, TP = mix_bwd_tile(C, P), T = (P + TP - 1) / TP;
+  const size_t smem = sizeof(float) * (2 * (size_t)C * (TP + 1) + (size_t)C * C);
+  NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_mix_bwd: %d channels do not fit shared memory (%zu bytes)", C, smem);
+  MixBwdArgs a{du, du_bs, da1, lda1, x, x_bs, mt, dx, dx_bs, part, B, C, H, W, TP};
   static bool attr_set = false;
   if (!attr_set) {
     NFDPM_CUDA(cudaFuncSetAttribute(mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  int threads = (int)((P * C + 31) / 32 * 32);
-  if (P < 64 && threads < 512) threads = 512;        // per-element partial sums at deep levels
+  int threads = (TP * C + 31) / 32 * 32;
+  if (TP < 64 && threads < 512) threads = 512;       // per-element partial sums at deep levels
   threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
-  mix_bwd_kernel<<<B, threads, smem, as_stream(stream)>>>(a);
+  mix_bwd_kernel<<<B * T, threads, smem, as_stream(stream)>>>(a);
   NFDPM_CHECK_LAUNCH("mix_bwd_kernel");
   return 0;
 }

@@ -67,8 +67,10 @@ def _load() -> C.CDLL:
                                  i32, vp], C.c_int),
         "nfdpm_coupling_fused": ([vp, i64, vp, vp, vp, vp, i64, i32, i32, vp, vp], C.c_int),
         "nfdpm_fold_actnorm": ([vp, vp, vp, vp, i32, vp], C.c_int),
-        "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i64, vp, vp, vp, vp, i32, i32, i32,
-                                i32, vp], C.c_int),
+        "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i64, vp, vp, vp, vp, vp, i32, i32,
+                                i32, i32, vp], C.c_int),
+        "nfdpm_coupling_bwd_tiles": ([i32, i32, i32], C.c_int),
+        "nfdpm_mix_bwd_tiles": ([i32, i32, i32], C.c_int),
         "nfdpm_flow_boundary_stash": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
                                        i32, i32, vp], C.c_int),
         "nfdpm_actnorm_relu_bwd": ([vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
@@ -109,7 +111,7 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
            "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch",
-           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary"]
+           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -247,12 +249,22 @@ def fold_actnorm(scale, bias, e_out, eb_out, n) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- backward
+def coupling_bwd_tiles(Cc, H, W) -> int:
+    return int(lib.nfdpm_coupling_bwd_tiles(Cc, H, W))
+
+
+def mix_bwd_tiles(Cc, H, W) -> int:
+    return int(lib.nfdpm_mix_bwd_tiles(Cc, H, W))
+
+
 def coupling_bwd(dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, Cc, H, W, dbias=None,
-                 dlogs=None) -> None:
-    """With dbias/dlogs the kernel's last CTA reduces the per-image partials itself (no nfdpm_reduce_rows2 launch)."""
+                 dlogs=None, dp_scratch=None) -> None:
+    """With dbias/dlogs the kernel's last CTA reduces the per-image partials itself (no nfdpm_reduce_rows2 launch);
+    images that do not fit one CTA (coupling_bwd_tiles > 1) need dp_scratch and a separate reduction of dpar."""
     cnt = _tn_counters(dy.device)[1023:] if dbias is not None else None
     _ok(lib.nfdpm_coupling_bwd(_p(dy), dy_bs, _p(dld), _p(u), u_bs, _p(pm), ldp, _p(bias3), _p(logs3), _p(du), du_bs,
-                               _p(dpm), _dt(dpm), ld_dpm, _p(dpar), _p(dbias), _p(dlogs), _p(cnt), B, Cc, H, W, _st()))
+                               _p(dpm), _dt(dpm), ld_dpm, _p(dpar), _p(dbias), _p(dlogs), _p(cnt), _p(dp_scratch), B, Cc,
+                               H, W, _st()), 1 if dp_scratch is None else 2)
 
 
 def flow_boundary_stash(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1, lda1,

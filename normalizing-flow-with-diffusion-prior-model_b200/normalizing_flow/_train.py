@@ -95,7 +95,12 @@ class Stash:
 
 
 def supported(glow, H: int, W: int) -> bool:
-    return glow._fast_ok(H, W)
+    return True
+
+
+def _level_fast(C: int, h: int, w: int) -> bool:
+    """Can the fused step-boundary kernel hold one image of this level in a CTA?"""
+    return h * w <= 256 and N.flow_boundary_smem(C, h, w, 1, 1) <= 200 * 1024
 
 
 def forward_train(glow, x: Tensor, with_logp: bool):
@@ -112,13 +117,20 @@ def forward_train(glow, x: Tensor, with_logp: bool):
     glow._pack_plan(steps, dt, True).refresh()      # every forward / transposed weight layout in one launch
     st = Stash()
     st.B, st.with_logp, st.in_shape, st.dt = B, with_logp, (B, c, H, W), dt
-    R_ld, R_lp = glow.L * K, glow.L - 1
+    R_ld, R_lp = 0, 0
+    hh, ww, cc = H, W, c
+    for li_ in range(glow.L):
+        hh, ww, CC = hh // 2, ww // 2, cc * 4
+        R_ld += K * (1 if _level_fast(CC, hh, ww) else N.ld_tiles(hh * ww))
+        if li_ < glow.L - 1:
+            R_lp += N.ld_tiles(hh * ww)
+        cc = CC // 2
     ld_part = torch.empty(R_ld * B, dtype=torch.float32, device=dev)
     lp_part = torch.empty(max(R_lp, 1) * B, dtype=torch.float32, device=dev) if with_logp else None
     latents: List[Tensor] = []
     cur, cur_bs = x, c * H * W
     h, w, ch = H, W, c
-    row = 0
+    row = lrow = 0
     for li, (flows, split) in enumerate(levels):
         h, w, C = h // 2, w // 2, ch * 4
         P, M = h * w, B * h * w
@@ -137,13 +149,21 @@ def forward_train(glow, x: Tensor, with_logp: bool):
         lv.pm = torch.empty(K, M, ldp, **f32)
         lv.state_out = torch.empty(B, C, h, w, **f32)
         fused_g3 = dt == torch.bfloat16 and E.fused_g3_ok(B, C, h, w, F, ldp)
-        # level entry: squeeze + stash x_0 + K-A of step 0 + im2col
-        N.flow_boundary_stash(cur, cur_bs, True, None, 0, None, None, None, flows[0]._mix.fwd_mt, flows[0]._mix.fwd_beta,
-                              lv.u[0], C * P, lv.x[0], C * P, lv.A1[0], K1p, B, C, h, w)
+        fast = _level_fast(C, h, w)
+        T_ld = 1 if fast else N.ld_tiles(P)
+        if fast:
+            # level entry: squeeze + stash x_0 + K-A of step 0 + im2col
+            N.flow_boundary_stash(cur, cur_bs, True, None, 0, None, None, None, flows[0]._mix.fwd_mt,
+                                  flows[0]._mix.fwd_beta, lv.u[0], C * P, lv.x[0], C * P, lv.A1[0], K1p, B, C, h, w)
+        else:
+            N.squeeze(cur, lv.x[0], B, C // 4, 2 * h, 2 * w, cur_bs, C * P)
         for k, step in enumerate(flows):
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
             cache = cp._cache
+            if not fast:      # images larger than one CTA: unfused K-A + im2col (any size)
+                N.channel_mix(lv.x[k], lv.u[k], step._mix.fwd_mt, step._mix.fwd_beta, B, C, P, C * P, C * P)
+                N.im2col3x3(lv.u[k], lv.A1[k], B, C // 2, h, w, C * P, K1p)
             N.gemm_nt(lv.A1[k], K1p, cache.w1, K1p, lv.h1[k], F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
             w2 = cache.w2 if dt != torch.float32 else conv2.weight
             N.gemm_nt(lv.h1[k], F, w2, F, lv.h2[k], F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
@@ -152,7 +172,11 @@ def forward_train(glow, x: Tensor, with_logp: bool):
             y = lv.u[k + 1] if nxt is not None else lv.state_out
             xs = lv.x[k + 1] if nxt is not None else None
             a1n = lv.A1[k + 1] if nxt is not None else None
-            if fused_g3:
+            if not fast:
+                N.gemm_nt(lv.h2[k], F, cache.w3, F, lv.pm[k], ldp, M, ldp, F)
+                N.coupling_apply(lv.pm[k], ldp, zc.bias, zc.logs, lv.u[k], xs if nxt is not None else lv.state_out,
+                                 ld_part[row * B:], B, C, h, w, C * P, C * P, False)
+            elif fused_g3:
                 # ZeroConv GEMM + coupling + next mix + sinks in one kernel; pm is also written out for the backward
                 N.gemm3_boundary(lv.h2[k], F, cache.w3, lv.pm[k], ldp, lv.u[k], C * P, zc.bias, zc.logs,
                                  ld_part[row * B:], mt, beta, y, C * P, xs, C * P if xs is not None else 0, a1n,
@@ -162,13 +186,15 @@ def forward_train(glow, x: Tensor, with_logp: bool):
                 N.flow_boundary_stash(lv.u[k], C * P, False, lv.pm[k], ldp, zc.bias, zc.logs, ld_part[row * B:],
                                       mt, beta, y, C * P, xs, C * P if xs is not None else 0, a1n,
                                       K1p if a1n is not None else 0, B, C, h, w)
+            row += T_ld - 1
             row += 1
         st.levels.append(lv)
         if split is None:
             latents.append(lv.state_out)
             break
         z = torch.empty(B, C // 2, h, w, **f32)
-        split._forward_views(lv.state_out, C * P, B, C, h, w, z, lp_part[li * B:] if lp_part is not None else None)
+        split._forward_views(lv.state_out, C * P, B, C, h, w, z, lp_part[lrow * B:] if lp_part is not None else None)
+        lrow += N.ld_tiles(P)
         latents.append(z)
         cur, cur_bs, ch = lv.state_out, C * P, C // 2
     return latents, ld_part, R_ld, lp_part, (R_lp if with_logp else 0), st
@@ -293,8 +319,10 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         dpre = torch.empty(M * F, dtype=dt, device=dev)
         dA1 = torch.empty(M * K1p, **f32)
         an_part = torch.empty(n_cta * 2 * F, **f32)
-        dpar3 = torch.empty(B * 2 * C, **f32)
-        mix_part = torch.empty(K, B * (C * C + C), **f32)
+        T_c, T_m = N.coupling_bwd_tiles(C, h, w), N.mix_bwd_tiles(C, h, w)     # pixel tiles per image (1: image per CTA)
+        dpar3 = torch.empty(B * T_c * 2 * C, **f32)
+        dp_scratch = torch.empty(M * C, **f32) if T_c > 1 else None
+        mix_part = torch.empty(K, B * T_m * (C * C + C), **f32)
         tc = dt == torch.bfloat16            # tensor-core wgrad: in-kernel split reduction + direct weight layouts
         d1 = torch.empty(F * K1p, **f32)
         d3 = torch.empty(ldp * F, **f32)
@@ -305,8 +333,13 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
             bc = cp._bwd_cache                   # refreshed by the forward's PackPlan
-            N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3, dpar3,
-                           B, C, h, w, sink.get(zc.bias), sink.get(zc.logs))
+            if T_c == 1:
+                N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3,
+                               dpar3, B, C, h, w, sink.get(zc.bias), sink.get(zc.logs))
+            else:
+                N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3,
+                               dpar3, B, C, h, w, dp_scratch=dp_scratch)
+                N.reduce_rows2(dpar3, sink.get(zc.bias), sink.get(zc.logs), B * T_c, C, C, 2 * C)
             # ZeroConv 3x3: weight gradient in the taps-as-N layout, then back to [C, F, 3, 3]
             if tc:      # the split reduction writes d(W3) straight in its [C, F, 3, 3] layout
                 N.gemm_tn(dpm, Kp3, lv.h2[k], F, sink.get(zc.weight), M, ldp, F, ws, out_mode=N.TN_OUT_TAPS, out_c=C)
@@ -340,7 +373,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             dW, dS, dB = sink.get(wgt), sink.get(sc), sink.get(bi)
             scratch = torch.empty(C * C + C, **f32)
             keep.append(scratch)
-            items.append(N.MixGradItem(part=mix_part[k].data_ptr(), B=B, C=C, weight=wgt.data_ptr(), scale=sc.data_ptr(),
+            items.append(N.MixGradItem(part=mix_part[k].data_ptr(), B=B * T_m, C=C, weight=wgt.data_ptr(), scale=sc.data_ptr(),
                                        bias=bi.data_ptr(), winv=step._mix.winv.data_ptr(), dld_sum=dld_sum.data_ptr(),
                                        P=float(P), pad_=0, d_weight=dW.data_ptr(), d_scale=dS.data_ptr(),
                                        d_bias=dB.data_ptr(), scratch=scratch.data_ptr()))
