@@ -21,7 +21,7 @@ from torch import Tensor
 from . import _engine as E
 from . import _native as N
 from .base import Transform
-from .transforms import ActNorm, AffineCoupling, InvConv2d, Split, Squeeze, _no_autograd
+from .transforms import ActNorm, AffineCoupling, InvConv2d, Split, Squeeze, _granular, _no_autograd
 from .utils import get_item
 
 
@@ -70,8 +70,8 @@ class StepFlow(Transform):
         self.affcoupling._run(y, ybs, t, tbs, B, C, H, W, True, None)
         N.channel_mix(t, x, self._mix.inv_mt, self._mix.inv_beta, B, C, P, tbs, xbs)
 
+    @_granular("StepFlow")
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        _no_autograd(x, self, "StepFlow.transform")
         x = E.check_input(x)
         B, C, H, W = x.shape
         if C != self._C:
@@ -85,8 +85,8 @@ class StepFlow(Transform):
             N.accumulate(log_det_jac, part, T, B, self._mix.logdet, E.scalar_f32(x.device, H * W), 1)
         return y, log_det_jac, logp
 
+    @_granular("StepFlow")
     def invert(self, y: Tensor) -> Tensor:
-        _no_autograd(y, self, "StepFlow.invert")
         y = E.check_input(y)
         B, C, H, W = y.shape
         t, x = torch.empty_like(y), torch.empty_like(y)
@@ -406,7 +406,14 @@ class Glow(Transform):
     # ---- inverse: latents -> x
     def invert(self, latents: list, temperature: float = 1.0) -> Tensor:
         z_last = E.check_input(latents[-1], "latents[-1]")
-        _no_autograd(z_last, self, "Glow.invert")
+        if E.autograd_needed(z_last, self) or any(isinstance(t, Tensor) and t.requires_grad for t in latents):
+            # the inverse has no backward kernels: compute it without recording and fail loudly on back-propagation
+            from .transforms import _NoBackward
+            deps = [t for t in latents if isinstance(t, Tensor) and t.requires_grad] + \
+                   [p for p in self.parameters() if p.requires_grad]
+            with torch.no_grad():
+                out = self.invert([t.detach() if isinstance(t, Tensor) else t for t in latents], temperature)
+            return _NoBackward.apply(out, "Glow.invert", False, *deps)
         B, Cf, h, w = z_last.shape
         if Cf != 2 ** (self.L + 1) * self.in_channel:
             raise ValueError(f"final latent has {Cf} channels, expected {2 ** (self.L + 1) * self.in_channel}")

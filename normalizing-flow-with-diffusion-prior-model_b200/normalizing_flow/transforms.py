@@ -17,11 +17,57 @@ from .base import Transform
 from .utils import ZeroConv2d, coupling_network
 
 
+class _NoBackward(torch.autograd.Function):
+    """Identity whose backward raises: granular modules (ActNorm, InvConv2d, AffineCoupling, Split, StepFlow, GlowBlock
+    called on their own) compute their FORWARD with the kernels in any grad mode — the reference's own unit tests call
+    them with autograd enabled (tests/transformations.py) — but only the whole-Glow path has backward kernels
+    (normalizing_flow/_train.py).  Back-propagating through a granular call therefore fails loudly instead of
+    silently dropping gradients."""
+
+    @staticmethod
+    def forward(ctx, t, what, inplace, *deps):
+        ctx.what = what
+        if inplace:
+            ctx.mark_dirty(t)
+            return t
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError(
+            f"{ctx.what}: backward through a stand-alone transform is not implemented; train through Glow.transform "
+            f"(its autograd Function covers every parameter) or call this module under torch.no_grad().")
+
+
 def _no_autograd(x: Tensor, mod: nn.Module, what: str) -> None:
     if E.autograd_needed(x, mod):
         raise NotImplementedError(
-            f"{what}: backward kernels are not part of this build yet (DESIGN.md, 'out of scope this round'). "
-            f"Call under torch.no_grad() or set requires_grad=False on the flow parameters.")
+            f"{what}: not available under autograd; call under torch.no_grad().")
+
+
+def _granular(what: str):
+    """Decorator for stand-alone transform / invert methods: run the kernels without recording, then attach the
+    loud-failure node to every floating-point tensor result (in place for the accumulators that were updated in place)."""
+    def deco(fn):
+        def wrapper(self, x, *args, **kw):
+            if not E.autograd_needed(x, self):
+                return fn(self, x, *args, **kw)
+            ins = [t for t in (x,) + tuple(args) + tuple(kw.values()) if isinstance(t, Tensor)]
+            deps = [t for t in ins if t.requires_grad] + [p for p in self.parameters() if p.requires_grad]
+            with torch.no_grad():
+                out = fn(self, x, *args, **kw)
+
+            def poison(t):
+                if not isinstance(t, Tensor) or not t.is_floating_point():
+                    return t
+                inplace = any(t is i for i in ins)
+                if inplace and t.requires_grad:
+                    return t
+                return _NoBackward.apply(t, what, inplace, *deps)
+            return tuple(poison(t) for t in out) if isinstance(out, tuple) else poison(out)
+        wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+        return wrapper
+    return deco
 
 
 class IdentityTransform(Transform):
@@ -74,8 +120,8 @@ class ActNorm(Transform):
             N.channel_stats(x, 0, B, C, P, xbs, self.scale, self.bias)
             self._mark_initialized()
 
+    @_granular("ActNorm")
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        _no_autograd(x, self, "ActNorm.transform")
         x = E.check_input(x)
         B, C, H, W = x.shape
         E.check_acc(log_det_jac, B, "log_det_jac")
@@ -87,8 +133,8 @@ class ActNorm(Transform):
             N.accumulate(log_det_jac, None, 0, B, self._mix.logdet, E.scalar_f32(x.device, H * W), 1)
         return y, log_det_jac, logp
 
+    @_granular("ActNorm")
     def invert(self, y: Tensor) -> Tensor:
-        _no_autograd(y, self, "ActNorm.invert")
         y = E.check_input(y)
         B, C, H, W = y.shape
         out = torch.empty_like(y)
@@ -115,8 +161,8 @@ class InvConv2d(Transform):
         self._mix = E.MixCache()
         return super()._apply(fn, *a, **k)
 
+    @_granular("InvConv2d")
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        _no_autograd(x, self, "InvConv2d.transform")
         x = E.check_input(x)
         B, C, H, W = x.shape
         E.check_acc(log_det_jac, B, "log_det_jac")
@@ -127,8 +173,8 @@ class InvConv2d(Transform):
             N.accumulate(log_det_jac, None, 0, B, self._mix.logdet, E.scalar_f32(x.device, H * W), 1)
         return y, log_det_jac, logp
 
+    @_granular("InvConv2d")
     def invert(self, y: Tensor) -> Tensor:
-        _no_autograd(y, self, "InvConv2d.invert")
         y = E.check_input(y)
         B, C, H, W = y.shape
         E.prepare_mix([(self._mix, self.weight, None, None, C, None)])
@@ -168,8 +214,8 @@ class AffineCoupling(Transform):
         pm, ldp = E.coupling_rows(self, x, xbs, B, C, H, W, init=True)
         N.coupling_apply(pm, ldp, zc.bias, zc.logs, x, y, ld_part, B, C, H, W, xbs, ybs, inverse)
 
+    @_granular("AffineCoupling")
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        _no_autograd(x, self, "AffineCoupling.transform")
         x = E.check_input(x)
         B, C, H, W = x.shape
         E.check_acc(log_det_jac, B, "log_det_jac")
@@ -181,8 +227,8 @@ class AffineCoupling(Transform):
             N.accumulate(log_det_jac, part, T, B)
         return y, log_det_jac, logp
 
+    @_granular("AffineCoupling")
     def invert(self, y: Tensor) -> Tensor:
-        _no_autograd(y, self, "AffineCoupling.invert")
         y = E.check_input(y)
         B, C, H, W = y.shape
         out = torch.empty_like(y)
@@ -193,6 +239,7 @@ class AffineCoupling(Transform):
 class Squeeze(Transform):
     """Space-to-depth by 2 (reference transforms.py:212-239): out channel = c*4 + h1*2 + w1."""
 
+    @_granular("Squeeze")
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         x = E.check_input(x)
         B, C, H, W = x.shape
@@ -202,6 +249,7 @@ class Squeeze(Transform):
         N.squeeze(x, y, B, C, H, W, C * H * W, C * H * W)
         return y, log_det_jac, logp
 
+    @_granular("Squeeze")
     def invert(self, y: Tensor) -> Tensor:
         y = E.check_input(y)
         B, C, H, W = y.shape
@@ -241,8 +289,8 @@ class Split(Transform):
         logs = self.conv.logs if self.conv is not None else None
         N.split_prior_logp(h, ldh, bias, logs, x, xbs, z_out, logp_part, B, C, H, W)
 
+    @_granular("Split")
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-        _no_autograd(x, self, "Split.transform")
         x = E.check_input(x)
         B, C, H, W = x.shape
         E.check_acc(logp, B, "logp")
@@ -257,8 +305,8 @@ class Split(Transform):
             N.accumulate(logp, part, T, B)
         return y, log_det_jac, z, logp
 
+    @_granular("Split")
     def invert(self, y: Tensor, inv_y_split: Tensor = None, temperature: float = 1.0) -> Tensor:
-        _no_autograd(y, self, "Split.invert")
         y = E.check_input(y)
         B, Ch, H, W = y.shape
         C, P = 2 * Ch, H * W

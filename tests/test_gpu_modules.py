@@ -331,8 +331,20 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         nf.Squeeze().transform(torch.zeros(1, 1, 3, 4, device=DEV), None, None)
     torch.set_grad_enabled(True)
+    # stand-alone transforms run their forward in grad mode (the reference's unit tests do that) ...
+    step = flow.blocks[0].flows[0]
+    xg = torch.randn(2, 4, 4, 4, device=DEV)
+    y, ld, _ = step.transform(xg, torch.zeros(2, device=DEV), None)
+    with torch.no_grad():
+        y0, ld0, _ = step.transform(xg, torch.zeros(2, device=DEV), None)
+    assert torch.equal(y, y0) and torch.equal(ld, ld0) and y.requires_grad
+    with pytest.raises(NotImplementedError):                          # ... but back-propagating through them is loud
+        y.sum().backward()
     with pytest.raises(NotImplementedError):
-        flow.blocks[0].flows[0].transform(torch.zeros(2, 4, 4, 4, device=DEV), torch.zeros(2, device=DEV), None)
+        (ld.sum() * 1.0).backward()
+    xr = flow.invert([torch.randn(2, 2, 4, 4, device=DEV), torch.randn(2, 8, 2, 2, device=DEV)])
+    with pytest.raises(NotImplementedError):
+        xr.sum().backward()
     with pytest.raises(RuntimeError):                                 # accumulators are updated in place
         flow.transform(x, torch.zeros(2, device=DEV, requires_grad=True), None)
     torch.set_grad_enabled(False)
