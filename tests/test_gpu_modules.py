@@ -317,6 +317,56 @@ def test_full_size_properties(cfg):
     assert (flow.invert(zs) - x).abs().max() < 1e-4
 
 
+def test_config4_geometry_celeba_128():
+    """BASELINE config 4 geometry (L5, 3x128x128, batch 8; K reduced to 4 to bound the fp32 run time): levels of
+    64x64 ... 4x4 pixels with 12 ... 192 channels — images larger than one CTA take the unfused kernels, 9C > 512
+    takes the multi-tile GEMMs.  Data-dependent init, round trip, oracle parity on one image."""
+    c, L, K, B, S = 3, 5, 4, 8, 128
+    torch.manual_seed(0)
+    flow = nf.Glow(c, L, K).to(DEV)
+    x = O.seeded_input((B, c, S, S), 321).to(DEV)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, lp = flow.transform(x, ld, lp)          # data-dependent init
+    assert [tuple(z.shape[1:]) for z in zs] == [(6, 64, 64), (12, 32, 32), (24, 16, 16), (48, 8, 8), (192, 4, 4)]
+    assert (flow.invert(zs) - x).abs().max() < 1e-4
+    sd = {k: v.cpu() for k, v in flow.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    for k in list(sd):
+        if k.endswith("net.4.weight") or k.endswith("net.4.bias") or k.endswith("net.4.logs") or ".split.conv." in k:
+            sd[k] = sd[k] + 0.003 * torch.randn(sd[k].shape, generator=g)
+    flow.load_state_dict(sd)
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, lp = flow.transform(x, ld, lp)
+    ld_o, lp_o = torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64)
+    zo, ld_o, lp_o = O.glow_transform(sd, x.cpu()[3:4], L, K, ld_o, lp_o)
+    for a, b in zip(zs, zo):
+        assert relerr(a[3:4], b) < 1e-4
+    np.testing.assert_allclose(ld.cpu().numpy()[3:4], ld_o.numpy(), rtol=1e-5, atol=5e-2)
+    np.testing.assert_allclose(lp.cpu().numpy()[3:4], lp_o.numpy(), rtol=1e-5, atol=5e-2)
+    assert (flow.invert(zs) - x).abs().max() < 1e-3
+
+
+def test_config5_sampling_decode_mnist():
+    """BASELINE config 5: Glow L3/K4 on 1x32x32, 128 latents per GPU (the diffusion prior's output, ~N(0,1)) decoded by
+    Glow.sample through NFBackbone's call pattern; transform(sample(z)) returns the latents (inverse-then-forward round
+    trip) and a subset matches the oracle's inverse."""
+    c, L, K, B, S = 1, 3, 4, 128, 32
+    flow, _, sd, _ = build(c, L, K, 17)
+    rng = np.random.default_rng(2)
+    lat = [torch.from_numpy(rng.standard_normal((B,) + shp).astype(np.float32)).to(DEV)
+           for shp in nf.calculate_output_shapes(L, c, S)]
+    x = flow.sample(lat, postprocess_func=None)
+    assert x.shape == (B, c, S, S) and flow.training
+    ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+    zs, ld, _ = flow.transform(x, ld, None)
+    for a, b in zip(zs, lat):
+        assert relerr(a, b) < 1e-3
+    xo = O.glow_invert(sd, [t.cpu()[:3] for t in lat], L, K)
+    assert relerr(x[:3], xo) < 1e-4
+
+
 def test_error_behaviour():
     flow, _, _, _ = build(1, 2, 1, 5)
     x = torch.zeros(2, 1, 8, 8, device=DEV)
