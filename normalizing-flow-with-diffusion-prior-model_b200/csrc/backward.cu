@@ -7,6 +7,8 @@
 //   gemm_tn_kernel             weight gradients: D[N1,N2] = sum_m A[m,N1]*B[m,N2] (split over M, deterministic partials)
 //   split_prior_bwd_kernel / gauss_const_bwd_kernel / col2im_add_kernel / reduce_rows_kernel
 // All reductions are two-stage with a fixed order (no float atomics): bitwise reproducible.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nfdpm {
@@ -17,6 +19,39 @@ template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloa
 template <typename T> __device__ __forceinline__ void stf(T* p, float v);
 template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 8-element vector load / store helpers (16-byte bf16, 2 x 16-byte fp32)
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------ coupling backward
 struct CouplingBwdArgs {
@@ -92,20 +127,43 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
     const int c = i / P, p = i - c * P;
     dub[i] = g_s[c * PS + p];
   }
-  // dpm rows: dpm[p', tap*C+co] = dP[co][p' - shift(tap)]  (zero outside the image / in the padding columns)
+  // dpm rows: dpm[p', tap*C+co] = dP[co][p' - shift(tap)]  (zero outside the image / in the padding columns).
+  // A thread produces 8 consecutive columns (one 16-byte bf16 / two 16-byte fp32 stores); (tap, co) advance
+  // incrementally, so there is one division per 8 elements instead of three per element.
   const int ldp = (int)a.ld_dpm;
   TD* dpmb = reinterpret_cast<TD*>(a.dpm) + (int64_t)b * P * ldp;
-  for (int i = tid; i < P * ldp; i += nt) {
-    const int pp = i / ldp, col = i - pp * ldp;
-    float v = 0.f;
-    if (col < 9 * C) {
-      const int tap = col / C, co = col - tap * C;
+  if ((ldp & 7) == 0 && (((uintptr_t)dpmb) & 15) == 0) {
+    const int n_g = ldp >> 3;
+    for (int it = tid; it < P * n_g; it += nt) {
+      const int pp = it / n_g, g = it - pp * n_g;
       const int py = pp / W, px = pp - py * W;
-      // pm row pp at tap feeds output pixel (py - (ky-1), px - (kx-1))
-      const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = dP_s[co * PS + yy * W + xx];
+      int col = g * 8;
+      int tap = col / C, co = col - tap * C;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float val = 0.f;
+        if (tap < 9) {
+          const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);   // pm row pp at tap feeds pixel (yy, xx)
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = dP_s[co * PS + yy * W + xx];
+        }
+        v[e] = val;
+        if (++co == C) { co = 0; ++tap; }
+      }
+      Vec8<TD>::store(dpmb + (int64_t)pp * ldp + g * 8, v);
     }
-    stf<TD>(dpmb + i, v);
+  } else {
+    for (int i = tid; i < P * ldp; i += nt) {
+      const int pp = i / ldp, col = i - pp * ldp;
+      float v = 0.f;
+      if (col < 9 * C) {
+        const int tap = col / C, co = col - tap * C;
+        const int py = pp / W, px = pp - py * W;
+        const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = dP_s[co * PS + yy * W + xx];
+      }
+      stf<TD>(dpmb + i, v);
+    }
   }
   // per-image parameter partials: one warp per (kind, j) row of r_s, fixed order
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
@@ -130,9 +188,23 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
     __syncthreads();
     if (s_last) {
       __threadfence();
-      for (int i = tid; i < 2 * C; i += nt) {
+      // [row group][2C] partial sums over interleaved images, then a fixed-order combine: deterministic and parallel
+      // (a single thread per column walking all B rows is ~B dependent L2 round trips)
+      const int n2c = 2 * C;
+      int RG = nt / n2c;
+      if (RG > 32) RG = 32;
+      if (RG < 1) RG = 1;
+      float* red = sm;                       // the image buffers are dead by now: RG * 2C floats
+      for (int idx = tid; idx < RG * n2c; idx += nt) {
+        const int rg = idx / n2c, i = idx - rg * n2c;
         float acc = 0.f;
-        for (int bb = 0; bb < a.B; ++bb) acc += __ldcg(a.dpar + (int64_t)bb * 2 * C + i);
+        for (int bb = rg; bb < a.B; bb += RG) acc += __ldcg(a.dpar + (int64_t)bb * n2c + i);
+        red[idx] = acc;
+      }
+      __syncthreads();
+      for (int i = tid; i < n2c; i += nt) {
+        float acc = 0.f;
+        for (int rg = 0; rg < RG; ++rg) acc += red[rg * n2c + i];
         if (i < C) a.dbias[i] = acc; else a.dlogs[i - C] = acc;
       }
       if (tid == 0) *a.counter = 0;
@@ -237,38 +309,6 @@ __global__ void dpm_expand_kernel(const float* __restrict__ dP, TD* __restrict__
 // rows [M, ld], channel fastest.  CTA = `rows_per_cta` rows x all N columns; a thread owns 8 consecutive columns
 // (16-byte bf16 / 32-byte fp32 vectors, fully coalesced rows), the CTA's 256 threads cover 256/(N/8) rows at a time and
 // loop over the rest; per-column partial sums are combined across the row groups in shared memory in a fixed order.
-template <typename T> struct Vec8;
-template <> struct Vec8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
-};
-template <> struct Vec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[2 * i] = __uint_as_float(w[i] << 16);
-      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-  }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&t);
-    }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
-
 template <typename TD, typename TH, typename TO>
 __global__ void __launch_bounds__(256) actnorm_relu_bwd_kernel(const TD* __restrict__ dh, const TH* __restrict__ h,
                                                                const float* __restrict__ scale, TO* __restrict__ dpre,
@@ -799,7 +839,13 @@ extern "C" int nfdpm_reduce_rows(const float* part, float* out, int R, int n, in
 }
 
 static int mix_bwd_tile(int C, int P) {
-  int tp = P < 256 ? P : 256;
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("NFDPM_MIXBWD_TP");
+    cap = e ? atoi(e) : 256;
+    if (cap < 8) cap = 256;
+  }
+  int tp = P < cap ? P : cap;
   while (tp > 8 && sizeof(float) * (2 * (size_t)C * (tp + 1) + (size_t)C * C) > 200 * 1024) tp = (tp + 1) / 2;
   return tp;
 }

@@ -10,6 +10,8 @@
 // its fp32 partial tile to a workspace slab; reduce_rows_kernel sums the slabs in a fixed order (deterministic, no
 // float atomics — `torch.use_deterministic_algorithms(True)` stays honest, reference utils.py:45-60).
 //   warp 0: TMA producer (4-stage ring) | warp 1: MMA issuer, TMEM owner | warps 2..5: epilogue (TMEM -> global)
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace nfdpm {
@@ -159,18 +161,28 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(const __grid_
   }
   __syncthreads();
   const int band = (128 + splits - 1) / splits;
-  const int r_lo = split * band, r_hi = min(128, r_lo + band);
+  const int r_lo = split * band;
+  const int r_hi = min(min(128, r_lo + band), N1 - t1 * 128);     // rows of this CTA's band that exist
   const int cols = min(BN, N2 - t2 * BN);
-  const int c4 = cols >> 2;
-  for (int r = r_lo; r < r_hi; ++r) {
-    const int n1 = t1 * 128 + r;
-    if (n1 >= N1) break;
-    const int64_t off = (int64_t)n1 * N2 + t2 * BN;
+  const int64_t slab = (int64_t)N1 * N2;
+  if (r_hi > r_lo) {
     if (out_mode == NFDPM_TN_OUT_PLAIN) {
-      for (int c = threadIdx.x; c < c4; c += TN_THREADS) {
+      // items = (row, float4 column) flattened over all threads; two items and all their slab loads in flight
+      const int c4 = cols >> 2, n_items = (r_hi - r_lo) * c4;
+      for (int it = threadIdx.x; it < n_items; it += TN_THREADS) {
+        const int r = it / c4, c = it - r * c4;
+        const int64_t off = (int64_t)(t1 * 128 + r_lo + r) * N2 + t2 * BN;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s2 = 0; s2 < splits; ++s2) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (int64_t)s2 * N1 * N2 + off) + c);
+        int s2 = 0;
+        for (; s2 + 4 <= splits; s2 += 4) {            // four slab loads in flight, added in slab order
+          float4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(ws + (s2 + j) * slab + off) + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        }
+        for (; s2 < splits; ++s2) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + s2 * slab + off) + c);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         float4* d = reinterpret_cast<float4*>(D + off) + c;
@@ -181,21 +193,45 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(const __grid_
         *d = acc;
       }
     } else {
-      // layout-changing outputs (the weight tensors' own layouts), element-wise
-      for (int c = threadIdx.x; c < cols; c += TN_THREADS) {
-        const int n2 = t2 * BN + c;
-        int64_t o;
+      // layout-changing outputs (the weight tensors' own layouts): float4 slab loads, four scalar stores
+      const int c4 = cols >> 2, n_items = (r_hi - r_lo) * c4;
+      for (int it = threadIdx.x; it < n_items; it += TN_THREADS) {
+        const int r = it / c4, c = it - r * c4;
+        const int n1 = t1 * 128 + r_lo + r, n2 = t2 * BN + 4 * c;
+        int tap = 0, co = 0;
         if (out_mode == NFDPM_TN_OUT_TAPS) {            // n1 = tap*out_c + co  ->  [co][n2][tap]  (ZeroConv weight)
-          const int tap = n1 / out_c, co = n1 - tap * out_c;
+          tap = n1 / out_c;
+          co = n1 - tap * out_c;
           if (tap >= 9) continue;
-          o = ((int64_t)co * N2 + n2) * 9 + tap;
-        } else {                                         // NFDPM_TN_OUT_STRIP: keep the first out_c columns
-          if (n2 >= out_c) continue;
-          o = (int64_t)n1 * out_c + n2;
+        } else if (n2 >= out_c) {                        // NFDPM_TN_OUT_STRIP: keep the first out_c columns
+          continue;
         }
-        float acc = 0.f;
-        for (int s2 = 0; s2 < splits; ++s2) acc += __ldcg(ws + (int64_t)s2 * N1 * N2 + off + c);
-        D[o] = accumulate ? D[o] + acc : acc;
+        const float4* src = reinterpret_cast<const float4*>(ws + (int64_t)n1 * N2 + t2 * BN) + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int s2 = 0;
+        for (; s2 + 4 <= splits; s2 += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (s2 + j) * slab));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        }
+        for (; s2 < splits; ++s2) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + s2 * slab));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int64_t o;
+          if (out_mode == NFDPM_TN_OUT_TAPS) {
+            o = ((int64_t)co * N2 + n2 + j) * 9 + tap;
+          } else {
+            if (n2 + j >= out_c) break;
+            o = (int64_t)n1 * out_c + n2 + j;
+          }
+          D[o] = accumulate ? D[o] + av[j] : av[j];
+        }
       }
     }
   }
@@ -225,9 +261,18 @@ void gemm_tn_tc_plan(int M, int N1, int N2, int* BN, int* tiles, int* splits, in
   const int n2t = (N2 + bn - 1) / bn, n1t = (N1 + 127) / 128;
   const int t = n1t * n2t;
   const int num_kb = (M + TN_BK - 1) / TN_BK;
+  // split the M reduction over the SMs, but keep >= 16 k-blocks (1024 rows) per CTA: below that the slab traffic and
+  // the wait of the in-kernel reduction cost more than the parallelism buys (measured: 17-25 us at M = 2048 with 18 splits)
+  static int min_kb = -1;
+  if (min_kb < 0) {
+    const char* e = getenv("NFDPM_TN_MIN_KB");
+    min_kb = e ? atoi(e) : 1;
+    if (min_kb < 1) min_kb = 1;
+  }
   int s = sm_count() / t;
   if (s < 1) s = 1;
-  if (s > num_kb) s = num_kb;
+  if (s > num_kb / min_kb) s = num_kb / min_kb;
+  if (s < 1) s = 1;
   const int per = (num_kb + s - 1) / s;
   s = (num_kb + per - 1) / per;
   *BN = bn; *tiles = t; *splits = s; *kb_per_split = per;
