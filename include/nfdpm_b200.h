@@ -38,6 +38,7 @@ extern "C" {
 /* GEMM epilogues */
 #define NFDPM_EPI_RAW 0          /* D = acc                                   */
 #define NFDPM_EPI_ACTNORM_RELU 1 /* D = max(0, exp(scale[n]) * (acc + bias[n])) (utils.py:69,84-87) */
+#define NFDPM_EPI_RELU_BWD 2     /* D = acc * (h > 0) * exp(scale[n]) + column partials (nfdpm_gemm_nt_relu_bwd) */
 
 typedef void* nfdpm_stream_t; /* cudaStream_t */
 
@@ -236,6 +237,11 @@ int nfdpm_coupling_bwd_tiles(int C, int H, int W);
 int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
                            const float* scale, void* dpre, int o_dtype, int64_t ld_o, float* part, int M, int N,
                            int rows_per_cta, nfdpm_stream_t stream);
+/* dgrad GEMM with the ActNorm+ReLU backward fused into the tcgen05 epilogue (bf16 operands and output):
+ * dpre = (A * Bw^T) * (h > 0) * exp(scale[n]); part [ceil(M/128)][2N] per-tile column sums -> d(scale), d(bias).
+ * Equivalent to nfdpm_gemm_nt (RAW) + nfdpm_actnorm_relu_bwd without the [M,N] round trip of dh. */
+int nfdpm_gemm_nt_relu_bwd(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* dpre, int64_t ldd, int M, int N,
+                           int K, const void* h, int64_t ldh, const float* scale, float* part, nfdpm_stream_t stream);
 /* out[i] (+)= sum_{r<R} part[r*stride + i], i < n */
 int nfdpm_reduce_rows(const float* part, float* out, int R, int n, int64_t stride, int accumulate, nfdpm_stream_t stream);
 /* out0[i] = sum_r part[r*stride + i] for i < n0, out1[i-n0] likewise for n0 <= i < n0+n1 (a parameter pair in one launch) */

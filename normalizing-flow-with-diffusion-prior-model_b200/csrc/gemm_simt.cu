@@ -10,7 +10,8 @@
 namespace nfdpm {
 
 int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
-               int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st);
+               int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st,
+               const void* ep_h = nullptr, int64_t ld_h = 0, float* ep_part = nullptr);
 
 constexpr int BK = 16;
 
@@ -192,4 +193,19 @@ extern "C" int nfdpm_gemm_nt(const void* A, int64_t lda, const void* Bw, int64_t
     else { if (wide) GO(128, NFDPM_EPI_ACTNORM_RELU, __nv_bfloat16); else GO(64, NFDPM_EPI_ACTNORM_RELU, __nv_bfloat16); }
   }
 #undef GO
+}
+
+/* dgrad GEMM with the ActNorm + ReLU backward fused into its epilogue (tensor-core path, bf16):
+ *   dpre[M,N] = (A[M,K] * Bw[N,K]^T) * (h > 0) * exp(scale[n]);   part[mt][2N]: per 128-row tile column sums of
+ *   g*h (-> d scale) and g*exp(scale) (-> d bias), g = acc * (h > 0).  Reduce part with nfdpm_reduce_rows2 over
+ *   ceil(M/128) rows.  Replaces nfdpm_gemm_nt + nfdpm_actnorm_relu_bwd (utils.py:69,84-87 backward). */
+extern "C" int nfdpm_gemm_nt_relu_bwd(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* dpre, int64_t ldd, int M,
+                                      int N, int K, const void* h, int64_t ldh, const float* scale, float* part,
+                                      nfdpm_stream_t stream) {
+  NFDPM_REQUIRE(A && Bw && dpre && h && scale && part, "nfdpm_gemm_nt_relu_bwd: null pointer");
+  NFDPM_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N <= 2048, "nfdpm_gemm_nt_relu_bwd: bad shape M=%d N=%d K=%d", M, N, K);
+  NFDPM_REQUIRE(lda >= K && ldb >= K && ldd >= N && ldh >= N && lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0,
+                "nfdpm_gemm_nt_relu_bwd: bad leading dimensions");
+  return nfdpm::gemm_nt_tc(A, lda, Bw, ldb, dpre, ldd, M, N, K, NFDPM_BF16, NFDPM_EPI_RELU_BWD, scale, nullptr,
+                           nfdpm::as_stream(stream), h, ldh, part);
 }

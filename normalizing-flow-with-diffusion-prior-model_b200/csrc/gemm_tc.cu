@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
                                                                    int BN, const float* __restrict__ ep_scale,
-                                                                   const float* __restrict__ ep_bias) {
+                                                                   const float* __restrict__ ep_bias,
+                                                                   const __nv_bfloat16* __restrict__ ep_h, int64_t ld_h,
+                                                                   float* __restrict__ ep_part) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 4];
   __shared__ uint32_t s_tmem_base;
@@ -81,6 +83,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       s_ep[n_pad + i] = (i < N) ? e * ep_bias[i] : 0.f;
     }
   }
+  if (EPI == NFDPM_EPI_RELU_BWD) {
+    for (int i = threadIdx.x; i < n_pad; i += TC_THREADS) s_ep[i] = (i < N) ? expf(ep_scale[i]) : 0.f;
+  }
+  // EPI_RELU_BWD: per-quadrant column partial sums of the tile [4][2][256], after the parameters
+  float* part_s = s_ep + 2 * n_pad;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,7 +155,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       // the previous tile's TMA stores must have finished READING the staging tile before it is overwritten
       if (warp == 2 && lane == 0) tma_store_wait_read();
       epi_barrier();
-      auto process = [&](const uint32_t (&r)[16], int c0) {
+      // EPI_RELU_BWD: 16 bf16 of the stashed activation h for this thread's row (two 16-byte loads)
+      const int64_t h_row = (int64_t)(m_blk * TC_BM + trow) * ld_h + n_blk * BN;
+      const bool row_ok = (m_blk * TC_BM + trow) < M;
+      auto load_h = [&](int c0, uint4 (&hh)[2]) {
+        if (EPI == NFDPM_EPI_RELU_BWD) {
+          if (row_ok && n_blk * BN + c0 < N) {
+            hh[0] = __ldg(reinterpret_cast<const uint4*>(ep_h + h_row + c0));
+            hh[1] = __ldg(reinterpret_cast<const uint4*>(ep_h + h_row + c0 + 8));
+          } else {
+            hh[0] = make_uint4(0, 0, 0, 0);
+            hh[1] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      };
+      auto process = [&](const uint32_t (&r)[16], const uint4 (&hh)[2], int c0) {
         const int n0 = n_blk * BN + c0;
         float v[16];
         if (EPI == NFDPM_EPI_ACTNORM_RELU) {
@@ -162,6 +183,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
             v[4 * j + 2] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 2]), e.z, b.z));
             v[4 * j + 3] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 3]), e.w, b.w));
           }
+        } else if (EPI == NFDPM_EPI_RELU_BWD) {
+          // dpre = dh * (h > 0) * e;  column partials ds += g*h, db += g*e   (utils.py:69,84-87 backward)
+          const uint32_t hw[8] = {hh[0].x, hh[0].y, hh[0].z, hh[0].w, hh[1].x, hh[1].y, hh[1].z, hh[1].w};
+          float ds[16], db[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float hv = __uint_as_float((j & 1) ? (hw[j >> 1] & 0xFFFF0000u) : (hw[j >> 1] << 16));
+            const float g = (hv > 0.f) ? __uint_as_float(r[j]) : 0.f;
+            v[j] = g * s_ep[n0 + j];
+            ds[j] = g * hv;
+            db[j] = v[j];
+          }
+          // transpose-reduce over the 32 rows of this warp: 16 shuffles per quantity, fixed order (deterministic)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            float* q_ = k == 0 ? ds : db;
+            float w8[8], w4[4], w2[2], w1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float send = (lane & 16) ? q_[i] : q_[i + 8], keep = (lane & 16) ? q_[i + 8] : q_[i];
+              w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = (lane & 8) ? w8[i] : w8[i + 4], keep = (lane & 8) ? w8[i + 4] : w8[i];
+              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = (lane & 4) ? w4[i] : w4[i + 2], keep = (lane & 4) ? w4[i + 2] : w4[i];
+              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+              const float send = (lane & 2) ? w2[0] : w2[1], keep = (lane & 2) ? w2[1] : w2[0];
+              w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+            if ((lane & 1) == 0) {
+              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              part_s[(q * 2 + k) * 256 + c0 + col] = w1;
+            }
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -170,17 +233,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       };
       // chunks half, half+2, half+4, ... ; the load of the next chunk is in flight while this one is processed
       uint32_t ra[16], rb[16];
+      uint4 ha[2], hb[2];
       int ch = half;
-      if (ch < n_chunks) tmem_ld16(taddr + ch * 16, ra);
+      if (ch < n_chunks) { tmem_ld16(taddr + ch * 16, ra); load_h(ch * 16, ha); }
       while (ch < n_chunks) {
         tmem_ld_wait();
-        if (ch + 2 < n_chunks) tmem_ld16(taddr + (ch + 2) * 16, rb);
-        process(ra, ch * 16);
+        if (ch + 2 < n_chunks) { tmem_ld16(taddr + (ch + 2) * 16, rb); load_h((ch + 2) * 16, hb); }
+        process(ra, ha, ch * 16);
         ch += 2;
         if (ch >= n_chunks) break;
         tmem_ld_wait();
-        if (ch + 2 < n_chunks) tmem_ld16(taddr + (ch + 2) * 16, ra);
-        process(rb, ch * 16);
+        if (ch + 2 < n_chunks) { tmem_ld16(taddr + (ch + 2) * 16, ra); load_h((ch + 2) * 16, ha); }
+        process(rb, hb, ch * 16);
         ch += 2;
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp before doing the stores
@@ -188,6 +252,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       mbar_arrive(bar_tempty + 8 * acc);
       fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA engine
       epi_barrier();
+      if (EPI == NFDPM_EPI_RELU_BWD) {
+        // combine the four row quadrants in order; one partial row per 128-row tile: part[m_blk][2N]
+        const int t = threadIdx.x - 64;
+        if (t < BN && n_blk * BN + t < N) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            s0 += part_s[(qq * 2 + 0) * 256 + t];
+            s1 += part_s[(qq * 2 + 1) * 256 + t];
+          }
+          ep_part[(int64_t)m_blk * 2 * N + n_blk * BN + t] = s0;
+          ep_part[(int64_t)m_blk * 2 * N + N + n_blk * BN + t] = s1;
+        }
+      }
       if (warp == 2 && lane == 0) {
         constexpr int CPB = TcStage<OutT>::kColsPerBox;
         const int n_boxes = (BN + CPB - 1) / CPB;
@@ -211,20 +289,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
 // ---------------------------------------------------------------- host side
 template <int EPI, typename OutT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, int M, int N, int K, int BN,
-                     const float* es, const float* eb, int grid, size_t smem, cudaStream_t st) {
+                     const float* es, const float* eb, int grid, size_t smem, cudaStream_t st,
+                     const __nv_bfloat16* ep_h = nullptr, int64_t ld_h = 0, float* ep_part = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     NFDPM_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    220 * 1024));
+                                    226 * 1024));
     attr_set = true;
   }
   NFDPM_CUDA(launch_pdl(gemm_nt_tc_kernel<EPI, OutT>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, tmD, M, N, K, BN,
-                        es, eb));
+                        es, eb, ep_h, ld_h, ep_part));
   return 0;
 }
 
 int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
-               int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st) {
+               int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st,
+               const void* ep_h, int64_t ld_h, float* ep_part) {
   NFDPM_REQUIRE(N % 16 == 0, "nfdpm_gemm_nt(bf16): N=%d must be a multiple of 16", N);
   NFDPM_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)D % 16 == 0),
                 "nfdpm_gemm_nt(bf16): operands must be 16-byte aligned");
@@ -250,7 +330,14 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sms ? tiles : sms;
   const size_t n_pad = (size_t)((N + BN - 1) / BN) * BN;
-  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_CSTAGE_BYTES + (epilogue == NFDPM_EPI_ACTNORM_RELU ? 2 * n_pad * 4 : 0);
+  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_CSTAGE_BYTES +
+                      (epilogue != NFDPM_EPI_RAW ? 2 * n_pad * 4 : 0) + (epilogue == NFDPM_EPI_RELU_BWD ? 4 * 2 * 256 * 4 : 0);
+  if (epilogue == NFDPM_EPI_RELU_BWD) {
+    NFDPM_REQUIRE(out_dtype == NFDPM_BF16 && ep_h && ep_part && ep_scale && ld_h % 8 == 0 && ((uintptr_t)ep_h % 16) == 0,
+                  "nfdpm_gemm_nt_relu_bwd: needs bf16 output, h (16-byte aligned, ld %% 8 == 0), scale and part");
+    return launch_tc<NFDPM_EPI_RELU_BWD, __nv_bfloat16>(tmA, tmB, tmD, M, N, K, BN, ep_scale, nullptr, grid, smem, st,
+                                                         (const __nv_bfloat16*)ep_h, ld_h, ep_part);
+  }
 #define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, tmD, M, N, K, BN, ep_scale, ep_bias, grid, smem, st)
   if (out_dtype == NFDPM_F32) {
     if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, float); else GO(NFDPM_EPI_ACTNORM_RELU, float);

@@ -78,6 +78,7 @@ def _load() -> C.CDLL:
         "nfdpm_gemm3_boundary_ok": ([i32, i32, i32, i32, i32, i64], C.c_int),
         "nfdpm_gemm3_boundary": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
                                   i32, i32, i32, i64, i32, vp], C.c_int),
+        "nfdpm_gemm_nt_relu_bwd": ([vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp, vp, vp], C.c_int),
         "nfdpm_opt_chunk": ([], C.c_int),
         "nfdpm_pack_elems": ([], C.c_int),
         "nfdpm_pack_batch": ([vp, i32, i32, vp], C.c_int),
@@ -111,7 +112,7 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
            "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch",
-           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles"]
+           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_nt_relu_bwd"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -361,3 +362,7 @@ def gemm3_boundary(h2, ldh, w3p, pm_out, ld_pm_out, src, src_bs, bias3, logs3, l
     _ok(lib.nfdpm_gemm3_boundary(_p(h2), ldh, _p(w3p), _p(pm_out), ld_pm_out, _p(src), src_bs, _p(bias3), _p(logs3),
                                  _p(ld_part), _p(mt), _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1),
                                  _dt(a1) if a1 is not None else F32, lda1, B, Cc, H, W, K, ldp, int(inverse), _st()))
+
+
+def gemm_nt_relu_bwd(A, lda, Bw, ldb, dpre, ldd, M, Nn, K, h, ldh, scale, part) -> None:
+    _ok(lib.nfdpm_gemm_nt_relu_bwd(_p(A), lda, _p(Bw), ldb, _p(dpre), ldd, M, Nn, K, _p(h), ldh, _p(scale), _p(part), _st()))

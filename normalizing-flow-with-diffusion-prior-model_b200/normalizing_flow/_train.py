@@ -19,6 +19,7 @@ into d(InvConv2d.weight), d(ActNorm.scale), d(ActNorm.bias).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -317,13 +318,16 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         dpm = torch.empty(M * Kp3, dtype=dt, device=dev)
         dh = torch.empty(M * F, dtype=dt, device=dev)
         dpre = torch.empty(M * F, dtype=dt, device=dev)
+        dpre1 = torch.empty(M * F, dtype=dt, device=dev)
+        n_mt = (M + 127) // 128
         dA1 = torch.empty(M * K1p, **f32)
-        an_part = torch.empty(n_cta * 2 * F, **f32)
+        an_part = torch.empty(max(n_cta, n_mt) * 2 * F, **f32)
         T_c, T_m = N.coupling_bwd_tiles(C, h, w), N.mix_bwd_tiles(C, h, w)     # pixel tiles per image (1: image per CTA)
         dpar3 = torch.empty(B * T_c * 2 * C, **f32)
         dp_scratch = torch.empty(M * C, **f32) if T_c > 1 else None
         mix_part = torch.empty(K, B * T_m * (C * C + C), **f32)
         tc = dt == torch.bfloat16            # tensor-core wgrad: in-kernel split reduction + direct weight layouts
+        fused_rb = tc and os.environ.get("NFDPM_FUSED_RELU_BWD", "0") == "1"
         d1 = torch.empty(F * K1p, **f32)
         d3 = torch.empty(ldp * F, **f32)
         ws = torch.empty(max(N.gemm_tn_workspace(M, F, F), N.gemm_tn_workspace(M, ldp, F),
@@ -346,15 +350,26 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             else:
                 N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws, fused_reduce=False)
                 N.pack_matrix(d3, sink.get(zc.weight), C, F, 9, F, 1, C * F, 9, C * F)
-            N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
-            # second Conv2dActNorm (1x1)
-            N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, rows_cta)
-            N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_cta, F, F, 2 * F)
+            # second Conv2dActNorm (1x1).  The dgrad GEMM with the ActNorm+ReLU backward fused into its epilogue exists
+            # (nfdpm_gemm_nt_relu_bwd) but is epilogue-bound today (measured in graph, level 0: 32.9 / 40.7 us fused vs
+            # 10.8+18.3 / 18.2+18.3 us GEMM + elementwise kernel; profiles/r01_levels_bwd_in_graph.txt): opt-in.
+            if fused_rb:
+                N.gemm_nt_relu_bwd(dpm, Kp3, bc.w3t, Kp3, dpre, F, M, F, Kp3, lv.h2[k], F, an2.scale, an_part)
+                N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_mt, F, F, 2 * F)
+            else:
+                N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
+                N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, rows_cta)
+                N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_cta, F, F, 2 * F)
             N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws, fused_reduce=tc)
-            N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
             # first Conv2dActNorm (3x3)
-            N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, rows_cta)
-            N.reduce_rows2(an_part, sink.get(an1.scale), sink.get(an1.bias), n_cta, F, F, 2 * F)
+            if fused_rb:
+                N.gemm_nt_relu_bwd(dpre, F, bc.w2t, F, dpre1, F, M, F, F, lv.h1[k], F, an1.scale, an_part)
+                N.reduce_rows2(an_part, sink.get(an1.scale), sink.get(an1.bias), n_mt, F, F, 2 * F)
+                dpre, dpre1 = dpre1, dpre
+            else:
+                N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
+                N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, rows_cta)
+                N.reduce_rows2(an_part, sink.get(an1.scale), sink.get(an1.bias), n_cta, F, F, 2 * F)
             if tc:
                 N.gemm_tn(dpre, F, lv.A1[k], K1p, sink.get(conv1.weight), M, F, K1p, ws, out_mode=N.TN_OUT_STRIP,
                           out_c=Ch * 9)

@@ -559,3 +559,28 @@ def test_gemm3_boundary_support_query():
     assert not N.gemm3_boundary_ok(2, 96, 8, 8, 512, 864)        # 9C > 512 TMEM columns
     assert not N.gemm3_boundary_ok(3, 16, 2, 2, 512, 144)        # 32 images per tile: more than one per warp
     assert N.gemm3_boundary_ok(128, 48, 4, 4, 512, 432)
+
+
+@pytest.mark.parametrize("M,N_,K", [(2048, 512, 512), (1000, 512, 128), (32768, 512, 512), (300, 64, 64)])
+def test_gemm_nt_relu_bwd_fused_epilogue(M, N_, K):
+    """dgrad GEMM with ActNorm+ReLU backward in the tcgen05 epilogue == GEMM followed by nfdpm_actnorm_relu_bwd:
+    dpre and the column sums (d scale, d bias), incl. rows beyond the last full 128-row tile."""
+    A = (rnd(M, K, seed=1, scale=0.5)).to(DEV).to(torch.bfloat16)
+    Bw = (rnd(N_, K, seed=2, scale=0.1)).to(DEV).to(torch.bfloat16)
+    h = rnd(M, N_, seed=3).to(DEV).clamp_min(0).to(torch.bfloat16)          # ~half the entries are zero (ReLU output)
+    scale = rnd(N_, seed=4, scale=0.2).to(DEV)
+    n_mt = (M + 127) // 128
+    dpre = torch.empty(M, N_, dtype=torch.bfloat16, device=DEV)
+    part = torch.full((n_mt * 2 * N_,), float("nan"), device=DEV)
+    N.gemm_nt_relu_bwd(A, K, Bw, K, dpre, N_, M, N_, K, h, N_, scale, part)
+    ds, db = torch.empty(N_, device=DEV), torch.empty(N_, device=DEV)
+    N.reduce_rows2(part, ds, db, n_mt, N_, N_, 2 * N_)
+    sync()
+    acc = A.float() @ Bw.float().T
+    g = torch.where(h.float() > 0, acc, torch.zeros_like(acc))
+    e = torch.exp(scale)
+    ref = g * e
+    assert float((dpre.float() - ref).norm() / ref.norm()) < 4e-3          # bf16 output rounding
+    ds_ref, db_ref = (g * h.float()).sum(0), ref.sum(0)
+    assert float((ds - ds_ref).norm() / ds_ref.norm()) < 1e-4
+    assert float((db - db_ref).norm() / db_ref.norm()) < 1e-4

@@ -70,13 +70,20 @@ for lvl, (C, hw) in enumerate([(12, 16), (24, 8), (48, 4)]):
     r["wgrad3"] = graph_time(lambda: N.gemm_tn(dpm, Kp3, h2, F, dw3, M, ldp, F, ws, out_mode=N.TN_OUT_TAPS, out_c=C))
     r["dgrad3"] = graph_time(lambda: N.gemm_nt(dpm, Kp3, w3t, Kp3, dh, F, M, F, Kp3))
     r["actnorm_relu_bwd"] = graph_time(lambda: N.actnorm_relu_bwd(dh, F, h2, F, scale, dpre, F, an_part, M, F, rows))
+    n_mt = (M + 127) // 128
+    part2 = torch.empty(n_mt * 2 * F, **f32)
+    r["dgrad3_fused"] = graph_time(lambda: N.gemm_nt_relu_bwd(dpm, Kp3, w3t, Kp3, dpre, F, M, F, Kp3, h2, F, scale, part2))
+    r["dgrad2_fused"] = graph_time(lambda: N.gemm_nt_relu_bwd(dh, F, w2t, F, dpre, F, M, F, F, h1, F, scale, part2))
     r["reduce_rows2"] = graph_time(lambda: N.reduce_rows2(an_part, gs, gbb, n_cta, F, F, 2 * F))
     r["wgrad2"] = graph_time(lambda: N.gemm_tn(dpre, F, h1, F, dw2, M, F, F, ws))
     r["dgrad2"] = graph_time(lambda: N.gemm_nt(dpre, F, w2t, F, dh, F, M, F, F))
     r["wgrad1"] = graph_time(lambda: N.gemm_tn(dpre, F, a1, K1p, dw1, M, F, K1p, ws, out_mode=N.TN_OUT_STRIP, out_c=Ch * 9))
     r["dgrad1"] = graph_time(lambda: N.gemm_nt(dpre, F, w1t, F, dA1, K1p, M, K1p, F))
     r["mix_bwd"] = graph_time(lambda: N.mix_bwd(du, C * P, dA1, K1p, x, C * P, mt, dxb, C * P, part, B, C, hw, hw))
-    r["sum"] = sum(v for k, v in r.items() if k not in ("level", "M")) + r["actnorm_relu_bwd"] + r["reduce_rows2"]
+    r["sum"] = (r["coupling_bwd"] + r["wgrad3"] + r["dgrad3_fused"] + r["wgrad2"] + r["dgrad2_fused"] + r["wgrad1"] +
+                r["dgrad1"] + r["mix_bwd"] + 2 * r["reduce_rows2"])
+    r["sum_unfused"] = (r["sum"] - r["dgrad3_fused"] - r["dgrad2_fused"] + r["dgrad3"] + r["dgrad2"] +
+                        2 * r["actnorm_relu_bwd"])
     out.append(r)
     print({k: (round(v, 2) if isinstance(v, float) else v) for k, v in r.items()})
 print(f"# backward chain per StepFlow, sum over levels: {sum(r['sum'] for r in out):.1f} us -> x16 = {sum(r['sum'] for r in out) * 16 / 1e3:.2f} ms")
