@@ -5,6 +5,8 @@
 //
 // Tile 128 x BN x 16, 256 threads, 8 x (BN/16) outputs per thread (split 4+4 so shared-memory reads are
 // conflict-free 128-bit), register-prefetched double buffering.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nfdpm {
@@ -12,6 +14,10 @@ namespace nfdpm {
 int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
                int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st,
                const void* ep_h = nullptr, int64_t ld_h = 0, float* ep_part = nullptr);
+
+// CTA-pair (cta_group::2) variant, gemm_tc2.cu; returns -1 for shapes it does not take
+int gemm_nt_tc2(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
+                int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st);
 
 constexpr int BK = 16;
 
@@ -176,6 +182,15 @@ extern "C" int nfdpm_gemm_nt(const void* A, int64_t lda, const void* Bw, int64_t
   cudaStream_t st = as_stream(stream);
   if (in_dtype == NFDPM_BF16) {
     NFDPM_REQUIRE(K % 64 == 0, "nfdpm_gemm_nt: bf16 path needs K %% 64 == 0 (K=%d)", K);
+    static int use_pair = -1;
+    if (use_pair < 0) {
+      const char* e = getenv("NFDPM_TC2");
+      use_pair = (e != nullptr && e[0] == '1') ? 1 : 0;   // opt-in: measured no faster (the kernels are epilogue-bound)
+    }
+    if (use_pair && ((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)D % 16 == 0)) {
+      const int r = gemm_nt_tc2(A, lda, Bw, ldb, D, ldd, M, N, K, out_dtype, epilogue, ep_scale, ep_bias, st);
+      if (r >= 0) return r;
+    }
     return gemm_nt_tc(A, lda, Bw, ldb, D, ldd, M, N, K, out_dtype, epilogue, ep_scale, ep_bias, st);
   }
   NFDPM_REQUIRE(in_dtype == NFDPM_F32, "nfdpm_gemm_nt: bad in_dtype %d", in_dtype);

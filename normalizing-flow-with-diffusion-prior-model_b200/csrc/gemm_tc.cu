@@ -28,7 +28,14 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_B_BYTES_MAX = 256 * TC_BK * 2;        // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+// Epilogue warps of THIS kernel: four per TMEM lane quadrant.  ncu r1 (source page): with two per quadrant the 8 epilogue
+// warps were busy ~73 % of the kernel (IPC 0.9/SM, latency-bound on tcgen05.ld -> FFMA -> F2FP -> STS chains) and the
+// tensor pipe idled at 41 % waiting for a drained accumulator stage: the kernel was EPILOGUE-bound, not operand-bound
+// (which is why the cta_group::2 variant, gemm_tc2.cu, did not help).  More warps = more chains in flight.
+constexpr int TCG_EPI_WARPS = 16;
+constexpr int TCG_EPQ = TCG_EPI_WARPS / 4;            // epilogue warps per quadrant = chunk stride
+constexpr int TC_THREADS = 64 + 32 * TCG_EPI_WARPS;
+__device__ __forceinline__ void epi_barrier_g() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TCG_EPI_WARPS) : "memory"); }
 constexpr int TC_ACC_COLS = 256;     // TMEM columns per accumulator stage
 constexpr int TC_CSTAGE_BYTES = 64 * 1024;   // output staging: 128 rows x 256 bf16 / 128 fp32, as 16 KB swizzled boxes
 
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 32 * TC_EPI_WARPS);
+      mbar_init(bar_tempty + 8 * a, 32 * TCG_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                               // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;                     // which of the two warps of the quadrant
+    const int half = (warp - 2) >> 2;                     // which of the TCG_EPQ warps of the quadrant
     const int n_chunks = BN >> 4;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_ACC_COLS;
       // the previous tile's TMA stores must have finished READING the staging tile before it is overwritten
       if (warp == 2 && lane == 0) tma_store_wait_read();
-      epi_barrier();
+      epi_barrier_g();
       // EPI_RELU_BWD: 16 bf16 of the stashed activation h for this thread's row (two 16-byte loads)
       const int64_t h_row = (int64_t)(m_blk * TC_BM + trow) * ld_h + n_blk * BN;
       const bool row_ok = (m_blk * TC_BM + trow) < M;
@@ -231,27 +238,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
         }
         TcStage<OutT>::put16(cstage, trow, c0, v);
       };
-      // chunks half, half+2, half+4, ... ; the load of the next chunk is in flight while this one is processed
+      // chunks half, half+TCG_EPQ, ... ; the load of the next chunk is in flight while this one is processed
       uint32_t ra[16], rb[16];
       uint4 ha[2], hb[2];
       int ch = half;
       if (ch < n_chunks) { tmem_ld16(taddr + ch * 16, ra); load_h(ch * 16, ha); }
       while (ch < n_chunks) {
         tmem_ld_wait();
-        if (ch + 2 < n_chunks) { tmem_ld16(taddr + (ch + 2) * 16, rb); load_h((ch + 2) * 16, hb); }
+        if (ch + TCG_EPQ < n_chunks) { tmem_ld16(taddr + (ch + TCG_EPQ) * 16, rb); load_h((ch + TCG_EPQ) * 16, hb); }
         process(ra, ha, ch * 16);
-        ch += 2;
+        ch += TCG_EPQ;
         if (ch >= n_chunks) break;
         tmem_ld_wait();
-        if (ch + 2 < n_chunks) { tmem_ld16(taddr + (ch + 2) * 16, ra); load_h((ch + 2) * 16, ha); }
+        if (ch + TCG_EPQ < n_chunks) { tmem_ld16(taddr + (ch + TCG_EPQ) * 16, ra); load_h((ch + TCG_EPQ) * 16, ha); }
         process(rb, hb, ch * 16);
-        ch += 2;
+        ch += TCG_EPQ;
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp before doing the stores
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
       fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA engine
-      epi_barrier();
+      epi_barrier_g();
       if (EPI == NFDPM_EPI_RELU_BWD) {
         // combine the four row quadrants in order; one partial row per 128-row tile: part[m_blk][2N]
         const int t = threadIdx.x - 64;
