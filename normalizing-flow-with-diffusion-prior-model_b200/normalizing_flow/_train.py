@@ -82,6 +82,16 @@ def _pack_bwd(cp, dt: torch.dtype) -> _BwdCache:
     return cache
 
 
+_SIDE = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    s = _SIDE.get(dev.index)
+    if s is None:
+        s = _SIDE[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
 class _LevelStash:
     __slots__ = ("C", "h", "w", "u", "x", "A1", "h1", "h2", "pm", "K1p", "ldp", "state_out")
 
@@ -315,25 +325,48 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         du = torch.empty(B, C, P, **f32)
         pong = (torch.empty(B, C, P, **f32), torch.empty(B, C, P, **f32))   # dx of successive steps alternate
         Kp3 = E.round_up(9 * C, 64)
-        dpm = torch.empty(M * Kp3, dtype=dt, device=dev)
         dh = torch.empty(M * F, dtype=dt, device=dev)
-        dpre = torch.empty(M * F, dtype=dt, device=dev)
-        dpre1 = torch.empty(M * F, dtype=dt, device=dev)
         n_mt = (M + 127) // 128
+        tc = dt == torch.bfloat16            # tensor-core wgrad: in-kernel split reduction + direct weight layouts
+        fused_rb = tc and os.environ.get("NFDPM_FUSED_RELU_BWD", "0") == "1"
+        # The weight-gradient GEMMs feed only the optimiser: they run on a SIDE stream, concurrently with the
+        # dgrad / elementwise chain of the same and the next StepFlow.  Their operands (dpm, dpre2, dpre1) are therefore
+        # double-buffered across steps, and a buffer set is rewritten only after the side stream has read it.
+        side = _side_stream(dev) if (tc and os.environ.get("NFDPM_WGRAD_STREAM", "1") != "0") else None
+        main = torch.cuda.current_stream(dev)
+        nbuf = 2 if side is not None else 1
+        dpm_b = [torch.empty(M * Kp3, dtype=dt, device=dev) for _ in range(nbuf)]
+        dpre2_b = [torch.empty(M * F, dtype=dt, device=dev) for _ in range(nbuf)]
+        dpre1_b = [torch.empty(M * F, dtype=dt, device=dev) for _ in range(nbuf)]
+        read_done = [None, None]
         dA1 = torch.empty(M * K1p, **f32)
-        an_part = torch.empty(max(n_cta, n_mt) * 2 * F, **f32)
+        # ActNorm partial-sum buffers: one per (buffer set, layer) so their reductions can run on the side stream too
+        an_part_b = [[torch.empty(max(n_cta, n_mt) * 2 * F, **f32) for _ in range(2)] for _ in range(nbuf)]
         T_c, T_m = N.coupling_bwd_tiles(C, h, w), N.mix_bwd_tiles(C, h, w)     # pixel tiles per image (1: image per CTA)
         dpar3 = torch.empty(B * T_c * 2 * C, **f32)
         dp_scratch = torch.empty(M * C, **f32) if T_c > 1 else None
         mix_part = torch.empty(K, B * T_m * (C * C + C), **f32)
-        tc = dt == torch.bfloat16            # tensor-core wgrad: in-kernel split reduction + direct weight layouts
-        fused_rb = tc and os.environ.get("NFDPM_FUSED_RELU_BWD", "0") == "1"
         d1 = torch.empty(F * K1p, **f32)
         d3 = torch.empty(ldp * F, **f32)
         ws = torch.empty(max(N.gemm_tn_workspace(M, F, F), N.gemm_tn_workspace(M, ldp, F),
                              N.gemm_tn_workspace(M, F, K1p)), **f32)
+
+        def wgrad(fn):
+            """Run a weight-gradient launch on the side stream once everything enqueued so far on main is done."""
+            if side is None:
+                fn()
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fn()
+
         for k in range(K - 1, -1, -1):
             step = flows[k]
+            sb = (K - 1 - k) % nbuf
+            dpm, dpre, dpre1 = dpm_b[sb], dpre2_b[sb], dpre1_b[sb]
+            an_part, an_part1 = an_part_b[sb]
+            if side is not None and read_done[sb] is not None:
+                main.wait_event(read_done[sb])          # the wgrads of two steps ago have read this buffer set
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
             bc = cp._bwd_cache                   # refreshed by the forward's PackPlan
@@ -346,7 +379,8 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
                 N.reduce_rows2(dpar3, sink.get(zc.bias), sink.get(zc.logs), B * T_c, C, C, 2 * C)
             # ZeroConv 3x3: weight gradient in the taps-as-N layout, then back to [C, F, 3, 3]
             if tc:      # the split reduction writes d(W3) straight in its [C, F, 3, 3] layout
-                N.gemm_tn(dpm, Kp3, lv.h2[k], F, sink.get(zc.weight), M, ldp, F, ws, out_mode=N.TN_OUT_TAPS, out_c=C)
+                wgrad(lambda: N.gemm_tn(dpm, Kp3, lv.h2[k], F, sink.get(zc.weight), M, ldp, F, ws,
+                                        out_mode=N.TN_OUT_TAPS, out_c=C))
             else:
                 N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws, fused_reduce=False)
                 N.pack_matrix(d3, sink.get(zc.weight), C, F, 9, F, 1, C * F, 9, C * F)
@@ -355,32 +389,43 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             # 10.8+18.3 / 18.2+18.3 us GEMM + elementwise kernel; profiles/r01_levels_bwd_in_graph.txt): opt-in.
             if fused_rb:
                 N.gemm_nt_relu_bwd(dpm, Kp3, bc.w3t, Kp3, dpre, F, M, F, Kp3, lv.h2[k], F, an2.scale, an_part)
-                N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_mt, F, F, 2 * F)
+                n_red = n_mt
             else:
                 N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
                 N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, rows_cta)
-                N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_cta, F, F, 2 * F)
-            N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws, fused_reduce=tc)
+                n_red = n_cta
+
+            def side2():
+                N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_red, F, F, 2 * F)
+                N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws, fused_reduce=tc)
+            wgrad(side2)
             # first Conv2dActNorm (3x3)
             if fused_rb:
-                N.gemm_nt_relu_bwd(dpre, F, bc.w2t, F, dpre1, F, M, F, F, lv.h1[k], F, an1.scale, an_part)
-                N.reduce_rows2(an_part, sink.get(an1.scale), sink.get(an1.bias), n_mt, F, F, 2 * F)
-                dpre, dpre1 = dpre1, dpre
+                N.gemm_nt_relu_bwd(dpre, F, bc.w2t, F, dpre1, F, M, F, F, lv.h1[k], F, an1.scale, an_part1)
             else:
                 N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
-                N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre, F, an_part, M, F, rows_cta)
-                N.reduce_rows2(an_part, sink.get(an1.scale), sink.get(an1.bias), n_cta, F, F, 2 * F)
-            if tc:
-                N.gemm_tn(dpre, F, lv.A1[k], K1p, sink.get(conv1.weight), M, F, K1p, ws, out_mode=N.TN_OUT_STRIP,
-                          out_c=Ch * 9)
-            else:
-                N.gemm_tn(dpre, F, lv.A1[k], K1p, d1, M, F, K1p, ws, fused_reduce=False)
-                _strip_cols(d1, sink.get(conv1.weight), F, K1p, Ch * 9)
-            N.gemm_nt(dpre, F, bc.w1t, F, dA1, K1p, M, K1p, F)
+                N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre1, F, an_part1, M, F, rows_cta)
+
+            def side1():
+                N.reduce_rows2(an_part1, sink.get(an1.scale), sink.get(an1.bias), n_red, F, F, 2 * F)
+                if tc:
+                    N.gemm_tn(dpre1, F, lv.A1[k], K1p, sink.get(conv1.weight), M, F, K1p, ws, out_mode=N.TN_OUT_STRIP,
+                              out_c=Ch * 9)
+                else:
+                    N.gemm_tn(dpre1, F, lv.A1[k], K1p, d1, M, F, K1p, ws, fused_reduce=False)
+                    _strip_cols(d1, sink.get(conv1.weight), F, K1p, Ch * 9)
+            wgrad(side1)
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                read_done[sb] = ev
+            N.gemm_nt(dpre1, F, bc.w1t, F, dA1, K1p, M, K1p, F)
             # fused ActNorm + 1x1 conv
             dxb = pong[k & 1]
             N.mix_bwd(du, C * P, dA1, K1p, lv.x[k], C * P, step._mix.fwd_mt, dxb, C * P, mix_part[k], B, C, h, w)
             dy = dxb
+        if side is not None:
+            main.wait_stream(side)                # every weight gradient of the level is complete (all-reduce, buffers)
         items = []
         keep = []
         for k, step in enumerate(flows):
