@@ -118,7 +118,7 @@ int nfdpm_pack_matrix(const float* in, void* out, int out_dtype, int na, int nb,
 /* nfdpm_pack_matrix for MANY matrices in one launch (all weight layouts of all StepFlows after an optimiser step).
  * jobs_dev: device table of 10 x int64 per job: in, out, sa, sb, sk, ld_out, na|nb<<32, nk|rows_out<<32,
  * out_dtype|first_block<<32, nk2|sk2<<32 (column k reads offset (k/nk2)*sk + (k%nk2)*sk2; nk2 = 1 is the plain form).
- * Job i owns blocks [first_block_i, first_block_{i+1}), ceil(rows_out*ld_out / nfdpm_pack_elems()) of them. */
+ * Job i owns blocks [first_block_i, first_block_{i+1}): ceil(rows_out/64) * ceil(ld_out/64) tiles of 64 x 64 elements. */
 int nfdpm_pack_elems(void);
 int nfdpm_pack_batch(const int64_t* jobs_dev, int n_jobs, int n_blocks, nfdpm_stream_t stream);
 

@@ -68,9 +68,10 @@ __global__ void pack_matrix_kernel(const float* __restrict__ in, T* __restrict__
 // separate packs per StepFlow were ~440 launches per training step).  jobs: device table, 10 x int64 per job:
 //   [0] in  [1] out  [2] sa  [3] sb  [4] sk  [5] ld_out  [6] na | nb<<32  [7] nk | rows_out<<32
 //   [8] out_dtype | first_block<<32  [9] nk2 | sk2<<32   (column k -> (k / nk2)*sk + (k % nk2)*sk2; nk2 = 1: plain)
-constexpr int PACK_ELEMS = 4096;
+constexpr int PACK_ELEMS = 4096;      // one CTA = a 64 (rows) x 64 (columns) tile of the output matrix
 __global__ void __launch_bounds__(256) pack_batch_kernel(const int64_t* __restrict__ jobs, int n_jobs) {
   __shared__ int s_job;
+  __shared__ float tile[64][65];
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_jobs - 1;                       // last job whose first_block <= blockIdx.x
     while (lo < hi) {
@@ -88,21 +89,34 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const int64_t* __restri
   const int dtype = (int)(j[8] & 0xffffffff), first = (int)(j[8] >> 32);
   const int nk2 = (int)(j[9] & 0xffffffff);
   const int64_t sk2 = j[9] >> 32;
-  const int64_t n = (int64_t)rows_out * ld;
-  const int64_t base = (int64_t)(blockIdx.x - first) * PACK_ELEMS;
-  for (int e = threadIdx.x; e < PACK_ELEMS; e += 256) {
-    const int64_t i = base + e;
-    if (i >= n) break;
-    const int64_t r = i / ld;
-    const int k = (int)(i - r * ld);
+  const int ct = (int)((ld + 63) >> 6);                // column tiles per row band
+  const int tb = blockIdx.x - first;
+  const int r0 = (tb / ct) << 6, c0 = (tb % ct) << 6;
+  // gather 64 x 64 source elements into shared memory.  Lanes walk the direction that is contiguous in the SOURCE:
+  // columns when sk == 1, rows when the source is row-contiguous (transposing jobs: sa == 1, nb == 1) -> coalesced reads
+  const bool rows_fast = (sk != 1) && (sa == 1) && (nb == 1);
+  for (int e = threadIdx.x; e < 4096; e += 256) {
+    const int rr = rows_fast ? (e & 63) : (e >> 6), cc = rows_fast ? (e >> 6) : (e & 63);
+    const int64_t r = r0 + rr;
+    const int k = c0 + cc;
     float v = 0.f;
-    if (r < (int64_t)na * nb && k < nk) {
+    if (r < (int64_t)na * nb && k < nk && r < rows_out) {
       const int a = (int)(r / nb), b = (int)(r - (int64_t)a * nb);
       const int k1 = k / nk2, k2 = k - k1 * nk2;
       v = __ldg(in + a * sa + b * sb + k1 * sk + k2 * sk2);
     }
-    if (dtype == NFDPM_F32) reinterpret_cast<float*>(j[1])[i] = v;
-    else reinterpret_cast<__nv_bfloat16*>(j[1])[i] = __float2bfloat16_rn(v);
+    tile[rr][cc] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 4096; e += 256) {
+    const int rr = e >> 6, cc = e & 63;
+    const int64_t r = r0 + rr;
+    const int k = c0 + cc;
+    if (r < rows_out && k < ld) {
+      const float v = tile[rr][cc];
+      if (dtype == NFDPM_F32) reinterpret_cast<float*>(j[1])[r * ld + k] = v;
+      else reinterpret_cast<__nv_bfloat16*>(j[1])[r * ld + k] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -340,6 +354,7 @@ extern "C" int nfdpm_pack_matrix(const float* in, void* out, int out_dtype, int 
 }
 
 extern "C" int nfdpm_pack_elems(void) { return PACK_ELEMS; }
+/* blocks of one job = ceil(rows_out/64) * ceil(ld_out/64) */
 
 extern "C" int nfdpm_pack_batch(const int64_t* jobs_dev, int n_jobs, int n_blocks, nfdpm_stream_t stream) {
   NFDPM_REQUIRE(jobs_dev && n_jobs > 0 && n_blocks > 0, "nfdpm_pack_batch: bad arguments");

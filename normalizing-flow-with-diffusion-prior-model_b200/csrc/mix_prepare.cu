@@ -1,13 +1,13 @@
 // K-LU + fold: batched fp64 partial-pivot LU of the invertible 1x1-conv weights, giving log|det W|
 // (replaces torch.slogdet(W.double()), normalizing_flow/transforms.py:131), W^-1 (replaces
 // W.inverse(), transforms.py:144) and the ActNorm-folded forward / inverse mixing matrices consumed by
-// nfdpm_channel_mix.  One CTA per StepFlow, up to 16 StepFlows per launch (items passed by value, so the
+// nfdpm_channel_mix.  One CTA per StepFlow, up to 64 StepFlows per launch (items passed by value, so the
 // call is CUDA-graph capturable and needs no device-side pointer table).
 #include "common.cuh"
 
 namespace nfdpm {
 
-constexpr int kPrepBatch = 16;
+constexpr int kPrepBatch = 64;     // 64 x 88-byte items by value: needs the >4 KB kernel-parameter space (CUDA 12.1+, sm_70+)
 struct PrepBatch {
   nfdpm_mix_item it[kPrepBatch];
 };

@@ -231,7 +231,7 @@ class PackPlan:
             nonlocal blocks
             jobs.append([src.data_ptr(), out.data_ptr(), sa, sb, sk, ld, na | (nb << 32), nk | (rows << 32),
                          out_code | (blocks << 32), nk2 | (sk2 << 32)])
-            blocks += (rows * ld + pe - 1) // pe
+            blocks += ((rows + 63) // 64) * ((ld + 63) // 64)
 
         for s in steps:
             cp = s.affcoupling

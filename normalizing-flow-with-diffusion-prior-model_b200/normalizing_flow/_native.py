@@ -155,7 +155,7 @@ def ld_tiles(P: int) -> int:
 
 def mix_prepare(items) -> None:
     arr = (MixItem * len(items))(*items)
-    _ok(lib.nfdpm_mix_prepare(arr, len(items), _st()), (len(items) + 15) // 16)
+    _ok(lib.nfdpm_mix_prepare(arr, len(items), _st()), (len(items) + 63) // 64)
 
 
 def channel_mix(x, y, mt, beta, B, Cc, P, xbs, ybs) -> None:
