@@ -198,7 +198,15 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
       for (int idx = tid; idx < RG * n2c; idx += nt) {
         const int rg = idx / n2c, i = idx - rg * n2c;
         float acc = 0.f;
-        for (int bb = rg; bb < a.B; bb += RG) acc += __ldcg(a.dpar + (int64_t)bb * n2c + i);
+        int bb = rg;
+        for (; bb + 7 * RG < a.B; bb += 8 * RG) {          // eight loads in flight, added in image order
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldcg(a.dpar + (int64_t)(bb + j * RG) * n2c + i);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += v[j];
+        }
+        for (; bb < a.B; bb += RG) acc += __ldcg(a.dpar + (int64_t)bb * n2c + i);
         red[idx] = acc;
       }
       __syncthreads();
@@ -503,7 +511,15 @@ __global__ void __launch_bounds__(256) mix_param_grad_kernel(const MixParamBatch
   const int C = it.C, n = C * C + C, tid = threadIdx.x;
   for (int e = tid; e < n; e += 256) {
     float acc = 0.f;
-    for (int b = 0; b < it.B; ++b) acc += it.part[(int64_t)b * n + e];
+    int b = 0;
+    for (; b + 8 <= it.B; b += 8) {                        // eight loads in flight, added in order (deterministic)
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcg(it.part + (int64_t)(b + j) * n + e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    for (; b < it.B; ++b) acc += __ldcg(it.part + (int64_t)b * n + e);
     it.scratch[e] = acc;
   }
   __syncthreads();

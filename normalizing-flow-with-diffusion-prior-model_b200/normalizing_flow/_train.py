@@ -351,8 +351,12 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         ws = torch.empty(max(N.gemm_tn_workspace(M, F, F), N.gemm_tn_workspace(M, ldp, F),
                              N.gemm_tn_workspace(M, F, K1p)), **f32)
 
+        ablate = int(os.environ.get("NFDPM_ABLATE", "0"))     # timing experiments only (results are wrong when set)
+
         def wgrad(fn):
             """Run a weight-gradient launch on the side stream once everything enqueued so far on main is done."""
+            if ablate & 1:
+                return
             if side is None:
                 fn()
                 return
@@ -370,7 +374,9 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
             bc = cp._bwd_cache                   # refreshed by the forward's PackPlan
-            if T_c == 1:
+            if ablate & 2:
+                pass
+            elif T_c == 1:
                 N.coupling_bwd(dy, C * P, dld32, lv.u[k], C * P, lv.pm[k], ldp, zc.bias, zc.logs, du, C * P, dpm, Kp3,
                                dpar3, B, C, h, w, sink.get(zc.bias), sink.get(zc.logs))
             else:
@@ -422,7 +428,8 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             N.gemm_nt(dpre1, F, bc.w1t, F, dA1, K1p, M, K1p, F)
             # fused ActNorm + 1x1 conv
             dxb = pong[k & 1]
-            N.mix_bwd(du, C * P, dA1, K1p, lv.x[k], C * P, step._mix.fwd_mt, dxb, C * P, mix_part[k], B, C, h, w)
+            if not (ablate & 4):
+                    N.mix_bwd(du, C * P, dA1, K1p, lv.x[k], C * P, step._mix.fwd_mt, dxb, C * P, mix_part[k], B, C, h, w)
             dy = dxb
         if side is not None:
             main.wait_stream(side)                # every weight gradient of the level is complete (all-reduce, buffers)
