@@ -123,6 +123,54 @@ def test_gradients_large_images(cfg, mode, tol, monkeypatch):
         assert _rel(p.grad, g_o[k]) <= tol, (k, _rel(p.grad, g_o[k]))
 
 
+@pytest.mark.parametrize("mode,tol,ztol", [("fp32", 2e-4, 1e-4), ("bf16", 8e-2, 5e-3)])
+def test_ragged_shapes_mnist_28(mode, tol, ztol, monkeypatch):
+    """Non-power-of-two geometry (MNIST 1x28x28, L=2: 14x14 = 196 and 7x7 = 49 pixels per image, batch 5, K=3): forward,
+    inverse and every gradient against the oracle — neither level fits the whole-image GEMM tiling, ragged tail tiles."""
+    monkeypatch.setenv("NFDPM_PRECISION", mode)
+    c, L, K, B, S, seed = 1, 2, 3, 5, 28, 83
+    flow, prior, sd, psd = _build(c, L, K, seed)
+    x_cpu = O.seeded_input((B, c, S, S), seed + 1)
+    with torch.no_grad():
+        ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+        lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+        zs, ld, lp = flow.transform(x_cpu.to(DEV), ld, lp)
+        xr = flow.invert(zs)
+    ld_o, lp_o = torch.zeros(B, dtype=torch.float64), torch.zeros(B, dtype=torch.float64)
+    zo, ld_o, lp_o = O.glow_transform(sd, x_cpu, L, K, ld_o, lp_o)
+    for a, b in zip(zs, zo):
+        assert _rel(a, b) < ztol
+    assert torch.allclose(ld.cpu(), ld_o, rtol=1e-4 if mode == "fp32" else 2e-4)
+    assert torch.allclose(lp.cpu(), lp_o, rtol=1e-4 if mode == "fp32" else 2e-3)
+    assert float((xr.cpu() - x_cpu).abs().max()) < (1e-4 if mode == "fp32" else 5e-2)
+    loss_o, g_o, pg_o = O.train_grads(sd, psd, x_cpu, L, K, 32.0, S * S * 3.0)
+    loss = _train_step(flow, prior, x_cpu.to(DEV), S)
+    assert abs(float(loss) - float(loss_o)) < (1e-5 if mode == "fp32" else 1e-3)
+    for k, p in flow.named_parameters():
+        assert _rel(p.grad, g_o[k]) <= tol, (k, _rel(p.grad, g_o[k]))
+
+
+def test_batch_of_one_and_repeated_backward(monkeypatch):
+    """B = 1 (every per-image reduction degenerates) and two training steps in a row on the same module (the stash of
+    the first step is released, caches are refreshed after the parameter update)."""
+    monkeypatch.setenv("NFDPM_PRECISION", "fp32")
+    c, L, K, B, S, seed = 3, 3, 1, 1, 32, 85
+    flow, prior, sd, psd = _build(c, L, K, seed)
+    x_cpu = O.seeded_input((B, c, S, S), seed + 1)
+    loss_o, g_o, _ = O.train_grads(sd, psd, x_cpu, L, K, 32.0, S * S * 3.0)
+    for it in range(2):
+        flow.zero_grad(set_to_none=True)
+        prior.zero_grad(set_to_none=True)
+        loss = _train_step(flow, prior, x_cpu.to(DEV), S)
+        assert abs(float(loss) - float(loss_o)) < 1e-5
+        for k, p in flow.named_parameters():
+            assert _rel(p.grad, g_o[k]) <= 2e-4, (it, k, _rel(p.grad, g_o[k]))
+    # gradient ACCUMULATION (p.grad already populated): a third backward adds to the existing gradients
+    loss = _train_step(flow, prior, x_cpu.to(DEV), S)
+    for k, p in flow.named_parameters():
+        assert _rel(p.grad, 2 * g_o[k]) <= 2e-4, (k, _rel(p.grad, 2 * g_o[k]))
+
+
 def test_logp_none_and_latent_gradients(monkeypatch):
     """NFBackbone-style call (logp=None, diffusion_prior/trainer.py:139): gradients arrive through the latents."""
     monkeypatch.setenv("NFDPM_PRECISION", "fp32")
