@@ -347,17 +347,14 @@ class Glow(Transform):
         return list(out[1:]), out[0], None
 
     def _fast_ok(self, H: int, W: int) -> bool:
-        """The fused step-boundary kernel needs every level's image to fit one CTA (P <= 256 + smem budget)."""
-        if os.environ.get("NFDPM_FUSED_BOUNDARY", "1") == "0":
-            return False
-        h, w, ch = H, W, self.in_channel
-        for _ in range(self.L):
-            h, w = h // 2, w // 2
-            C = ch * 4
-            if h * w > 256 or N.flow_boundary_smem(C, h, w, 1, 1) > 200 * 1024:
-                return False
-            ch = C // 2
-        return True
+        """Use the fused step-boundary kernels?  They are chosen PER LEVEL (`_level_fast`): a level whose image does not
+        fit one CTA (more than 256 pixels, e.g. the 64x64 and 32x32 levels of a 128x128 input) runs the unfused
+        kernels, the deeper levels of the same model still run the fused ones."""
+        return os.environ.get("NFDPM_FUSED_BOUNDARY", "1") != "0"
+
+    @staticmethod
+    def _level_fast(C: int, h: int, w: int) -> bool:
+        return h * w <= 256 and N.flow_boundary_smem(C, h, w, 1, 1) <= 200 * 1024
 
     def _transform_core(self, x: Tensor, with_logp: bool, levels, slots, steps, ready: bool):
         B, c, H, W = x.shape
@@ -455,17 +452,45 @@ class Glow(Transform):
         B, c, H, W = x.shape
         dev = x.device
         E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
-        R_ld = self.L * self.K
-        R_lp = self.L - 1
+        # partial-sum rows: one per step at fused levels, ld_tiles(P) per step at unfused ones
+        R_ld = R_lp = 0
+        hh, ww, cc = H, W, c
+        for li in range(self.L):
+            hh, ww, CC = hh // 2, ww // 2, cc * 4
+            T = 1 if self._level_fast(CC, hh, ww) else N.ld_tiles(hh * ww)
+            R_ld += self.K * T
+            if li < self.L - 1:
+                R_lp += N.ld_tiles(hh * ww)
+            cc = CC // 2
         ld_part = E.WS.get("ld_part", R_ld * B, torch.float32, dev)
         lp_part = E.WS.get("lp_part", max(R_lp, 1) * B, torch.float32, dev) if with_logp else None
         latents: List[Tensor] = []
         cur, cur_bs = x, c * H * W
         h, w, ch = H, W, c
-        row = 0
+        row = lrow = 0
         for li, (flows, split) in enumerate(levels):
             h, w, C = h // 2, w // 2, ch * 4
             P = h * w
+            if not self._level_fast(C, h, w):
+                # image larger than one CTA: squeeze + unfused K-A / im2col / GEMMs / coupling per step
+                T = N.ld_tiles(P)
+                a = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+                b = torch.empty_like(a)
+                N.squeeze(cur, a, B, ch, 2 * h, 2 * w, cur_bs, C * P)
+                for step in flows:
+                    step._forward_views(a, C * P, b, C * P, B, h, w, ld_part[row * B:], None)
+                    a, b = b, a
+                    row += T
+                st = a
+                if split is None:
+                    latents.append(st)
+                    break
+                z = torch.empty(B, C // 2, h, w, dtype=torch.float32, device=dev)
+                split._forward_views(st, C * P, B, C, h, w, z, lp_part[lrow * B:] if lp_part is not None else None)
+                lrow += T
+                latents.append(z)
+                cur, cur_bs, ch = st, C * P, C // 2
+                continue
             st = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)     # flow state of this level (in place)
             first = flows[0]
             A1, K1p = E.coupling_a1(first.affcoupling, B, C, h, w, dev)
@@ -488,7 +513,8 @@ class Glow(Transform):
                 latents.append(st)
                 break
             z = torch.empty(B, C // 2, h, w, dtype=torch.float32, device=dev)
-            split._forward_views(st, C * P, B, C, h, w, z, lp_part[li * B:] if lp_part is not None else None)
+            split._forward_views(st, C * P, B, C, h, w, z, lp_part[lrow * B:] if lp_part is not None else None)
+            lrow += N.ld_tiles(P)
             latents.append(z)
             cur, cur_bs, ch = st, C * P, C // 2
         return latents, ld_part, R_ld, lp_part, (R_lp if with_logp else 0)
@@ -503,7 +529,38 @@ class Glow(Transform):
         for li in range(self.L - 1, -1, -1):
             flows, _ = levels[li]
             P = h * w
-            st = src if li < self.L - 1 else torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+            if not self._level_fast(C, h, w):
+                # image larger than one CTA: unfused inverse steps (coupling^-1 in place, then K-A^-1)
+                cur, own = src, li < self.L - 1        # the deepest level reads caller memory
+                other = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+                for step in reversed(flows):
+                    if own:
+                        step._inverse_views(cur, C * P, cur, C * P, other, C * P, B, h, w)
+                        cur, other = other, cur
+                    else:
+                        tmp = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+                        step._inverse_views(cur, C * P, tmp, C * P, other, C * P, B, h, w)
+                        cur, other, own = other, tmp, True
+                st = cur
+            else:
+                st = self._invert_level_fast(flows, src, li < self.L - 1, B, C, h, w, dev)
+            if li == 0:
+                out = torch.empty(B, C // 4, h * 2, w * 2, dtype=torch.float32, device=dev)
+                N.unsqueeze(st, out, B, C, h, w, C * P, (C // 4) * P * 4)
+                return out
+            Cn, hn, wn = 2 * (C // 4), h * 2, w * 2
+            nxt = torch.empty(B, Cn, hn, wn, dtype=torch.float32, device=dev)
+            N.unsqueeze(st, nxt, B, C, h, w, C * P, Cn * hn * wn)
+            latent = get_item(latents, -(self.L - li + 1))
+            levels[li - 1][1]._fill_second_half(nxt, Cn * hn * wn, B, Cn, hn, wn, latent, temperature)
+            src, C, h, w = nxt, Cn, hn, wn
+        raise AssertionError("unreachable")
+
+    def _invert_level_fast(self, flows, src, own: bool, B: int, C: int, h: int, w: int, dev) -> Tensor:
+        """K inverse StepFlows of one level with the fused kernels; returns the level's input state."""
+        P = h * w
+        if True:
+            st = src if own else torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
             last = flows[-1]
             A1, K1p = E.coupling_a1(last.affcoupling, B, C, h, w, dev)
             N.flow_boundary(src, C * P, False, None, 0, None, None, None, None, None, None, 0, A1, K1p, B, C, h, w,
@@ -520,17 +577,7 @@ class Glow(Transform):
                     E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
                                         st, C * P, None, 0, True)
                 src = st
-            if li == 0:
-                out = torch.empty(B, C // 4, h * 2, w * 2, dtype=torch.float32, device=dev)
-                N.unsqueeze(st, out, B, C, h, w, C * P, (C // 4) * P * 4)
-                return out
-            Cn, hn, wn = 2 * (C // 4), h * 2, w * 2
-            nxt = torch.empty(B, Cn, hn, wn, dtype=torch.float32, device=dev)
-            N.unsqueeze(st, nxt, B, C, h, w, C * P, Cn * hn * wn)
-            latent = get_item(latents, -(self.L - li + 1))
-            levels[li - 1][1]._fill_second_half(nxt, Cn * hn * wn, B, Cn, hn, wn, latent, temperature)
-            src, C, h, w = nxt, Cn, hn, wn
-        raise AssertionError("unreachable")
+            return st
 
     def _invert_core(self, latents, temperature, levels, slots, steps, ready: bool) -> Tensor:
         z_last = E.check_input(latents[-1], "latents[-1]")
