@@ -42,44 +42,13 @@ def _f32(t: Optional[Tensor], B: int, dev) -> Tensor:
 
 
 class _BwdCache:
-    """Transposed (dgrad) copies of the three conv weights of one coupling network, per parameter version."""
+    """Transposed (dgrad) copies of the three conv weights of one coupling network (filled by _engine.PackPlan):
+    w1t[k, o] = W1[o, k] (rows K1..K1p zero), w2t[i, o] = W2[o, i], w3t[ci, tap*C+co] = W3[co, ci, tap]."""
 
     def __init__(self):
         self.key = None
-        self.w1t = self.w2t = self.w3t = self.w3p32 = None
+        self.w1t = self.w2t = self.w3t = None
         self.Kp3 = 0
-
-
-def _pack_bwd(cp, dt: torch.dtype) -> _BwdCache:
-    conv1, _, conv2, _, zc = cp._parts()
-    cache = getattr(cp, "_bwd_cache", None)
-    if cache is None:
-        cache = cp._bwd_cache = _BwdCache()
-    w1, w2, w3 = conv1.weight, conv2.weight, zc.weight
-    key = (E._vkey(w1, w2, w3), dt)
-    if E.cache_hit(cache.key, key):
-        return cache
-    F, Ch = w1.shape[0], w1.shape[1]
-    C = w3.shape[0]
-    dev = w1.device
-    K1, K1p = Ch * 9, E.round_up(Ch * 9, 64)
-    ldp = E.round_up(9 * C, 16)
-    Kp3 = E.round_up(9 * C, 64)
-    if cache.w1t is None or cache.w1t.dtype != dt:
-        cache.w1t = torch.empty(K1p * F, dtype=dt, device=dev)
-        cache.w2t = torch.empty(F * F, dtype=dt, device=dev)
-        cache.w3t = torch.empty(F * Kp3, dtype=dt, device=dev)
-        cache.w3p32 = torch.empty(ldp * F, dtype=torch.float32, device=dev)
-    # w1t[k, o] = W1[o, k]           (rows K1..K1p zero)      -> dgrad1: dA1[M,K1p] = dpre1[M,F] x w1t[K1p,F]^T
-    N.pack_matrix(w1, cache.w1t, K1, 1, F, 1, 0, K1, F, K1p)
-    # w2t[i, o] = W2[o, i]                                     -> dgrad2: dh1[M,F] = dpre2[M,F] x w2t[F,F]^T
-    N.pack_matrix(w2, cache.w2t, F, 1, F, 1, 0, F, F, F)
-    # w3p32[tap*C+co, ci] = W3[co, ci, tap] (fp32), then w3t[ci, tap*C+co] (columns 9C..Kp3 zero)
-    N.pack_matrix(w3, cache.w3p32, 9, C, F, 1, F * 9, 9, F, ldp)
-    N.pack_matrix(cache.w3p32, cache.w3t, F, 1, ldp, 1, 0, F, Kp3, F)
-    cache.Kp3 = Kp3
-    cache.key = key
-    return cache
 
 
 _SIDE = {}

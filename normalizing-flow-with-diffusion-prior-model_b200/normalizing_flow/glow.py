@@ -559,25 +559,24 @@ class Glow(Transform):
     def _invert_level_fast(self, flows, src, own: bool, B: int, C: int, h: int, w: int, dev) -> Tensor:
         """K inverse StepFlows of one level with the fused kernels; returns the level's input state."""
         P = h * w
-        if True:
-            st = src if own else torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
-            last = flows[-1]
-            A1, K1p = E.coupling_a1(last.affcoupling, B, C, h, w, dev)
-            N.flow_boundary(src, C * P, False, None, 0, None, None, None, None, None, None, 0, A1, K1p, B, C, h, w,
-                            False)                     # im2col of the level's entry state
-            for k in range(len(flows) - 1, -1, -1):
-                step = flows[k]
-                cp = step.affcoupling
-                if k > 0:
-                    A1n, K1p = E.coupling_a1(flows[k - 1].affcoupling, B, C, h, w, dev)
-                    E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
-                                        st, C * P, A1n, K1p, True)
-                    A1 = A1n
-                else:
-                    E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
-                                        st, C * P, None, 0, True)
-                src = st
-            return st
+        st = src if own else torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+        last = flows[-1]
+        A1, K1p = E.coupling_a1(last.affcoupling, B, C, h, w, dev)
+        N.flow_boundary(src, C * P, False, None, 0, None, None, None, None, None, None, 0, A1, K1p, B, C, h, w,
+                        False)                     # im2col of the level's entry state
+        for k in range(len(flows) - 1, -1, -1):
+            step = flows[k]
+            cp = step.affcoupling
+            if k > 0:
+                A1n, K1p = E.coupling_a1(flows[k - 1].affcoupling, B, C, h, w, dev)
+                E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
+                                    st, C * P, A1n, K1p, True)
+                A1 = A1n
+            else:
+                E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
+                                    st, C * P, None, 0, True)
+            src = st
+        return st
 
     def _invert_core(self, latents, temperature, levels, slots, steps, ready: bool) -> Tensor:
         z_last = E.check_input(latents[-1], "latents[-1]")
