@@ -207,6 +207,24 @@ int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p, float* pm
                          int64_t lda1, int B, int C, int H, int W, int K, int64_t ldp, int inverse,
                          nfdpm_stream_t stream);
 
+/* One StepFlow of a deep level in ONE launch (tensor-core mode, H*W <= 64 dividing 128): GEMM1 -> ActNorm/ReLU -> GEMM2 ->
+ * ActNorm/ReLU -> GEMM3 -> step boundary.  A thread-block cluster of min(8, 128/(H*W)) CTAs owns one 128-row tile, splits
+ * every GEMM along N and hands the h1 / h2 / pm rows from CTA to CTA through distributed shared memory (no L2 round trip).
+ * Replaces 3 x nfdpm_gemm_nt (transforms.py:169-175 via utils.py:44) + nfdpm_flow_boundary (transforms.py:179-184 /
+ * :196-200 and the neighbouring ActNorm + 1x1 conv, :80,132 / :144,93).
+ * a1_in bf16 [M,K1p] im2col rows; w1p [F,K1p], w2p [F,F], w3p [ldp,F] packed bf16 weights; s1,b1,s2,b2 the inner ActNorm
+ * parameters; h1,h2 (bf16 [M,F]) and pm (fp32 [M,ld_pm]) are OPTIONAL global copies of the intermediates (the training
+ * stash; NULL = not written).  The remaining arguments are those of nfdpm_flow_boundary_stash (+ inverse).
+ * nfdpm_deep_step_debug: profiling hook, per-CTA timeline into a device int64 [grid][16] buffer (NULL = off). */
+int nfdpm_deep_step_debug(void* timeline);
+int nfdpm_deep_step_ok(int B, int C, int H, int W, int F, int64_t K1p, int64_t ldp);
+int nfdpm_deep_step(const void* a1_in, const void* w1p, const void* w2p, const void* w3p, const float* s1, const float* b1,
+                    const float* s2, const float* b2, void* h1, void* h2, float* pm, int64_t ld_pm, const float* in,
+                    int64_t in_bs, const float* bias3, const float* logs3, float* ld_part, const float* mt,
+                    const float* beta, float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype,
+                    int64_t lda1, int B, int C, int H, int W, int F, int64_t K1p, int64_t ldp, int inverse,
+                    nfdpm_stream_t stream);
+
 /* Layout converters for stand-alone ZeroConv2d / Conv2dActNorm module calls (normalizing_flow/utils.py:43-44, :68-69).
  *   rows_to_nchw: out[b,n,p] = f(h[(b*P+p)*ldh + n]); mode 0: identity; 1: (v+p1[n])*exp(3*p2[n]) (ZeroConv2d gain);
  *                 2: exp(p1[n])*(v+p2[n]) (ActNorm).   nchw_to_rows: rows[m, c] = x[b,c,p], columns Cc..ld-1 zero. */

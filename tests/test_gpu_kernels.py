@@ -561,6 +561,74 @@ def test_gemm3_boundary_support_query():
     assert N.gemm3_boundary_ok(128, 48, 4, 4, 512, 432)
 
 
+# ------------------------------------------------------------------ cluster-fused StepFlow of a deep level
+@pytest.mark.parametrize("B,C,H,W", [(5, 24, 8, 8), (4, 8, 8, 8), (13, 48, 4, 4), (8, 16, 4, 4), (6, 32, 4, 2)])
+@pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16])
+def test_deep_step_equals_four_kernel_chain(B, C, H, W, a1_dt):
+    """nfdpm_deep_step (one launch: thread-block cluster per 128-row tile, GEMMs split along N, h1/h2/pm exchanged through
+    distributed shared memory) == 3 x nfdpm_gemm_nt + nfdpm_flow_boundary(_stash), BIT EXACT for every output (state,
+    pre-mix stash, im2col rows, log-det partials and the optional global copies of h1 / h2 / pm), forward and inverse,
+    with and without the next mix; B deliberately not a multiple of the images-per-tile count."""
+    P, Ch, F = H * W, C // 2, 512
+    ldp = (9 * C + 15) // 16 * 16
+    K1p = (9 * Ch + 63) // 64 * 64
+    M = B * P
+    assert N.deep_step_ok(B, C, H, W, F, K1p, ldp)
+    bf = torch.bfloat16
+    a1_in = (rnd(M, K1p, seed=1, scale=0.5).cuda()).to(bf)
+    a1_in[:, 9 * Ch:] = 0
+    w1 = (rnd(F, K1p, seed=2, scale=0.1).cuda()).to(bf)
+    w2 = (rnd(F, F, seed=3, scale=0.05).cuda()).to(bf)
+    w3 = (rnd(ldp, F, seed=4, scale=0.02).cuda()).to(bf)
+    w3[9 * C:] = 0
+    s1, b1, s2, b2 = (rnd(F, seed=5 + i, scale=0.2).cuda() for i in range(4))
+    x = rnd(B, C, H, W, seed=9).cuda()
+    bias3, logs3 = rnd(C, seed=10, scale=0.1).cuda(), rnd(C, seed=11, scale=0.1).cuda()
+    mt, beta = rnd(C, C, seed=12, scale=0.4).cuda(), rnd(C, seed=13).cuda()
+    h1_ref, h2_ref = torch.empty(M, F, dtype=bf, device=DEV), torch.empty(M, F, dtype=bf, device=DEV)
+    pm_ref = torch.empty(M, ldp, device=DEV)
+    N.gemm_nt(a1_in, K1p, w1, K1p, h1_ref, F, M, F, K1p, N.EPI_ACTNORM_RELU, s1, b1)
+    N.gemm_nt(h1_ref, F, w2, F, h2_ref, F, M, F, F, N.EPI_ACTNORM_RELU, s2, b2)
+    N.gemm_nt(h2_ref, F, w3, F, pm_ref, ldp, M, ldp, F)
+    for inverse in (False, True):
+        for with_mix in (True, False):
+            for stash in (True, False):
+                m_, b_ = (mt, beta) if with_mix else (None, None)
+                y_ref, xs_ref = torch.empty_like(x), torch.empty_like(x)
+                a_ref = torch.full((M, K1p), 3.0, dtype=a1_dt, device=DEV) if with_mix else None
+                part_ref = torch.zeros(B, device=DEV)
+                if inverse:
+                    N.flow_boundary(x, C * P, False, pm_ref, ldp, bias3, logs3, None, m_, b_, y_ref, C * P, a_ref,
+                                    K1p if with_mix else 0, B, C, H, W, True)
+                else:
+                    N.flow_boundary_stash(x, C * P, False, pm_ref, ldp, bias3, logs3, part_ref, m_, b_, y_ref, C * P, xs_ref,
+                                          C * P, a_ref, K1p if with_mix else 0, B, C, H, W)
+                y, xs = torch.empty_like(x), torch.empty_like(x)
+                a1 = torch.full((M, K1p), 5.0, dtype=a1_dt, device=DEV) if with_mix else None
+                part = torch.zeros(B, device=DEV)
+                h1 = torch.full((M, F), float("nan"), dtype=bf, device=DEV) if stash else None
+                h2 = torch.full((M, F), float("nan"), dtype=bf, device=DEV) if stash else None
+                pm = torch.full((M, ldp), float("nan"), device=DEV) if stash else None
+                N.deep_step(a1_in, w1, w2, w3, s1, b1, s2, b2, h1, h2, pm, ldp if stash else 0, x, C * P, bias3, logs3,
+                            None if inverse else part, m_, b_, y, C * P, None if inverse else xs, 0 if inverse else C * P,
+                            a1, K1p if with_mix else 0, B, C, H, W, F, K1p, ldp, inverse)
+                sync()
+                if stash:
+                    assert torch.equal(h1, h1_ref) and torch.equal(h2, h2_ref) and torch.equal(pm, pm_ref)
+                assert torch.equal(y, y_ref)
+                if with_mix:
+                    assert torch.equal(a1, a_ref)
+                if not inverse:
+                    assert torch.equal(xs, xs_ref) and torch.equal(part, part_ref)
+
+
+def test_deep_step_support_query():
+    assert not N.deep_step_ok(2, 12, 16, 16, 512, 64, 112)        # 256 pixels: an image is larger than a tile
+    assert not N.deep_step_ok(2, 6, 7, 7, 512, 64, 64)            # 49 pixels do not divide 128
+    assert not N.deep_step_ok(2, 96, 8, 8, 512, 448, 864)         # boundary scratch + operand buffers exceed 227 KB
+    assert N.deep_step_ok(128, 24, 8, 8, 512, 128, 224) and N.deep_step_ok(128, 48, 4, 4, 512, 256, 432)
+
+
 @pytest.mark.parametrize("M,N_,K", [(2048, 512, 512), (1000, 512, 128), (32768, 512, 512), (300, 64, 64)])
 def test_gemm_nt_relu_bwd_fused_epilogue(M, N_, K):
     """dgrad GEMM with ActNorm+ReLU backward in the tcgen05 epilogue == GEMM followed by nfdpm_actnorm_relu_bwd:
