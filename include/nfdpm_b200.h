@@ -207,6 +207,17 @@ int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p, float* pm
                          int64_t lda1, int B, int C, int H, int W, int K, int64_t ldp, int inverse,
                          nfdpm_stream_t stream);
 
+/* nfdpm_flow_boundary_stash + the FIRST GEMM of the next coupling network in one launch (tensor-core mode): the im2col rows
+ * of the new state are built in shared memory as the tcgen05 A operand and h1 = relu(actnorm(A1 * w1p^T)) [B*H*W, F] (bf16)
+ * is written instead of (a1 == NULL) or in addition to (a1 != NULL, bf16 [B*H*W, K1p]: training stash) the im2col rows.
+ * Replaces nfdpm_flow_boundary + nfdpm_gemm_nt(EPI_ACTNORM_RELU) (transforms.py:169 via utils.py:47-69).  One CTA per image;
+ * needs F == 512, K1p a multiple of 64 (<= 512), H*W == 256 or H*W <= 128 with H*W % 8 == 0 (nfdpm_boundary_gemm1_ok). */
+int nfdpm_boundary_gemm1_ok(int C, int H, int W, int F, int64_t K1p);
+int nfdpm_boundary_gemm1(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp, const float* bias3,
+                         const float* logs3, float* ld_part, const float* mt, const float* beta, float* y, int64_t y_bs,
+                         float* xs, int64_t xs_bs, void* a1, const void* w1p, const float* s1, const float* b1, void* h1,
+                         int B, int C, int H, int W, int F, int64_t K1p, int inverse, nfdpm_stream_t stream);
+
 /* One StepFlow of a deep level in ONE launch (tensor-core mode, H*W <= 64 dividing 128): GEMM1 -> ActNorm/ReLU -> GEMM2 ->
  * ActNorm/ReLU -> GEMM3 -> step boundary.  A thread-block cluster of min(8, 128/(H*W)) CTAs owns one 128-row tile, splits
  * every GEMM along N and hands the h1 / h2 / pm rows from CTA to CTA through distributed shared memory (no L2 round trip).
@@ -217,6 +228,10 @@ int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p, float* pm
  * stash; NULL = not written).  The remaining arguments are those of nfdpm_flow_boundary_stash (+ inverse).
  * nfdpm_deep_step_debug: profiling hook, per-CTA timeline into a device int64 [grid][16] buffer (NULL = off). */
 int nfdpm_deep_step_debug(void* timeline);
+/* profiling hook: per-CTA wait/work cycle counters of the tcgen05 GEMM kernel (device int64 [grid][16], NULL = off) */
+int nfdpm_gemm_debug(void* counters);
+/* profiling hook: per-image phase timeline of nfdpm_flow_boundary (device int64 [B][16], NULL = off) */
+int nfdpm_flow_boundary_debug(void* timeline);
 int nfdpm_deep_step_ok(int B, int C, int H, int W, int F, int64_t K1p, int64_t ldp);
 int nfdpm_deep_step(const void* a1_in, const void* w1p, const void* w2p, const void* w3p, const float* s1, const float* b1,
                     const float* s2, const float* b2, void* h1, void* h2, float* pm, int64_t ld_pm, const float* in,

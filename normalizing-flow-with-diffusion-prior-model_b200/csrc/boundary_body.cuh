@@ -1,10 +1,23 @@
 // The arithmetic of one step boundary for ONE image, shared by flow_boundary_kernel (one CTA per image) and the fused
 // deep-level StepFlow kernel (deep_step.cu).  See flow_boundary.cu for the description.  Internal header.
 #pragma once
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nfdpm {
 
+
+// Division by a run-time constant as multiply-high: the kernels below are issue-bound on index arithmetic (r1 timeline: a
+// 32-bit division costs ~35 instructions and there were ~14 per thread).  Exact for n * d < 2^32.
+struct FastDiv {
+  uint32_t d, m;                          // m = ceil(2^32 / d); m == 0 encodes d == 1
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv f) { return f.m ? (int)__umulhi((uint32_t)n, f.m) : n; }
 
 struct BoundaryArgs {
   const float* in; int64_t in_bs;       // source state [B,C,P] (or [B,C/4,2H,2W] when squeeze_in)
@@ -17,7 +30,20 @@ struct BoundaryArgs {
   void* a1; int64_t lda1;               // im2col sink (may be null)
   int B, C, H, W;
   int squeeze_in, inverse;
+  FastDiv dP, dW, dCp, dCh, dNg;        // H*W, W, round4(C), C/2, lda1/8 (boundary_fill_div)
 };
+
+// host: fill the divisors once every other field is set
+static inline void boundary_fill_div(BoundaryArgs& a) {
+  a.dP = make_fastdiv(a.H * a.W);
+  a.dW = make_fastdiv(a.W);
+  a.dCp = make_fastdiv((a.C + 3) & ~3);
+  a.dCh = make_fastdiv(a.C / 2 > 0 ? a.C / 2 : 1);
+  a.dNg = make_fastdiv(a.lda1 >= 8 ? (int)(a.lda1 >> 3) : 1);
+}
+
+// profiling hook of this translation unit (nfdpm_flow_boundary_debug): per-CTA phase timeline [B][16] int64, NULL = off
+static __device__ long long* g_bd_dbg = nullptr;
 
 template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
 template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
@@ -35,45 +61,122 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
 }
 
 
+// Shared-memory scratch of the body in floats (nfdpm_flow_boundary_smem() returns it in bytes):
+//   x_s [C][P+1] | u_s [C][P+1] (mix only) | m_s [C][Cp] + beta [Cp] (mix only) | par_s [2C] | ls_s [P*C/2] (coupling only)
+//   | pad_s [C/2][(H+2)*(W+2)]  zero-bordered copy of the channels the next coupling network reads (im2col source)
+//   | kt_s  [9*C/2] int         im2col column k -> offset of its (channel, tap) inside pad_s
+__host__ __device__ __forceinline__ size_t boundary_scratch_floats(int C, int H, int W, bool coupling, bool mix, size_t* pad_off,
+                                                                   size_t* kt_off) {
+  const size_t P = (size_t)H * W, PS = P + 1, Cp = (C + 3) & ~3, Ch = C / 2;
+  size_t fl = (size_t)C * PS * (mix ? 2 : 1);
+  if (mix) fl += (size_t)C * Cp + Cp;
+  if (coupling) fl += 2 * (size_t)C + P * Ch;
+  fl = (fl + 3) & ~(size_t)3;
+  if (pad_off) *pad_off = fl;
+  fl += (Ch * (size_t)(H + 2) * (W + 2) + 3) & ~(size_t)3;
+  if (kt_off) *kt_off = fl;
+  fl += (9 * Ch + 3) & ~(size_t)3;
+  return fl;
+}
+
 // `sm`: shared-memory scratch of nfdpm_flow_boundary_smem() bytes; all `nt` threads of the CTA must call this together.
-// PM_SMEM: the taps-as-N rows of image b are already in shared memory at `pm_img` (row stride `pm_ld` floats) instead of
-// a.pm in global memory (deep_step.cu).
+// PM_SMEM: the taps-as-N rows of image b are (or will be: pm_bar) in shared memory at `pm_img` (row stride `pm_ld` floats)
+// instead of a.pm in global memory; pm_bar != 0: shared-memory address of an mbarrier (phase 0) that completes when a bulk
+// copy has landed them (flow_boundary.cu).
+// a1_tile (bf16 only): ALSO write the im2col rows of the image as the A operand of a tcgen05 GEMM into shared memory — 16 KB
+// boxes [128 rows][64 columns] in the K-major SWIZZLE_128B layout, box (p / 128) * (lda1 / 64) + k / 64, 16-byte unit u of row
+// r at r*128 + ((u ^ (r & 7)) << 4) — for the boundary + GEMM1 kernel (boundary_gemm1.cu); a.a1 may then be NULL.
 template <bool COUPLING, typename A1T, bool PM_SMEM = false>
 __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const int b, float* sm, const int tid, const int nt,
-                                                   const float* pm_img = nullptr, const int pm_ld = 0) {
-
+                                                   const float* pm_img = nullptr, const int pm_ld = 0,
+                                                   uint8_t* a1_tile = nullptr, const uint32_t pm_bar = 0) {
   const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
+  long long* const dbg = g_bd_dbg;
+  auto stamp = [&](int slot) {
+    if (dbg != nullptr && tid == 0) dbg[(int64_t)b * 16 + slot] = clock64();
+  };
+  stamp(0);
   const int PS = P + 1;                       // padded pixel stride: conflict-free for lanes over channels
   const int Cp = (C + 3) & ~3;
+  const int W2p = W + 2, PP = (H + 2) * W2p;  // zero-bordered image of one channel
+  const bool mix = a.mt != nullptr;
+  const bool want_a1 = a.a1 != nullptr || a1_tile != nullptr;
+  size_t pad_off, kt_off;
+  boundary_scratch_floats(C, H, W, COUPLING, mix, &pad_off, &kt_off);
   float* x_s = sm;                            // [C][PS]  source / coupling result
   float* u_s = x_s + C * PS;                  // [C][PS]  mixed result (aliases x_s when there is no mix)
-  float* m_s = (a.mt != nullptr) ? u_s + C * PS : u_s;      // [C][Cp] + beta [Cp]
-  float* par_s = m_s + ((a.mt != nullptr) ? (C * Cp + Cp) : 0);   // [2C] bias3, exp(3 logs3)
+  float* m_s = mix ? u_s + C * PS : u_s;      // [C][Cp] + beta [Cp]
+  float* par_s = m_s + (mix ? (C * Cp + Cp) : 0);                 // [2C] bias3, exp(3 logs3)
   float* ls_s = par_s + (COUPLING ? 2 * C : 0);                   // [P*Ch] log-det terms
-  if (a.mt == nullptr) u_s = x_s;
+  float* pad_s = sm + pad_off;                                    // [Ch][PP]
+  int* kt_s = reinterpret_cast<int*>(sm + kt_off);                // [9*Ch]
+  if (!mix) u_s = x_s;
 
-  // ---- parameters
-  if (a.mt != nullptr) {
-    for (int i = tid; i < C * Cp; i += nt) {
-      const int r = i / Cp, c = i - r * Cp;
+  // ---- phase 0: parameters + the image, channel-major (lanes over pixels -> coalesced).  Every global load of a batch is
+  // issued before the first dependent shared-memory store: the warps issue in order, so load -> store -> load chains would
+  // serialise one L2 round trip per element (r1 timeline: 2.1 us for 3 elements per thread).
+  const float* inb = a.in + (int64_t)b * a.in_bs;
+  const int nx = C * P;
+  float xv[4];
+  if (!a.squeeze_in) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + u * nt;
+      xv[u] = (i < nx) ? inb[i] : 0.f;
+    }
+  }
+  {
+    const int n_m = mix ? C * Cp : 0;
+    float mv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + u * nt;
+      mv[u] = 0.f;
+      if (i < n_m) {
+        const int r = fdiv(i, a.dCp), c = i - r * Cp;
+        if (c < C) mv[u] = a.mt[r * C + c];
+      }
+    }
+    const float bev = (mix && tid < C) ? a.beta[tid] : 0.f;
+    const float b3v = (COUPLING && tid < C) ? a.bias3[tid] : 0.f;
+    const float l3v = (COUPLING && tid < C) ? a.logs3[tid] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + u * nt;
+      if (i < n_m) m_s[i] = mv[u];
+    }
+    for (int i = tid + 4 * nt; i < n_m; i += nt) {                // shapes with more than 4 matrix entries per thread
+      const int r = fdiv(i, a.dCp), c = i - r * Cp;
       m_s[i] = (c < C) ? a.mt[r * C + c] : 0.f;
     }
-    for (int i = tid; i < Cp; i += nt) m_s[C * Cp + i] = (i < C) ? a.beta[i] : 0.f;
-  }
-  if (COUPLING) {
-    for (int i = tid; i < C; i += nt) {
-      par_s[i] = a.bias3[i];
-      par_s[C + i] = expf(3.f * a.logs3[i]);
+    if (mix) {
+      if (tid < Cp) m_s[C * Cp + tid] = bev;
+      for (int i = tid + nt; i < Cp; i += nt) m_s[C * Cp + i] = (i < C) ? a.beta[i] : 0.f;
+    }
+    if (COUPLING) {
+      if (tid < C) {
+        par_s[tid] = b3v;
+        par_s[C + tid] = expf(3.f * l3v);
+      }
+      for (int i = tid + nt; i < C; i += nt) {
+        par_s[i] = a.bias3[i];
+        par_s[C + i] = expf(3.f * a.logs3[i]);
+      }
     }
   }
-  // ---- phase 0: stage the image channel-major (lanes over pixels -> coalesced)
-  const float* inb = a.in + (int64_t)b * a.in_bs;
+  if (want_a1) {
+    for (int i = tid; i < Ch * PP; i += nt) pad_s[i] = 0.f;       // borders stay zero; the interior is filled below
+    for (int k = tid; k < 9 * Ch; k += nt) {
+      const int c = k / 9, tap = k - c * 9;
+      kt_s[k] = c * PP + (tap / 3) * W2p + (tap % 3);
+    }
+  }
   if (a.squeeze_in) {
     // in is [C/4, 2H, 2W]; channel c = cc*4 + h1*2 + w1 reads in[cc, 2y+h1, 2x+w1]
     const int W2 = 2 * W;
     for (int i = tid; i < (C >> 2) * P; i += nt) {
-      const int cc = i / P, p = i - cc * P;
-      const int py = p / W, px = p - py * W;
+      const int cc = fdiv(i, a.dP), p = i - cc * P;
+      const int py = fdiv(p, a.dW), px = p - py * W;
       const float* s = inb + ((int64_t)cc * 2 * H + 2 * py) * W2 + 2 * px;
       const float2 t0 = *reinterpret_cast<const float2*>(s), t1 = *reinterpret_cast<const float2*>(s + W2);
       x_s[(cc * 4 + 0) * PS + p] = t0.x;
@@ -82,20 +185,42 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
       x_s[(cc * 4 + 3) * PS + p] = t1.y;
     }
   } else {
-    for (int i = tid; i < C * P; i += nt) {
-      const int c = i / P, p = i - c * P;
-      x_s[c * PS + p] = inb[i];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + u * nt;
+      if (i < nx) {
+        const int c = fdiv(i, a.dP), p = i - c * P;
+        x_s[c * PS + p] = xv[u];
+      }
+    }
+    for (int base = tid + 4 * nt; base < nx; base += 4 * nt) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * nt;
+        v[u] = (i < nx) ? inb[i] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * nt;
+        if (i < nx) {
+          const int c = fdiv(i, a.dP), p = i - c * P;
+          x_s[c * PS + p] = v[u];
+        }
+      }
     }
   }
   __syncthreads();
+  stamp(1);
 
   // ---- phase 1: affine coupling, item = (pixel, j) with j fastest (pm rows read contiguously)
   if (COUPLING) {
+    if (PM_SMEM && pm_bar != 0) mbar_wait(pm_bar, 0);             // the bulk copy of the image's pm rows has landed
     const float* pmb = PM_SMEM ? pm_img : a.pm + (int64_t)b * P * a.ldp;
     const int64_t ldp = PM_SMEM ? (int64_t)pm_ld : a.ldp;
     for (int it = tid; it < P * Ch; it += nt) {
-      const int p = it / Ch, j = it - p * Ch;
-      const int py = p / W, px = p - py * W;
+      const int p = fdiv(it, a.dCh), j = it - p * Ch;
+      const int py = fdiv(p, a.dW), px = p - py * W;
       // all 18 loads are issued before the first use (each pm element is consumed exactly once: plain streaming reads)
       float lv[9], tv[9];
 #pragma unroll
@@ -125,6 +250,7 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
       }
     }
     __syncthreads();
+    stamp(2);
     if (!a.inverse && a.ld_part != nullptr && tid < 32) {
       // deterministic per-image sum: fixed lane-strided order + shuffle tree
       float acc = 0.f;
@@ -134,29 +260,32 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
     }
   }
 
+  stamp(3);
   // ---- phase 1b: stash the pre-mix state (the next StepFlow's input, needed by its backward)
   if (a.xs != nullptr) {
     float* xb = a.xs + (int64_t)b * a.xs_bs;
     for (int i = tid; i < C * P; i += nt) {
-      const int c = i / P, p = i - c * P;
+      const int c = fdiv(i, a.dP), p = i - c * P;
       xb[i] = x_s[c * PS + p];
     }
   }
 
+  stamp(4);
   // ---- phase 2: channel mix, item = (group of 4 outputs, pixel), lanes over pixels
-  if (a.mt != nullptr) {
+  if (mix) {
     const int n_og = Cp >> 2;
     for (int it = tid; it < n_og * P; it += nt) {
-      const int og = it / P, p = it - og * P;
+      const int og = fdiv(it, a.dP), p = it - og * P;
       const float4 b4 = *reinterpret_cast<const float4*>(m_s + C * Cp + og * 4);
       float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
-      for (int c = 0; c < C; ++c) {
-        const float xv = x_s[c * PS + p];
+#pragma unroll 4
+      for (int c = 0; c < C; ++c) {                                // same summation order; unrolled so the loads pipeline
+        const float xv_ = x_s[c * PS + p];
         const float4 w = *reinterpret_cast<const float4*>(m_s + c * Cp + og * 4);
-        a0 = fmaf(w.x, xv, a0);
-        a1 = fmaf(w.y, xv, a1);
-        a2 = fmaf(w.z, xv, a2);
-        a3 = fmaf(w.w, xv, a3);
+        a0 = fmaf(w.x, xv_, a0);
+        a1 = fmaf(w.y, xv_, a1);
+        a2 = fmaf(w.z, xv_, a2);
+        a3 = fmaf(w.w, xv_, a3);
       }
       const int o = og * 4;
       u_s[o * PS + p] = a0;
@@ -166,39 +295,52 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
     }
     __syncthreads();
   }
+  if (want_a1) {
+    // interior of the zero-bordered copy: the channels the next coupling network reads (without a mix: x_a, which passes
+    // through the coupling unchanged)
+    for (int i = tid; i < Ch * P; i += nt) {
+      const int c = fdiv(i, a.dP), p = i - c * P;
+      const int py = fdiv(p, a.dW), px = p - py * W;
+      pad_s[c * PP + (py + 1) * W2p + px + 1] = u_s[c * PS + p];
+    }
+  }
 
+  stamp(5);
   // ---- phase 3a: NCHW sink (lanes over pixels)
   if (a.y != nullptr) {
     float* yb = a.y + (int64_t)b * a.y_bs;
     for (int i = tid; i < C * P; i += nt) {
-      const int c = i / P, p = i - c * P;
+      const int c = fdiv(i, a.dP), p = i - c * P;
       yb[i] = u_s[c * PS + p];
     }
   }
-  // ---- phase 3b: im2col sink, item = (pixel, 8-column group), group fastest -> 128-byte runs per row
-  if (a.a1 != nullptr) {
+  stamp(6);
+  if (want_a1) __syncthreads();
+  // ---- phase 3b: im2col sink, item = (pixel, 8-column group), group fastest -> 128-byte runs per row.  Column k = c*9 + tap
+  // of pixel (py, px) is pad_s[kt_s[k] + py*(W+2) + px]: no bounds tests, no divisions by 9 in the inner loop.
+  if (want_a1) {
     const int K = Ch * 9;
     const int n_g = (int)(a.lda1 >> 3);
     A1T* a1b = reinterpret_cast<A1T*>(a.a1) + (int64_t)b * P * a.lda1;
     for (int it = tid; it < P * n_g; it += nt) {
-      const int p = it / n_g, g = it - p * n_g;
-      const int py = p / W, px = p - py * W;
+      const int p = fdiv(it, a.dNg), g = it - p * n_g;
+      const int py = fdiv(p, a.dW), px = p - py * W;
+      const float* win = pad_s + py * W2p + px;
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = g * 8 + e;
-        float val = 0.f;
-        if (k < K) {
-          const int c = k / 9, tap = k - c * 9;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const int yy = py + ky - 1, xx = px + kx - 1;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = u_s[c * PS + yy * W + xx];
-        }
-        v[e] = val;
+        v[e] = (k < K) ? win[kt_s[k]] : 0.f;
       }
-      store8<A1T>(a1b + (int64_t)p * a.lda1 + g * 8, v);
+      if (a.a1 != nullptr) store8<A1T>(a1b + (int64_t)p * a.lda1 + g * 8, v);
+      if (a1_tile != nullptr) {
+        const int r = p & 127;
+        uint8_t* box = a1_tile + (size_t)((p >> 7) * (n_g >> 3) + (g >> 3)) * 16384 + r * 128 + (((g & 7) ^ (r & 7)) << 4);
+        store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(box), v);
+      }
     }
   }
+  stamp(7);
 }
 
 }  // namespace nfdpm

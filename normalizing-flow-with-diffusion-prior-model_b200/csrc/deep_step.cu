@@ -378,6 +378,7 @@ extern "C" int nfdpm_deep_step(const void* a1_in, const void* w1p, const void* w
   d.in = in; d.in_bs = in_bs; d.pm = nullptr; d.ldp = 0; d.bias3 = bias3; d.logs3 = logs3; d.ld_part = ld_part;
   d.mt = mt; d.beta = beta; d.y = y; d.y_bs = y_bs; d.xs = xs; d.xs_bs = xs_bs; d.a1 = a1; d.lda1 = lda1;
   d.B = B; d.C = C; d.H = H; d.W = W; d.squeeze_in = 0; d.inverse = inverse;
+  boundary_fill_div(d);
   CUtensorMap tmA1, tmW1, tmW2, tmW3;
   if (make_map(&tmA1, a1_in, M, K1p, K1p, 128)) return 1;
   if (make_map(&tmW1, w1p, F, K1p, K1p, a.NS)) return 1;

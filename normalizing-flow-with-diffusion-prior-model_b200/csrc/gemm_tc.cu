@@ -41,6 +41,9 @@ __device__ __forceinline__ void epi_barrier_g() { asm volatile("bar.sync 1, %0;"
 constexpr int TC_ACC_COLS = 256;     // TMEM columns per accumulator stage
 constexpr int TC_CSTAGE_BYTES = 64 * 1024;   // output staging: 128 rows x 256 bf16 / 128 fp32, as 16 KB swizzled boxes
 
+// profiling hook (nfdpm_gemm_debug): per-CTA cycle counters [grid][16] int64; NULL = off
+__device__ long long* g_tc_dbg = nullptr;
+
 template <int EPI, typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
@@ -82,25 +85,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), 512);
-  // everything above overlaps the tail of the previous kernel in the stream (PDL); global memory is touched below
-  pdl_trigger();
-  pdl_wait();
-  if (EPI == NFDPM_EPI_ACTNORM_RELU) {
-    for (int i = threadIdx.x; i < n_pad; i += TC_THREADS) {
-      const float e = (i < N) ? expf(ep_scale[i]) : 0.f;
-      s_ep[i] = e;                                   // y = max(0, e*acc + e*b)
-      s_ep[n_pad + i] = (i < N) ? e * ep_bias[i] : 0.f;
-    }
-  }
-  if (EPI == NFDPM_EPI_RELU_BWD) {
-    for (int i = threadIdx.x; i < n_pad; i += TC_THREADS) s_ep[i] = (i < N) ? expf(ep_scale[i]) : 0.f;
-  }
-  // EPI_RELU_BWD: per-quadrant column partial sums of the tile [4][2][256], after the parameters
-  float* part_s = s_ep + 2 * n_pad;
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                     // barriers initialised, tensor memory allocated
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  // everything above overlaps the tail of the previous kernel in the stream (PDL); global memory is touched below
+  const long long t_entry = clock64();
+  const unsigned long long g_entry = global_timer_ns();
+  pdl_trigger();
+  pdl_wait();
+  const long long t_dep = clock64();
+  // EPI_RELU_BWD: per-quadrant column partial sums of the tile [4][2][256], after the parameters
+  float* part_s = s_ep + 2 * n_pad;
+  long long* const dbg = g_tc_dbg;
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;       // wait / work cycle counters of this warp (profiling hook)
+  const long long t_start = clock64();
+  if (warp >= 2 && EPI != NFDPM_EPI_RAW) {
+    // the epilogue warps stage the folded ActNorm parameters while the producer / MMA warps already run the main loop
+    // (r1 counters: staging them with all warps in front of the role split cost 0.6 us per launch)
+    for (int i = threadIdx.x - 64; i < n_pad; i += 32 * TCG_EPI_WARPS) {
+      const float e = (i < N) ? expf(ep_scale[i]) : 0.f;
+      s_ep[i] = e;                                   // y = max(0, e*acc + e*b)
+      if (EPI == NFDPM_EPI_ACTNORM_RELU) s_ep[n_pad + i] = (i < N) ? e * ep_bias[i] : 0.f;
+    }
+    epi_barrier_g();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -110,7 +119,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       for (int kb = 0; kb < num_kb; ++kb) {
+        const long long c0 = dbg ? clock64() : 0;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (dbg) w0 += clock64() - c0;
         if (lane == 0) {
           const uint32_t sa = ring + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
           mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
@@ -127,11 +138,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     uint32_t phase = 0, acc_phase = 0;
     const uint32_t idesc = make_idesc(TC_BM, BN);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long c0 = dbg ? clock64() : 0;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator stage
+      if (dbg) w1 += clock64() - c0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * TC_ACC_COLS;
       for (int kb = 0; kb < num_kb; ++kb) {
+        const long long c1 = dbg ? clock64() : 0;
         mbar_wait(bar_full + 8 * stage, phase);           // TMA bytes have landed
+        if (dbg) w0 += clock64() - c1;
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = ring + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
@@ -157,13 +172,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const long long c0 = dbg ? clock64() : 0;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
+      const long long c1 = dbg ? clock64() : 0;
+      w0 += c1 - c0;
       const int trow = q * 32 + lane;                      // row inside the tile == TMEM lane
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_ACC_COLS;
       // the previous tile's TMA stores must have finished READING the staging tile before it is overwritten
       if (warp == 2 && lane == 0) tma_store_wait_read();
       epi_barrier_g();
+      const long long c2 = dbg ? clock64() : 0;
+      w1 += c2 - c1;
       // EPI_RELU_BWD: 16 bf16 of the stashed activation h for this thread's row (two 16-byte loads)
       const int64_t h_row = (int64_t)(m_blk * TC_BM + trow) * ld_h + n_blk * BN;
       const bool row_ok = (m_blk * TC_BM + trow) < M;
@@ -259,8 +279,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       // accumulator drained: hand the TMEM stage back to the MMA warp before doing the stores
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
+      const long long c3 = dbg ? clock64() : 0;
+      w2 += c3 - c2;
       fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA engine
       epi_barrier_g();
+      if (dbg) { w3 += clock64() - c3; w4 += 1; }
       if (EPI == NFDPM_EPI_RELU_BWD) {
         // combine the four row quadrants in order; one partial row per 128-row tile: part[m_blk][2N]
         const int t = threadIdx.x - 64;
@@ -285,7 +308,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (warp == 2 && lane == 0) tma_store_wait_all();      // global writes complete before the kernel exits
+    // the staging tile must have been READ before the CTA gives its shared memory back; the writes themselves are
+    // complete and visible to the next kernel at grid completion (what griddepcontrol.wait / stream order wait for)
+    if (warp == 2 && lane == 0) tma_store_wait_read();
+  }
+  if (dbg != nullptr && lane == 0 && warp <= 2) {
+    long long* o = dbg + (int64_t)blockIdx.x * 16;
+    const long long total = clock64() - t_start;
+    if (warp == 0) { o[0] = total; o[1] = w0; }                       // producer: cycles waiting for a free smem stage
+    if (warp == 1) { o[2] = total; o[3] = w0; o[4] = w1; }            // MMA: waiting for TMA bytes / for a drained accumulator
+    if (warp == 2) { o[5] = total; o[6] = w0; o[7] = w1; o[8] = w2; o[9] = w3; o[10] = w4; }   // epilogue: wait tfull /
+                                                                      // wait staging free / TMEM->smem / barrier / tiles
+    if (warp == 2) {                                                  // CTA lifetime: entry -> dependency resolved -> roles start -> end
+      o[11] = t_dep - t_entry; o[12] = t_start - t_dep; o[13] = (long long)g_entry; o[14] = (long long)global_timer_ns();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -367,3 +403,10 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
 }
 
 }  // namespace nfdpm
+
+// profiling hook: per-CTA cycle counters of nfdpm_gemm_nt's tcgen05 kernel into a device int64 [148][16] buffer (NULL = off)
+extern "C" int nfdpm_gemm_debug(void* buf) {
+  long long* p = reinterpret_cast<long long*>(buf);
+  NFDPM_CUDA(cudaMemcpyToSymbol(nfdpm::g_tc_dbg, &p, sizeof(p)));
+  return 0;
+}

@@ -9,7 +9,7 @@
 //   warp 0 (both CTAs)  TMA producer: cp.async.bulk.tensor .cta_group::2, completion bytes land on the LEADER's barrier
 //   warp 1 (leader)     MMA issuer; tcgen05.commit ...multicast::cluster releases the smem stage in BOTH CTAs and
 //                       publishes the accumulator to BOTH epilogues
-//   warps 2..9 (both)   epilogue as in gemm_tc.cu on the CTA's own 128 rows; one thread per CTA hands the accumulator
+//   warps 2..17 (both)  epilogue as in gemm_tc.cu on the CTA's own 128 rows; one thread per CTA hands the accumulator
 //                       stage back to the leader's MMA warp (remote mbarrier arrive from the peer)
 // Every mbarrier wait is bounded (2 s) and traps instead of hanging.
 #include "tc_common.cuh"
@@ -22,7 +22,10 @@ constexpr int T2_STAGES = 4;
 constexpr int T2_A_BYTES = T2_BM * T2_BK * 2;           // 16 KB
 constexpr int T2_B_BYTES_MAX = 128 * T2_BK * 2;         // 16 KB: this CTA's half of the B tile (BN <= 256)
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES_MAX;
-constexpr int T2_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int T2_EPI_WARPS = 16;           // four per TMEM lane quadrant (as gemm_tc.cu)
+constexpr int T2_EPQ = T2_EPI_WARPS / 4;
+constexpr int T2_THREADS = 64 + 32 * T2_EPI_WARPS;
+__device__ __forceinline__ void epi_barrier2() { asm volatile("bar.sync 1, %0;" ::"n"(32 * T2_EPI_WARPS) : "memory"); }
 constexpr int T2_ACC_COLS = 256;
 constexpr int T2_CSTAGE_BYTES = 64 * 1024;
 
@@ -178,7 +181,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9, both CTAs, own 128 rows) =====================
+    // ===================== epilogue (warps 2..17, both CTAs, own 128 rows) =====================
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int n_chunks = BN >> 4;
@@ -191,7 +194,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
       const int trow = q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * T2_ACC_COLS;
       if (warp == 2 && lane == 0) tma_store_wait_read();
-      epi_barrier();
+      epi_barrier2();
       auto process = [&](const uint32_t (&r)[16], int c0) {
         const int n0 = n_blk * BN + c0;
         float v[16];
@@ -217,18 +220,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
       if (ch < n_chunks) tmem_ld16(taddr + ch * 16, ra);
       while (ch < n_chunks) {
         tmem_ld_wait();
-        if (ch + 2 < n_chunks) tmem_ld16(taddr + (ch + 2) * 16, rb);
+        if (ch + T2_EPQ < n_chunks) tmem_ld16(taddr + (ch + T2_EPQ) * 16, rb);
         process(ra, ch * 16);
-        ch += 2;
+        ch += T2_EPQ;
         if (ch >= n_chunks) break;
         tmem_ld_wait();
-        if (ch + 2 < n_chunks) tmem_ld16(taddr + (ch + 2) * 16, ra);
+        if (ch + T2_EPQ < n_chunks) tmem_ld16(taddr + (ch + T2_EPQ) * 16, ra);
         process(rb, ch * 16);
-        ch += 2;
+        ch += T2_EPQ;
       }
       tc_fence_before();
       fence_proxy_async();
-      epi_barrier();                                          // every TMEM read and staging write of this CTA is done
+      epi_barrier2();                                         // every TMEM read and staging write of this CTA is done
       if (warp == 2 && lane == 0) {
         mbar_arrive_cluster(bar_tempty + 8 * acc, 0);         // hand the accumulator stage back to the leader's MMA warp
         constexpr int CPB = TcStage<OutT>::kColsPerBox;

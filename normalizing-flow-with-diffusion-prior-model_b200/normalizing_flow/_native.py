@@ -78,7 +78,12 @@ def _load() -> C.CDLL:
         "nfdpm_gemm3_boundary_ok": ([i32, i32, i32, i32, i32, i64], C.c_int),
         "nfdpm_gemm3_boundary": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
                                   i32, i32, i32, i64, i32, vp], C.c_int),
+        "nfdpm_boundary_gemm1_ok": ([i32, i32, i32, i32, i64], C.c_int),
+        "nfdpm_boundary_gemm1": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32,
+                                  i32, i32, i32, i64, i32, vp], C.c_int),
         "nfdpm_deep_step_debug": ([vp], C.c_int),
+        "nfdpm_gemm_debug": ([vp], C.c_int),
+        "nfdpm_flow_boundary_debug": ([vp], C.c_int),
         "nfdpm_deep_step_ok": ([i32, i32, i32, i32, i32, i64, i64], C.c_int),
         "nfdpm_deep_step": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64,
                              vp, i32, i64, i32, i32, i32, i32, i32, i64, i64, i32, vp], C.c_int),
@@ -116,7 +121,7 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
            "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch",
-           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_nt_relu_bwd", "nfdpm_deep_step_debug", "nfdpm_deep_step_ok", "nfdpm_deep_step"]
+           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_nt_relu_bwd", "nfdpm_boundary_gemm1_ok", "nfdpm_boundary_gemm1", "nfdpm_deep_step_debug", "nfdpm_gemm_debug", "nfdpm_flow_boundary_debug", "nfdpm_deep_step_ok", "nfdpm_deep_step"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -366,6 +371,17 @@ def gemm3_boundary(h2, ldh, w3p, pm_out, ld_pm_out, src, src_bs, bias3, logs3, l
     _ok(lib.nfdpm_gemm3_boundary(_p(h2), ldh, _p(w3p), _p(pm_out), ld_pm_out, _p(src), src_bs, _p(bias3), _p(logs3),
                                  _p(ld_part), _p(mt), _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1),
                                  _dt(a1) if a1 is not None else F32, lda1, B, Cc, H, W, K, ldp, int(inverse), _st()))
+
+
+def boundary_gemm1_ok(Cc, H, W, Fh, K1p) -> bool:
+    return bool(lib.nfdpm_boundary_gemm1_ok(Cc, H, W, Fh, K1p))
+
+
+def boundary_gemm1(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1, w1p, s1, b1, h1,
+                   B, Cc, H, W, Fh, K1p, inverse) -> None:
+    _ok(lib.nfdpm_boundary_gemm1(_p(src), src_bs, int(squeeze_in), _p(pm), ldp, _p(bias3), _p(logs3), _p(ld_part), _p(mt),
+                                 _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1), _p(w1p), _p(s1), _p(b1), _p(h1), B, Cc, H, W,
+                                 Fh, K1p, int(inverse), _st()))
 
 
 def deep_step_ok(B, Cc, H, W, Fh, K1p, ldp) -> bool:

@@ -561,6 +561,63 @@ def test_gemm3_boundary_support_query():
     assert N.gemm3_boundary_ok(128, 48, 4, 4, 512, 432)
 
 
+# ------------------------------------------------------------------ step boundary + GEMM1 of the next StepFlow
+@pytest.mark.parametrize("B,C,H,W", [(3, 12, 16, 16), (5, 24, 8, 8), (7, 48, 4, 4), (4, 8, 8, 8), (6, 32, 4, 2),
+                                     (2, 16, 8, 16)])
+def test_boundary_gemm1_equals_boundary_plus_gemm(B, C, H, W):
+    """nfdpm_boundary_gemm1 == nfdpm_flow_boundary(_stash) -> nfdpm_gemm_nt(EPI_ACTNORM_RELU), BIT EXACT: state, pre-mix
+    stash, log-det partials, the optional global im2col copy and h1; coupling source (forward / inverse), plain source and
+    squeeze source; one and two 128-row tiles per image, resident and ring-fed weights."""
+    P, Ch, F = H * W, C // 2, 512
+    ldp = (9 * C + 15) // 16 * 16
+    K1p = (9 * Ch + 63) // 64 * 64
+    M = B * P
+    bf = torch.bfloat16
+    assert N.boundary_gemm1_ok(C, H, W, F, K1p)
+    pm = rnd(M, ldp, seed=1, scale=0.3).cuda()
+    w1 = (rnd(F, K1p, seed=2, scale=0.1).cuda()).to(bf)
+    w1[:, 9 * Ch:] = 0
+    s1, b1 = rnd(F, seed=3, scale=0.1).cuda(), rnd(F, seed=4, scale=0.3).cuda()
+    x = rnd(B, C, H, W, seed=5).cuda()
+    xsq = rnd(B, C // 4, 2 * H, 2 * W, seed=6).cuda()
+    mt, beta = rnd(C, C, seed=7, scale=0.3).cuda(), rnd(C, seed=8).cuda()
+    bias3, logs3 = rnd(C, seed=9, scale=0.1).cuda(), rnd(C, seed=10, scale=0.1).cuda()
+    for mode in ("coupling_fwd", "coupling_inv", "plain", "squeeze"):
+        for stash in (True, False):
+            cp, inv, sq = mode.startswith("coupling"), mode == "coupling_inv", mode == "squeeze"
+            src = xsq if sq else x
+            cargs = (pm, ldp, bias3, logs3) if cp else (None, 0, None, None)
+            y_ref, xs_ref = torch.empty_like(x), torch.empty_like(x)
+            a_ref = torch.empty(M, K1p, dtype=bf, device=DEV)
+            part_ref = torch.zeros(B, device=DEV)
+            if inv:
+                N.flow_boundary(src, C * P, False, *cargs, None, mt, beta, y_ref, C * P, a_ref, K1p, B, C, H, W, True)
+            else:
+                N.flow_boundary_stash(src, C * P, sq, *cargs, part_ref if cp else None, mt, beta, y_ref, C * P, xs_ref, C * P,
+                                      a_ref, K1p, B, C, H, W)
+            h1_ref = torch.empty(M, F, dtype=bf, device=DEV)
+            N.gemm_nt(a_ref, K1p, w1, K1p, h1_ref, F, M, F, K1p, N.EPI_ACTNORM_RELU, s1, b1)
+            y, xs = torch.empty_like(x), torch.empty_like(x)
+            a1 = torch.full((M, K1p), 7.0, dtype=bf, device=DEV) if stash else None
+            part = torch.zeros(B, device=DEV)
+            h1 = torch.full((M, F), float("nan"), dtype=bf, device=DEV)
+            N.boundary_gemm1(src, C * P, sq, *cargs, part if (cp and not inv) else None, mt, beta, y, C * P,
+                             None if inv else xs, 0 if inv else C * P, a1, w1, s1, b1, h1, B, C, H, W, F, K1p, inv)
+            sync()
+            assert torch.equal(y, y_ref) and torch.equal(h1, h1_ref), (mode, stash)
+            if stash:
+                assert torch.equal(a1, a_ref)
+            if not inv:
+                assert torch.equal(xs, xs_ref) and torch.equal(part, part_ref)
+
+
+def test_boundary_gemm1_support_query():
+    assert not N.boundary_gemm1_ok(12, 64, 64, 512, 64)         # image larger than two 128-row tiles
+    assert not N.boundary_gemm1_ok(6, 14, 14, 512, 64)          # 196 pixels
+    assert not N.boundary_gemm1_ok(12, 16, 16, 256, 64)         # hidden width other than 512
+    assert N.boundary_gemm1_ok(12, 16, 16, 512, 64) and N.boundary_gemm1_ok(48, 4, 4, 512, 256)
+
+
 # ------------------------------------------------------------------ cluster-fused StepFlow of a deep level
 @pytest.mark.parametrize("B,C,H,W", [(5, 24, 8, 8), (4, 8, 8, 8), (13, 48, 4, 4), (8, 16, 4, 4), (6, 32, 4, 2)])
 @pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16])
