@@ -9,7 +9,7 @@
 // All reductions are two-stage with a fixed order (no float atomics): bitwise reproducible.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nfdpm {
 
@@ -65,44 +65,109 @@ struct CouplingBwdArgs {
   float* dpar;                         // out: [B][2C] per-image partials: dbias3[C], dlogs3[C]
   int B, C, H, W;
   float* dbias; float* dlogs; int* counter;   // optional: the last CTA sums the partials (image order) into these
+  FastDiv dP, dW, dCh, dNg, d2C;              // H*W, W, C/2, ld_dpm/8, 2C
+  int pm_bulk;                                // stage the image's pm rows in shared memory with the bulk-copy engine
 };
 
+// Shared-memory floats of coupling_bwd_kernel without the optional pm block (coupling_bwd_smem)
+__host__ __device__ __forceinline__ size_t coupling_bwd_floats(int C, int H, int W, size_t* pad_off, size_t* kt_off) {
+  const size_t P = (size_t)H * W, PS = P + 1, Ch = C / 2, PP = (size_t)(H + 2) * (W + 2);
+  size_t fl = (size_t)C * PS + Ch * PS + 4 * P * Ch + 2 * C;          // g_s, ub_s, r_s, par_s
+  fl = (fl + 3) & ~(size_t)3;
+  if (pad_off) *pad_off = fl;
+  fl += ((size_t)C * PP + 3) & ~(size_t)3;                            // dP_pad: zero-bordered [C][(H+2)(W+2)]
+  if (kt_off) *kt_off = fl;
+  fl += (9 * (size_t)C + 3) & ~(size_t)3;                             // kt_s: dpm column -> offset inside dP_pad
+  return fl;
+}
+
+// One CTA per image.  Same structure as the forward step boundary (boundary_body.cuh): the image's pm block arrives by
+// bulk copy while the gradients are staged; index divisions are multiply-high; the dpm rows (the transposed-conv scatter
+// dpm[p, tap*C+co] = dP[co][p - shift(tap)]) are gathered from a zero-bordered copy of dP through a column table.
 template <typename TD>
 __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArgs a) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm_raw[];
+  __shared__ __align__(8) uint64_t pm_bar;
   const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1, PS = P + 1;
+  const int W2p = W + 2, PP = (H + 2) * W2p;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const size_t n_pm = a.pm_bulk ? (size_t)P * a.ldp : 0;
+  float* sm = sm_raw + n_pm;
+  size_t pad_off, kt_off;
+  coupling_bwd_floats(C, H, W, &pad_off, &kt_off);
   float* g_s = sm;                  // [C][PS] dy, second half becomes du_b
   float* ub_s = g_s + C * PS;       // [Ch][PS] u_b
-  float* dP_s = ub_s + Ch * PS;     // [C][PS] grad wrt gathered conv output
-  float* r_s = dP_s + C * PS;       // [4][P*Ch] reduction terms
+  float* r_s = ub_s + Ch * PS;      // [4][P*Ch] reduction terms
   float* par_s = r_s + 4 * P * Ch;  // [2C]
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < C; i += nt) {
-    par_s[i] = a.bias3[i];
-    par_s[C + i] = expf(3.f * a.logs3[i]);
+  float* dP_pad = sm + pad_off;     // [C][PP] grad wrt gathered conv output, zero border
+  int* kt_s = reinterpret_cast<int*>(sm + kt_off);   // [9C]
+  if (a.pm_bulk && tid == 0) {
+    const uint32_t bar = smem_u32(&pm_bar);
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    const char* src = reinterpret_cast<const char*>(a.pm + (size_t)b * n_pm);
+    mbar_arrive_expect_tx(bar, (uint32_t)(n_pm * 4));
+    for (size_t off = 0; off < n_pm * 4; off += 32768) {
+      const uint32_t len = (uint32_t)((n_pm * 4 - off) < 32768 ? (n_pm * 4 - off) : 32768);
+      bulk_load(smem_u32(sm_raw) + (uint32_t)off, src + off, len, bar);
+    }
   }
+  // ---- stage dy and u_b: every global load of a batch is issued before the first dependent shared-memory store
   const float* dyb = a.dy + (int64_t)b * a.dy_bs;
   const float* ub = a.u + (int64_t)b * a.u_bs;
-  for (int i = tid; i < C * P; i += nt) {
-    const int c = i / P, p = i - c * P;
-    g_s[c * PS + p] = dyb[i];
-    if (c >= Ch) ub_s[(c - Ch) * PS + p] = ub[i];
+  const int nx = C * P;
+  for (int base = tid; base < nx || base == tid; base += 4 * nt) {   // (every thread runs the first pass: tables below)
+    float v[4], w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      v[u] = (i < nx) ? dyb[i] : 0.f;
+      w[u] = (i < nx && i >= Ch * P) ? ub[i] : 0.f;
+    }
+    if (base == tid) {                                               // parameters and tables ride on the first batch
+      for (int i = tid; i < C; i += nt) {
+        par_s[i] = a.bias3[i];
+        par_s[C + i] = expf(3.f * a.logs3[i]);
+      }
+      for (int i = tid; i < C * PP; i += nt) dP_pad[i] = 0.f;
+      for (int k = tid; k < 9 * C; k += nt) {
+        const int tap = k / C, co = k - tap * C;                     // (runs once per thread at most a few times)
+        kt_s[k] = co * PP + (2 - tap / 3) * W2p + (2 - tap % 3);     // pm row (py,px) at tap feeds pixel (py-dy, px-dx)
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      if (i < nx) {
+        const int c = fdiv(i, a.dP), p = i - c * P;
+        g_s[c * PS + p] = v[u];
+        if (c >= Ch) ub_s[(c - Ch) * PS + p] = w[u];
+      }
+    }
   }
   __syncthreads();
   const float gld = (a.dld != nullptr) ? a.dld[b] : 0.f;
-  const float* pmb = a.pm + (int64_t)b * P * a.ldp;
+  if (a.pm_bulk) mbar_wait(smem_u32(&pm_bar), 0);
+  const float* pmb = a.pm_bulk ? sm_raw : a.pm + (int64_t)b * P * a.ldp;
+  const bool pm_smem = a.pm_bulk != 0;
   for (int it = tid; it < P * Ch; it += nt) {
-    const int p = it / Ch, j = it - p * Ch;
-    const int py = p / W, px = p - py * W;
-    float ls = 0.f, tt = 0.f;
+    const int p = fdiv(it, a.dCh), j = it - p * Ch;
+    const int py = fdiv(p, a.dW), px = p - py * W;
+    float lv[9], tv[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
       const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
       const float* r = pmb + (int64_t)(ok ? yy * W + xx : p) * a.ldp + tap * C + j;
-      const float l0 = __ldg(r), t0 = __ldg(r + Ch);
-      ls += ok ? l0 : 0.f;
-      tt += ok ? t0 : 0.f;
+      const float l0 = pm_smem ? r[0] : __ldg(r), t0 = pm_smem ? r[Ch] : __ldg(r + Ch);
+      lv[tap] = ok ? l0 : 0.f;
+      tv[tap] = ok ? t0 : 0.f;
+    }
+    float ls = 0.f, tt = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      ls += lv[tap];
+      tt += tv[tap];
     }
     const float g_l = par_s[C + j], g_t = par_s[C + Ch + j];
     const float log_s = (ls + par_s[j]) * g_l;
@@ -113,8 +178,9 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
     const float dt = dyv * s;
     const float dls = ds * s * (1.f - s);
     g_s[(Ch + j) * PS + p] = dyv * s;            // du_b
-    dP_s[j * PS + p] = dls * g_l;
-    dP_s[(Ch + j) * PS + p] = dt * g_t;
+    const int pq = (py + 1) * W2p + px + 1;
+    dP_pad[j * PP + pq] = dls * g_l;
+    dP_pad[(Ch + j) * PP + pq] = dt * g_t;
     r_s[0 * P * Ch + j * P + p] = dls * g_l;         // -> dbias3[j]
     r_s[1 * P * Ch + j * P + p] = dt * g_t;          // -> dbias3[Ch+j]
     r_s[2 * P * Ch + j * P + p] = 3.f * dls * log_s; // -> dlogs3[j]
@@ -124,31 +190,24 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
   // outputs: du (coalesced over pixels)
   float* dub = a.du + (int64_t)b * a.du_bs;
   for (int i = tid; i < C * P; i += nt) {
-    const int c = i / P, p = i - c * P;
+    const int c = fdiv(i, a.dP), p = i - c * P;
     dub[i] = g_s[c * PS + p];
   }
-  // dpm rows: dpm[p', tap*C+co] = dP[co][p' - shift(tap)]  (zero outside the image / in the padding columns).
-  // A thread produces 8 consecutive columns (one 16-byte bf16 / two 16-byte fp32 stores); (tap, co) advance
-  // incrementally, so there is one division per 8 elements instead of three per element.
+  // dpm rows: dpm[p', tap*C+co] = dP[co][p' - shift(tap)] = dP_pad[kt_s[col] + py'*(W+2) + px'] (zero outside the image and
+  // in the padding columns).  A thread produces 8 consecutive columns (one 16-byte bf16 / two 16-byte fp32 stores).
   const int ldp = (int)a.ld_dpm;
   TD* dpmb = reinterpret_cast<TD*>(a.dpm) + (int64_t)b * P * ldp;
   if ((ldp & 7) == 0 && (((uintptr_t)dpmb) & 15) == 0) {
-    const int n_g = ldp >> 3;
+    const int n_g = ldp >> 3, K = 9 * C;
     for (int it = tid; it < P * n_g; it += nt) {
-      const int pp = it / n_g, g = it - pp * n_g;
-      const int py = pp / W, px = pp - py * W;
-      int col = g * 8;
-      int tap = col / C, co = col - tap * C;
+      const int pp = fdiv(it, a.dNg), g = it - pp * n_g;
+      const int py = fdiv(pp, a.dW), px = pp - py * W;
+      const float* win = dP_pad + py * W2p + px;
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float val = 0.f;
-        if (tap < 9) {
-          const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);   // pm row pp at tap feeds pixel (yy, xx)
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = dP_s[co * PS + yy * W + xx];
-        }
-        v[e] = val;
-        if (++co == C) { co = 0; ++tap; }
+        const int col = g * 8 + e;
+        v[e] = (col < K) ? win[kt_s[col]] : 0.f;
       }
       Vec8<TD>::store(dpmb + (int64_t)pp * ldp + g * 8, v);
     }
@@ -157,10 +216,8 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
       const int pp = i / ldp, col = i - pp * ldp;
       float v = 0.f;
       if (col < 9 * C) {
-        const int tap = col / C, co = col - tap * C;
-        const int py = pp / W, px = pp - py * W;
-        const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = dP_s[co * PS + yy * W + xx];
+        const int py = fdiv(pp, a.dW), px = pp - py * W;
+        v = dP_pad[kt_s[col] + py * W2p + px];
       }
       stf<TD>(dpmb + i, v);
     }
@@ -173,7 +230,7 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
     for (int p = lane; p < P; p += 32) acc += rp[p];
     acc = warp_sum(acc);
     if (lane == 0) {
-      const int kind = row / Ch, j = row - kind * Ch;
+      const int kind = fdiv(row, a.dCh), j = row - kind * Ch;
       // kind 0: dbias[j], 1: dbias[Ch+j], 2: dlogs[j], 3: dlogs[Ch+j]
       const int dst = (kind < 2 ? 0 : C) + ((kind & 1) ? Ch : 0) + j;
       a.dpar[(int64_t)b * 2 * C + dst] = acc;
@@ -196,9 +253,16 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
       if (RG < 1) RG = 1;
       float* red = sm;                       // the image buffers are dead by now: RG * 2C floats
       for (int idx = tid; idx < RG * n2c; idx += nt) {
-        const int rg = idx / n2c, i = idx - rg * n2c;
+        const int rg = fdiv(idx, a.d2C), i = idx - rg * n2c;
         float acc = 0.f;
         int bb = rg;
+        for (; bb + 31 * RG < a.B; bb += 32 * RG) {        // 32 loads in flight, added in image order
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __ldcg(a.dpar + (int64_t)(bb + j * RG) * n2c + i);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += v[j];
+        }
         for (; bb + 7 * RG < a.B; bb += 8 * RG) {          // eight loads in flight, added in image order
           float v[8];
 #pragma unroll
@@ -411,43 +475,75 @@ struct MixBwdArgs {
   float* part;                        // out: [B*T][C*C + C]: dW^x[o*C+i] = sum_p du[o]x[i];  db^[o] = sum_p du[o]
   int B, C, H, W;
   int TP;                             // pixels per CTA tile (T = ceil(P/TP) tiles per image)
+  FastDiv dC, dCh, dW, dT, dNpFull, dNpLast;   // C, C/2, W, tiles per image, pixels of a full / of the last tile
 };
 
 __global__ void __launch_bounds__(1024) mix_bwd_kernel(const MixBwdArgs a) {
   // CTA = (image b, pixel tile t): pixels [p0, p0 + np) of the image; images up to 256 pixels are one tile
   extern __shared__ __align__(16) float sm[];
   const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
-  const int T = (P + a.TP - 1) / a.TP;
-  const int b = blockIdx.x / T, t = blockIdx.x - b * T;
+  const int T = (int)a.dT.d;
+  const int b = fdiv((int)blockIdx.x, a.dT), t = blockIdx.x - b * T;
   const int p0 = t * a.TP, np = min(a.TP, P - p0), PS = a.TP + 1;
   float* d_s = sm;                 // [C][PS] du (complete)
   float* x_s = d_s + C * PS;       // [C][PS]
   float* w_s = x_s + C * PS;       // [C][C]  w_s[o*C+i] = W^[o][i]
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < C * C; i += nt) {
-    const int o = i / C, ii = i - o * C;
-    w_s[i] = a.mt[ii * C + o];
-  }
+  // index divisions are multiply-high (run-time divisors; exact for these ranges)
+  const FastDiv dNp = (t == T - 1) ? a.dNpLast : a.dNpFull;
   const float* dub = a.du + (int64_t)b * a.du_bs;
   const float* xb = a.x + (int64_t)b * a.x_bs;
-  for (int i = tid; i < C * np; i += nt) {
-    const int c = i / np, pl = i - c * np;
-    d_s[c * PS + pl] = dub[(int64_t)c * P + p0 + pl];
-    x_s[c * PS + pl] = xb[(int64_t)c * P + p0 + pl];
+  // staging: the global loads of a batch are issued before the first dependent shared-memory store
+  const int nx = C * np;
+  for (int base = tid; base < nx || base == tid; base += 4 * nt) {   // (every thread runs the first pass: w_s below)
+    float dv[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      dv[u] = xv[u] = 0.f;
+      if (i < nx) {
+        const int c = fdiv(i, dNp), pl = i - c * np;
+        dv[u] = dub[(int64_t)c * P + p0 + pl];
+        xv[u] = xb[(int64_t)c * P + p0 + pl];
+      }
+    }
+    if (base == tid) {
+      for (int i = tid; i < C * C; i += nt) {
+        const int o = fdiv(i, a.dC), ii = i - o * C;
+        w_s[i] = a.mt[ii * C + o];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      if (i < nx) {
+        const int c = fdiv(i, dNp), pl = i - c * np;
+        d_s[c * PS + pl] = dv[u];
+        x_s[c * PS + pl] = xv[u];
+      }
+    }
   }
   __syncthreads();
   if (a.da1 != nullptr) {
     // col2im: A1[m, c*9+tap] = u[c][m + shift(tap)]  =>  du[c][p] += sum_tap dA1[p - shift(tap), c*9+tap]
     const float* dab = a.da1 + (int64_t)b * P * a.lda1;
     for (int it = tid; it < np * Ch; it += nt) {
-      const int pl = it / Ch, c = it - pl * Ch;
+      const int pl = fdiv(it, a.dCh), c = it - pl * Ch;
       const int p = p0 + pl;
-      const int py = p / W, px = p - py * W;
+      const int py = fdiv(p, a.dW), px = p - py * W;
+      float v[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {                            // all nine loads in flight, added in tap order
+        const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const float l = __ldg(dab + (int64_t)(ok ? yy * W + xx : p) * a.lda1 + c * 9 + tap);
+        v[tap] = ok ? l : 0.f;
+      }
       float acc = 0.f;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += __ldg(dab + (int64_t)(yy * W + xx) * a.lda1 + c * 9 + tap);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += v[tap];
       }
       d_s[c * PS + pl] += acc;
     }
@@ -456,36 +552,54 @@ __global__ void __launch_bounds__(1024) mix_bwd_kernel(const MixBwdArgs a) {
   // dx[i][p] = sum_o W^[o][i] du[o][p]
   float* dxb = a.dx + (int64_t)b * a.dx_bs;
   for (int it = tid; it < C * np; it += nt) {
-    const int i = it / np, pl = it - i * np;
+    const int i = fdiv(it, dNp), pl = it - i * np;
     float acc = 0.f;
+#pragma unroll 4
     for (int o = 0; o < C; ++o) acc = fmaf(w_s[o * C + i], d_s[o * PS + pl], acc);
     dxb[(int64_t)i * P + p0 + pl] = acc;
   }
   // partials of d(W^) and d(b^), fixed summation order.  Many pixels: one warp per element, lanes over pixels + shuffle
-  // tree.  Few pixels (deep levels, C up to 48..192 -> thousands of elements): one THREAD per element, sequential over p.
+  // tree, FOUR elements per warp in flight (their shuffle chains interleave; each element's own order is unchanged).
+  // Few pixels (deep levels, C up to 48..192 -> thousands of elements): one THREAD per element, sequential over p.
   float* pb = a.part + (int64_t)blockIdx.x * (C * C + C);
+  const int n_e = C * C + C;
   if (np >= 64) {
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-    for (int e = warp; e < C * C + C; e += nw) {
-      float acc = 0.f;
-      if (e < C * C) {
-        const int o = e / C, i = e - o * C;
-        for (int pl = lane; pl < np; pl += 32) acc = fmaf(d_s[o * PS + pl], x_s[i * PS + pl], acc);
-      } else {
-        const int o = e - C * C;
-        for (int pl = lane; pl < np; pl += 32) acc += d_s[o * PS + pl];
+    for (int e0 = warp * 4; e0 < n_e; e0 += nw * 4) {
+      float acc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k;
+        acc[k] = 0.f;
+        if (e < C * C) {
+          const int o = fdiv(e, a.dC), i = e - o * C;
+          for (int pl = lane; pl < np; pl += 32) acc[k] = fmaf(d_s[o * PS + pl], x_s[i * PS + pl], acc[k]);
+        } else if (e < n_e) {
+          const int o = e - C * C;
+          for (int pl = lane; pl < np; pl += 32) acc[k] += d_s[o * PS + pl];
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) pb[e] = acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (e0 + k < n_e) pb[e0 + k] = acc[k];
+      }
     }
   } else {
-    for (int e = tid; e < C * C + C; e += nt) {
+    for (int e = tid; e < n_e; e += nt) {
       float acc = 0.f;
       if (e < C * C) {
-        const int o = e / C, i = e - o * C;       // lanes share o (broadcast) and walk i: rows PS apart -> no conflicts
+        const int o = fdiv(e, a.dC), i = e - o * C;   // lanes share o (broadcast) and walk i: rows PS apart -> no conflicts
+#pragma unroll 4
         for (int pl = 0; pl < np; ++pl) acc = fmaf(d_s[o * PS + pl], x_s[i * PS + pl], acc);
       } else {
         const int o = e - C * C;
+#pragma unroll 4
         for (int pl = 0; pl < np; ++pl) acc += d_s[o * PS + pl];
       }
       pb[e] = acc;
@@ -738,9 +852,8 @@ int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* w
 
 using namespace nfdpm;
 
-static size_t coupling_bwd_smem(int C, int P) {
-  const size_t PS = P + 1, Ch = C / 2;
-  return sizeof(float) * (2 * (size_t)C * PS + Ch * PS + 4 * (size_t)P * Ch + 2 * C);
+static size_t coupling_bwd_smem(int C, int H, int W) {
+  return sizeof(float) * coupling_bwd_floats(C, H, W, nullptr, nullptr);
 }
 static int coupling_bwd_tile(int C, int P) {
   int tp = P < 128 ? P : 128;
@@ -752,7 +865,7 @@ static int coupling_bwd_tile(int C, int P) {
  * B*tiles rows, dp_scratch [B*H*W*C] floats is required and the last-CTA reduction (counter) is not used. */
 extern "C" int nfdpm_coupling_bwd_tiles(int C, int H, int W) {
   const int P = H * W;
-  if (coupling_bwd_smem(C, P) <= 200 * 1024) return 1;
+  if (coupling_bwd_smem(C, H, W) <= 200 * 1024) return 1;
   const int tp = coupling_bwd_tile(C, P);
   return (P + tp - 1) / tp;
 }
@@ -776,10 +889,15 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
     NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
-  const size_t smem = coupling_bwd_smem(C, P);
+  size_t smem = coupling_bwd_smem(C, H, W);
   if (smem <= 200 * 1024) {
     CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W, dbias, dlogs,
                       counter};
+    a.dP = make_fastdiv(P); a.dW = make_fastdiv(W); a.dCh = make_fastdiv(Ch);
+    a.dNg = make_fastdiv(ld_dpm >= 8 ? (int)(ld_dpm >> 3) : 1); a.d2C = make_fastdiv(2 * C);
+    const size_t pm_bytes = (size_t)P * (size_t)ldp * sizeof(float);
+    a.pm_bulk = (ldp % 4 == 0 && ((uintptr_t)pm % 16) == 0 && smem + pm_bytes <= 200 * 1024) ? 1 : 0;
+    if (a.pm_bulk) smem += pm_bytes;
     int threads = (P * Ch + 31) / 32 * 32;
     threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
     if (dpm_dtype == NFDPM_F32) coupling_bwd_kernel<float><<<B, threads, smem, st>>>(a);
@@ -792,6 +910,9 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
   const int TP = coupling_bwd_tile(C, P), T = (P + TP - 1) / TP;
   CouplingBwdArgs a{dy, dy_bs, dld, u, u_bs, pm, ldp, bias3, logs3, du, du_bs, dpm, ld_dpm, dpar, B, C, H, W, nullptr,
                     nullptr, nullptr};
+  a.dP = make_fastdiv(P); a.dW = make_fastdiv(W); a.dCh = make_fastdiv(Ch);
+  a.dNg = make_fastdiv(ld_dpm >= 8 ? (int)(ld_dpm >> 3) : 1); a.d2C = make_fastdiv(2 * C);
+  a.pm_bulk = 0;
   const size_t smem_t = sizeof(float) * (4 * (size_t)Ch * TP + 2 * C);
   coupling_bwd_tiled_kernel<<<B * T, 256, smem_t, st>>>(a, dp_scratch, TP);
   NFDPM_CHECK_LAUNCH("coupling_bwd_tiled_kernel");
@@ -881,6 +1002,8 @@ extern "C" int nfdpm_mix_bwd(const float* du, int64_t du_bs, const float* da1, i
   const size_t smem = sizeof(float) * (2 * (size_t)C * (TP + 1) + (size_t)C * C);
   NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_mix_bwd: %d channels do not fit shared memory (%zu bytes)", C, smem);
   MixBwdArgs a{du, du_bs, da1, lda1, x, x_bs, mt, dx, dx_bs, part, B, C, H, W, TP};
+  a.dC = make_fastdiv(C); a.dCh = make_fastdiv(C / 2 > 0 ? C / 2 : 1); a.dW = make_fastdiv(W); a.dT = make_fastdiv(T);
+  a.dNpFull = make_fastdiv(TP); a.dNpLast = make_fastdiv(P - (T - 1) * TP);
   static bool attr_set = false;
   if (!attr_set) {
     NFDPM_CUDA(cudaFuncSetAttribute(mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -6,19 +6,6 @@
 namespace nfdpm {
 
 
-// Division by a run-time constant as multiply-high: the kernels below are issue-bound on index arithmetic (r1 timeline: a
-// 32-bit division costs ~35 instructions and there were ~14 per thread).  Exact for n * d < 2^32.
-struct FastDiv {
-  uint32_t d, m;                          // m = ceil(2^32 / d); m == 0 encodes d == 1
-};
-static inline FastDiv make_fastdiv(int d) {
-  FastDiv f;
-  f.d = (uint32_t)d;
-  f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u;
-  return f;
-}
-__device__ __forceinline__ int fdiv(int n, const FastDiv f) { return f.m ? (int)__umulhi((uint32_t)n, f.m) : n; }
-
 struct BoundaryArgs {
   const float* in; int64_t in_bs;       // source state [B,C,P] (or [B,C/4,2H,2W] when squeeze_in)
   const float* pm; int64_t ldp;         // SRC_COUPLING: taps-as-N rows [B*P, ldp]

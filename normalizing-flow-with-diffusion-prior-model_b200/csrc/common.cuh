@@ -76,6 +76,19 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Division by a run-time constant as multiply-high: the kernels below are issue-bound on index arithmetic (r1 timeline: a
+// 32-bit division costs ~35 instructions and there were ~14 per thread).  Exact for n * d < 2^32.
+struct FastDiv {
+  uint32_t d, m;                          // m = ceil(2^32 / d); m == 0 encodes d == 1
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.m = d > 1 ? (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d) : 0u;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv f) { return f.m ? (int)__umulhi((uint32_t)n, f.m) : n; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

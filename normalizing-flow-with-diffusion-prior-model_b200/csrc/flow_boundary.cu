@@ -21,12 +21,6 @@ namespace nfdpm {
 // (cp.async.bulk, completion on an mbarrier) into shared memory while the CTA stages the state and the parameters; the
 // coupling then gathers its 18 values per item from shared memory instead of issuing 18 scattered L2 loads per thread
 // (r1 timeline: 4.2 / 2.0 / 1.1 us of the 12.3 / 7.7 / 6.1 us kernel at the three levels of config 2).
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
 template <bool COUPLING, typename A1T, bool PM_BULK>
 __global__ void __launch_bounds__(1024) flow_boundary_kernel(const BoundaryArgs a) {
   extern __shared__ __align__(128) float sm[];

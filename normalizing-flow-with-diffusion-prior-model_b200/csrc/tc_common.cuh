@@ -61,6 +61,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                ::"l"(map), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy global -> shared memory (size a multiple of 16 bytes, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
