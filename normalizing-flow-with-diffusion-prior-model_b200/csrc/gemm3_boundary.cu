@@ -34,6 +34,7 @@ struct G3Args {
   int ipp;                               // images per boundary pass (smem budget for the pm rows)
   int stages, stage_bytes, a_bytes, b_box_rows, n_bbox;
   int pm_region;                         // bytes of max(ring, pm staging)
+  FastDiv dCP, dP, dPCh, dCh, dW, dOgP, dPNg, dNg, dCp, dLdp;   // index divisors (multiply-high, common.cuh)
 };
 
 template <typename A1T> __device__ __forceinline__ void g3_store8(A1T* p, const float (&v)[8]);
@@ -69,6 +70,10 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
   float* m_s = (a.mt != nullptr) ? u_s + a.ipc * C * PS : u_s;     // [C][Cp] + beta[Cp]
   float* par_s = m_s + ((a.mt != nullptr) ? (C * Cp + Cp) : 0);    // [2C]
   float* ls_s = par_s + 2 * C;                              // [ipp][P*Ch]
+  const int W2p = W + 2, PP = (H + 2) * W2p;
+  // after the coupling passes the pm rows are dead: their memory holds the zero-bordered im2col source and its column table
+  float* pad_s = reinterpret_cast<float*>(base);            // [ipc][Ch][PP]
+  int* kt_s = reinterpret_cast<int*>(pad_s + ((a.ipc * Ch * PP + 3) & ~3));   // [9*Ch] im2col column -> offset in pad_s
   if (a.mt == nullptr) u_s = x_s;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[3]), bar_done = smem_u32(&bars[6]);
 
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
     const int t2 = tid - 64, nt2 = G3_THREADS - 64;
     if (a.mt != nullptr) {
       for (int i = t2; i < C * Cp; i += nt2) {
-        const int r = i / Cp, c = i - r * Cp;
+        const int r = fdiv(i, a.dCp), c = i - r * Cp;
         m_s[i] = (c < C) ? a.mt[r * C + c] : 0.f;
       }
       for (int i = t2; i < Cp; i += nt2) m_s[C * Cp + i] = (i < C) ? a.beta[i] : 0.f;
@@ -154,10 +159,29 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
       par_s[i] = a.bias3[i];
       par_s[C + i] = expf(3.f * a.logs3[i]);
     }
-    for (int i = t2; i < n_img * C * P; i += nt2) {
-      const int im = i / (C * P), r = i - im * C * P;
-      const int c = r / P, p = r - c * P;
-      x_s[(im * C + c) * PS + p] = a.in[(int64_t)(img0 + im) * a.in_bs + r];
+    // batches of four loads in flight before the dependent shared-memory stores
+    const int nx = n_img * C * P;
+    for (int base = t2; base < nx; base += 4 * nt2) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * nt2;
+        float val = 0.f;
+        if (i < nx) {
+          const int im = fdiv(i, a.dCP), r = i - im * C * P;
+          val = a.in[(int64_t)(img0 + im) * a.in_bs + r];
+        }
+        v[u] = val;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * nt2;
+        if (i < nx) {
+          const int im = fdiv(i, a.dCP), r = i - im * C * P;
+          const int c = fdiv(r, a.dP), p = r - c * P;
+          x_s[(im * C + c) * PS + p] = v[u];
+        }
+      }
     }
   }
   // accumulator complete (every thread observes the commit), operand ring free for reuse
@@ -195,7 +219,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
       const int n = im_n * P * ldp;
       float* o = a.pm_out + (int64_t)(row0 + r_lo) * a.ld_pm_out;
       for (int i = tid; i < n; i += G3_THREADS) {
-        const int r = i / ldp, c = i - r * ldp;
+        const int r = fdiv(i, a.dLdp), c = i - r * ldp;
         o[(int64_t)r * a.ld_pm_out + c] = pm_s[(size_t)r * lds + c];
       }
     }
@@ -203,9 +227,9 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
     {
       const int n_it = im_n * P * Ch;
       for (int it = tid; it < n_it; it += G3_THREADS) {
-        const int im = it / (P * Ch), r = it - im * P * Ch;
-        const int p = r / Ch, j = r - p * Ch;
-        const int py = p / W, px = p - py * W;
+        const int im = fdiv(it, a.dPCh), r = it - im * P * Ch;
+        const int p = fdiv(r, a.dCh), j = r - p * Ch;
+        const int py = fdiv(p, a.dW), px = p - py * W;
         const float* pmi = pm_s + (size_t)(im * P) * lds;
         float ls = 0.f, tt = 0.f;
 #pragma unroll
@@ -241,11 +265,19 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
     __syncthreads();                                         // pm_s / ls_s are rewritten by the next pass
   }
 
+  if (a.a1 != nullptr) {
+    for (int i = tid; i < a.ipc * Ch * PP; i += G3_THREADS) pad_s[i] = 0.f;
+    for (int k = tid; k < 9 * Ch; k += G3_THREADS) {
+      const int c = k / 9, tap = k - c * 9;
+      kt_s[k] = c * PP + (tap / 3) * W2p + (tap % 3);
+    }
+    if (a.mt == nullptr) __syncthreads();                    // (with a mix, its barrier orders the zero fill)
+  }
   // ---- pre-mix stash (the next StepFlow's input)
   if (a.xs != nullptr) {
     for (int i = tid; i < n_img * C * P; i += G3_THREADS) {
-      const int im = i / (C * P), r = i - im * C * P;
-      const int c = r / P, p = r - c * P;
+      const int im = fdiv(i, a.dCP), r = i - im * C * P;
+      const int c = fdiv(r, a.dP), p = r - c * P;
       a.xs[(int64_t)(img0 + im) * a.xs_bs + r] = x_s[(im * C + c) * PS + p];
     }
   }
@@ -253,11 +285,12 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
   if (a.mt != nullptr) {
     const int n_og = Cp >> 2;
     for (int it = tid; it < n_img * n_og * P; it += G3_THREADS) {
-      const int im = it / (n_og * P), r = it - im * n_og * P;
-      const int og = r / P, p = r - og * P;
+      const int im = fdiv(it, a.dOgP), r = it - im * n_og * P;
+      const int og = fdiv(r, a.dP), p = r - og * P;
       const float4 b4 = *reinterpret_cast<const float4*>(m_s + C * Cp + og * 4);
       float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
       const float* xi = x_s + (size_t)im * C * PS + p;
+#pragma unroll 4
       for (int c = 0; c < C; ++c) {
         const float xv = xi[c * PS];
         const float4 w = *reinterpret_cast<const float4*>(m_s + c * Cp + og * 4);
@@ -275,35 +308,40 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
     }
     __syncthreads();
   }
+  // ---- interior of the zero-bordered copy of the channels the next coupling network reads
+  if (a.a1 != nullptr) {
+    for (int i = tid; i < n_img * C * P; i += G3_THREADS) {
+      const int im = fdiv(i, a.dCP), r = i - im * C * P;
+      const int c = fdiv(r, a.dP), p = r - c * P;
+      if (c < Ch) {
+        const int py = fdiv(p, a.dW), px = p - py * W;
+        pad_s[(im * Ch + c) * PP + (py + 1) * W2p + px + 1] = u_s[(im * C + c) * PS + p];
+      }
+    }
+  }
   // ---- NCHW sink
   if (a.y != nullptr) {
     for (int i = tid; i < n_img * C * P; i += G3_THREADS) {
-      const int im = i / (C * P), r = i - im * C * P;
-      const int c = r / P, p = r - c * P;
+      const int im = fdiv(i, a.dCP), r = i - im * C * P;
+      const int c = fdiv(r, a.dP), p = r - c * P;
       a.y[(int64_t)(img0 + im) * a.y_bs + r] = u_s[(im * C + c) * PS + p];
     }
   }
+  if (a.a1 != nullptr) __syncthreads();
   // ---- im2col sink, item = (image, pixel, 8-column group), group fastest
   if (a.a1 != nullptr) {
     const int Kc = Ch * 9;
     const int n_g = (int)(a.lda1 >> 3);
     for (int it = tid; it < n_img * P * n_g; it += G3_THREADS) {
-      const int im = it / (P * n_g), r = it - im * P * n_g;
-      const int p = r / n_g, g = r - p * n_g;
-      const int py = p / W, px = p - py * W;
-      const float* ui = u_s + (size_t)im * C * PS;
+      const int im = fdiv(it, a.dPNg), r = it - im * P * n_g;
+      const int p = fdiv(r, a.dNg), g = r - p * n_g;
+      const int py = fdiv(p, a.dW), px = p - py * W;
+      const float* win = pad_s + (size_t)im * Ch * PP + py * W2p + px;
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = g * 8 + e;
-        float val = 0.f;
-        if (k < Kc) {
-          const int c = k / 9, tap = k - c * 9;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const int yy = py + ky - 1, xx = px + kx - 1;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = ui[c * PS + yy * W + xx];
-        }
-        v[e] = val;
+        v[e] = (k < Kc) ? win[kt_s[k]] : 0.f;
       }
       g3_store8<A1T>(reinterpret_cast<A1T*>(a.a1) + ((int64_t)(img0 + im) * P + p) * a.lda1 + g * 8, v);
     }
@@ -342,9 +380,11 @@ static bool g3_plan(int B, int C, int H, int W, int K, int64_t ldp, bool mix, G3
   const size_t PS = P + 1, Cp = (C + 3) & ~3;
   size_t body = (size_t)ipc * C * PS * (mix ? 2 : 1) + (mix ? C * Cp + Cp : 0) + 2 * C + (size_t)ipp * P * (C / 2);
   body *= sizeof(float);
+  // the im2col source (zero-bordered copy + column table) reuses the pm rows' memory
+  const size_t pad_bytes = sizeof(float) * ((((size_t)ipc * (C / 2) * (H + 2) * (W + 2) + 3) & ~(size_t)3) + 9 * (size_t)(C / 2));
   int stages = 3;
   while (stages > 2 && 1024 + std::max((size_t)stages * stage_bytes, pm_bytes) + body > 224 * 1024) --stages;
-  size_t region = std::max((size_t)stages * stage_bytes, pm_bytes);
+  size_t region = std::max(std::max((size_t)stages * stage_bytes, pm_bytes), pad_bytes);
   region = (region + 15) & ~(size_t)15;
   if (1024 + region + body > 224 * 1024) return false;
   if (a) {
@@ -385,6 +425,12 @@ extern "C" int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p
   a.pm_out = pm_out; a.ld_pm_out = ld_pm_out; a.in = in; a.in_bs = in_bs; a.bias3 = bias3; a.logs3 = logs3;
   a.ld_part = ld_part; a.mt = mt; a.beta = beta; a.y = y; a.y_bs = y_bs; a.xs = xs; a.xs_bs = xs_bs; a.a1 = a1;
   a.lda1 = lda1; a.B = B; a.C = C; a.H = H; a.W = W; a.inverse = inverse; a.K = K; a.ldp = (int)ldp;
+  {
+    const int P = H * W, Ch = C / 2, Cp = (C + 3) & ~3, n_g = lda1 >= 8 ? (int)(lda1 >> 3) : 1;
+    a.dCP = make_fastdiv(C * P); a.dP = make_fastdiv(P); a.dPCh = make_fastdiv(P * Ch); a.dCh = make_fastdiv(Ch);
+    a.dW = make_fastdiv(W); a.dOgP = make_fastdiv((Cp >> 2) * P); a.dPNg = make_fastdiv(P * n_g); a.dNg = make_fastdiv(n_g);
+    a.dCp = make_fastdiv(Cp); a.dLdp = make_fastdiv((int)ldp);
+  }
   const int64_t M = (int64_t)B * H * W;
   CUtensorMap tmA, tmB;
   if (make_map(&tmA, h2, M, K, ldh, 128)) return 1;
