@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
   for (int row = warp; row < 4 * Ch; row += nw) {
     float acc = 0.f;
     const float* rp = r_s + row * P;      // row = kind*Ch + j  (r_s laid out [kind][j][p])
+#pragma unroll 8
     for (int p = lane; p < P; p += 32) acc += rp[p];
     acc = warp_sum(acc);
     if (lane == 0) {

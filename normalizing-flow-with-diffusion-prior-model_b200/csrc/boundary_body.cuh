@@ -241,7 +241,8 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
     if (!a.inverse && a.ld_part != nullptr && tid < 32) {
       // deterministic per-image sum: fixed lane-strided order + shuffle tree
       float acc = 0.f;
-      for (int i = tid; i < P * Ch; i += 32) acc += ls_s[i];
+#pragma unroll 8
+      for (int i = tid; i < P * Ch; i += 32) acc += ls_s[i];        // (unrolled: the loads pipeline, the order is unchanged)
       acc = warp_sum(acc);
       if (tid == 0) a.ld_part[b] = acc;
     }

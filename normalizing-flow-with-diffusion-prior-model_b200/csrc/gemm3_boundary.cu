@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
       // deterministic per-image sum: one warp per image, fixed lane-strided order + shuffle tree
       float acc = 0.f;
       const float* l = ls_s + warp * P * Ch;
+#pragma unroll 8
       for (int i = lane; i < P * Ch; i += 32) acc += l[i];
       acc = warp_sum(acc);
       if (lane == 0) a.ld_part[img0 + im_lo + warp] = acc;

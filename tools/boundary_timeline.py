@@ -30,12 +30,5 @@ for lvl, (C, hw) in enumerate([(12, 16), (24, 8), (48, 4)]):
     t = buf.cpu().double()
     d = (t[:, 1:8] - t[:, 0:7]) / 1.9e3
     names = ["stage params+x", "coupling", "log-det reduce(w0)", "(xs stash)", "mix", "y store", "im2col"]
-    ph0 = [(8, "loads issued"), (9, "mt stored"), (10, "params stored"), (11, "pad/LUT"), (12, "x stored"), (1, "sync")]
-    prev = 0
-    line = []
-    for slot, nm in ph0:
-        line.append(f"{nm} +{float((t[:, slot] - t[:, prev]).mean()) / 1.9e3:.2f}")
-        prev = slot
-    print("   phase 0 (thread 0):", " | ".join(line))
     print(f"level {lvl} C={C} P={P}: total {float((t[:, 7] - t[:, 0]).mean()) / 1.9e3:.2f} us |",
           " | ".join(f"{n} {float(d[:, i].mean()):.2f}" for i, n in enumerate(names)))
