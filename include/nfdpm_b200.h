@@ -340,6 +340,37 @@ int nfdpm_fused_clip_adam(const void* refs, const int32_t* chunks, int n_chunks,
 int nfdpm_accumulate(void* acc, int acc_dtype, const float* part, int R, int B, const float* cval,
                      const float* cmul, int nc, nfdpm_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data formats either side of the flow: the diffusion prior's latent formater and the
+ * image pre/post-processing of the training / sampling loops.  Pure HBM-bound byte work.
+ *
+ * CatFormater (diffusion_prior/latent_formaters.py:163-236): process_latents squeezes / unsqueezes every
+ * latent part to the resolution of the middle part and concatenates along channels; postprocess is the
+ * inverse.  ONE launch moves all parts.  Part i is the contiguous latent [B,C,H,W]; `degree` = number of
+ * squeezes (>0) or unsqueezes (<0) that bring it to Ht x Wt; its slice of cat is [ch_offset, ch_offset+ch_count).
+ * to_cat != 0: latents -> cat [B,Ct,Ht,Wt] (process_latents); to_cat == 0: cat -> latents (postprocess). */
+#define NFDPM_MAX_LATENT_PARTS 8
+typedef struct {
+  float* ptr;
+  int32_t C, H, W;
+  int32_t degree;
+  int32_t ch_offset;
+  int32_t ch_count;
+} nfdpm_latent_part;
+int nfdpm_latent_format(const nfdpm_latent_part* parts_host, int n_parts, float* cat, int B, int Ct, int Ht, int Wt,
+                        int to_cat, nfdpm_stream_t stream);
+
+/* postprocess_batch (normalizing_flow/utils.py:199-210) on the device:
+ *   out[i] = (uint8) clip(floor((x[i] + 0.5) * n_bins) * out_scale, 0, 255),  out_scale = (float)(256.0 / n_bins).
+ * The caller copies the uint8 result to the host (1 byte per value instead of 4). */
+int nfdpm_postprocess_u8(const float* x, uint8_t* out, int64_t n, float n_bins, float out_scale, nfdpm_stream_t stream);
+
+/* preprocess_batch (normalizing_flow/utils.py:175-196) fused with the dequantisation-noise add of the training
+ * step (normalizing_flow/trainer.py:155):  y = floor(x*255 / 2^(8-n_bits)) / n_bins - 0.5  [+ noise / n_bins]
+ * (floor only when n_bits < 8; noise may be NULL).  Same fp32 operation order as the reference: bit-identical. */
+int nfdpm_preprocess(const float* x, const float* noise, float* y, int64_t n, int n_bits, float n_bins,
+                     nfdpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

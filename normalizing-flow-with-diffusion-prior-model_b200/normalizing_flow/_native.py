@@ -26,6 +26,12 @@ class MixItem(C.Structure):
                 ("inv_beta", C.c_void_p), ("winv", C.c_void_p), ("logdet", C.c_void_p), ("lu_ws", C.c_void_p)]
 
 
+class LatentPart(C.Structure):
+    """struct nfdpm_latent_part (include/nfdpm_b200.h)."""
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("degree", C.c_int32),
+                ("ch_offset", C.c_int32), ("ch_count", C.c_int32)]
+
+
 class MixGradItem(C.Structure):
     """struct nfdpm_mix_grad_item (include/nfdpm_b200.h)."""
     _fields_ = [("part", C.c_void_p), ("B", C.c_int32), ("C", C.c_int32), ("weight", C.c_void_p), ("scale", C.c_void_p),
@@ -102,6 +108,9 @@ def _load() -> C.CDLL:
         "nfdpm_gauss_const_bwd": ([vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_col2im_add": ([vp, i64, vp, i64, i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_accumulate": ([vp, i32, vp, i32, i32, vp, vp, i32, vp], C.c_int),
+        "nfdpm_latent_format": ([C.POINTER(LatentPart), i32, vp, i32, i32, i32, i32, i32, vp], C.c_int),
+        "nfdpm_postprocess_u8": ([vp, vp, i64, f32, f32, vp], C.c_int),
+        "nfdpm_preprocess": ([vp, vp, vp, i64, i32, f32, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)   # AttributeError here == header / library mismatch: fail loudly
@@ -121,7 +130,8 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
            "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch",
-           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_nt_relu_bwd", "nfdpm_boundary_gemm1_ok", "nfdpm_boundary_gemm1", "nfdpm_deep_step_debug", "nfdpm_gemm_debug", "nfdpm_flow_boundary_debug", "nfdpm_deep_step_ok", "nfdpm_deep_step"]
+           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_nt_relu_bwd", "nfdpm_boundary_gemm1_ok", "nfdpm_boundary_gemm1", "nfdpm_deep_step_debug", "nfdpm_gemm_debug", "nfdpm_flow_boundary_debug", "nfdpm_deep_step_ok", "nfdpm_deep_step",
+           "nfdpm_latent_format", "nfdpm_postprocess_u8", "nfdpm_preprocess"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -398,3 +408,20 @@ def deep_step(a1_in, w1p, w2p, w3p, s1, b1, s2, b2, h1, h2, pm, ld_pm, src, src_
 
 def gemm_nt_relu_bwd(A, lda, Bw, ldb, dpre, ldd, M, Nn, K, h, ldh, scale, part) -> None:
     _ok(lib.nfdpm_gemm_nt_relu_bwd(_p(A), lda, _p(Bw), ldb, _p(dpre), ldd, M, Nn, K, _p(h), ldh, _p(scale), _p(part), _st()))
+
+
+def latent_format(parts, cat, B, Ct, Ht, Wt, to_cat: bool) -> None:
+    """parts: list of (tensor [B,C,H,W] contiguous fp32, degree, ch_offset, ch_count)."""
+    arr = (LatentPart * len(parts))()
+    for i, (t, degree, off, cnt) in enumerate(parts):
+        arr[i].ptr, arr[i].C, arr[i].H, arr[i].W = t.data_ptr(), t.shape[1], t.shape[2], t.shape[3]
+        arr[i].degree, arr[i].ch_offset, arr[i].ch_count = degree, off, cnt
+    _ok(lib.nfdpm_latent_format(arr, len(parts), _p(cat), B, Ct, Ht, Wt, int(to_cat), _st()))
+
+
+def postprocess_u8(x, out, n_bins: float) -> None:
+    _ok(lib.nfdpm_postprocess_u8(_p(x), _p(out), x.numel(), float(n_bins), float(256.0 / n_bins), _st()))
+
+
+def preprocess(x, noise, y, n_bits: int, n_bins: float) -> None:
+    _ok(lib.nfdpm_preprocess(_p(x), _p(noise), _p(y), x.numel(), int(n_bits), float(n_bins), _st()))

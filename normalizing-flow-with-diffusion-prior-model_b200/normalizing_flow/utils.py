@@ -132,18 +132,37 @@ def init_optimizer(name: str, params, lr: float) -> torch.optim.Optimizer:
     return cls(params, lr=lr if lr else params[0]["lr"])
 
 
+def _kernel_ok(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.dtype == torch.float32 and t.numel() > 0
+
+
 @torch.no_grad()
-def preprocess_batch(batch: torch.Tensor, n_bits: int, n_bins: int) -> torch.Tensor:
-    """[0,1] images -> n_bits levels centred on 0 (reference utils.py:175-196)."""
+def preprocess_batch(batch: torch.Tensor, n_bits: int, n_bins: int, noise: torch.Tensor = None) -> torch.Tensor:
+    """[0,1] images -> n_bits levels centred on 0 (reference utils.py:175-196).  CUDA tensors take one
+    ``nfdpm_preprocess`` launch, bit-identical to the reference's op sequence; with ``noise`` (U[0,1), same shape) the
+    dequantisation add of the training step (trainer.py:155, ``batch + rand_like(batch) / n_bins``) is fused into the
+    same pass.  Host tensors (the reference also calls this before ``.to(device)`` in places) keep the torch expression."""
+    if _kernel_ok(batch) and 1 <= n_bits <= 8 and (noise is None or (_kernel_ok(noise) and noise.shape == batch.shape)):
+        x = batch.contiguous()
+        out = torch.empty_like(x)
+        N.preprocess(x, None if noise is None else noise.contiguous(), out, n_bits, n_bins)
+        return out
     out = batch * 255
     if n_bits < 8:
         out = torch.floor(out / 2 ** (8 - n_bits))
-    return out / n_bins - 0.5
+    out = out / n_bins - 0.5
+    return out if noise is None else out + noise / n_bins
 
 
 @torch.no_grad()
 def postprocess_batch(batch: torch.Tensor, n_bins: int) -> torch.Tensor:
-    """Model space -> uint8 pixels on the CPU (reference utils.py:199-210)."""
+    """Model space -> uint8 pixels on the CPU (reference utils.py:199-210).  CUDA tensors are quantised on the device
+    (``nfdpm_postprocess_u8``) and only the uint8 image crosses PCIe."""
+    if _kernel_ok(batch):
+        x = batch.contiguous()
+        out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        N.postprocess_u8(x, out, n_bins)
+        return out.to("cpu")
     return torch.clip(torch.floor((batch + 0.5) * n_bins) * (256.0 / n_bins), 0, 255).to("cpu", torch.uint8)
 
 
@@ -165,9 +184,9 @@ def data_dependent_nf_initialization(flow, dataloader, device: torch.device, n_b
     flow.eval()
     sample = next(iter(dataloader))
     batch = sample[0].to(device) if isinstance(sample, list) else sample.to(device)
-    batch = preprocess_batch(batch, n_bits, n_bins)
+    batch = preprocess_batch(batch, n_bits, n_bins, noise=torch.rand_like(batch))
     ll, lp = initialize_with_zeros(2, batch.size(0), device)
-    flow.transform(batch + torch.rand_like(batch) / n_bins, ll, lp)
+    flow.transform(batch, ll, lp)
 
 
 def get_item(sequence: Sequence, index: int):

@@ -263,6 +263,46 @@ def bpd_loss(log_likelihood: Tensor, n_bins: float, n_pixel: float) -> Tensor:
     """Bits per dimension (normalizing_flow/utils.py:255-256)."""
     return ((np.log(n_bins) * n_pixel - log_likelihood) * (np.log2(np.e) / n_pixel)).mean(dim=0)
 
+# --------------------------------------------------------------------------- data formats either side of the path (§8f)
+def dequantize(batch: Tensor, n_bits: int, n_bins: float, noise: Tensor) -> Tensor:
+    """preprocess_batch followed by the dequantisation-noise add of the training step
+    (normalizing_flow/trainer.py:152-155: ``batch + torch.rand_like(batch) / n_bins``)."""
+    return preprocess_batch(batch, n_bits, n_bins) + noise / n_bins
+
+
+def cat_format(latents: Sequence[Tensor]) -> Tensor:
+    """CatFormater.process_latents (diffusion_prior/latent_formaters.py:163-189): latent ``pos`` is squeezed
+    ``target - pos`` times (or unsqueezed ``pos - target`` times), target = (L-1)//2; channel concat."""
+    target = (len(latents) - 1) // 2
+    parts = []
+    for pos, t in enumerate(latents):
+        deg = target - pos
+        for _ in range(abs(deg)):
+            t = squeeze2x2(t) if deg > 0 else unsqueeze2x2(t)
+        parts.append(t)
+    return torch.cat(parts, dim=1)
+
+
+def cat_unformat(cat: Tensor, latent_dims: Sequence[Sequence[int]]) -> List[Tensor]:
+    """CatFormater.postprocess (diffusion_prior/latent_formaters.py:191-236).  The reference walks outwards from the
+    target part, un/squeezing the *remaining concatenation* once per hop and cutting one latent off its inner edge; for
+    Glow's latent shapes (leading channels = 2(2^t - 1) x trailing channels) that equals cutting the concatenation at
+    the parts' channel offsets and un/squeezing every part on its own, which is what is written here (checked against
+    the reference's output in tests/golden/formats.npz)."""
+    target = (len(latent_dims) - 1) // 2
+    out, off = [], 0
+    for pos, (C, H, W) in enumerate(latent_dims):
+        deg = target - pos
+        cnt = int(C) * 4 ** deg if deg >= 0 else int(C) // 4 ** (-deg)
+        t = cat[:, off:off + cnt]
+        off += cnt
+        for _ in range(abs(deg)):
+            t = unsqueeze2x2(t) if deg > 0 else squeeze2x2(t)
+        out.append(t.contiguous())
+    assert off == cat.shape[1]
+    return out
+
+
 
 def nll_bpd(sd: Dict[str, Tensor], psd: Dict[str, Tensor], x: Tensor, L: int, K: int,
             n_bins: float, n_pixel: float) -> Tensor:

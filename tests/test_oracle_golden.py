@@ -163,3 +163,42 @@ def test_train_gradients(golden_dir, name):
         assert abs(proj - ref_p) <= 1e-4 * max(ref_n, abs(ref_p)) * np.sqrt(t.numel()) ** 0 + 1e-6 * ref_n + 1e-9, k
         if ("grad/" + k) in g.files:
             assert np.allclose(t.numpy(), g["grad/" + k], rtol=1e-4, atol=1e-7), k
+
+
+FORMAT_CASES = [("L3_c1_s32", 3, 1, 32, 2), ("L3_c3_s32", 3, 3, 32, 2), ("L4_c1_s32", 4, 1, 32, 1), ("L5_c3_s32", 5, 3, 32, 2),
+                ("L5_c3_s64", 5, 3, 64, 1)]
+
+
+def seeded_latents(dims, B, seed):
+    rng = np.random.default_rng(seed)
+    return [torch.from_numpy(rng.standard_normal((B,) + tuple(int(v) for v in d)).astype(np.float32)) for d in dims]
+
+
+@pytest.mark.parametrize("idx", range(len(FORMAT_CASES)))
+def test_cat_formater_oracle_against_reference(golden_dir, idx):
+    """oracle.cat_format / cat_unformat against the unmodified reference CatFormater (tests/golden/formats.npz,
+    oracle/make_golden_formats.py): bit-exact, both directions, L = 3, 4, 5."""
+    g = np.load(os.path.join(golden_dir, "formats.npz"))
+    name, L, c, S, B = FORMAT_CASES[idx]
+    dims = g[name + "_dims"]
+    assert [tuple(d) for d in dims] == O.output_shapes(L, c, S)
+    lat = seeded_latents(dims, B, 700 + idx)
+    cat = O.cat_format(lat)
+    assert np.array_equal(cat.numpy(), g[name + "_cat"])
+    for a, b in zip(O.cat_unformat(cat, dims), lat):
+        assert torch.equal(a, b)
+    rng = np.random.default_rng(800 + idx)
+    q = torch.from_numpy(rng.standard_normal(tuple(cat.shape)).astype(np.float32))
+    for j, t in enumerate(O.cat_unformat(q, dims)):
+        assert np.array_equal(t.numpy(), g[f"{name}_post{j}"])
+
+
+def test_pixel_formats_oracle_against_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "formats.npz"))
+    xs = torch.from_numpy(g["post_x"])
+    assert np.array_equal(O.postprocess_batch(xs, 32.0).numpy(), g["post_u8_32"])
+    assert np.array_equal(O.postprocess_batch(xs, 256.0).numpy(), g["post_u8_256"])
+    img, u = torch.from_numpy(g["pre_img"]), torch.from_numpy(g["pre_noise"])
+    for n_bits in (5, 8, 3):
+        assert np.array_equal(O.preprocess_batch(img, n_bits, 2.0 ** n_bits).numpy(), g[f"pre_{n_bits}"])
+        assert np.array_equal(O.dequantize(img, n_bits, 2.0 ** n_bits, u).numpy(), g[f"dq_{n_bits}"])
