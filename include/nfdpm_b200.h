@@ -340,6 +340,19 @@ int nfdpm_fused_clip_adam(const void* refs, const int32_t* chunks, int n_chunks,
 int nfdpm_accumulate(void* acc, int acc_dtype, const float* part, int R, int B, const float* cval,
                      const float* cmul, int nc, nfdpm_stream_t stream);
 
+/* Row-band variant of nfdpm_flow_boundary (csrc/flow_boundary_tiled.cu): the same arithmetic and arguments, but a CTA owns a
+ * band of image rows (plus one recomputed halo row above and below when there is an im2col sink), so images of any size
+ * take the fused boundary and small batches spread over B * tiles CTAs.  `in` and `y` / `xs` must NOT alias (a band reads
+ * halo rows another band writes).  nfdpm_flow_boundary_tiles() returns the number of bands per image for a shape and
+ * sink combination (0: one row does not fit in shared memory); the forward log-det is written as `tiles` partial rows:
+ * ld_part[t * B + b].  Replaces, like nfdpm_flow_boundary: transforms.py:179-184 / :196-200 (coupling), :80 + :132 /
+ * :144 + :93 (ActNorm + 1x1 conv), :226 (squeeze) and the im2col of utils.py:64's 3x3 conv. */
+int nfdpm_flow_boundary_tiles(int B, int C, int H, int W, int coupling, int mix, int want_a1);
+int nfdpm_flow_boundary_tiled(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp,
+                              const float* bias3, const float* logs3, float* ld_part, const float* mt, const float* beta,
+                              float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype, int64_t lda1, int B,
+                              int C, int H, int W, int inverse, int tiles, nfdpm_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Data formats either side of the flow: the diffusion prior's latent formater and the
  * image pre/post-processing of the training / sampling loops.  Pure HBM-bound byte work.

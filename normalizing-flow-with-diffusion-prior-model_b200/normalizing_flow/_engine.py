@@ -362,7 +362,7 @@ def fused_g3_ok(B: int, C: int, H: int, W: int, F: int, ldp: int) -> bool:
 
 
 def coupling_boundary(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int, src, src_bs, ld_part, mt, beta, y, y_bs,
-                      a1_next, lda1_next, inverse: bool, pm_out=None, xs=None) -> None:
+                      a1_next, lda1_next, inverse: bool, pm_out=None, xs=None, tiles: int = 0) -> None:
     """One StepFlow's coupling network + everything up to the next network's first GEMM:
     GEMM1 -> GEMM2 -> [GEMM3 + coupling + next mix + sinks].  In tensor-core mode the bracketed part is ONE kernel
     (nfdpm_gemm3_boundary: the ZeroConv output stays in tensor/shared memory); otherwise GEMM3 and
@@ -374,6 +374,12 @@ def coupling_boundary(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int, src,
     dev = A1.device
     M = B * H * W
     K1p, ldp = cache.K1p, cache.ldp
+    if tiles > 0:
+        # row-band boundary (images beyond one CTA, small batches): GEMM1 -> GEMM2 -> GEMM3, then nfdpm_flow_boundary_tiled
+        pm, _ = coupling_gemms(cp, A1, B, C, H, W)
+        N.flow_boundary_tiled(src, src_bs, False, pm, ldp, zc.bias, zc.logs, ld_part, mt, beta, y, y_bs, None, 0, a1_next,
+                              lda1_next, B, C, H, W, inverse, tiles)
+        return
     fused = dt == torch.bfloat16 and not fused_coupling_enabled() and fused_g3_ok(B, C, H, W, F, ldp)
     if not fused:
         if pm_out is None:

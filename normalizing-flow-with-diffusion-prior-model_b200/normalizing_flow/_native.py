@@ -108,6 +108,9 @@ def _load() -> C.CDLL:
         "nfdpm_gauss_const_bwd": ([vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_col2im_add": ([vp, i64, vp, i64, i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_accumulate": ([vp, i32, vp, i32, i32, vp, vp, i32, vp], C.c_int),
+        "nfdpm_flow_boundary_tiles": ([i32, i32, i32, i32, i32, i32, i32], C.c_int),
+        "nfdpm_flow_boundary_tiled": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
+                                       i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_latent_format": ([C.POINTER(LatentPart), i32, vp, i32, i32, i32, i32, i32, vp], C.c_int),
         "nfdpm_postprocess_u8": ([vp, vp, i64, f32, f32, vp], C.c_int),
         "nfdpm_preprocess": ([vp, vp, vp, i64, i32, f32, vp], C.c_int),
@@ -131,7 +134,8 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
            "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch",
            "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_nt_relu_bwd", "nfdpm_boundary_gemm1_ok", "nfdpm_boundary_gemm1", "nfdpm_deep_step_debug", "nfdpm_gemm_debug", "nfdpm_flow_boundary_debug", "nfdpm_deep_step_ok", "nfdpm_deep_step",
-           "nfdpm_latent_format", "nfdpm_postprocess_u8", "nfdpm_preprocess"]
+           "nfdpm_latent_format", "nfdpm_postprocess_u8", "nfdpm_preprocess",
+           "nfdpm_flow_boundary_tiles", "nfdpm_flow_boundary_tiled"]
 
 #: number of kernels launched through this binding (bench.py reports it as ``gpu_launches``)
 launch_count = 0
@@ -425,3 +429,14 @@ def postprocess_u8(x, out, n_bins: float) -> None:
 
 def preprocess(x, noise, y, n_bits: int, n_bins: float) -> None:
     _ok(lib.nfdpm_preprocess(_p(x), _p(noise), _p(y), x.numel(), int(n_bits), float(n_bins), _st()))
+
+
+def flow_boundary_tiles(B, Cc, H, W, coupling, mix, want_a1) -> int:
+    return int(lib.nfdpm_flow_boundary_tiles(B, Cc, H, W, int(coupling), int(mix), int(want_a1)))
+
+
+def flow_boundary_tiled(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1, lda1,
+                        B, Cc, H, W, inverse, tiles) -> None:
+    _ok(lib.nfdpm_flow_boundary_tiled(_p(src), src_bs, int(squeeze_in), _p(pm), ldp, _p(bias3), _p(logs3), _p(ld_part),
+                                      _p(mt), _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1),
+                                      _dt(a1) if a1 is not None else F32, lda1, B, Cc, H, W, int(inverse), tiles, _st()))

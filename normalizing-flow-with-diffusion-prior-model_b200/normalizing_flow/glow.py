@@ -356,6 +356,18 @@ class Glow(Transform):
     def _level_fast(C: int, h: int, w: int) -> bool:
         return h * w <= 256 and N.flow_boundary_smem(C, h, w, 1, 1) <= 200 * 1024
 
+    @classmethod
+    def _level_mode(cls, B: int, C: int, h: int, w: int) -> str:
+        """Which kernels run the StepFlow boundaries of a level:
+          "image"   one CTA per image (flow_boundary / gemm3_boundary): images of at most 256 pixels in batches that fill the GPU
+          "tiled"   row bands with a recomputed halo (flow_boundary_tiled): larger images (the 64x64 / 32x32 levels of a
+                    128x128 input) and small batches (config 4: 8 images per GPU would occupy 8 of 148 SMs)
+          "unfused" separate K-A / im2col / coupling kernels (NFDPM_TILED=0, or a single image row beyond shared memory)"""
+        tiled = os.environ.get("NFDPM_TILED", "1") != "0" and N.flow_boundary_tiles(B, C, h, w, 1, 1, 1) > 0
+        if cls._level_fast(C, h, w) and (B >= 64 or not tiled):
+            return "image"
+        return "tiled" if tiled else "unfused"
+
     def _transform_core(self, x: Tensor, with_logp: bool, levels, slots, steps, ready: bool):
         B, c, H, W = x.shape
         dev = x.device
@@ -457,8 +469,11 @@ class Glow(Transform):
         hh, ww, cc = H, W, c
         for li in range(self.L):
             hh, ww, CC = hh // 2, ww // 2, cc * 4
-            T = 1 if self._level_fast(CC, hh, ww) else N.ld_tiles(hh * ww)
-            R_ld += self.K * T
+            mode = self._level_mode(B, CC, hh, ww)
+            if mode == "tiled":     # K-1 boundaries with an im2col sink and the level's last one without
+                R_ld += (self.K - 1) * N.flow_boundary_tiles(B, CC, hh, ww, 1, 1, 1) + N.flow_boundary_tiles(B, CC, hh, ww, 1, 0, 0)
+            else:
+                R_ld += self.K * (1 if mode == "image" else N.ld_tiles(hh * ww))
             if li < self.L - 1:
                 R_lp += N.ld_tiles(hh * ww)
             cc = CC // 2
@@ -471,8 +486,21 @@ class Glow(Transform):
         for li, (flows, split) in enumerate(levels):
             h, w, C = h // 2, w // 2, ch * 4
             P = h * w
-            if not self._level_fast(C, h, w):
-                # image larger than one CTA: squeeze + unfused K-A / im2col / GEMMs / coupling per step
+            mode = self._level_mode(B, C, h, w)
+            if mode == "tiled":
+                st, rows = self._transform_level_tiled(flows, cur, cur_bs, B, C, h, w, ld_part, row, dev)
+                row += rows
+                if split is None:
+                    latents.append(st)
+                    break
+                z = torch.empty(B, C // 2, h, w, dtype=torch.float32, device=dev)
+                split._forward_views(st, C * P, B, C, h, w, z, lp_part[lrow * B:] if lp_part is not None else None)
+                lrow += N.ld_tiles(P)
+                latents.append(z)
+                cur, cur_bs, ch = st, C * P, C // 2
+                continue
+            if mode == "unfused":
+                # NFDPM_TILED=0: squeeze + unfused K-A / im2col / GEMMs / coupling per step
                 T = N.ld_tiles(P)
                 a = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
                 b = torch.empty_like(a)
@@ -529,8 +557,11 @@ class Glow(Transform):
         for li in range(self.L - 1, -1, -1):
             flows, _ = levels[li]
             P = h * w
-            if not self._level_fast(C, h, w):
-                # image larger than one CTA: unfused inverse steps (coupling^-1 in place, then K-A^-1)
+            mode = self._level_mode(B, C, h, w)
+            if mode == "tiled":
+                st = self._invert_level_tiled(flows, src, B, C, h, w, dev)
+            elif mode == "unfused":
+                # NFDPM_TILED=0: unfused inverse steps (coupling^-1 in place, then K-A^-1)
                 cur, own = src, li < self.L - 1        # the deepest level reads caller memory
                 other = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
                 for step in reversed(flows):
@@ -555,6 +586,55 @@ class Glow(Transform):
             levels[li - 1][1]._fill_second_half(nxt, Cn * hn * wn, B, Cn, hn, wn, latent, temperature)
             src, C, h, w = nxt, Cn, hn, wn
         raise AssertionError("unreachable")
+
+    def _transform_level_tiled(self, flows, cur, cur_bs: int, B: int, C: int, h: int, w: int, ld_part, row: int, dev):
+        """K forward StepFlows of one level with the row-band boundary kernel.  A band reads halo rows that a neighbouring
+        band writes, so the flow state ping-pongs between two buffers.  Returns (state, log-det partial rows used)."""
+        P = h * w
+        bufs = [torch.empty(B, C, h, w, dtype=torch.float32, device=dev) for _ in range(2)]
+        first = flows[0]
+        A1, K1p = E.coupling_a1(first.affcoupling, B, C, h, w, dev)
+        N.flow_boundary_tiled(cur, cur_bs, True, None, 0, None, None, None, first._mix.fwd_mt, first._mix.fwd_beta,
+                              bufs[0], C * P, None, 0, A1, K1p, B, C, h, w, False,
+                              N.flow_boundary_tiles(B, C, h, w, 0, 1, 1))       # level entry: squeeze + K-A + im2col
+        src, rows = 0, 0
+        for k, step in enumerate(flows):
+            nxt = flows[k + 1] if k + 1 < len(flows) else None
+            T = N.flow_boundary_tiles(B, C, h, w, 1, int(nxt is not None), int(nxt is not None))
+            if nxt is not None:
+                A1n, K1p = E.coupling_a1(nxt.affcoupling, B, C, h, w, dev)
+                E.coupling_boundary(step.affcoupling, A1, B, C, h, w, bufs[src], C * P, ld_part[(row + rows) * B:],
+                                    nxt._mix.fwd_mt, nxt._mix.fwd_beta, bufs[1 - src], C * P, A1n, K1p, False, tiles=T)
+                A1 = A1n
+            else:
+                E.coupling_boundary(step.affcoupling, A1, B, C, h, w, bufs[src], C * P, ld_part[(row + rows) * B:],
+                                    None, None, bufs[1 - src], C * P, None, 0, False, tiles=T)
+            src = 1 - src
+            rows += T
+        return bufs[src], rows
+
+    def _invert_level_tiled(self, flows, src, B: int, C: int, h: int, w: int, dev) -> Tensor:
+        """K inverse StepFlows of one level with the row-band boundary kernel (state ping-pongs between two buffers;
+        `src` — caller memory or the previous level's output — is only read)."""
+        P = h * w
+        bufs = [torch.empty(B, C, h, w, dtype=torch.float32, device=dev) for _ in range(2)]
+        A1, K1p = E.coupling_a1(flows[-1].affcoupling, B, C, h, w, dev)
+        N.flow_boundary_tiled(src, C * P, False, None, 0, None, None, None, None, None, None, 0, None, 0, A1, K1p, B, C,
+                              h, w, False, N.flow_boundary_tiles(B, C, h, w, 0, 0, 1))   # im2col of the level's entry state
+        cur, dst = src, 0
+        for k in range(len(flows) - 1, -1, -1):
+            step = flows[k]
+            T = N.flow_boundary_tiles(B, C, h, w, 1, 1, int(k > 0))
+            if k > 0:
+                A1n, K1p = E.coupling_a1(flows[k - 1].affcoupling, B, C, h, w, dev)
+                E.coupling_boundary(step.affcoupling, A1, B, C, h, w, cur, C * P, None, step._mix.inv_mt,
+                                    step._mix.inv_beta, bufs[dst], C * P, A1n, K1p, True, tiles=T)
+                A1 = A1n
+            else:
+                E.coupling_boundary(step.affcoupling, A1, B, C, h, w, cur, C * P, None, step._mix.inv_mt,
+                                    step._mix.inv_beta, bufs[dst], C * P, None, 0, True, tiles=T)
+            cur, dst = bufs[dst], 1 - dst
+        return cur
 
     def _invert_level_fast(self, flows, src, own: bool, B: int, C: int, h: int, w: int, dev) -> Tensor:
         """K inverse StepFlows of one level with the fused kernels; returns the level's input state."""

@@ -471,3 +471,51 @@ def test_cuda_graph_path_equals_eager(monkeypatch):
     # earlier outputs were not overwritten by later replays
     for a, b in zip(e1[0], g1[0]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cfg", [(1, 2, 2, 3, 28, 28), (3, 3, 2, 2, 24, 40), (3, 2, 3, 5, 64, 64), (1, 3, 2, 1, 32, 32),
+                                 (3, 4, 1, 2, 80, 48)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_row_band_boundary_small_batches_and_large_images(cfg, mode, monkeypatch):
+    """nfdpm_flow_boundary_tiled (row bands + recomputed halo) through Glow.transform / invert: small batches and images
+    beyond one CTA, ragged geometry (28x28: 14 and 7 rows; 24x40: non-square; bands that do not divide H).  fp32 mode
+    against the CPU oracle; both modes against the unfused kernels (NFDPM_TILED=0), which share the GEMMs, so the two
+    paths must agree to summation-order noise."""
+    c, L, K, B, H, W = cfg
+    monkeypatch.setenv("NFDPM_PRECISION", mode)
+    flow, prior, sd, psd = build(c, L, K, 77)
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy((rng.random((B, c, H, W)) - 0.5).astype(np.float32)).to(DEV)
+    assert "tiled" in {flow._level_mode(B, 4 * c, H // 2, W // 2), flow._level_mode(B, 2 ** (L + 1) * c, H >> L, W >> L)}
+
+    def run():
+        ld = torch.zeros(B, dtype=torch.float64, device=DEV)
+        lp = torch.zeros(B, dtype=torch.float64, device=DEV)
+        zs, ld, lp = flow.transform(x, ld, lp)
+        return zs, ld, lp, flow.invert(zs), flow.invert([zs[-1]], temperature=0.0)
+    l0 = nf._native.launch_count
+    zs, ld, lp, xr, xs0 = run()
+    n_tiled = nf._native.launch_count - l0
+    zs2, ld2, lp2, xr2, _ = run()                      # second call: CUDA-graph replay of the same chain
+    for a, b in zip(zs + [xr], zs2 + [xr2]):
+        assert torch.equal(a, b)
+    monkeypatch.setenv("NFDPM_TILED", "0")
+    flow_u, _, _, _ = build(c, L, K, 77)
+    flow, flow_t = flow_u, flow
+    l0 = nf._native.launch_count
+    zu, ldu, lpu, xru, xsu = run()
+    assert n_tiled <= nf._native.launch_count - l0     # never more launches than the unfused chain
+    # fp32: summation-order noise only; bf16: the same, but it can flip the bf16 rounding of single GEMM operand entries
+    tol = 1e-5 if mode == "fp32" else 3e-3
+    for a, b in zip(zs + [xr, xs0], zu + [xru, xsu]):
+        assert relerr(a, b) < tol
+    np.testing.assert_allclose(ld.cpu().numpy(), ldu.cpu().numpy(), rtol=tol, atol=1e-3 if mode == "fp32" else 0.3)
+    np.testing.assert_allclose(lp.cpu().numpy(), lpu.cpu().numpy(), rtol=tol, atol=1e-3 if mode == "fp32" else 0.3)
+    if mode == "fp32":
+        ld_o, lp_o = torch.zeros(B, dtype=torch.float64), torch.zeros(B, dtype=torch.float64)
+        zo, ld_o, lp_o = O.glow_transform(sd, x.cpu(), L, K, ld_o, lp_o)
+        for a, b in zip(zs, zo):
+            assert relerr(a, b) < 1e-4
+        np.testing.assert_allclose(ld.cpu().numpy(), ld_o.numpy(), rtol=1e-4, atol=1e-2)
+        np.testing.assert_allclose(lp.cpu().numpy(), lp_o.numpy(), rtol=1e-4, atol=1e-2)
+        assert relerr(xr, O.glow_invert(sd, zo, L, K)) < 1e-4
