@@ -9,12 +9,14 @@
 // are skipped, so every index division is by a launch constant (multiply-high, common.cuh).
 // The per-image log-det is written as one partial per band: ld_part[t * B + b] (nfdpm_accumulate sums the rows in order).
 #include "boundary_body.cuh"
+#include <stdlib.h>
 
 namespace nfdpm {
 
 struct TileGeom {
   int R, T, halo, Rv, Pv;              // own rows per band, bands per image, halo rows (0/1), R + 2*halo, Rv * W
   FastDiv dPv, dT;
+  int bulk_m;                          // the mix matrix + beta arrive by cp.async.bulk (C % 4 == 0, 16-byte aligned)
 };
 
 //   x_s [C][Pv+1] | u_s [C][Pv+1] (mix only) | m_s [C][Cp] + beta [Cp] (mix only) | par_s [2C] | ls_s [R*W*C/2] (coupling only)
@@ -36,9 +38,14 @@ static __host__ __device__ size_t tiled_scratch_floats(int C, int W, int R, int 
 template <bool COUPLING, typename A1T>
 __global__ void __launch_bounds__(1024) flow_boundary_tiled_kernel(const BoundaryArgs a, const TileGeom g) {
   extern __shared__ __align__(16) float sm[];
-  pdl_trigger();
-  pdl_wait();
+  __shared__ __align__(8) uint64_t m_bar;
   const int tid = threadIdx.x, nt = blockDim.x;
+  pdl_trigger();
+  if (g.bulk_m && tid == 0) {
+    mbar_init(smem_u32(&m_bar), 1);
+    fence_barrier_init();
+  }
+  pdl_wait();
   const int b = fdiv((int)blockIdx.x, g.dT), t = (int)blockIdx.x - b * g.T;
   const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
   const int R = g.R, halo = g.halo, Pv = g.Pv, PS = Pv + 1, Cp = (C + 3) & ~3;
@@ -57,7 +64,18 @@ __global__ void __launch_bounds__(1024) flow_boundary_tiled_kernel(const Boundar
   int* kt_s = reinterpret_cast<int*>(sm + kt_off);
 
   // ---- phase 0: parameters and the band of the image, channel-major (lanes over pixels: coalesced runs of Pv floats)
-  if (mix) {
+  if (mix && g.bulk_m) {
+    // [C][C] matrix + beta [C]: two contiguous blocks, fetched by the bulk-copy engine while the CTA stages the band
+    // (C = 192: 147 KB per CTA, which took 36 dependent load rounds per thread as a loop)
+    if (tid == 0) {
+      const uint32_t bar = smem_u32(&m_bar);
+      const uint32_t nb = (uint32_t)C * C * 4;
+      mbar_arrive_expect_tx(bar, nb + (uint32_t)C * 4);
+      for (uint32_t off = 0; off < nb; off += 32768)
+        bulk_load(smem_u32(m_s) + off, reinterpret_cast<const char*>(a.mt) + off, min(nb - off, 32768u), bar);
+      bulk_load(smem_u32(m_s + C * Cp), a.beta, (uint32_t)C * 4, bar);
+    }
+  } else if (mix) {
     for (int i = tid; i < C * Cp; i += nt) {
       const int r = fdiv(i, a.dCp), c = i - r * Cp;
       m_s[i] = (c < C) ? __ldg(a.mt + r * C + c) : 0.f;
@@ -162,6 +180,7 @@ __global__ void __launch_bounds__(1024) flow_boundary_tiled_kernel(const Boundar
 
   // ---- phase 2: channel mix of the band, item = (group of 4 outputs, pixel), lanes over pixels
   if (mix) {
+    if (g.bulk_m) mbar_wait(smem_u32(&m_bar), 0);
     const int n_og = Cp >> 2;
     for (int it = tid; it < n_og * Pv; it += nt) {
       const int og = fdiv(it, g.dPv), q = it - og * Pv;
@@ -225,11 +244,16 @@ __global__ void __launch_bounds__(1024) flow_boundary_tiled_kernel(const Boundar
 }
 
 // rows per band: about 256 own pixels per CTA, fewer when that would leave most SMs without a CTA
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 static int choose_rows(int B, int C, int H, int W, bool coupling, bool mix, bool want_a1) {
-  int R = 256 / W;
+  static const int pix = env_int("NFDPM_TILE_PIX", 256), ctas = env_int("NFDPM_TILE_CTAS", 112);   // tuning knobs
+  int R = pix / W;
   if (R < 1) R = 1;
   if (R > H) R = H;
-  while (R > 1 && (int64_t)B * ((H + R - 1) / R) < 112) --R;
+  while (R > 1 && (int64_t)B * ((H + R - 1) / R) < ctas) --R;
   const int halo = want_a1 ? 1 : 0;
   while (R > 1 && tiled_scratch_floats(C, W, R, halo, coupling, mix, nullptr, nullptr) * sizeof(float) > 200 * 1024) --R;
   return R;
@@ -272,6 +296,7 @@ extern "C" int nfdpm_flow_boundary_tiled(const float* in, int64_t in_bs, int squ
   TileGeom g;
   g.R = R; g.T = tiles; g.halo = a1 != nullptr ? 1 : 0; g.Rv = R + 2 * g.halo; g.Pv = g.Rv * W;
   g.dPv = make_fastdiv(g.Pv); g.dT = make_fastdiv(tiles);
+  g.bulk_m = (mt != nullptr && C % 4 == 0 && ((uintptr_t)mt % 16) == 0 && ((uintptr_t)beta % 16) == 0) ? 1 : 0;
   const size_t smem = tiled_scratch_floats(C, W, R, g.halo, pm != nullptr, mt != nullptr, nullptr, nullptr) * sizeof(float);
   int64_t items = (int64_t)g.Pv * (C / 2);
   if (a1 != nullptr && (int64_t)R * W * (lda1 / 8) > items) items = (int64_t)R * W * (lda1 / 8);

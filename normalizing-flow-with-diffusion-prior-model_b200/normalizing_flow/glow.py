@@ -364,7 +364,8 @@ class Glow(Transform):
                     128x128 input) and small batches (config 4: 8 images per GPU would occupy 8 of 148 SMs)
           "unfused" separate K-A / im2col / coupling kernels (NFDPM_TILED=0, or a single image row beyond shared memory)"""
         tiled = os.environ.get("NFDPM_TILED", "1") != "0" and N.flow_boundary_tiles(B, C, h, w, 1, 1, 1) > 0
-        if cls._level_fast(C, h, w) and (B >= 64 or not tiled):
+        deep = os.environ.get("NFDPM_TILED_DEEP", "0") == "1" and h * w < 256        # experiment knob
+        if cls._level_fast(C, h, w) and ((B >= 64 and not deep) or not tiled):
             return "image"
         return "tiled" if tiled else "unfused"
 

