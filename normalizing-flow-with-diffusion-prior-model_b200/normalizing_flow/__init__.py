@@ -15,7 +15,7 @@ from . import _native
 from .glow import StepFlow, GlowBlock, Glow
 from ._dp import GradAllReduce, shard
 from ._optim import FusedClipAdam
-from .prior import IsotropicGaussian, GaussianPrior
+from .prior import IsotropicGaussian, GaussianPrior, save_model
 from .transforms import InvConv2d, ActNorm, AffineCoupling, Squeeze, Split, IdentityTransform
 from .utils import (init_optimizer, preprocess_batch, postprocess_batch, initialize_with_zeros,
                     calculate_output_shapes, calculate_loss, data_dependent_nf_initialization, get_item,
@@ -63,4 +63,4 @@ __all__ = ["InvConv2d", "ActNorm", "AffineCoupling", "StepFlow", "Squeeze", "Spl
            "IsotropicGaussian", "GaussianPrior", "NFBackbone", "init_optimizer", "preprocess_batch",
            "postprocess_batch", "calculate_output_shapes", "calculate_loss", "initialize_with_zeros",
            "data_dependent_nf_initialization", "IdentityTransform", "ZeroConv2d", "Conv2dActNorm",
-           "coupling_network", "get_item", "GradAllReduce", "shard", "FusedClipAdam"]
+           "coupling_network", "get_item", "save_model", "GradAllReduce", "shard", "FusedClipAdam"]

@@ -3,9 +3,10 @@
 ``GaussianPrior`` keeps the ZeroConv2d(2C,2C) parameter container under the reference's mangled name
 (``_GaussianPrior__conv``) so checkpoints interchange, but does not run the convolution: the reference feeds it
 an all-zero map (prior.py:79-81), whose output is exactly bias*exp(3*logs) per channel, so mean / log-sd are
-per-channel constants and log p(z) is a single reduction kernel (K-G).  The reference's checkpoint writer
-``save_model`` (prior.py:102-115) is I/O and is not mirrored.
+per-channel constants and log p(z) is a single reduction kernel (K-G).  ``save_model`` writes the reference's
+checkpoint wire format (prior.py:102-115), so checkpoints travel in both directions.
 """
+import os
 from typing import Optional
 
 import numpy as np
@@ -103,3 +104,20 @@ class GaussianPrior(Prior):
         out = torch.empty_like(eps)
         N.gauss_sample_const(eps, bias, logs, temperature, out, B, C, H * W)
         return out
+
+
+def save_model(logger_obj, model, p_dist, optim, current_epoch, current_iteration, checkpoint_directory, text=""):
+    """Checkpoint writer with the reference's wire format (prior.py:102-115): one ``torch.save`` dict holding the
+    flow's and the prior's ``state_dict()``, the optimiser state and the iteration counter.  With a ``GaussianPrior``
+    the keys are ``flow`` / ``prior_dist`` and the file is ``model_gaussian_<epoch:03d>.pt`` (what ``NFBackbone`` and
+    ``run_baseline_experiment.py:112-114`` read back); with any other prior (the diffusion prior) they are
+    ``nf_backbone`` / ``diffusion_prior`` and the file is ``model_diffusion_<epoch:03d>.pt``.  Returns the path."""
+    if logger_obj is not None:
+        logger_obj.info(f"Saving the model. {text}")
+    gaussian = isinstance(p_dist, GaussianPrior)
+    names = ("flow", "prior_dist") if gaussian else ("nf_backbone", "diffusion_prior")
+    path = os.path.join(checkpoint_directory,
+                        f"model_{'gaussian' if gaussian else 'diffusion'}_{str(current_epoch).zfill(3)}.pt")
+    torch.save({names[0]: model.state_dict(), names[1]: p_dist.state_dict(), "optimizer": optim.state_dict(),
+                "current_iter": current_iteration}, path)
+    return path

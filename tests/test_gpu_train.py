@@ -263,3 +263,51 @@ def test_fused_clip_adam_matches_torch(decoupled, wd):
     opt2 = nf.FusedClipAdam(ps, lr=1e-3)
     opt2.load_state_dict(ref.state_dict())
     assert torch.allclose(opt2.state[ps[3]]["exp_avg"], ref.state[qs[3]]["exp_avg"])
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path, monkeypatch):
+    """save_model -> load (reference wire format, prior.py:102-115) in the middle of training: the resumed run's next step
+    equals the uninterrupted run's bit for bit (parameters, moments, step counter), also when the checkpoint is loaded
+    into a model whose cached LU / packed-weight state was built from OTHER weights (cache invalidation on
+    load_state_dict)."""
+    monkeypatch.setenv("NFDPM_PRECISION", "bf16")
+    c, L, K, B, S = 3, 2, 2, 4, 16
+    x = O.seeded_input((B, c, S, S), 21).to(DEV)
+
+    def make(seed):
+        flow, prior, _, _ = _build(c, L, K, seed)
+        params = list(flow.parameters()) + list(prior.parameters())
+        return flow, prior, nf.FusedClipAdam(params, lr=1e-3, clip_params=list(flow.parameters()))
+
+    def step(flow, prior, opt):
+        opt.zero_grad(set_to_none=False)
+        loss = _train_step(flow, prior, x, S)
+        opt.step()
+        return float(loss)
+
+    flow, prior, opt = make(31)
+    for _ in range(2):
+        step(flow, prior, opt)
+    path = nf.save_model(None, flow, prior, opt, 2, 2, str(tmp_path))
+    l3 = step(flow, prior, opt)
+
+    flow2, prior2, opt2 = make(32)                     # other weights; one step warms every cache with them
+    step(flow2, prior2, opt2)
+    ck = torch.load(path, map_location="cpu")
+    flow2.load_state_dict(ck["flow"], strict=True)
+    prior2.load_state_dict(ck["prior_dist"], strict=True)
+    opt2.load_state_dict(ck["optimizer"])
+    assert ck["current_iter"] == 2 and float(opt2.state[next(iter(flow2.parameters()))]["step"]) == 2.0
+    l3b = step(flow2, prior2, opt2)
+    assert l3 == l3b
+    for (k, a), b in zip(flow.state_dict().items(), flow2.state_dict().values()):
+        assert torch.equal(a, b), k
+    for a, b in zip(prior.parameters(), prior2.parameters()):
+        assert torch.equal(a, b)
+    for p, q in zip(flow.parameters(), flow2.parameters()):
+        assert torch.equal(opt.state[p]["exp_avg"], opt2.state[q]["exp_avg"])
+        assert torch.equal(opt.state[p]["exp_avg_sq"], opt2.state[q]["exp_avg_sq"])
+    # and a torch Adam (what the reference's trainer constructs, utils.py:120-137) accepts the same optimiser state
+    ref_opt = nf.init_optimizer("adam", list(flow2.parameters()) + list(prior2.parameters()), 1e-3)
+    ref_opt.load_state_dict(ck["optimizer"])
+    assert float(ref_opt.state[next(iter(flow2.parameters()))]["step"]) == 2.0
