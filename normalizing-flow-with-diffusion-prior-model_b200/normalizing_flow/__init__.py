@@ -13,7 +13,7 @@ from torch import Tensor
 
 from . import _native
 from .glow import StepFlow, GlowBlock, Glow
-from ._dp import GradAllReduce, shard
+from ._dp import GradAllReduce, shard, combine_init_stats
 from ._optim import FusedClipAdam
 from .prior import IsotropicGaussian, GaussianPrior, save_model
 from .transforms import InvConv2d, ActNorm, AffineCoupling, Squeeze, Split, IdentityTransform
@@ -63,4 +63,4 @@ __all__ = ["InvConv2d", "ActNorm", "AffineCoupling", "StepFlow", "Squeeze", "Spl
            "IsotropicGaussian", "GaussianPrior", "NFBackbone", "init_optimizer", "preprocess_batch",
            "postprocess_batch", "calculate_output_shapes", "calculate_loss", "initialize_with_zeros",
            "data_dependent_nf_initialization", "IdentityTransform", "ZeroConv2d", "Conv2dActNorm",
-           "coupling_network", "get_item", "save_model", "GradAllReduce", "shard", "FusedClipAdam"]
+           "coupling_network", "get_item", "save_model", "GradAllReduce", "shard", "combine_init_stats", "FusedClipAdam"]

@@ -13,9 +13,17 @@ The reference has no distributed code; a trainer adopts this with three lines (I
     dp = GradAllReduce(flow, prior)          # after torch.distributed.init_process_group("nccl")
     dp.broadcast_parameters()                # once, after the data-dependent initialisation on rank 0's first batch
     loss.backward(); dp.finish()             # every step, before clip_grad_* / optimizer.step()
+
+Data-dependent initialisation over the GLOBAL first batch (what a single process with the whole batch computes,
+normalizing_flow/utils.py:275-292) instead of rank 0's shard:
+
+    dp.broadcast_parameters()                # equal random init on every rank
+    with dp.global_initialization():         # every rank runs the init pass on ITS shard of the first batch;
+        nf.data_dependent_nf_initialization(flow, local_loader, device, n_bits, n_bins)   # statistics are combined
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Optional
 
 import torch
@@ -29,6 +37,34 @@ def shard(n: int, rank: int, world: int) -> slice:
         raise ValueError(f"global batch {n} is not divisible by the world size {world}")
     per = n // world
     return slice(rank * per, (rank + 1) * per)
+
+
+@torch.no_grad()
+def combine_init_stats(scale: torch.Tensor, bias: torch.Tensor, n_local: int, group=None, eps: float = 1e-6) -> None:
+    """Replace a freshly initialised ActNorm's ``scale = -log(std + eps)``, ``bias = -mean`` (statistics of THIS rank's
+    ``n_local`` samples per channel, reference transforms.py:74-78) by the values of the union of all ranks' samples,
+    in place.  The per-rank mean and unbiased variance are recovered from the parameters, gathered (one small
+    all-gather of 2C doubles) and merged with the pairwise-variance identity
+
+        M2 = sum_r [(n-1) var_r + n (mean_r - mean)^2],   var = M2 / (world n - 1)
+
+    in float64 on every rank identically, so the replicas stay bit-equal without a broadcast.  Shards must be equal
+    (``shard`` enforces it)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    mean = -bias.detach().double().reshape(-1)
+    std = (torch.exp(-scale.detach().double().reshape(-1)) - eps).clamp_min_(0.0)
+    mine = torch.stack([mean, std * std])
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    allp = torch.stack(parts)                                   # [world, 2, C]
+    g_mean = allp[:, 0].mean(dim=0)
+    n = float(n_local)
+    m2 = ((n - 1.0) * allp[:, 1] + n * (allp[:, 0] - g_mean) ** 2).sum(dim=0)
+    g_std = torch.sqrt(m2 / (world * n - 1.0))
+    scale.copy_((-torch.log(g_std + eps)).to(scale.dtype).view_as(scale))
+    bias.copy_((-g_mean).to(bias.dtype).view_as(bias))
 
 
 class GradAllReduce:
@@ -75,6 +111,18 @@ class GradAllReduce:
         for m in self.flow.modules():                  # host-side caches of the flags / prepared matrices
             if hasattr(m, "_init_known"):
                 m._init_known = None
+
+    @contextlib.contextmanager
+    def global_initialization(self):
+        """Inside this context every data-dependent ActNorm initialisation (144 of them in an L3/K16 Glow, each depending
+        on the layers before it) uses the statistics of all ranks' shards: see ``combine_init_stats``."""
+        from . import _engine as E
+        prev = E.stats_hook
+        E.stats_hook = lambda scale, bias, n: combine_init_stats(scale, bias, n, self.group)
+        try:
+            yield self
+        finally:
+            E.stats_hook = prev
 
     # ---- hooks called by _train.GlowTransformFn.backward
     def begin(self, glow, sink) -> None:

@@ -18,6 +18,20 @@ import torch
 from . import _native as N
 
 
+#: installed by _dp.GradAllReduce.global_initialization(): called as ``hook(scale, bias, n_local)`` right after every
+#: data-dependent ActNorm initialisation so that the statistics of the ranks' shards can be combined
+stats_hook = None
+
+
+def channel_stats(x, layout: int, B: int, C: int, P: int, xs: int, scale, bias) -> None:
+    """Data-dependent ActNorm initialisation from this rank's batch (reference transforms.py:74-78): one launch writes
+    ``scale = -log(std_unbiased + 1e-6)`` and ``bias = -mean`` per channel; under data parallelism the hook replaces them
+    by the values of the GLOBAL batch."""
+    N.channel_stats(x, layout, B, C, P, xs, scale, bias)
+    if stats_hook is not None:
+        stats_hook(scale, bias, B * P)
+
+
 def precision() -> str:
     p = os.environ.get("NFDPM_PRECISION", "bf16").lower()
     if p not in ("fp32", "bf16"):
@@ -421,7 +435,7 @@ def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int,
     if need_init and not an1._initialized():
         raw = WS.get("raw", M * F, torch.float32, dev)
         N.gemm_nt(A1, K1p, cache.w1, K1p, raw, F, M, F, K1p)
-        N.channel_stats(raw, 1, B, F, H * W, F, an1.scale, an1.bias)
+        channel_stats(raw, 1, B, F, H * W, F, an1.scale, an1.bias)
         an1._mark_initialized()
     N.gemm_nt(A1, K1p, cache.w1, K1p, h1, F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
     w2 = cache.w2 if dt != torch.float32 else conv2.weight
@@ -429,7 +443,7 @@ def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int,
     if need_init and not an2._initialized():
         raw = WS.get("raw", M * F, torch.float32, dev)
         N.gemm_nt(h1, F, w2, F, raw, F, M, F, F)
-        N.channel_stats(raw, 1, B, F, H * W, F, an2.scale, an2.bias)
+        channel_stats(raw, 1, B, F, H * W, F, an2.scale, an2.bias)
         an2._mark_initialized()
     N.gemm_nt(h1, F, w2, F, h2, F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
     pm = WS.get("pm", M * ldp, torch.float32, dev)

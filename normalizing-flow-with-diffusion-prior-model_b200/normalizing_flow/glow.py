@@ -151,7 +151,11 @@ class Glow(Transform):
         return super()._apply(fn, *a, **k)
 
     def _load_from_state_dict(self, *args, **kwargs):
+        # the coupling networks start new weight caches on load (transforms.py): the batched packing plans hold the OLD
+        # cache objects and buffer addresses, so they are rebuilt too (found by the checkpoint-resume test: a model that
+        # had already run, then loaded a checkpoint, packed into the orphaned buffers and launched with null operands)
         self._pver = None
+        self._plans = {}
         return super()._load_from_state_dict(*args, **kwargs)
 
     # ---- CUDA graphs: the ~300-kernel chain of one call is captured once per (direction, shape, precision) and

@@ -117,7 +117,7 @@ class ActNorm(Transform):
     @torch.no_grad()
     def _maybe_init(self, x: Tensor, xbs: int, B: int, C: int, P: int) -> None:
         if not self._initialized():
-            N.channel_stats(x, 0, B, C, P, xbs, self.scale, self.bias)
+            E.channel_stats(x, 0, B, C, P, xbs, self.scale, self.bias)
             self._mark_initialized()
 
     @_granular("ActNorm")

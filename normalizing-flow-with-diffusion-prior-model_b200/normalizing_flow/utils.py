@@ -89,7 +89,7 @@ class Conv2dActNorm(nn.Module):
         else:
             raise ValueError("Conv2dActNorm kernels support 3x3 (pad 1) and 1x1 convolutions with stride 1")
         if not an._initialized():
-            N.channel_stats(h, 1, B, Cout, P, ld, an.scale, an.bias)
+            E.channel_stats(h, 1, B, Cout, P, ld, an.scale, an.bias)
             an._mark_initialized()
         out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x.device)
         N.rows_to_nchw(h, ld, 2, an.scale, an.bias, out, B, Cout, P)

@@ -66,6 +66,26 @@ def _worker(rank, world, port, q):
             raise AssertionError("finish() accepted an incomplete all-reduce")
         except RuntimeError:
             pass
+        # --- data-dependent ActNorm initialisation over the GLOBAL batch: every rank initialises from its shard
+        # (reference formula, transforms.py:74-78), combine_init_stats merges the shards' statistics
+        g = torch.Generator().manual_seed(7)
+        xg = torch.randn(8, 5, 6, 6, generator=g) * torch.tensor([0.5, 1.0, 2.0, 3.0, 10.0]).view(1, 5, 1, 1) + 3.0
+        xs = xg[nf.shard(8, rank, world)]
+        scale = -torch.log(xs.std(dim=(0, 2, 3)) + 1e-6).view(5, 1, 1).clone()
+        bias = -xs.mean(dim=(0, 2, 3)).view(5, 1, 1).clone()
+        nf.combine_init_stats(scale, bias, xs.shape[0] * 36)
+        want_s = -torch.log(xg.double().std(dim=(0, 2, 3)) + 1e-6)
+        want_b = -xg.double().mean(dim=(0, 2, 3))
+        assert torch.allclose(scale.double().view(-1), want_s, rtol=0, atol=2e-6), (scale.view(-1), want_s)
+        assert torch.allclose(bias.double().view(-1), want_b, rtol=0, atol=2e-6)
+        both = [torch.zeros(10) for _ in range(world)]
+        dist.all_gather(both, torch.cat([scale.view(-1), bias.view(-1)]))
+        assert all(torch.equal(b, both[0]) for b in both), "replicas must end bit-identical"
+        # the context manager installs / removes the hook the init kernels' wrapper calls
+        from normalizing_flow import _engine as E
+        with dp.global_initialization():
+            assert E.stats_hook is not None
+        assert E.stats_hook is None
         # --- sharding
         sl = nf.shard(8, rank, world)
         assert (sl.start, sl.stop) == (rank * 4, rank * 4 + 4)

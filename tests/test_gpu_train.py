@@ -291,8 +291,10 @@ def test_checkpoint_resume_is_bit_identical(tmp_path, monkeypatch):
     path = nf.save_model(None, flow, prior, opt, 2, 2, str(tmp_path))
     l3 = step(flow, prior, opt)
 
-    flow2, prior2, opt2 = make(32)                     # other weights; one step warms every cache with them
-    step(flow2, prior2, opt2)
+    flow2, prior2, opt2 = make(32)                     # other weights; one step and one inference call warm every
+    step(flow2, prior2, opt2)                          # cache (LU, packed weights, pack plans, graphs) with them
+    with torch.no_grad():
+        flow2.invert(flow2.transform(x, nf.initialize_with_zeros(1, B, DEV), None)[0])
     ck = torch.load(path, map_location="cpu")
     flow2.load_state_dict(ck["flow"], strict=True)
     prior2.load_state_dict(ck["prior_dist"], strict=True)
@@ -307,6 +309,11 @@ def test_checkpoint_resume_is_bit_identical(tmp_path, monkeypatch):
     for p, q in zip(flow.parameters(), flow2.parameters()):
         assert torch.equal(opt.state[p]["exp_avg"], opt2.state[q]["exp_avg"])
         assert torch.equal(opt.state[p]["exp_avg_sq"], opt2.state[q]["exp_avg_sq"])
+    with torch.no_grad():                              # the inference path (its own pack plan and graphs) follows too
+        za = flow.transform(x, nf.initialize_with_zeros(1, B, DEV), None)[0]
+        zb = flow2.transform(x, nf.initialize_with_zeros(1, B, DEV), None)[0]
+        assert all(torch.equal(a, b) for a, b in zip(za, zb))
+        assert torch.equal(flow.invert(za), flow2.invert(zb))
     # and a torch Adam (what the reference's trainer constructs, utils.py:120-137) accepts the same optimiser state
     ref_opt = nf.init_optimizer("adam", list(flow2.parameters()) + list(prior2.parameters()), 1e-3)
     ref_opt.load_state_dict(ck["optimizer"])
