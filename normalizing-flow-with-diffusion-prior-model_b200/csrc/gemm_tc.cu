@@ -41,6 +41,33 @@ __device__ __forceinline__ void epi_barrier_g() { asm volatile("bar.sync 1, %0;"
 constexpr int TC_ACC_COLS = 256;     // TMEM columns per accumulator stage
 constexpr int TC_CSTAGE_BYTES = 64 * 1024;   // output staging: 128 rows x 256 bf16 / 128 fp32, as 16 KB swizzled boxes
 
+// One unit of work of a CTA: a BM x bn output tile at column n0.  Persistent schedule: every CTA runs the same number of
+// full tiles (tile = blockIdx.x + it * gridDim.x); when the tile count is not a multiple of the grid (512 tiles on 148
+// SMs: 68 CTAs would run a 4th tile while 80 idle for a whole tile time), the REMAINING tiles are split into two
+// half-width tiles each and handed to 2 * rem CTAs (`split` mode: the B tensor-map box is BN/2 rows, a full tile takes
+// two B loads per stage), so the last wave costs half a tile on (almost) every SM instead of a whole tile on some.
+struct TcWork { int m_blk, n0, bn; };
+__device__ __forceinline__ bool tc_work(int it, int num_tiles, int num_n, int BN, int split, TcWork& w) {
+  const int G = gridDim.x;
+  int tile = blockIdx.x + it * G, half = -1;
+  if (split) {
+    const int full_per = num_tiles / G;
+    if (it > full_per) return false;
+    if (it == full_per) {
+      const int rem = num_tiles - full_per * G;
+      if ((int)blockIdx.x >= 2 * rem) return false;
+      tile = full_per * G + (blockIdx.x >> 1);
+      half = blockIdx.x & 1;
+    }
+  }
+  if (tile >= num_tiles) return false;
+  w.m_blk = tile / num_n;
+  const int n_blk = tile - w.m_blk * num_n;
+  w.n0 = n_blk * BN + (half > 0 ? (BN >> 1) : 0);
+  w.bn = half >= 0 ? (BN >> 1) : BN;
+  return true;
+}
+
 // profiling hook (nfdpm_gemm_debug): per-CTA cycle counters [grid][16] int64; NULL = off
 __device__ long long* g_tc_dbg = nullptr;
 
@@ -48,7 +75,7 @@ template <int EPI, typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
-                                                                   int BN, const float* __restrict__ ep_scale,
+                                                                   int BN, int split, const float* __restrict__ ep_scale,
                                                                    const float* __restrict__ ep_bias,
                                                                    const __nv_bfloat16* __restrict__ ep_h, int64_t ld_h,
                                                                    float* __restrict__ ep_part) {
@@ -115,9 +142,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + BN * TC_BK * 2);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+    TcWork wk;
+    for (int it = 0; tc_work(it, num_tiles, num_n, BN, split, wk); ++it) {
+      const int m_blk = wk.m_blk;
+      const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + wk.bn * TC_BK * 2);
+      const bool two_b = split && wk.bn == BN;            // split mode: the B box holds BN/2 rows
       for (int kb = 0; kb < num_kb; ++kb) {
         const long long c0 = dbg ? clock64() : 0;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -126,7 +155,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
           const uint32_t sa = ring + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
           mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
           tma_load_2d(sa, &tmA, kb * TC_BK, m_blk * TC_BM, bar_full + 8 * stage);
-          tma_load_2d(sb, &tmB, kb * TC_BK, n_blk * BN, bar_full + 8 * stage);
+          tma_load_2d(sb, &tmB, kb * TC_BK, wk.n0, bar_full + 8 * stage);
+          if (two_b) tma_load_2d(sb + (uint32_t)(BN >> 1) * TC_BK * 2, &tmB, kb * TC_BK, wk.n0 + (BN >> 1), bar_full + 8 * stage);
         }
         __syncwarp();
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -136,8 +166,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     // ===================== MMA issuer =====================
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    const uint32_t idesc = make_idesc(TC_BM, BN);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    TcWork wk;
+    for (int it = 0; tc_work(it, num_tiles, num_n, BN, split, wk); ++it) {
+      const uint32_t idesc = make_idesc(TC_BM, wk.bn);
       const long long c0 = dbg ? clock64() : 0;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);     // epilogue has drained this accumulator stage
       if (dbg) w1 += clock64() - c0;
@@ -167,11 +198,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                               // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;                     // which of the TCG_EPQ warps of the quadrant
-    const int n_chunks = BN >> 4;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+    TcWork wk;
+    for (int it = 0; tc_work(it, num_tiles, num_n, BN, split, wk); ++it) {
+      const int m_blk = wk.m_blk, n_base = wk.n0, n_chunks = wk.bn >> 4;
       const long long c0 = dbg ? clock64() : 0;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
@@ -185,11 +216,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       const long long c2 = dbg ? clock64() : 0;
       w1 += c2 - c1;
       // EPI_RELU_BWD: 16 bf16 of the stashed activation h for this thread's row (two 16-byte loads)
-      const int64_t h_row = (int64_t)(m_blk * TC_BM + trow) * ld_h + n_blk * BN;
+      const int64_t h_row = (int64_t)(m_blk * TC_BM + trow) * ld_h + n_base;
       const bool row_ok = (m_blk * TC_BM + trow) < M;
       auto load_h = [&](int c0, uint4 (&hh)[2]) {
         if (EPI == NFDPM_EPI_RELU_BWD) {
-          if (row_ok && n_blk * BN + c0 < N) {
+          if (row_ok && n_base + c0 < N) {
             hh[0] = __ldg(reinterpret_cast<const uint4*>(ep_h + h_row + c0));
             hh[1] = __ldg(reinterpret_cast<const uint4*>(ep_h + h_row + c0 + 8));
           } else {
@@ -199,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
         }
       };
       auto process = [&](const uint32_t (&r)[16], const uint4 (&hh)[2], int c0) {
-        const int n0 = n_blk * BN + c0;
+        const int n0 = n_base + c0;
         float v[16];
         if (EPI == NFDPM_EPI_ACTNORM_RELU) {
           const float4* pe = reinterpret_cast<const float4*>(s_ep + n0);
@@ -287,22 +318,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       if (EPI == NFDPM_EPI_RELU_BWD) {
         // combine the four row quadrants in order; one partial row per 128-row tile: part[m_blk][2N]
         const int t = threadIdx.x - 64;
-        if (t < BN && n_blk * BN + t < N) {
+        if (t < wk.bn && n_base + t < N) {
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             s0 += part_s[(qq * 2 + 0) * 256 + t];
             s1 += part_s[(qq * 2 + 1) * 256 + t];
           }
-          ep_part[(int64_t)m_blk * 2 * N + n_blk * BN + t] = s0;
-          ep_part[(int64_t)m_blk * 2 * N + N + n_blk * BN + t] = s1;
+          ep_part[(int64_t)m_blk * 2 * N + n_base + t] = s0;
+          ep_part[(int64_t)m_blk * 2 * N + N + n_base + t] = s1;
         }
       }
       if (warp == 2 && lane == 0) {
         constexpr int CPB = TcStage<OutT>::kColsPerBox;
-        const int n_boxes = (BN + CPB - 1) / CPB;
+        const int n_boxes = (wk.bn + CPB - 1) / CPB;
         for (int j = 0; j < n_boxes; ++j)                  // rows >= M and columns >= N are clipped by the tensor map
-          tma_store_2d(&tmD, cstage + (uint32_t)j * 16384u, n_blk * BN + j * CPB, m_blk * TC_BM);
+          tma_store_2d(&tmD, cstage + (uint32_t)j * 16384u, n_base + j * CPB, m_blk * TC_BM);
         tma_store_commit();
       }
       acc ^= 1;
@@ -334,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
 // ---------------------------------------------------------------- host side
 template <int EPI, typename OutT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, int M, int N, int K, int BN,
-                     const float* es, const float* eb, int grid, size_t smem, cudaStream_t st,
+                     int split, const float* es, const float* eb, int grid, size_t smem, cudaStream_t st,
                      const __nv_bfloat16* ep_h = nullptr, int64_t ld_h = 0, float* ep_part = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -343,7 +374,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     attr_set = true;
   }
   NFDPM_CUDA(launch_pdl(gemm_nt_tc_kernel<EPI, OutT>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, tmD, M, N, K, BN,
-                        es, eb, ep_h, ld_h, ep_part));
+                        split, es, eb, ep_h, ld_h, ep_part));
   return 0;
 }
 
@@ -372,10 +403,6 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   // one N block: any multiple of 16 (columns >= N are clipped by the D tensor map); several N blocks: BN must be a
   // whole number of store boxes, otherwise a tile's last box would spill into its neighbour's columns
   const int BN = (nblk == 1) ? (N + 15) / 16 * 16 : ((N + nblk - 1) / nblk + cpb - 1) / cpb * cpb;
-  CUtensorMap tmA, tmB, tmD;
-  if (make_map(&tmA, A, M, K, lda, TC_BM)) return 1;
-  if (make_map(&tmB, Bw, N, K, ldb, BN)) return 1;
-  if (make_map(&tmD, D, M, N, ldd, TC_BM, out_dtype == NFDPM_F32)) return 1;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -384,16 +411,30 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   }
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sms ? tiles : sms;
+  // last-wave balancing (TcWork): split the tiles beyond the last full round into half-width tiles when that puts
+  // them on (almost) every SM; NFDPM_TC_SPLIT=0 keeps whole tiles
+  static int split_on = -1;
+  if (split_on < 0) {
+    const char* e = getenv("NFDPM_TC_SPLIT");
+    split_on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const int rem = tiles % grid;
+  const int split = (split_on && tiles > grid && rem > 0 && 2 * rem <= grid && BN % 128 == 0 && N % BN == 0 &&
+                     epilogue != NFDPM_EPI_RELU_BWD) ? 1 : 0;
+  CUtensorMap tmA, tmB, tmD;
+  if (make_map(&tmA, A, M, K, lda, TC_BM)) return 1;
+  if (make_map(&tmB, Bw, N, K, ldb, split ? BN / 2 : BN)) return 1;
+  if (make_map(&tmD, D, M, N, ldd, TC_BM, out_dtype == NFDPM_F32)) return 1;
   const size_t n_pad = (size_t)((N + BN - 1) / BN) * BN;
   const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_CSTAGE_BYTES +
                       (epilogue != NFDPM_EPI_RAW ? 2 * n_pad * 4 : 0) + (epilogue == NFDPM_EPI_RELU_BWD ? 4 * 2 * 256 * 4 : 0);
   if (epilogue == NFDPM_EPI_RELU_BWD) {
     NFDPM_REQUIRE(out_dtype == NFDPM_BF16 && ep_h && ep_part && ep_scale && ld_h % 8 == 0 && ((uintptr_t)ep_h % 16) == 0,
                   "nfdpm_gemm_nt_relu_bwd: needs bf16 output, h (16-byte aligned, ld %% 8 == 0), scale and part");
-    return launch_tc<NFDPM_EPI_RELU_BWD, __nv_bfloat16>(tmA, tmB, tmD, M, N, K, BN, ep_scale, nullptr, grid, smem, st,
+    return launch_tc<NFDPM_EPI_RELU_BWD, __nv_bfloat16>(tmA, tmB, tmD, M, N, K, BN, 0, ep_scale, nullptr, grid, smem, st,
                                                          (const __nv_bfloat16*)ep_h, ld_h, ep_part);
   }
-#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, tmD, M, N, K, BN, ep_scale, ep_bias, grid, smem, st)
+#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, tmD, M, N, K, BN, split, ep_scale, ep_bias, grid, smem, st)
   if (out_dtype == NFDPM_F32) {
     if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, float); else GO(NFDPM_EPI_ACTNORM_RELU, float);
   } else {
