@@ -26,7 +26,8 @@ namespace nfdpm {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 3;           // classic layout: 3 x 48 KB ring + a whole-tile (64 KB) output staging buffer
+constexpr int TC_MAX_STAGES = 6;       // deep layout: as many (16 KB + BN x 128 B) stages as fit next to a 64-column staging buffer
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_B_BYTES_MAX = 256 * TC_BK * 2;        // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
@@ -47,6 +48,14 @@ constexpr int TC_CSTAGE_BYTES = 64 * 1024;   // output staging: 128 rows x 256 b
 // half-width tiles each and handed to 2 * rem CTAs (`split` mode: the B tensor-map box is BN/2 rows, a full tile takes
 // two B loads per stage), so the last wave costs half a tile on (almost) every SM instead of a whole tile on some.
 struct TcWork { int m_blk, n0, bn; };
+// Shared-memory plan chosen by the host (gemm_nt_tc):
+//   classic  n_stages = 3, stage_bytes = 48 KB, the epilogue converts the WHOLE tile into a 64 KB staging buffer (cpw = all
+//            chunks of a warp in one pass) and stores it with one burst of TMA box stores;
+//   deep     stage_bytes = 16 KB + BN x 128 B, the staging buffer holds one 64-column PASS (16 KB bf16 / 32 KB fp32, cpw = 1
+//            chunk per warp per pass) and the space goes to the operand ring: 4 x 48 KB stages at BN = 256 (r1 counters: with
+//            3 stages the MMA warp waited for TMA bytes ~25 % of its loop - two stages in flight while one is consumed is
+//            about one L2 round trip at the MMA rate).
+struct TcPlan { int n_stages, stage_bytes, cstage_bytes, cpw; };
 __device__ __forceinline__ bool tc_work(int it, int num_tiles, int num_n, int BN, int split, TcWork& w) {
   const int G = gridDim.x;
   int tile = blockIdx.x + it * G, half = -1;
@@ -75,21 +84,24 @@ template <int EPI, typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
-                                                                   int BN, int split, const float* __restrict__ ep_scale,
+                                                                   int BN, int split, const TcPlan plan,
+                                                                   const float* __restrict__ ep_scale,
                                                                    const float* __restrict__ ep_bias,
                                                                    const __nv_bfloat16* __restrict__ ep_h, int64_t ld_h,
                                                                    float* __restrict__ ep_part) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1024-byte aligned tile ring (swizzle-128B requirement), then the epilogue parameters
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t cstage = ring + TC_STAGES * TC_STAGE_BYTES;          // 1024-aligned output staging tile
-  float* s_ep = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + TC_STAGES * TC_STAGE_BYTES + TC_CSTAGE_BYTES);
-  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[TC_STAGES]);
-  const uint32_t bar_tfull = smem_u32(&bars[2 * TC_STAGES]), bar_tempty = smem_u32(&bars[2 * TC_STAGES + 2]);
+  const int n_stages = plan.n_stages;
+  const uint32_t stage_bytes = (uint32_t)plan.stage_bytes;
+  const uint32_t cstage = ring + n_stages * stage_bytes;               // 1024-aligned output staging tile
+  float* s_ep = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + n_stages * stage_bytes + plan.cstage_bytes);
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[TC_MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * TC_MAX_STAGES]), bar_tempty = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
 
   const int num_n = (N + BN - 1) / BN;
   const int num_m = (M + TC_BM - 1) / TC_BM;
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -152,14 +164,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (dbg) w0 += clock64() - c0;
         if (lane == 0) {
-          const uint32_t sa = ring + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+          const uint32_t sa = ring + stage * stage_bytes, sb = sa + TC_A_BYTES;
           mbar_arrive_expect_tx(bar_full + 8 * stage, tx_bytes);
           tma_load_2d(sa, &tmA, kb * TC_BK, m_blk * TC_BM, bar_full + 8 * stage);
           tma_load_2d(sb, &tmB, kb * TC_BK, wk.n0, bar_full + 8 * stage);
           if (two_b) tma_load_2d(sb + (uint32_t)(BN >> 1) * TC_BK * 2, &tmB, kb * TC_BK, wk.n0 + (BN >> 1), bar_full + 8 * stage);
         }
         __syncwarp();
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
         if (dbg) w0 += clock64() - c1;
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = ring + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+          const uint32_t sa = ring + stage * stage_bytes, sb = sa + TC_A_BYTES;
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)              // +32 bytes (= 2 x 16 B) per K=16 slice inside the swizzle row
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
           if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
         }
         __syncwarp();
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -210,9 +222,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       w0 += c1 - c0;
       const int trow = q * 32 + lane;                      // row inside the tile == TMEM lane
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_ACC_COLS;
-      // the previous tile's TMA stores must have finished READING the staging tile before it is overwritten
-      if (warp == 2 && lane == 0) tma_store_wait_read();
-      epi_barrier_g();
       const long long c2 = dbg ? clock64() : 0;
       w1 += c2 - c1;
       // EPI_RELU_BWD: 16 bf16 of the stashed activation h for this thread's row (two 16-byte loads)
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
           }
         }
       };
-      auto process = [&](const uint32_t (&r)[16], const uint4 (&hh)[2], int c0) {
+      auto process = [&](const uint32_t (&r)[16], const uint4 (&hh)[2], int c0, int c_stage) {
         const int n0 = n_base + c0;
         float v[16];
         if (EPI == NFDPM_EPI_ACTNORM_RELU) {
@@ -289,32 +298,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
-        TcStage<OutT>::put16(cstage, trow, c0, v);
+        TcStage<OutT>::put16(cstage, trow, c_stage, v);
       };
-      // chunks half, half+TCG_EPQ, ... ; the load of the next chunk is in flight while this one is processed
+      // This warp owns chunks half, half + TCG_EPQ, ... (16 columns each); the TMEM load of its next chunk is in flight
+      // while the current one is processed.  The chunks are written to the staging buffer in PASSES of cpw chunks per
+      // warp (= cpw * 64 columns): [staging free] -> convert -> [fence, barrier] -> one thread issues the pass's TMA box
+      // stores.  Classic plan: one pass = the whole tile; deep plan: cpw = 1, one 64-column box group per pass.
+      constexpr int CPB = TcStage<OutT>::kColsPerBox;
+      const int cpw = plan.cpw;
+      const int k_total = ((n_chunks + TCG_EPQ - 1) / TCG_EPQ + cpw - 1) / cpw * cpw;   // same trip count for every warp
+      auto chunk_step = [&](uint32_t (&cur)[16], uint32_t (&nxt)[16], uint4 (&hc)[2], uint4 (&hn)[2], int k) {
+        const int ch = half + TCG_EPQ * k;
+        const int pass = k / cpw;
+        const int col0 = pass * cpw * (16 * TCG_EPQ);        // first tile column of this pass
+        if (k - pass * cpw == 0) {
+          // the previous pass's (or tile's) TMA stores must have finished READING the staging buffer
+          if (warp == 2 && lane == 0) tma_store_wait_read();
+          epi_barrier_g();
+        }
+        if (ch < n_chunks) {
+          tmem_ld_wait();
+          if (ch + TCG_EPQ < n_chunks) { tmem_ld16(taddr + (ch + TCG_EPQ) * 16, nxt); load_h((ch + TCG_EPQ) * 16, hn); }
+          process(cur, hc, ch * 16, ch * 16 - col0);
+        }
+        if (k - pass * cpw == cpw - 1) {
+          if (k == k_total - 1) {
+            // accumulator drained: hand the TMEM stage back to the MMA warp before doing the stores
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);
+          }
+          fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA engine
+          epi_barrier_g();
+          if (warp == 2 && lane == 0) {
+            const int cols = min(wk.bn - col0, cpw * (16 * TCG_EPQ));
+            const int n_boxes = (cols + CPB - 1) / CPB;
+            for (int j = 0; j < n_boxes; ++j)              // rows >= M and columns >= N are clipped by the tensor map
+              tma_store_2d(&tmD, cstage + (uint32_t)j * 16384u, n_base + col0 + j * CPB, m_blk * TC_BM);
+            tma_store_commit();
+          }
+        }
+      };
       uint32_t ra[16], rb[16];
       uint4 ha[2], hb[2];
-      int ch = half;
-      if (ch < n_chunks) { tmem_ld16(taddr + ch * 16, ra); load_h(ch * 16, ha); }
-      while (ch < n_chunks) {
-        tmem_ld_wait();
-        if (ch + TCG_EPQ < n_chunks) { tmem_ld16(taddr + (ch + TCG_EPQ) * 16, rb); load_h((ch + TCG_EPQ) * 16, hb); }
-        process(ra, ha, ch * 16);
-        ch += TCG_EPQ;
-        if (ch >= n_chunks) break;
-        tmem_ld_wait();
-        if (ch + TCG_EPQ < n_chunks) { tmem_ld16(taddr + (ch + TCG_EPQ) * 16, ra); load_h((ch + TCG_EPQ) * 16, ha); }
-        process(rb, hb, ch * 16);
-        ch += TCG_EPQ;
+      if (half < n_chunks) { tmem_ld16(taddr + half * 16, ra); load_h(half * 16, ha); }
+      for (int k = 0; k < k_total; k += 2) {
+        chunk_step(ra, rb, ha, hb, k);
+        if (k + 1 < k_total) chunk_step(rb, ra, hb, ha, k + 1);
       }
-      // accumulator drained: hand the TMEM stage back to the MMA warp before doing the stores
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
       const long long c3 = dbg ? clock64() : 0;
       w2 += c3 - c2;
-      fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA engine
-      epi_barrier_g();
-      if (dbg) { w3 += clock64() - c3; w4 += 1; }
+      if (dbg) w4 += 1;
       if (EPI == NFDPM_EPI_RELU_BWD) {
         // combine the four row quadrants in order; one partial row per 128-row tile: part[m_blk][2N]
         const int t = threadIdx.x - 64;
@@ -328,13 +361,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
           ep_part[(int64_t)m_blk * 2 * N + n_base + t] = s0;
           ep_part[(int64_t)m_blk * 2 * N + N + n_base + t] = s1;
         }
-      }
-      if (warp == 2 && lane == 0) {
-        constexpr int CPB = TcStage<OutT>::kColsPerBox;
-        const int n_boxes = (wk.bn + CPB - 1) / CPB;
-        for (int j = 0; j < n_boxes; ++j)                  // rows >= M and columns >= N are clipped by the tensor map
-          tma_store_2d(&tmD, cstage + (uint32_t)j * 16384u, n_base + j * CPB, m_blk * TC_BM);
-        tma_store_commit();
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -365,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
 // ---------------------------------------------------------------- host side
 template <int EPI, typename OutT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, int M, int N, int K, int BN,
-                     int split, const float* es, const float* eb, int grid, size_t smem, cudaStream_t st,
+                     int split, const TcPlan& plan, const float* es, const float* eb, int grid, size_t smem, cudaStream_t st,
                      const __nv_bfloat16* ep_h = nullptr, int64_t ld_h = 0, float* ep_part = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -374,7 +400,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     attr_set = true;
   }
   NFDPM_CUDA(launch_pdl(gemm_nt_tc_kernel<EPI, OutT>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, tmD, M, N, K, BN,
-                        split, es, eb, ep_h, ld_h, ep_part));
+                        split, plan, es, eb, ep_h, ld_h, ep_part));
   return 0;
 }
 
@@ -426,15 +452,33 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   if (make_map(&tmB, Bw, N, K, ldb, split ? BN / 2 : BN)) return 1;
   if (make_map(&tmD, D, M, N, ldd, TC_BM, out_dtype == NFDPM_F32)) return 1;
   const size_t n_pad = (size_t)((N + BN - 1) / BN) * BN;
-  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_CSTAGE_BYTES +
-                      (epilogue != NFDPM_EPI_RAW ? 2 * n_pad * 4 : 0) + (epilogue == NFDPM_EPI_RELU_BWD ? 4 * 2 * 256 * 4 : 0);
+  const size_t extra = (epilogue != NFDPM_EPI_RAW ? 2 * n_pad * 4 : 0) + (epilogue == NFDPM_EPI_RELU_BWD ? 4 * 2 * 256 * 4 : 0);
+  // shared-memory plan (TcPlan): the deep ring pays when the main loop is long enough to be fed from L2 continuously;
+  // NFDPM_TC_DEEP=0 keeps the classic plan everywhere, =2 forces the deep plan for every shape
+  static int deep_on = -1;
+  if (deep_on < 0) {
+    const char* e = getenv("NFDPM_TC_DEEP");
+    deep_on = e ? atoi(e) : 1;
+  }
+  TcPlan plan = {TC_STAGES, TC_STAGE_BYTES, TC_CSTAGE_BYTES, 4};
+  // measured (tools/bench_gemms.py): M=32768 N=K=512 22.2 -> 21.7 us, N=112 fp32-out 11.0 -> 10.5 us; with ONE tile per CTA
+  // (deep levels) the pass-wise epilogue has no next main loop to hide behind and costs 0.5 us, so those keep the classic plan
+  if (deep_on == 2 || (deep_on == 1 && K / TC_BK >= 4 && tiles > grid)) {
+    plan.stage_bytes = TC_A_BYTES + BN * TC_BK * 2;
+    plan.cstage_bytes = 128 * 64 * (out_dtype == NFDPM_F32 ? 4 : 2);
+    plan.cpw = 1;
+    const size_t avail = 226 * 1024 - 1024 - (size_t)plan.cstage_bytes - extra;   // 226 KB dynamic (launch_tc) + static barriers
+    plan.n_stages = (int)(avail / (size_t)plan.stage_bytes);
+    if (plan.n_stages > TC_MAX_STAGES) plan.n_stages = TC_MAX_STAGES;
+  }
+  const size_t smem = 1024 + (size_t)plan.n_stages * plan.stage_bytes + plan.cstage_bytes + extra;
   if (epilogue == NFDPM_EPI_RELU_BWD) {
     NFDPM_REQUIRE(out_dtype == NFDPM_BF16 && ep_h && ep_part && ep_scale && ld_h % 8 == 0 && ((uintptr_t)ep_h % 16) == 0,
                   "nfdpm_gemm_nt_relu_bwd: needs bf16 output, h (16-byte aligned, ld %% 8 == 0), scale and part");
-    return launch_tc<NFDPM_EPI_RELU_BWD, __nv_bfloat16>(tmA, tmB, tmD, M, N, K, BN, 0, ep_scale, nullptr, grid, smem, st,
+    return launch_tc<NFDPM_EPI_RELU_BWD, __nv_bfloat16>(tmA, tmB, tmD, M, N, K, BN, 0, plan, ep_scale, nullptr, grid, smem, st,
                                                          (const __nv_bfloat16*)ep_h, ld_h, ep_part);
   }
-#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, tmD, M, N, K, BN, split, ep_scale, ep_bias, grid, smem, st)
+#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, tmD, M, N, K, BN, split, plan, ep_scale, ep_bias, grid, smem, st)
   if (out_dtype == NFDPM_F32) {
     if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, float); else GO(NFDPM_EPI_ACTNORM_RELU, float);
   } else {
