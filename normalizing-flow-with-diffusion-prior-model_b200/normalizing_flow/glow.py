@@ -436,12 +436,23 @@ class Glow(Transform):
         slots = self._slots(dev)
         steps = [s for flows, _ in levels for s in flows]
         ready = all(s._ready() for s in steps)
-        if self._use_graph(ready) and len(latents) == self.L:
+        if self._use_graph(ready) and 1 <= len(latents) <= self.L and all(isinstance(t, Tensor) for t in latents):
+            # decoding (all L latents supplied) and sampling (fewer: every Split without a latent draws its half from the
+            # learned conditional prior, transforms.py:305-307) replay one captured chain; the normal draws inside a
+            # captured chain come from torch's default CUDA generator, whose Philox offset advances on every replay
             lat_in = [E.check_input(t, "latent") for t in latents]
             if self._params_changed():
                 self._refresh_caches(steps, slots)
-            key = ("inv", B, h, w, E.precision(), dev.index)
+            key = ("inv", B, h, w, E.precision(), dev.index) if len(latents) == self.L else \
+                  ("inv", B, h, w, E.precision(), dev.index, len(latents), float(temperature))
             ent = self._graphs.get(key)
+            if ent is None and len(key) > 6:
+                # the temperature is baked into a sampling graph: keep at most four of them (a temperature sweep would
+                # otherwise pin one captured chain and its workspace per value)
+                old = [k for k in self._graphs if k[0] == "inv" and len(k) > 6]
+                for k in old[:max(0, len(old) - 3)]:
+                    E.WS.drop_scope(("glow", id(self), k))
+                    del self._graphs[k]
             statics = ent["lat"] if ent is not None else [torch.empty_like(t) for t in lat_in]
             for s_, t in zip(statics, lat_in):
                 if s_.shape != t.shape:

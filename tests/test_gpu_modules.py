@@ -257,6 +257,41 @@ def test_nfbackbone_and_sample_api(tmp_path):
     assert img.shape == (B, c, S, S) and torch.isfinite(img).all()
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_sampling_replays_a_captured_chain(mode, monkeypatch):
+    """Glow.invert with fewer than L latents (every Split without one draws from its conditional prior,
+    transforms.py:305-307) takes the CUDA-graph path like decoding does: at temperature 0 the draw is the prior mean, so the
+    replayed chain must equal the eager chain exactly; at temperature 1 every replay must draw NEW noise; a partially
+    supplied list keeps the given latents; temperatures get their own graphs (at most four are kept)."""
+    monkeypatch.setenv("NFDPM_PRECISION", mode)
+    c, L, K, B, S = 3, 3, 2, 4, 32
+    flow, prior, sd, psd = build(c, L, K, 51)
+    x = O.seeded_input((B, c, S, S), 52).to(DEV)
+    with torch.no_grad():
+        zs, _, _ = flow.transform(x, torch.zeros(B, dtype=torch.float64, device=DEV), None)
+        zs = [z.clone() for z in zs]
+        for _ in range(2):                                          # second call replays
+            mean_g = flow.invert([zs[-1]], temperature=0.0)
+        monkeypatch.setenv("NFDPM_GRAPHS", "0")
+        mean_e = flow.invert([zs[-1]], temperature=0.0)
+        monkeypatch.setenv("NFDPM_GRAPHS", "1")
+        assert torch.equal(mean_g, mean_e)
+        n0 = len(flow._graphs)
+        a = flow.invert([zs[-1]], temperature=1.0)
+        b = flow.invert([zs[-1]], temperature=1.0)
+        assert len(flow._graphs) == n0 + 1
+        assert torch.isfinite(a).all() and float((a - b).abs().max()) > 1e-3, "a replay must draw fresh noise"
+        assert float((a - mean_g).abs().max()) > 1e-3
+        # the two deepest latents given, the shallowest sampled: differs from full decoding only through that draw
+        part = flow.invert(zs[1:], temperature=0.0)
+        full = flow.invert(zs)
+        assert part.shape == full.shape and torch.isfinite(part).all() and not torch.equal(part, full)
+        assert torch.equal(flow.invert(zs), full)
+        for t in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6):
+            flow.invert([zs[-1]], temperature=t)
+        assert sum(1 for k in flow._graphs if k[0] == "inv" and len(k) > 6) <= 4
+
+
 @pytest.mark.parametrize("cfg", [(1, 3, 4, 64, 32), (3, 3, 16, 128, 32)])
 def test_full_size_properties(cfg):
     """BASELINE configs 1 and 2 at full size: reference-style random init + data-dependent initialisation,

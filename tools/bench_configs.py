@@ -96,6 +96,16 @@ def run(cfg, mode, steps, do_train, flush):
         out["inv_ms"], out["inv_img_s"] = ms_i, B / ms_i * 1e3
         out["inv_tflops"] = FLOP[cfg] * B / ms_i / 1e9
         out["inv_launches"] = (N.launch_count - l0) // steps
+        # sampling variant: only the final latent is supplied, every Split draws its half from the
+        # learned conditional prior (split-prior conv + Gaussian sample inside the inverse chain, transforms.py:292-309)
+        last_only = [lat[-1]]
+
+        def inv_last():
+            return flow.invert(last_only)
+        for _ in range(3):
+            inv_last()
+        ms_s = timed(inv_last, steps, flush)
+        out["sample_last_latent_ms"], out["sample_last_latent_img_s"] = ms_s, B / ms_s * 1e3
         if cfg == 5:
             # the whole decode step of NFDPM sampling as the reference runs it (diffusion_prior/model.py:132,
             # normalizing_flow/__init__.py:106, utils.py:210): CatFormater.postprocess -> Glow.sample -> postprocess_batch
