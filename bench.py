@@ -139,6 +139,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the other ranks have exited, so rank 0 takes all host cores
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     B = 32                                   # bounded sample of the 128-image batch: ~1-2 s per step on 8+ cores
     step = oracle_step_fn(B)
     for _ in range(max(1, min(args.warmup, 1))):
