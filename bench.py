@@ -89,7 +89,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_style_state(nf, O, torch, dev):
+def reference_style_state(nf, SY, torch, dev):
     """Weights as SURVEY §8(d) specifies them: the module constructors under torch.manual_seed(0) (QR-initialised 1x1
     convs, N(0, 0.05) coupling convs, zero ZeroConvs: transforms.py:112-114, utils.py:37-38,64-65), the data-dependent
     ActNorm initialisation on the first batch (transforms.py:74-78, always fp32), then N(0, 1e-3) (generator seed 1) on
@@ -98,7 +98,7 @@ def reference_style_state(nf, O, torch, dev):
     torch.manual_seed(0)
     flow = nf.Glow(c, L, K).to(dev)
     prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
-    x = O.seeded_input((CFG["batch"], c, S, S), 1).to(dev)          # rank 0's batch on every rank: identical replicas
+    x = SY.seeded_input((CFG["batch"], c, S, S), 1).to(dev)         # rank 0's batch on every rank: identical replicas
     with torch.no_grad():
         ld, lp = nf.initialize_with_zeros(2, x.shape[0], dev)
         flow.transform(x, ld, lp)
@@ -162,7 +162,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def bench_train(args, torch, dist, nf, N, O, dev, world, rank, B, x_host, timed, flush_buf, state):
+def bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, flush_buf, state):
     """Full training step of the reference recipe (normalizing_flow/trainer.py:150-167): dequantisation noise,
     transform, prior log-prob, bits/dim loss, backward, [gradient all-reduce over NCCL when N > 1], clip value 1,
     clip norm 1, Adam(1e-4).  The whole step is captured once in a CUDA graph and replayed (host launch overhead of
@@ -299,7 +299,7 @@ def main():
     import torch.distributed as dist
     import normalizing_flow as nf
     from normalizing_flow import _native as N, _engine as E
-    from oracle import glow_oracle as O
+    import synthetic as SY            # synthetic inputs; the oracle is imported only by the cpu_baseline / reference legs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -313,13 +313,13 @@ def main():
     mode = E.precision()
 
     # random-init weights of the named architecture (SURVEY §8(d) recipe), synthetic dequantised images
-    state = reference_style_state(nf, O, torch, dev)
+    state = reference_style_state(nf, SY, torch, dev)
     sd, psd = state
     flow = nf.Glow(c, L, K).to(dev)
     flow.load_state_dict(sd)
     prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
     prior.load_state_dict(psd)
-    x_host = O.seeded_input((B, c, S, S), 1 + rank).pin_memory()
+    x_host = SY.seeded_input((B, c, S, S), 1 + rank).pin_memory()
     x_dev = x_host.to(dev)
     ll_host = torch.empty(B, dtype=torch.float64).pin_memory()
     xr_host = torch.empty(B, c, S, S).pin_memory()
@@ -455,7 +455,7 @@ def main():
 
     train = None
     if not args.no_train:
-        train = bench_train(args, torch, dist, nf, N, O, dev, world, rank, B, x_host, timed, flush_buf, state)
+        train = bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, flush_buf, state)
 
     if rank == 0:
         imgs = B * world * args.steps

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "normalizing-flow-with-diffusion-prior-mod
 import torch  # noqa: E402
 import normalizing_flow as nf  # noqa: E402
 from normalizing_flow import _native as N  # noqa: E402
-from oracle import glow_oracle as O  # noqa: E402
+import synthetic as O  # noqa: E402  (seeded synthetic inputs)
 
 CONFIGS = {                      # BASELINE.json configs: (in_channel, L, K, batch per GPU, size, what)
     1: (1, 3, 4, 64, 32, "L3 K4 MNIST 1x32x32 batch 64"),

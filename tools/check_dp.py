@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "normalizing-flo
 import torch
 import torch.distributed as dist
 import normalizing_flow as nf
-from oracle import glow_oracle as O
+import synthetic as O
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "normalizing-flow-with-diffusion-prior-model_b200"))
 import torch
 import normalizing_flow as nf
-from oracle import glow_oracle as O
+import synthetic as O
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
