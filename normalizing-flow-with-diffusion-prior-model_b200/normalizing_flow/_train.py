@@ -20,6 +20,7 @@ into d(InvConv2d.weight), d(ActNorm.scale), d(ActNorm.bias).
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -426,6 +427,116 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
     return dx
 
 
+# ------------------------------------------------------------------------------------------- captured training chains
+# An UNCAPTURED training loop (the reference trainer as is) issues ~1 600 launches per step from Python and is host-bound
+# (25 ms vs 8.7 ms per 128-image step when the whole step sits in a torch.cuda.graph, bench.py --train-eager).  With
+# NFDPM_TRAIN_GRAPHS=1 the autograd Function captures its stash-forward chain and its backward chain once per
+# (shape, precision) and replays them, like the inference entry points do.  Bit-identical to the eager chain over several
+# optimiser steps (tests/test_gpu_train.py::test_captured_training_chains_equal_eager, run on a B200); opt-in until it has
+# been TIMED and run through the whole parity suite (round 1 ended without GPU time for that).  Not used under a caller's own capture or with the
+# data-parallel hook (NCCL launches from inside the backward); parameter caches are refreshed INSIDE the chains
+# (E.own_capture stays False), because the parameters change between replays.
+def train_graphs_enabled() -> bool:
+    return os.environ.get("NFDPM_TRAIN_GRAPHS", "0") == "1"
+
+
+class _TrainChains:
+    """Static buffers and graphs of one key.  ``busy`` marks a forward whose backward has not run yet: its stash lives in
+    the graph's buffers, so a second forward before that backward (gradient accumulation over micro-batches in one
+    autograd graph) takes the eager path instead of overwriting it."""
+
+    def __init__(self):
+        self.x = None
+        self.fwd = None
+        self.fwd_out = None
+        self.n_fwd = 0
+        self.bwd = {}
+        self.owner = None             # weak reference to the autograd context whose stash is in the buffers
+        self.epoch = -1
+        self.scope = None
+
+    @property
+    def busy(self) -> bool:
+        o = self.owner() if self.owner is not None else None
+        return o is not None and getattr(o, "chains", None) is self
+
+    def claim(self, ctx) -> None:
+        try:
+            self.owner = weakref.ref(ctx)
+        except TypeError:             # context objects that cannot be weakly referenced: hold it until backward
+            self.owner = lambda c=ctx: c
+
+    def release(self) -> None:
+        self.owner = None
+
+
+def _capture(scope, build):
+    """build() once eagerly (parameter caches, one-time kernel attributes), then under capture; buffers taken from the
+    workspace pool inside the chain live under ``scope``."""
+    prev = E.WS.scope
+    try:
+        E.WS.scope = ("warm",) + tuple(scope)
+        build()
+        torch.cuda.current_stream().synchronize()
+        E.WS.drop_scope(("warm",) + tuple(scope))
+        E.WS.scope = scope
+        g = torch.cuda.CUDAGraph()
+        n0 = N.launch_count
+        with torch.cuda.graph(g):
+            out = build()
+        n = N.launch_count - n0
+    finally:
+        E.WS.scope = prev
+    N.launch_count -= n                               # counted per replay
+    return g, out, n
+
+
+def _train_chains(glow, x: Tensor, with_logp: bool) -> Optional["_TrainChains"]:
+    if not train_graphs_enabled() or torch.cuda.is_current_stream_capturing() or \
+            getattr(glow, "_grad_hook", None) is not None:
+        return None
+    store = glow.__dict__.setdefault("_train_chains", {})
+    key = (tuple(x.shape), with_logp, E.precision(), x.device.index)
+    tc = store.get(key)
+    if tc is not None and tc.epoch != E.alloc_epoch:  # a cache was re-allocated: the captured addresses are stale
+        E.WS.drop_scope(tc.scope)
+        tc = None
+    if tc is None:
+        tc = _TrainChains()
+        tc.scope = ("train", id(glow), key)
+        tc.x = torch.empty_like(x)
+        tc.x.copy_(x)
+        tc.fwd, tc.fwd_out, tc.n_fwd = _capture(tc.scope + ("fwd",), lambda: forward_train(glow, tc.x, with_logp))
+        tc.epoch = E.alloc_epoch
+        store[key] = tc
+    return None if tc.busy else tc
+
+
+def _bwd_chain(tc: "_TrainChains", glow, params, g_lat, g_ld, g_lp, need_dx: bool):
+    """Static gradient inputs + captured backward of ``tc``'s stash for this pattern of present / absent gradients."""
+    key = (tuple(None if g is None else (tuple(g.shape), g.dtype) for g in g_lat),
+           None if g_ld is None else g_ld.dtype, None if g_lp is None else g_lp.dtype, need_dx)
+    ent = tc.bwd.get(key)
+    if ent is None:
+        s_lat = [None if g is None else torch.empty_like(g) for g in g_lat]
+        s_ld = None if g_ld is None else torch.empty_like(g_ld)
+        s_lp = None if g_lp is None else torch.empty_like(g_lp)
+        for s_, g in zip(s_lat + [s_ld, s_lp], list(g_lat) + [g_ld, g_lp]):
+            if s_ is not None:
+                s_.copy_(g)
+
+        def build():
+            sink = GradSink(params)
+            dx = backward_train(glow, tc.fwd_out[5], s_lat, s_ld, s_lp, need_dx, sink, None)
+            for p in params:                           # parameters the backward does not reach: exact zeros
+                if p.requires_grad and id(p) not in sink.written:
+                    sink.get(p).zero_()
+            return sink, dx
+        g, (sink, dx), n = _capture(tc.scope + ("bwd", len(tc.bwd)), build)
+        ent = tc.bwd[key] = dict(graph=g, sink=sink, dx=dx, n=n, lat=s_lat, ld=s_ld, lp=s_lp)
+    return ent
+
+
 class GlowTransformFn(torch.autograd.Function):
     """(x, log_det_jac, logp, *parameters) -> (log_det_jac, logp, *latents); both accumulators are updated in place
     like the reference (`+=`, transforms.py:81,131,184,288) and marked dirty."""
@@ -434,7 +545,17 @@ class GlowTransformFn(torch.autograd.Function):
     def forward(ctx, glow, x, ld, lp, *params):
         with_logp = lp is not None
         B, c, H, W = x.shape
-        latents, ld_part, R_ld, lp_part, R_lp, st = forward_train(glow, x, with_logp)
+        tc = _train_chains(glow, x, with_logp)
+        if tc is not None:
+            tc.x.copy_(x)
+            tc.fwd.replay()
+            N.launch_count += tc.n_fwd
+            latents, ld_part, R_ld, lp_part, R_lp, st = tc.fwd_out
+            latents = [t.clone() for t in latents]      # the caller may keep latents across steps
+            tc.claim(ctx)
+        else:
+            latents, ld_part, R_ld, lp_part, R_lp, st = forward_train(glow, x, with_logp)
+        ctx.chains = tc
         dev = x.device
         N.accumulate(ld, ld_part, R_ld, B, glow._slots(dev), glow._multipliers(H, W, dev), glow.L * glow.K)
         dirty = [ld]
@@ -459,6 +580,40 @@ class GlowTransformFn(torch.autograd.Function):
         else:
             g_ld, g_lp, g_lat = gout[0], None, list(gout[1:])
         glow, params = ctx.glow, list(ctx.params)
+        tc = ctx.chains
+        if tc is not None:
+            ent = _bwd_chain(tc, glow, params, g_lat, g_ld, g_lp, ctx.needs_input_grad[1])
+            for s_, g in zip(ent["lat"] + [ent["ld"], ent["lp"]], g_lat + [g_ld, g_lp]):
+                if s_ is not None:
+                    s_.copy_(g)
+            sink = ent["sink"]
+            # a .grad that still IS a view of this chain's flat buffer (zero_grad(set_to_none=False), or accumulation
+            # over several backward calls) would be overwritten by the replay: keep its values and add them back
+            aliased = {id(p) for p in params if p.grad is not None and p.requires_grad and
+                       p.grad.data_ptr() == sink.flat.data_ptr() + 4 * sink.offsets[id(p)][0]}
+            old = sink.flat.clone() if aliased else None
+            ent["graph"].replay()
+            N.launch_count += ent["n"]
+            if old is not None:
+                sink.flat.add_(old)
+            dx = ent["dx"].clone() if ent["dx"] is not None else None
+            tc.release()
+            ctx.stash = None
+            ctx.params = None
+            ctx.chains = None
+            glow._last_grad_flat = sink.flat
+            pg = []
+            for p in params:
+                if not p.requires_grad:
+                    pg.append(None)
+                elif p.grad is None and DIRECT_GRADS:
+                    p.grad = sink.get(p)
+                    pg.append(None)
+                elif id(p) in aliased:
+                    pg.append(None)                        # already accumulated in place above
+                else:
+                    pg.append(sink.get(p).clone())         # autograd accumulates into a .grad held elsewhere
+            return (None, dx, g_ld, g_lp) + tuple(pg)
         sink = GradSink(params)
         hook = getattr(glow, "_grad_hook", None)           # data-parallel all-reduce (normalizing_flow/_dp.py)
         if hook is not None:

@@ -144,6 +144,7 @@ class Glow(Transform):
 
     def _apply(self, fn, *a, **k):
         self._plans = {}
+        self.__dict__.pop("_train_chains", None)      # captured training chains hold the old parameter addresses
         self._logdet_all = None
         self._cmul = {}
         self._drop_graphs()
