@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "tc_sched.h"
 
 namespace nfdpm {
 
@@ -42,12 +43,11 @@ __device__ __forceinline__ void epi_barrier_g() { asm volatile("bar.sync 1, %0;"
 constexpr int TC_ACC_COLS = 256;     // TMEM columns per accumulator stage
 constexpr int TC_CSTAGE_BYTES = 64 * 1024;   // output staging: 128 rows x 256 bf16 / 128 fp32, as 16 KB swizzled boxes
 
-// One unit of work of a CTA: a BM x bn output tile at column n0.  Persistent schedule: every CTA runs the same number of
-// full tiles (tile = blockIdx.x + it * gridDim.x); when the tile count is not a multiple of the grid (512 tiles on 148
-// SMs: 68 CTAs would run a 4th tile while 80 idle for a whole tile time), the REMAINING tiles are split into two
-// half-width tiles each and handed to 2 * rem CTAs (`split` mode: the B tensor-map box is BN/2 rows, a full tile takes
-// two B loads per stage), so the last wave costs half a tile on (almost) every SM instead of a whole tile on some.
-struct TcWork { int m_blk, n0, bn; };
+// persistent tile schedule (tc_sched.h: shared with the host-side unit test)
+__device__ __forceinline__ bool tc_work(int it, int num_tiles, int num_n, int BN, int split, TcWork& w) {
+  return tc_work_for((int)blockIdx.x, (int)gridDim.x, it, num_tiles, num_n, BN, split, w);
+}
+
 // Shared-memory plan chosen by the host (gemm_nt_tc):
 //   classic  n_stages = 3, stage_bytes = 48 KB, the epilogue converts the WHOLE tile into a 64 KB staging buffer (cpw = all
 //            chunks of a warp in one pass) and stores it with one burst of TMA box stores;
@@ -56,26 +56,6 @@ struct TcWork { int m_blk, n0, bn; };
 //            3 stages the MMA warp waited for TMA bytes ~25 % of its loop - two stages in flight while one is consumed is
 //            about one L2 round trip at the MMA rate).
 struct TcPlan { int n_stages, stage_bytes, cstage_bytes, cpw; };
-__device__ __forceinline__ bool tc_work(int it, int num_tiles, int num_n, int BN, int split, TcWork& w) {
-  const int G = gridDim.x;
-  int tile = blockIdx.x + it * G, half = -1;
-  if (split) {
-    const int full_per = num_tiles / G;
-    if (it > full_per) return false;
-    if (it == full_per) {
-      const int rem = num_tiles - full_per * G;
-      if ((int)blockIdx.x >= 2 * rem) return false;
-      tile = full_per * G + (blockIdx.x >> 1);
-      half = blockIdx.x & 1;
-    }
-  }
-  if (tile >= num_tiles) return false;
-  w.m_blk = tile / num_n;
-  const int n_blk = tile - w.m_blk * num_n;
-  w.n0 = n_blk * BN + (half > 0 ? (BN >> 1) : 0);
-  w.bn = half >= 0 ? (BN >> 1) : BN;
-  return true;
-}
 
 // profiling hook (nfdpm_gemm_debug): per-CTA cycle counters [grid][16] int64; NULL = off
 __device__ long long* g_tc_dbg = nullptr;
@@ -444,9 +424,7 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
     const char* e = getenv("NFDPM_TC_SPLIT");
     split_on = (e && atoi(e) == 0) ? 0 : 1;
   }
-  const int rem = tiles % grid;
-  const int split = (split_on && tiles > grid && rem > 0 && 2 * rem <= grid && BN % 128 == 0 && N % BN == 0 &&
-                     epilogue != NFDPM_EPI_RELU_BWD) ? 1 : 0;
+  const int split = (split_on && tc_split_ok(tiles, grid, BN, N) && epilogue != NFDPM_EPI_RELU_BWD) ? 1 : 0;
   CUtensorMap tmA, tmB, tmD;
   if (make_map(&tmA, A, M, K, lda, TC_BM)) return 1;
   if (make_map(&tmB, Bw, N, K, ldb, split ? BN / 2 : BN)) return 1;
