@@ -39,3 +39,11 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _optional_captured_training_chains(monkeypatch):
+    """NFDPM_TEST_TRAIN_GRAPHS=1 runs EVERY test with the opt-in captured training chains (NFDPM_TRAIN_GRAPHS=1,
+    normalizing_flow/_train.py) — the switch for promoting them to the default: the whole parity suite must stay green."""
+    if os.environ.get("NFDPM_TEST_TRAIN_GRAPHS", "0") == "1":
+        monkeypatch.setenv("NFDPM_TRAIN_GRAPHS", "1")
