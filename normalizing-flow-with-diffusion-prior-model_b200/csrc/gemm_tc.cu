@@ -2,18 +2,21 @@
 //   A  [M,K] bf16 row-major (pixel-major activations), Bw [N,K] bf16 row-major (packed conv weights),
 //   fp32 accumulation in tensor memory, output bf16 or fp32.
 //
-// Persistent, warp-specialised CTA (one per SM, 320 threads):
+// Persistent, warp-specialised CTA (one per SM, 64 + 32 * TCG_EPI_WARPS = 576 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A box and a BNx64 B box (128B swizzle)
-//               into a 3-stage shared-memory ring, completion on mbarriers
+//               into a shared-memory ring (TcPlan: 3 x 48 KB stages, or as many 16 KB + BN x 128 B stages as fit - 4 at
+//               BN = 256 - for multi-tile K >= 256 shapes), completion on mbarriers
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage,
 //               tcgen05.commit releases the smem stage / publishes the accumulator; also owns TMEM alloc/dealloc
-//   warps 2..9  epilogue: software-pipelined tcgen05.ld (32x32b.x16) of the accumulator quadrant, fused
-//               ActNorm+ReLU as one FMA + max per element (utils.py:69,84-87), convert, conflict-free 16-byte
-//               stores into a 128B-swizzled staging tile, then ONE thread issues cp.async.bulk.tensor stores
-//               (full 128-byte lines; r1 profile: per-thread row-strided global stores capped output at 2.3 TB/s).
+//   warps 2..17 epilogue (four per TMEM lane quadrant): software-pipelined tcgen05.ld (32x32b.x16) of the accumulator
+//               quadrant, fused ActNorm+ReLU as one FMA + max per element (utils.py:69,84-87), convert, conflict-free
+//               16-byte stores into a 128B-swizzled staging buffer, then ONE thread issues cp.async.bulk.tensor stores
+//               (full 128-byte lines; r1 profile: per-thread row-strided global stores capped output at 2.3 TB/s).  The
+//               staging buffer holds the whole tile (classic plan) or one 64-column pass (deep plan).
 //               Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the main loop of
 //               tile i+1.  (r1 profile: with 4 epilogue warps and scalar parameter loads the kernel was
 //               issue-bound in the epilogue at 30% tensor-pipe activity.)
+// Tiles are scheduled by tc_sched.h (persistent stride + half-width tiles in the last round when that balances it).
 // BN (<= 256, multiple of 16) is a runtime value: it only enters through the B tensor map box, the expected
 // transaction bytes and the instruction descriptor.
 //
