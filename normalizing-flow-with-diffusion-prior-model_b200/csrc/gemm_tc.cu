@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;                               // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;                     // which of the TCG_EPQ warps of the quadrant
     int acc = 0;
