@@ -499,7 +499,9 @@ def _train_chains(glow, x: Tensor, with_logp: bool) -> Optional["_TrainChains"]:
     key = (tuple(x.shape), with_logp, E.precision(), x.device.index)
     tc = store.get(key)
     if tc is not None and tc.epoch != E.alloc_epoch:  # a cache was re-allocated: the captured addresses are stale
-        E.WS.drop_scope(tc.scope)
+        E.WS.drop_scope(tc.scope + ("fwd",))
+        for i in range(len(tc.bwd)):
+            E.WS.drop_scope(tc.scope + ("bwd", i))
         tc = None
     if tc is None:
         tc = _TrainChains()
