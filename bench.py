@@ -34,7 +34,7 @@ for p in (ROOT, PKG):
 
 CFG = dict(in_channel=3, L=3, K=16, S=32, batch=128)          # BASELINE.json configs[1]
 WORKLOAD = "Glow L3 K16, CIFAR-10 shape 3x32x32, batch 128 per GPU, fwd+logdet+logp then inverse"
-METRIC = "Glow L3/K16 32x32 fwd+logdet & inverse imgs/sec"
+METRIC = "Glow L3/K16 32\u00d732 fwd+logdet & inverse imgs/sec"      # BASELINE.json's metric (its leading clause)
 FLOP_PER_IMG_FWD = 4.0119e9                                   # SURVEY.md §8 (verified with torch flop counter)
 
 
