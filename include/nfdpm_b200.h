@@ -15,7 +15,8 @@
  *   - flow tensors are NCHW fp32 ("[B,C,P]" below, P = H*W) with an explicit batch stride so
  *     channel halves of a wider tensor can be read/written in place (chunk/concat without copies);
  *   - coupling-network activations are pixel-major rows "[M,ld]" (M = B*P, channel fastest),
- *     fp32 (NFDPM_F32, exact CUDA-core path) or bf16 (NFDPM_BF16, tcgen05 tensor-core path);
+ *     fp32 (NFDPM_F32, exact CUDA-core path), bf16 (NFDPM_BF16, tcgen05 tensor-core path) or split bf16 pairs
+ *     (NFDPM_BF16X2, tcgen05 path with fp32-faithful products);
  *   - no CPU fallback exists anywhere in the library.
  */
 #ifndef NFDPM_B200_H_
@@ -34,11 +35,17 @@ extern "C" {
 #define NFDPM_F32 0
 #define NFDPM_F64 1
 #define NFDPM_BF16 2
+/* Split bf16 pairs, the operand format of the fp32-faithful tensor-core mode: a logical value v is stored as
+ * hi = bf16(v) and lo = bf16(v - hi) (v = hi + lo to 2^-17 relative).  A row of ld logical columns (ld % 32 == 0)
+ * occupies 2*ld bf16 = 4*ld bytes; group g = k/32 owns 64 consecutive bf16: [hi(32g .. 32g+31) | lo(32g .. 32g+31)].
+ * The GEMM kernels compute A*B as Ahi*Bhi + Alo*Bhi + Ahi*Blo with fp32 accumulation in tensor memory (three
+ * tcgen05.mma per K slice), which reproduces the reference's fp32 convolutions (utils.py:36,64, transforms.py:266)
+ * to ~1e-6 relative instead of bf16's ~2e-3.  Sizes / leading dimensions of such matrices count LOGICAL elements. */
+#define NFDPM_BF16X2 3
 
 /* GEMM epilogues */
 #define NFDPM_EPI_RAW 0          /* D = acc                                   */
 #define NFDPM_EPI_ACTNORM_RELU 1 /* D = max(0, exp(scale[n]) * (acc + bias[n])) (utils.py:69,84-87) */
-#define NFDPM_EPI_RELU_BWD 2     /* D = acc * (h > 0) * exp(scale[n]) + column partials (nfdpm_gemm_nt_relu_bwd) */
 
 typedef void* nfdpm_stream_t; /* cudaStream_t */
 
@@ -123,23 +130,13 @@ int nfdpm_pack_elems(void);
 int nfdpm_pack_batch(const int64_t* jobs_dev, int n_jobs, int n_blocks, nfdpm_stream_t stream);
 
 /* D[M,N] = epilogue(A[M,K] * Bw[N,K]^T).  A, Bw: in_dtype (NFDPM_F32 -> CUDA-core fp32 kernel,
- * NFDPM_BF16 -> tcgen05/TMEM kernel, fp32 accumulate); D: out_dtype (F32 or BF16).  K must be a multiple
- * of 16 (F32) / 64 (BF16) and lda, ldb, ldd multiples of 8.  Replaces nn.Conv2d.forward at
+ * NFDPM_BF16 / NFDPM_BF16X2 -> tcgen05/TMEM kernel, fp32 accumulate); D: out_dtype (F32, BF16, or BF16X2 from
+ * BF16X2 operands).  K must be a multiple of 16 (F32) / 64 (BF16) / 32 (BF16X2, with lda, ldb, ldd % 32 == 0) and
+ * lda, ldb, ldd multiples of 8.  Replaces nn.Conv2d.forward at
  * utils.py:69 (x2) and ZeroConv2d's conv at utils.py:44, transforms.py:266. */
 int nfdpm_gemm_nt(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N,
                   int K, int in_dtype, int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias,
                   nfdpm_stream_t stream);
-
-/* Fused coupling network on tcgen05 (bf16 operands, fp32 TMEM accumulation): the three convolutions of
- * utils.py:83-89 in ONE kernel per 128-row tile; h1/h2 stay in shared memory, only a1 is read and pm written.
- *   a1 [M,lda1] bf16 im2col rows (K1p = padded 9*C/2, multiple of 64, <= 512); w1 [512,K1p], w2 [512,512],
- *   w3 [ldp,512] bf16 (nfdpm_pack_matrix layouts); pm [M,ldp] fp32, ldp = 9C rounded up to 16, <= 512;
- *   ep [4][512] fp32 = exp(s1), exp(s1)*b1, exp(s2), exp(s2)*b2 of the two inner ActNorms (nfdpm_fold_actnorm).
- * Equivalent to three nfdpm_gemm_nt calls (ACTNORM_RELU, ACTNORM_RELU, RAW). */
-int nfdpm_coupling_fused(const void* a1, int64_t lda1, const void* w1, const void* w2, const void* w3, float* pm,
-                         int64_t ldp, int M, int K1p, const float* ep, nfdpm_stream_t stream);
-/* e_out[i] = exp(scale[i]), eb_out[i] = exp(scale[i])*bias[i]  (ActNorm folded to one FMA: y = e*x + e*b). */
-int nfdpm_fold_actnorm(const float* scale, const float* bias, float* e_out, float* eb_out, int n, nfdpm_stream_t stream);
 
 /* Affine-coupling epilogue (transforms.py:179-184 forward, :196-200 inverse).
  *   pm   [M, ldp]: taps-as-N output of the ZeroConv GEMM (column = tap*C + co, tap = ky*3+kx)
@@ -198,47 +195,20 @@ int nfdpm_flow_boundary_stash(const float* in, int64_t in_bs, int squeeze_in, co
 /* ZeroConv GEMM + step boundary in ONE launch (tensor-core mode): pm = h2[M,K] * w3p[ldp,K]^T is accumulated in tensor
  * memory, staged in shared memory and consumed by the arithmetic of nfdpm_flow_boundary (coupling source), so the
  * taps-as-N rows never reach L2/HBM.  Same reference lines as nfdpm_gemm_nt (utils.py:44) + nfdpm_flow_boundary.
- * h2, w3p bf16; CTAs own whole images: needs H*W == 256 or H*W dividing 128, ldp <= 512 (nfdpm_gemm3_boundary_ok).
+ * h2, w3p: h_dtype = NFDPM_BF16 or NFDPM_BF16X2 (K, ldh count logical columns); CTAs own whole images: needs H*W == 256 or
+ * H*W dividing 128, ldp <= 512 (nfdpm_gemm3_boundary_ok, whose K counts bf16 columns: 2 x logical K for split pairs).
  * pm_out (optional, fp32 [M, ld_pm_out]): copy of pm for the training stash; xs: pre-mix stash as in ..._stash. */
 int nfdpm_gemm3_boundary_ok(int B, int C, int H, int W, int K, int64_t ldp);
-int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p, float* pm_out, int64_t ld_pm_out, const float* in,
+int nfdpm_gemm3_boundary(const void* h2, int h_dtype, int64_t ldh, const void* w3p, float* pm_out, int64_t ld_pm_out, const float* in,
                          int64_t in_bs, const float* bias3, const float* logs3, float* ld_part, const float* mt,
                          const float* beta, float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype,
                          int64_t lda1, int B, int C, int H, int W, int K, int64_t ldp, int inverse,
                          nfdpm_stream_t stream);
 
-/* nfdpm_flow_boundary_stash + the FIRST GEMM of the next coupling network in one launch (tensor-core mode): the im2col rows
- * of the new state are built in shared memory as the tcgen05 A operand and h1 = relu(actnorm(A1 * w1p^T)) [B*H*W, F] (bf16)
- * is written instead of (a1 == NULL) or in addition to (a1 != NULL, bf16 [B*H*W, K1p]: training stash) the im2col rows.
- * Replaces nfdpm_flow_boundary + nfdpm_gemm_nt(EPI_ACTNORM_RELU) (transforms.py:169 via utils.py:47-69).  One CTA per image;
- * needs F == 512, K1p a multiple of 64 (<= 512), H*W == 256 or H*W <= 128 with H*W % 8 == 0 (nfdpm_boundary_gemm1_ok). */
-int nfdpm_boundary_gemm1_ok(int C, int H, int W, int F, int64_t K1p);
-int nfdpm_boundary_gemm1(const float* in, int64_t in_bs, int squeeze_in, const float* pm, int64_t ldp, const float* bias3,
-                         const float* logs3, float* ld_part, const float* mt, const float* beta, float* y, int64_t y_bs,
-                         float* xs, int64_t xs_bs, void* a1, const void* w1p, const float* s1, const float* b1, void* h1,
-                         int B, int C, int H, int W, int F, int64_t K1p, int inverse, nfdpm_stream_t stream);
-
-/* One StepFlow of a deep level in ONE launch (tensor-core mode, H*W <= 64 dividing 128): GEMM1 -> ActNorm/ReLU -> GEMM2 ->
- * ActNorm/ReLU -> GEMM3 -> step boundary.  A thread-block cluster of min(8, 128/(H*W)) CTAs owns one 128-row tile, splits
- * every GEMM along N and hands the h1 / h2 / pm rows from CTA to CTA through distributed shared memory (no L2 round trip).
- * Replaces 3 x nfdpm_gemm_nt (transforms.py:169-175 via utils.py:44) + nfdpm_flow_boundary (transforms.py:179-184 /
- * :196-200 and the neighbouring ActNorm + 1x1 conv, :80,132 / :144,93).
- * a1_in bf16 [M,K1p] im2col rows; w1p [F,K1p], w2p [F,F], w3p [ldp,F] packed bf16 weights; s1,b1,s2,b2 the inner ActNorm
- * parameters; h1,h2 (bf16 [M,F]) and pm (fp32 [M,ld_pm]) are OPTIONAL global copies of the intermediates (the training
- * stash; NULL = not written).  The remaining arguments are those of nfdpm_flow_boundary_stash (+ inverse).
- * nfdpm_deep_step_debug: profiling hook, per-CTA timeline into a device int64 [grid][16] buffer (NULL = off). */
-int nfdpm_deep_step_debug(void* timeline);
 /* profiling hook: per-CTA wait/work cycle counters of the tcgen05 GEMM kernel (device int64 [grid][16], NULL = off) */
 int nfdpm_gemm_debug(void* counters);
 /* profiling hook: per-image phase timeline of nfdpm_flow_boundary (device int64 [B][16], NULL = off) */
 int nfdpm_flow_boundary_debug(void* timeline);
-int nfdpm_deep_step_ok(int B, int C, int H, int W, int F, int64_t K1p, int64_t ldp);
-int nfdpm_deep_step(const void* a1_in, const void* w1p, const void* w2p, const void* w3p, const float* s1, const float* b1,
-                    const float* s2, const float* b2, void* h1, void* h2, float* pm, int64_t ld_pm, const float* in,
-                    int64_t in_bs, const float* bias3, const float* logs3, float* ld_part, const float* mt,
-                    const float* beta, float* y, int64_t y_bs, float* xs, int64_t xs_bs, void* a1, int a1_dtype,
-                    int64_t lda1, int B, int C, int H, int W, int F, int64_t K1p, int64_t ldp, int inverse,
-                    nfdpm_stream_t stream);
 
 /* Layout converters for stand-alone ZeroConv2d / Conv2dActNorm module calls (normalizing_flow/utils.py:43-44, :68-69).
  *   rows_to_nchw: out[b,n,p] = f(h[(b*P+p)*ldh + n]); mode 0: identity; 1: (v+p1[n])*exp(3*p2[n]) (ZeroConv2d gain);
@@ -270,11 +240,6 @@ int nfdpm_coupling_bwd_tiles(int C, int H, int W);
 int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
                            const float* scale, void* dpre, int o_dtype, int64_t ld_o, float* part, int M, int N,
                            int rows_per_cta, nfdpm_stream_t stream);
-/* dgrad GEMM with the ActNorm+ReLU backward fused into the tcgen05 epilogue (bf16 operands and output):
- * dpre = (A * Bw^T) * (h > 0) * exp(scale[n]); part [ceil(M/128)][2N] per-tile column sums -> d(scale), d(bias).
- * Equivalent to nfdpm_gemm_nt (RAW) + nfdpm_actnorm_relu_bwd without the [M,N] round trip of dh. */
-int nfdpm_gemm_nt_relu_bwd(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* dpre, int64_t ldd, int M, int N,
-                           int K, const void* h, int64_t ldh, const float* scale, float* part, nfdpm_stream_t stream);
 /* out[i] (+)= sum_{r<R} part[r*stride + i], i < n */
 int nfdpm_reduce_rows(const float* part, float* out, int R, int n, int64_t stride, int accumulate, nfdpm_stream_t stream);
 /* out0[i] = sum_r part[r*stride + i] for i < n0, out1[i-n0] likewise for n0 <= i < n0+n1 (a parameter pair in one launch) */

@@ -32,20 +32,35 @@ static inline void boundary_fill_div(BoundaryArgs& a) {
 // profiling hook of this translation unit (nfdpm_flow_boundary_debug): per-CTA phase timeline [B][16] int64, NULL = off
 static __device__ long long* g_bd_dbg = nullptr;
 
-template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
-template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+// eight consecutive columns k0..k0+7 (k0 % 8 == 0) of row `row` of the im2col sink [rows, ld] (ld counts logical columns)
+template <typename T> __device__ __forceinline__ void store8(T* base, int64_t row, int64_t ld, int k0, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* base, int64_t row, int64_t ld, int k0, const float (&v)[8]) {
+  float* p = base + row * ld + k0;
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* base, int64_t row, int64_t ld, int k0,
+                                                                  const float (&v)[8]) {
   uint32_t w[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     w[i] = *reinterpret_cast<uint32_t*>(&t);
   }
-  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(base + row * ld + k0) = make_uint4(w[0], w[1], w[2], w[3]);
 }
+template <> __device__ __forceinline__ void store8<bf16x2_t>(bf16x2_t* base, int64_t row, int64_t ld, int k0,
+                                                             const float (&v)[8]) {
+  split_store8(reinterpret_cast<__nv_bfloat16*>(base) + 2 * row * ld, k0, v);
+}
+
+// host: run `GO(type)` with the element type of an im2col sink of dtype code `dt` (NFDPM_F32 when there is no sink)
+#define NFDPM_A1_DISPATCH(dt, GO)                    \
+  do {                                               \
+    if ((dt) == NFDPM_BF16) { GO(__nv_bfloat16); }   \
+    else if ((dt) == NFDPM_BF16X2) { GO(bf16x2_t); } \
+    else { GO(float); }                              \
+  } while (0)
 
 
 // Shared-memory scratch of the body in floats (nfdpm_flow_boundary_smem() returns it in bytes):
@@ -70,13 +85,10 @@ __host__ __device__ __forceinline__ size_t boundary_scratch_floats(int C, int H,
 // PM_SMEM: the taps-as-N rows of image b are (or will be: pm_bar) in shared memory at `pm_img` (row stride `pm_ld` floats)
 // instead of a.pm in global memory; pm_bar != 0: shared-memory address of an mbarrier (phase 0) that completes when a bulk
 // copy has landed them (flow_boundary.cu).
-// a1_tile (bf16 only): ALSO write the im2col rows of the image as the A operand of a tcgen05 GEMM into shared memory — 16 KB
-// boxes [128 rows][64 columns] in the K-major SWIZZLE_128B layout, box (p / 128) * (lda1 / 64) + k / 64, 16-byte unit u of row
-// r at r*128 + ((u ^ (r & 7)) << 4) — for the boundary + GEMM1 kernel (boundary_gemm1.cu); a.a1 may then be NULL.
 template <bool COUPLING, typename A1T, bool PM_SMEM = false>
 __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const int b, float* sm, const int tid, const int nt,
                                                    const float* pm_img = nullptr, const int pm_ld = 0,
-                                                   uint8_t* a1_tile = nullptr, const uint32_t pm_bar = 0) {
+                                                   const uint32_t pm_bar = 0) {
   const int C = a.C, H = a.H, W = a.W, P = H * W, Ch = C >> 1;
   long long* const dbg = g_bd_dbg;
   auto stamp = [&](int slot) {
@@ -87,7 +99,7 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
   const int Cp = (C + 3) & ~3;
   const int W2p = W + 2, PP = (H + 2) * W2p;  // zero-bordered image of one channel
   const bool mix = a.mt != nullptr;
-  const bool want_a1 = a.a1 != nullptr || a1_tile != nullptr;
+  const bool want_a1 = a.a1 != nullptr;
   size_t pad_off, kt_off;
   boundary_scratch_floats(C, H, W, COUPLING, mix, &pad_off, &kt_off);
   float* x_s = sm;                            // [C][PS]  source / coupling result
@@ -309,7 +321,7 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
   if (want_a1) {
     const int K = Ch * 9;
     const int n_g = (int)(a.lda1 >> 3);
-    A1T* a1b = reinterpret_cast<A1T*>(a.a1) + (int64_t)b * P * a.lda1;
+    A1T* a1b = reinterpret_cast<A1T*>(a.a1);
     for (int it = tid; it < P * n_g; it += nt) {
       const int p = fdiv(it, a.dNg), g = it - p * n_g;
       const int py = fdiv(p, a.dW), px = p - py * W;
@@ -320,12 +332,7 @@ __device__ __forceinline__ void flow_boundary_body(const BoundaryArgs& a, const 
         const int k = g * 8 + e;
         v[e] = (k < K) ? win[kt_s[k]] : 0.f;
       }
-      if (a.a1 != nullptr) store8<A1T>(a1b + (int64_t)p * a.lda1 + g * 8, v);
-      if (a1_tile != nullptr) {
-        const int r = p & 127;
-        uint8_t* box = a1_tile + (size_t)((p >> 7) * (n_g >> 3) + (g >> 3)) * 16384 + r * 128 + (((g & 7) ^ (r & 7)) << 4);
-        store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(box), v);
-      }
+      store8<A1T>(a1b, (int64_t)b * P + p, a.lda1, g * 8, v);
     }
   }
   stamp(7);

@@ -56,6 +56,46 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---------------------------------------------------------------- split bf16 pairs (NFDPM_BF16X2)
+// A logical fp32 value v is carried as hi = bf16(v), lo = bf16(v - hi): v = hi + lo up to 2^-17 |v|.  A row of K logical
+// columns (K % 32 == 0) occupies 2K bf16: the group g = k / 32 owns 64 consecutive bf16, [hi(32g..32g+31) | lo(32g..32g+31)],
+// i.e. one 128-byte swizzle row of a TMA box holds both planes of 32 logical columns and the four K=16 UMMA slices of a
+// [rows][64] operand tile are hi(0..15), hi(16..31), lo(0..15), lo(16..31).  The tensor-core kernels then form
+// A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo (three tcgen05.mma per slice pair into ONE fp32 TMEM accumulator): the dropped
+// lo*lo term and the rounding of lo are both <= 2^-17 relative, against 2^-9 for plain bf16 operands.
+struct __align__(4) bf16x2_t { __nv_bfloat16 hi, lo; };          // storage unit: 4 bytes per logical element
+__host__ __device__ __forceinline__ int64_t split_col(int64_t k) { return ((k >> 5) << 6) + (k & 31); }   // bf16 index of hi(k); lo(k) is +32
+__device__ __forceinline__ void split_pair(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// eight consecutive logical columns k0..k0+7 (k0 % 8 == 0) of the split row starting at `row` (bf16 units): two 16-byte stores
+__device__ __forceinline__ void split_store8(__nv_bfloat16* row, int64_t k0, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 th = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 back = __bfloat1622float2(th);
+    __nv_bfloat162 tl = __floats2bfloat162_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+    h[i] = *reinterpret_cast<uint32_t*>(&th);
+    l[i] = *reinterpret_cast<uint32_t*>(&tl);
+  }
+  __nv_bfloat16* p = row + split_col(k0);
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(p + 32) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// element (r, k) of a row-major [rows, ld] matrix of fp32 / bf16 / split pairs (ld counts LOGICAL columns)
+template <typename T> __device__ __forceinline__ void put_rc(T* out, int64_t r, int64_t ld, int64_t k, float v);
+template <> __device__ __forceinline__ void put_rc<float>(float* out, int64_t r, int64_t ld, int64_t k, float v) { out[r * ld + k] = v; }
+template <> __device__ __forceinline__ void put_rc<__nv_bfloat16>(__nv_bfloat16* out, int64_t r, int64_t ld, int64_t k, float v) {
+  out[r * ld + k] = __float2bfloat16_rn(v);
+}
+template <> __device__ __forceinline__ void put_rc<bf16x2_t>(bf16x2_t* out, int64_t r, int64_t ld, int64_t k, float v) {
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(out) + 2 * r * ld + split_col(k);
+  split_pair(v, p[0], p[32]);
+}
+
 // streaming 128-bit access: read-once / write-once tensors should not pollute L1
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;

@@ -11,9 +11,6 @@ namespace nfdpm {
 
 constexpr int TPB = 256;  // pixels per CTA in the per-pixel kernels (must match nfdpm_ld_tiles)
 
-template <typename T> __device__ __forceinline__ T cvt_out(float v);
-template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
-template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // One thread per (pixel m, input channel c): writes the 9 taps of that channel, columns c*9 .. c*9+8.
 // Threads of a warp share c and walk consecutive pixels => coalesced NCHW reads.  Pad columns are zeroed
@@ -31,7 +28,6 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, T* __restrict__ ou
     const int p = (int)(m - b * P);
     const int py = p / W, px = p - py * W;
     const float* xc = x + b * xbs + (int64_t)c * P;
-    T* o = out + m * ld + c * 9;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = py + ky - 1;
@@ -40,11 +36,11 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, T* __restrict__ ou
         const int xx = px + kx - 1;
         float v = 0.f;
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(xc + yy * W + xx);
-        o[ky * 3 + kx] = cvt_out<T>(v);
+        put_rc<T>(out, m, ld, c * 9 + ky * 3 + kx, v);
       }
     }
     if (c == Cin - 1)
-      for (int k = K; k < ld; ++k) out[m * ld + k] = cvt_out<T>(0.f);
+      for (int k = K; k < ld; ++k) put_rc<T>(out, m, ld, k, 0.f);
   }
 }
 
@@ -60,7 +56,7 @@ __global__ void pack_matrix_kernel(const float* __restrict__ in, T* __restrict__
       const int a = (int)(r / nb), b = (int)(r - (int64_t)a * nb);
       v = __ldg(in + a * sa + b * sb + k * sk);
     }
-    out[i] = cvt_out<T>(v);
+    put_rc<T>(out, r, ld, k, v);
   }
 }
 
@@ -115,6 +111,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const int64_t* __restri
     if (r < rows_out && k < ld) {
       const float v = tile[rr][cc];
       if (dtype == NFDPM_F32) reinterpret_cast<float*>(j[1])[r * ld + k] = v;
+      else if (dtype == NFDPM_BF16X2) put_rc<bf16x2_t>(reinterpret_cast<bf16x2_t*>(j[1]), r, ld, k, v);
       else reinterpret_cast<__nv_bfloat16*>(j[1])[r * ld + k] = __float2bfloat16_rn(v);
     }
   }
@@ -305,7 +302,7 @@ __global__ void nchw_to_rows_kernel(const float* __restrict__ x, T* __restrict__
     const int64_t m = i / ld;
     const int64_t b = m / P;
     const int p = (int)(m - b * P);
-    out[i] = cvt_out<T>(c < Cc ? x[b * xbs + (int64_t)c * P + p] : 0.f);
+    put_rc<T>(out, m, ld, c, c < Cc ? x[b * xbs + (int64_t)c * P + p] : 0.f);
   }
 }
 
@@ -332,6 +329,8 @@ extern "C" int nfdpm_im2col3x3(const float* x, void* out, int out_dtype, int B, 
     im2col3x3_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(x, (float*)out, Cin, H, W, M, xbs, ld);
   else if (out_dtype == NFDPM_BF16)
     im2col3x3_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)out, Cin, H, W, M, xbs, ld);
+  else if (out_dtype == NFDPM_BF16X2 && ld % 32 == 0)
+    im2col3x3_kernel<bf16x2_t><<<grid, 256, 0, as_stream(stream)>>>(x, (bf16x2_t*)out, Cin, H, W, M, xbs, ld);
   else
     return fail("nfdpm_im2col3x3: out_dtype %d unsupported", out_dtype);
   NFDPM_CHECK_LAUNCH("im2col3x3_kernel");
@@ -347,6 +346,8 @@ extern "C" int nfdpm_pack_matrix(const float* in, void* out, int out_dtype, int 
     pack_matrix_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in, (float*)out, na, nb, nk, sa, sb, sk, ld, rows_out);
   else if (out_dtype == NFDPM_BF16)
     pack_matrix_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(in, (__nv_bfloat16*)out, na, nb, nk, sa, sb, sk, ld, rows_out);
+  else if (out_dtype == NFDPM_BF16X2 && ld % 32 == 0)
+    pack_matrix_kernel<bf16x2_t><<<grid, 256, 0, as_stream(stream)>>>(in, (bf16x2_t*)out, na, nb, nk, sa, sb, sk, ld, rows_out);
   else
     return fail("nfdpm_pack_matrix: out_dtype %d unsupported", out_dtype);
   NFDPM_CHECK_LAUNCH("pack_matrix_kernel");

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(1024) flow_boundary_kernel(const BoundaryArgs 
         bulk_load(smem_u32(sm) + (uint32_t)off, src + off, len, bar);
       }
     }
-    flow_boundary_body<COUPLING, A1T, true>(a, blockIdx.x, sm + n, threadIdx.x, blockDim.x, sm, (int)a.ldp, nullptr,
+    flow_boundary_body<COUPLING, A1T, true>(a, blockIdx.x, sm + n, threadIdx.x, blockDim.x, sm, (int)a.ldp,
                                             smem_u32(&pm_bar));
   } else {
     flow_boundary_body<COUPLING, A1T, false>(a, blockIdx.x, sm, threadIdx.x, blockDim.x);
@@ -74,7 +74,7 @@ static int flow_boundary_impl(const float* in, int64_t in_bs, int squeeze_in, co
   NFDPM_REQUIRE(pm == nullptr || (bias3 && logs3 && ldp >= 9 * (int64_t)C), "nfdpm_flow_boundary: coupling source needs bias3/logs3/ldp");
   NFDPM_REQUIRE(!squeeze_in || (C % 4 == 0 && in_bs % 2 == 0 && ((uintptr_t)in % 8) == 0), "nfdpm_flow_boundary: squeeze source needs C %% 4 == 0 and 8-byte alignment");
   NFDPM_REQUIRE(a1 == nullptr || (lda1 % 8 == 0 && lda1 >= 9 * (int64_t)(C / 2) && ((uintptr_t)a1 % 16) == 0), "nfdpm_flow_boundary: bad im2col sink");
-  NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16, "nfdpm_flow_boundary: bad a1 dtype");
+  NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16 || (a1_dtype == NFDPM_BF16X2 && lda1 % 32 == 0), "nfdpm_flow_boundary: bad a1 dtype");
   NFDPM_REQUIRE(y != nullptr || a1 != nullptr || xs != nullptr, "nfdpm_flow_boundary: no sink");
   size_t smem = nfdpm_flow_boundary_smem(C, H, W, pm != nullptr, mt != nullptr);
   NFDPM_REQUIRE(smem <= 200 * 1024, "nfdpm_flow_boundary: image too large for the fused path (%zu bytes of shared memory); "
@@ -85,7 +85,7 @@ static int flow_boundary_impl(const float* in, int64_t in_bs, int squeeze_in, co
   a.B = B; a.C = C; a.H = H; a.W = W; a.squeeze_in = squeeze_in; a.inverse = inverse;
   boundary_fill_div(a);
   cudaStream_t st = as_stream(stream);
-  const bool bf = (a1 != nullptr && a1_dtype == NFDPM_BF16);
+  const int a1dt = a1 != nullptr ? a1_dtype : NFDPM_F32;
   // one CTA per image: give it as many warps as its largest phase has work items (latency hiding), up to 1024 threads
   int64_t items = (int64_t)H * W * (C / 2);
   if (a1 != nullptr && (int64_t)H * W * (lda1 / 8) > items) items = (int64_t)H * W * (lda1 / 8);
@@ -106,10 +106,15 @@ static int flow_boundary_impl(const float* in, int64_t in_bs, int squeeze_in, co
     }                                                                                                              \
     NFDPM_CUDA(launch_pdl(flow_boundary_kernel<CP, T, BK>, dim3(B), dim3(threads), smem, st, a));                  \
   } while (0)
-  if (pm != nullptr) {
-    if (bulk) { if (bf) LAUNCH(true, __nv_bfloat16, true); else LAUNCH(true, float, true); }
-    else { if (bf) LAUNCH(true, __nv_bfloat16, false); else LAUNCH(true, float, false); }
-  } else { if (bf) LAUNCH(false, __nv_bfloat16, false); else LAUNCH(false, float, false); }
+#define GO_BULK(T) LAUNCH(true, T, true)
+#define GO_CP(T) LAUNCH(true, T, false)
+#define GO_NC(T) LAUNCH(false, T, false)
+  if (pm != nullptr && bulk) NFDPM_A1_DISPATCH(a1dt, GO_BULK);
+  else if (pm != nullptr) NFDPM_A1_DISPATCH(a1dt, GO_CP);
+  else NFDPM_A1_DISPATCH(a1dt, GO_NC);
+#undef GO_BULK
+#undef GO_CP
+#undef GO_NC
 #undef LAUNCH
   NFDPM_CHECK_LAUNCH("flow_boundary_kernel");
   return 0;

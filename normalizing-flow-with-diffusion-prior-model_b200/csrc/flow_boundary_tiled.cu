@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(1024) flow_boundary_tiled_kernel(const Boundar
     __syncthreads();
     const int K = Ch * 9;
     const int n_g = (int)(a.lda1 >> 3);
-    A1T* a1b = reinterpret_cast<A1T*>(a.a1) + (int64_t)b * P * a.lda1;
+    A1T* a1b = reinterpret_cast<A1T*>(a.a1);
     for (int it = tid; it < R * W * n_g; it += nt) {
       const int po = fdiv(it, a.dNg), gg = it - po * n_g;
       const int vo = fdiv(po, a.dW), px = po - vo * W, py = r0 + vo;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(1024) flow_boundary_tiled_kernel(const Boundar
         const int k = gg * 8 + e;
         vv[e] = (k < K) ? win[kt_s[k]] : 0.f;
       }
-      store8<A1T>(a1b + (int64_t)(py * W + px) * a.lda1 + gg * 8, vv);
+      store8<A1T>(a1b, (int64_t)b * P + py * W + px, a.lda1, gg * 8, vv);
     }
   }
 }
@@ -281,7 +281,7 @@ extern "C" int nfdpm_flow_boundary_tiled(const float* in, int64_t in_bs, int squ
   NFDPM_REQUIRE(pm == nullptr || (bias3 && logs3 && ldp >= 9 * (int64_t)C), "nfdpm_flow_boundary_tiled: coupling source needs bias3/logs3/ldp");
   NFDPM_REQUIRE(!squeeze_in || (C % 4 == 0 && in_bs % 2 == 0 && ((uintptr_t)in % 8) == 0), "nfdpm_flow_boundary_tiled: squeeze source needs C %% 4 == 0 and 8-byte alignment");
   NFDPM_REQUIRE(a1 == nullptr || (lda1 % 8 == 0 && lda1 >= 9 * (int64_t)(C / 2) && ((uintptr_t)a1 % 16) == 0), "nfdpm_flow_boundary_tiled: bad im2col sink");
-  NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16, "nfdpm_flow_boundary_tiled: bad a1 dtype");
+  NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16 || (a1_dtype == NFDPM_BF16X2 && lda1 % 32 == 0), "nfdpm_flow_boundary_tiled: bad a1 dtype");
   NFDPM_REQUIRE(y != nullptr || a1 != nullptr || xs != nullptr, "nfdpm_flow_boundary_tiled: no sink");
   NFDPM_REQUIRE((int64_t)B * C * H * W < (1ll << 31), "nfdpm_flow_boundary_tiled: tensor too large for 32-bit indices");
   const int want = nfdpm_flow_boundary_tiles(B, C, H, W, pm != nullptr, mt != nullptr, a1 != nullptr);
@@ -305,7 +305,7 @@ extern "C" int nfdpm_flow_boundary_tiled(const float* in, int64_t in_bs, int squ
   if (threads > 1024) threads = 1024;
   if (threads < 128) threads = 128;
   cudaStream_t st = as_stream(stream);
-  const bool bf = (a1 != nullptr && a1_dtype == NFDPM_BF16);
+  const int a1dt = a1 != nullptr ? a1_dtype : NFDPM_F32;
 #define LAUNCH(CP, T)                                                                                               \
   do {                                                                                                              \
     static bool attr_set = false;                                                                                   \
@@ -316,8 +316,12 @@ extern "C" int nfdpm_flow_boundary_tiled(const float* in, int64_t in_bs, int squ
     }                                                                                                               \
     NFDPM_CUDA(launch_pdl(flow_boundary_tiled_kernel<CP, T>, dim3((unsigned)(B * tiles)), dim3(threads), smem, st, a, g)); \
   } while (0)
-  if (pm != nullptr) { if (bf) LAUNCH(true, __nv_bfloat16); else LAUNCH(true, float); }
-  else { if (bf) LAUNCH(false, __nv_bfloat16); else LAUNCH(false, float); }
+#define GO_CP(T) LAUNCH(true, T)
+#define GO_NC(T) LAUNCH(false, T)
+  if (pm != nullptr) NFDPM_A1_DISPATCH(a1dt, GO_CP);
+  else NFDPM_A1_DISPATCH(a1dt, GO_NC);
+#undef GO_CP
+#undef GO_NC
 #undef LAUNCH
   NFDPM_CHECK_LAUNCH("flow_boundary_tiled_kernel");
   return 0;

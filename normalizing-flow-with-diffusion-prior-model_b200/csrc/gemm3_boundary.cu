@@ -12,7 +12,7 @@
 // parameters while the main loop runs; afterwards all 16 warps dump TMEM -> smem and run the boundary phases.
 #include <algorithm>
 
-#include "tc_common.cuh"
+#include "boundary_body.cuh"   // store8<A1T>, NFDPM_A1_DISPATCH (includes tc_common.cuh)
 
 namespace nfdpm {
 
@@ -29,7 +29,8 @@ struct G3Args {
   float* xs; int64_t xs_bs;              // pre-mix stash sink (may be null)
   void* a1; int64_t lda1;                // im2col sink (may be null)
   int B, C, H, W, inverse;
-  int K, ldp;                            // GEMM reduction length (multiple of 64), padded 9C (multiple of 16)
+  int K, ldp;                            // GEMM reduction length in bf16 columns of the operand rows (multiple of 64; 2 x the
+                                         // logical length for split pairs), padded 9C (multiple of 16)
   int ipc;                               // images per CTA
   int ipp;                               // images per boundary pass (smem budget for the pm rows)
   int stages, stage_bytes, a_bytes, b_box_rows, n_bbox;
@@ -37,22 +38,7 @@ struct G3Args {
   FastDiv dCP, dP, dPCh, dCh, dW, dOgP, dPNg, dNg, dCp, dLdp;   // index divisors (multiply-high, common.cuh)
 };
 
-template <typename A1T> __device__ __forceinline__ void g3_store8(A1T* p, const float (&v)[8]);
-template <> __device__ __forceinline__ void g3_store8<float>(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-template <> __device__ __forceinline__ void g3_store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
-  uint32_t w[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&t);
-  }
-  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-template <typename A1T>
+template <typename A1T, bool X3>
 __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const G3Args a) {
@@ -133,11 +119,8 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
           const uint64_t adesc = make_smem_desc(sa + t * 16384);
           const uint64_t b0 = make_smem_desc(sb), b1 = make_smem_desc(sb + n0 * 128);
           const uint32_t d = tmem_base + t * 256;
-#pragma unroll
-          for (int k = 0; k < G3_BK / 16; ++k) {
-            umma_bf16(d, adesc + 2 * k, b0 + 2 * k, idesc0, (kb | k) != 0 ? 1u : 0u);
-            if (n1 > 0) umma_bf16(d + n0, adesc + 2 * k, b1 + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
-          }
+          umma_stage<X3>(d, adesc, b0, idesc0, kb == 0);
+          if (n1 > 0) umma_stage<X3>(d + n0, adesc, b1, idesc1, kb == 0);
         }
         umma_commit(bar_empty + 8 * stage);
         if (kb == num_kb - 1) umma_commit(bar_done);
@@ -344,7 +327,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) gemm3_boundary_kernel(const __g
         const int k = g * 8 + e;
         v[e] = (k < Kc) ? win[kt_s[k]] : 0.f;
       }
-      g3_store8<A1T>(reinterpret_cast<A1T*>(a.a1) + ((int64_t)(img0 + im) * P + p) * a.lda1 + g * 8, v);
+      store8<A1T>(reinterpret_cast<A1T*>(a.a1), (int64_t)(img0 + im) * P + p, a.lda1, g * 8, v);
     }
   }
   tc_fence_before();
@@ -400,11 +383,12 @@ static bool g3_plan(int B, int C, int H, int W, int K, int64_t ldp, bool mix, G3
 
 using namespace nfdpm;
 
+// K counts bf16 columns of the operand rows (2 x the logical reduction length for split pairs)
 extern "C" int nfdpm_gemm3_boundary_ok(int B, int C, int H, int W, int K, int64_t ldp) {
   return g3_plan(B, C, H, W, K, ldp, true, nullptr, nullptr) ? 1 : 0;
 }
 
-extern "C" int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p, float* pm_out, int64_t ld_pm_out,
+extern "C" int nfdpm_gemm3_boundary(const void* h2, int h_dtype, int64_t ldh, const void* w3p, float* pm_out, int64_t ld_pm_out,
                                     const float* in, int64_t in_bs, const float* bias3, const float* logs3, float* ld_part,
                                     const float* mt, const float* beta, float* y, int64_t y_bs, float* xs, int64_t xs_bs,
                                     void* a1, int a1_dtype, int64_t lda1, int B, int C, int H, int W, int K, int64_t ldp,
@@ -414,18 +398,23 @@ extern "C" int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p
   NFDPM_REQUIRE(y != nullptr || a1 != nullptr || xs != nullptr, "nfdpm_gemm3_boundary: no sink");
   NFDPM_REQUIRE(a1 == nullptr || (lda1 % 8 == 0 && lda1 >= 9 * (int64_t)(C / 2) && ((uintptr_t)a1 % 16) == 0),
                 "nfdpm_gemm3_boundary: bad im2col sink");
-  NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16, "nfdpm_gemm3_boundary: bad a1 dtype");
+  NFDPM_REQUIRE(a1 == nullptr || a1_dtype == NFDPM_F32 || a1_dtype == NFDPM_BF16 || (a1_dtype == NFDPM_BF16X2 && lda1 % 32 == 0),
+                "nfdpm_gemm3_boundary: bad a1 dtype");
+  NFDPM_REQUIRE(h_dtype == NFDPM_BF16 || (h_dtype == NFDPM_BF16X2 && ldh % 32 == 0 && K % 32 == 0),
+                "nfdpm_gemm3_boundary: h2 / w3p must be bf16 or split pairs (dtype %d)", h_dtype);
+  const bool x3 = h_dtype == NFDPM_BF16X2;
+  const int kmul = x3 ? 2 : 1;
   NFDPM_REQUIRE(ldh >= K && ldh % 8 == 0 && ((uintptr_t)h2 % 16) == 0 && ((uintptr_t)w3p % 16) == 0,
                 "nfdpm_gemm3_boundary: bad GEMM operands");
   NFDPM_REQUIRE(pm_out == nullptr || ld_pm_out >= ldp, "nfdpm_gemm3_boundary: bad pm_out");
   G3Args a;
   size_t smem = 0;
-  NFDPM_REQUIRE(g3_plan(B, C, H, W, K, ldp, mt != nullptr, &a, &smem),
+  NFDPM_REQUIRE(g3_plan(B, C, H, W, K * kmul, ldp, mt != nullptr, &a, &smem),
                 "nfdpm_gemm3_boundary: unsupported shape B=%d C=%d H=%d W=%d K=%d ldp=%lld (use nfdpm_gemm_nt + "
                 "nfdpm_flow_boundary)", B, C, H, W, K, (long long)ldp);
   a.pm_out = pm_out; a.ld_pm_out = ld_pm_out; a.in = in; a.in_bs = in_bs; a.bias3 = bias3; a.logs3 = logs3;
   a.ld_part = ld_part; a.mt = mt; a.beta = beta; a.y = y; a.y_bs = y_bs; a.xs = xs; a.xs_bs = xs_bs; a.a1 = a1;
-  a.lda1 = lda1; a.B = B; a.C = C; a.H = H; a.W = W; a.inverse = inverse; a.K = K; a.ldp = (int)ldp;
+  a.lda1 = lda1; a.B = B; a.C = C; a.H = H; a.W = W; a.inverse = inverse; a.K = K * kmul; a.ldp = (int)ldp;
   {
     const int P = H * W, Ch = C / 2, Cp = (C + 3) & ~3, n_g = lda1 >= 8 ? (int)(lda1 >> 3) : 1;
     a.dCP = make_fastdiv(C * P); a.dP = make_fastdiv(P); a.dPCh = make_fastdiv(P * Ch); a.dCh = make_fastdiv(Ch);
@@ -434,18 +423,26 @@ extern "C" int nfdpm_gemm3_boundary(const void* h2, int64_t ldh, const void* w3p
   }
   const int64_t M = (int64_t)B * H * W;
   CUtensorMap tmA, tmB;
-  if (make_map(&tmA, h2, M, K, ldh, 128)) return 1;
-  if (make_map(&tmB, w3p, ldp, K, K, a.b_box_rows)) return 1;
+  if (make_map(&tmA, h2, M, K * kmul, ldh * kmul, 128)) return 1;
+  if (make_map(&tmB, w3p, ldp, K * kmul, K * kmul, a.b_box_rows)) return 1;
   const int grid = (B + a.ipc - 1) / a.ipc;
   cudaStream_t st = as_stream(stream);
-  const bool bf = (a1 != nullptr && a1_dtype == NFDPM_BF16);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NFDPM_CUDA(cudaFuncSetAttribute(gemm3_boundary_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    NFDPM_CUDA(cudaFuncSetAttribute(gemm3_boundary_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    attr_set = true;
-  }
-  if (bf) NFDPM_CUDA(launch_pdl(gemm3_boundary_kernel<__nv_bfloat16>, dim3(grid), dim3(G3_THREADS), smem, st, tmA, tmB, a));
-  else NFDPM_CUDA(launch_pdl(gemm3_boundary_kernel<float>, dim3(grid), dim3(G3_THREADS), smem, st, tmA, tmB, a));
+  const int a1dt = a1 != nullptr ? a1_dtype : NFDPM_F32;
+#define LAUNCH(T, X)                                                                                                   \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      NFDPM_CUDA(cudaFuncSetAttribute(gemm3_boundary_kernel<T, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    NFDPM_CUDA(launch_pdl(gemm3_boundary_kernel<T, X>, dim3(grid), dim3(G3_THREADS), smem, st, tmA, tmB, a));          \
+  } while (0)
+#define GO_X3(T) LAUNCH(T, true)
+#define GO_BF(T) LAUNCH(T, false)
+  if (x3) NFDPM_A1_DISPATCH(a1dt, GO_X3);
+  else NFDPM_A1_DISPATCH(a1dt, GO_BF);
+#undef GO_X3
+#undef GO_BF
+#undef LAUNCH
   return 0;
 }

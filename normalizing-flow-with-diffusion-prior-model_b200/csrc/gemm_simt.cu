@@ -12,12 +12,7 @@
 namespace nfdpm {
 
 int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
-               int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st,
-               const void* ep_h = nullptr, int64_t ld_h = 0, float* ep_part = nullptr);
-
-// CTA-pair (cta_group::2) variant, gemm_tc2.cu; returns -1 for shapes it does not take
-int gemm_nt_tc2(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
-                int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st);
+               int in_dtype, int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st);
 
 constexpr int BK = 16;
 
@@ -178,21 +173,14 @@ extern "C" int nfdpm_gemm_nt(const void* A, int64_t lda, const void* Bw, int64_t
   NFDPM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0, "nfdpm_gemm_nt: lda/ldb/ldd must be multiples of 8");
   NFDPM_REQUIRE(epilogue == NFDPM_EPI_RAW || epilogue == NFDPM_EPI_ACTNORM_RELU, "nfdpm_gemm_nt: bad epilogue %d", epilogue);
   NFDPM_REQUIRE(epilogue == NFDPM_EPI_RAW || (ep_scale && ep_bias), "nfdpm_gemm_nt: epilogue needs scale/bias");
-  NFDPM_REQUIRE(out_dtype == NFDPM_F32 || out_dtype == NFDPM_BF16, "nfdpm_gemm_nt: bad out_dtype %d", out_dtype);
+  NFDPM_REQUIRE(out_dtype == NFDPM_F32 || out_dtype == NFDPM_BF16 || out_dtype == NFDPM_BF16X2, "nfdpm_gemm_nt: bad out_dtype %d", out_dtype);
   cudaStream_t st = as_stream(stream);
-  if (in_dtype == NFDPM_BF16) {
-    NFDPM_REQUIRE(K % 64 == 0, "nfdpm_gemm_nt: bf16 path needs K %% 64 == 0 (K=%d)", K);
-    static int use_pair = -1;
-    if (use_pair < 0) {
-      const char* e = getenv("NFDPM_TC2");
-      use_pair = (e != nullptr && e[0] == '1') ? 1 : 0;   // opt-in: measured no faster (the kernels are epilogue-bound)
-    }
-    if (use_pair && ((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)D % 16 == 0)) {
-      const int r = gemm_nt_tc2(A, lda, Bw, ldb, D, ldd, M, N, K, out_dtype, epilogue, ep_scale, ep_bias, st);
-      if (r >= 0) return r;
-    }
-    return gemm_nt_tc(A, lda, Bw, ldb, D, ldd, M, N, K, out_dtype, epilogue, ep_scale, ep_bias, st);
+  if (in_dtype == NFDPM_BF16 || in_dtype == NFDPM_BF16X2) {
+    if (in_dtype == NFDPM_BF16) NFDPM_REQUIRE(K % 64 == 0, "nfdpm_gemm_nt: bf16 path needs K %% 64 == 0 (K=%d)", K);
+    else NFDPM_REQUIRE(K % 32 == 0 && lda % 32 == 0 && ldb % 32 == 0, "nfdpm_gemm_nt: split-pair path needs K, lda, ldb %% 32 == 0 (K=%d)", K);
+    return gemm_nt_tc(A, lda, Bw, ldb, D, ldd, M, N, K, in_dtype, out_dtype, epilogue, ep_scale, ep_bias, st);
   }
+  NFDPM_REQUIRE(out_dtype != NFDPM_BF16X2, "nfdpm_gemm_nt: the fp32 CUDA-core path writes fp32 or bf16");
   NFDPM_REQUIRE(in_dtype == NFDPM_F32, "nfdpm_gemm_nt: bad in_dtype %d", in_dtype);
   NFDPM_REQUIRE(K % 16 == 0, "nfdpm_gemm_nt: fp32 path needs K %% 16 == 0 (K=%d)", K);
   NFDPM_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0), "nfdpm_gemm_nt: operands must be 16-byte aligned");
@@ -208,19 +196,4 @@ extern "C" int nfdpm_gemm_nt(const void* A, int64_t lda, const void* Bw, int64_t
     else { if (wide) GO(128, NFDPM_EPI_ACTNORM_RELU, __nv_bfloat16); else GO(64, NFDPM_EPI_ACTNORM_RELU, __nv_bfloat16); }
   }
 #undef GO
-}
-
-/* dgrad GEMM with the ActNorm + ReLU backward fused into its epilogue (tensor-core path, bf16):
- *   dpre[M,N] = (A[M,K] * Bw[N,K]^T) * (h > 0) * exp(scale[n]);   part[mt][2N]: per 128-row tile column sums of
- *   g*h (-> d scale) and g*exp(scale) (-> d bias), g = acc * (h > 0).  Reduce part with nfdpm_reduce_rows2 over
- *   ceil(M/128) rows.  Replaces nfdpm_gemm_nt + nfdpm_actnorm_relu_bwd (utils.py:69,84-87 backward). */
-extern "C" int nfdpm_gemm_nt_relu_bwd(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* dpre, int64_t ldd, int M,
-                                      int N, int K, const void* h, int64_t ldh, const float* scale, float* part,
-                                      nfdpm_stream_t stream) {
-  NFDPM_REQUIRE(A && Bw && dpre && h && scale && part, "nfdpm_gemm_nt_relu_bwd: null pointer");
-  NFDPM_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && N <= 2048, "nfdpm_gemm_nt_relu_bwd: bad shape M=%d N=%d K=%d", M, N, K);
-  NFDPM_REQUIRE(lda >= K && ldb >= K && ldd >= N && ldh >= N && lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0,
-                "nfdpm_gemm_nt_relu_bwd: bad leading dimensions");
-  return nfdpm::gemm_nt_tc(A, lda, Bw, ldb, dpre, ldd, M, N, K, NFDPM_BF16, NFDPM_EPI_RELU_BWD, scale, nullptr,
-                           nfdpm::as_stream(stream), h, ldh, part);
 }

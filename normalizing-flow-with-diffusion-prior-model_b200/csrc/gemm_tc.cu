@@ -1,6 +1,8 @@
-// tcgen05 / TMEM / TMA bf16 GEMM for the coupling networks:  D[M,N] = epilogue(A[M,K] * Bw[N,K]^T)
-//   A  [M,K] bf16 row-major (pixel-major activations), Bw [N,K] bf16 row-major (packed conv weights),
-//   fp32 accumulation in tensor memory, output bf16 or fp32.
+// tcgen05 / TMEM / TMA GEMM for the coupling networks:  D[M,N] = epilogue(A[M,K] * Bw[N,K]^T)
+//   A  [M,K] row-major (pixel-major activations), Bw [N,K] row-major (packed conv weights), fp32 accumulation in tensor
+//   memory.  Operands are bf16 (NFDPM_BF16: one tcgen05.mma per K=16 slice, 2^-9 operand rounding) or SPLIT bf16 pairs
+//   (NFDPM_BF16X2, common.cuh: v = hi + lo, three tcgen05.mma per slice pair, 2^-17 — the fp32-faithful mode that meets the
+//   reference's 1e-4 parity bar on the tensor cores).  Output fp32, bf16 or split pairs (the next GEMM's A operand).
 //
 // Persistent, warp-specialised CTA (one per SM, 64 + 32 * TCG_EPI_WARPS = 576 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A box and a BNx64 B box (128B swizzle)
@@ -63,15 +65,13 @@ struct TcPlan { int n_stages, stage_bytes, cstage_bytes, cpw; };
 // profiling hook (nfdpm_gemm_debug): per-CTA cycle counters [grid][16] int64; NULL = off
 __device__ long long* g_tc_dbg = nullptr;
 
-template <int EPI, typename OutT>
+template <int EPI, typename OutT, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmD, int M, int N, int K,
                                                                    int BN, int split, const TcPlan plan,
                                                                    const float* __restrict__ ep_scale,
-                                                                   const float* __restrict__ ep_bias,
-                                                                   const __nv_bfloat16* __restrict__ ep_h, int64_t ld_h,
-                                                                   float* __restrict__ ep_part) {
+                                                                   const float* __restrict__ ep_bias) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
   __shared__ uint32_t s_tmem_base;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
   const int num_n = (N + BN - 1) / BN;
   const int num_m = (M + TC_BM - 1) / TC_BM;
   const int num_tiles = num_m * num_n;
-  const int num_kb = K / TC_BK;
+  const int num_kb = K / TC_BK;          // K counts bf16 columns of the operand rows (2 x logical K for split pairs)
 
   const int n_pad = num_n * BN;        // columns covered by the tiles (>= N); parameters are zero beyond N
   if (warp == 0 && lane == 0) {
@@ -117,8 +117,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
   pdl_trigger();
   pdl_wait();
   const long long t_dep = clock64();
-  // EPI_RELU_BWD: per-quadrant column partial sums of the tile [4][2][256], after the parameters
-  float* part_s = s_ep + 2 * n_pad;
   long long* const dbg = g_tc_dbg;
   long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;       // wait / work cycle counters of this warp (profiling hook)
   const long long t_start = clock64();
@@ -177,9 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
         if (lane == 0) {
           const uint32_t sa = ring + stage * stage_bytes, sb = sa + TC_A_BYTES;
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)              // +32 bytes (= 2 x 16 B) per K=16 slice inside the swizzle row
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_stage<X3>(tmem_d, adesc, bdesc, idesc, kb == 0);
           umma_commit(bar_empty + 8 * stage);             // smem stage reusable once these MMAs retire
           if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
         }
@@ -207,21 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_ACC_COLS;
       const long long c2 = dbg ? clock64() : 0;
       w1 += c2 - c1;
-      // EPI_RELU_BWD: 16 bf16 of the stashed activation h for this thread's row (two 16-byte loads)
-      const int64_t h_row = (int64_t)(m_blk * TC_BM + trow) * ld_h + n_base;
-      const bool row_ok = (m_blk * TC_BM + trow) < M;
-      auto load_h = [&](int c0, uint4 (&hh)[2]) {
-        if (EPI == NFDPM_EPI_RELU_BWD) {
-          if (row_ok && n_base + c0 < N) {
-            hh[0] = __ldg(reinterpret_cast<const uint4*>(ep_h + h_row + c0));
-            hh[1] = __ldg(reinterpret_cast<const uint4*>(ep_h + h_row + c0 + 8));
-          } else {
-            hh[0] = make_uint4(0, 0, 0, 0);
-            hh[1] = make_uint4(0, 0, 0, 0);
-          }
-        }
-      };
-      auto process = [&](const uint32_t (&r)[16], const uint4 (&hh)[2], int c0, int c_stage) {
+      auto process = [&](const uint32_t (&r)[16], int c0, int c_stage) {
         const int n0 = n_base + c0;
         float v[16];
         if (EPI == NFDPM_EPI_ACTNORM_RELU) {
@@ -234,48 +216,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
             v[4 * j + 1] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 1]), e.y, b.y));
             v[4 * j + 2] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 2]), e.z, b.z));
             v[4 * j + 3] = fmaxf(0.f, fmaf(__uint_as_float(r[4 * j + 3]), e.w, b.w));
-          }
-        } else if (EPI == NFDPM_EPI_RELU_BWD) {
-          // dpre = dh * (h > 0) * e;  column partials ds += g*h, db += g*e   (utils.py:69,84-87 backward)
-          const uint32_t hw[8] = {hh[0].x, hh[0].y, hh[0].z, hh[0].w, hh[1].x, hh[1].y, hh[1].z, hh[1].w};
-          float ds[16], db[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float hv = __uint_as_float((j & 1) ? (hw[j >> 1] & 0xFFFF0000u) : (hw[j >> 1] << 16));
-            const float g = (hv > 0.f) ? __uint_as_float(r[j]) : 0.f;
-            v[j] = g * s_ep[n0 + j];
-            ds[j] = g * hv;
-            db[j] = v[j];
-          }
-          // transpose-reduce over the 32 rows of this warp: 16 shuffles per quantity, fixed order (deterministic)
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            float* q_ = k == 0 ? ds : db;
-            float w8[8], w4[4], w2[2], w1;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float send = (lane & 16) ? q_[i] : q_[i + 8], keep = (lane & 16) ? q_[i + 8] : q_[i];
-              w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = (lane & 8) ? w8[i] : w8[i + 4], keep = (lane & 8) ? w8[i + 4] : w8[i];
-              w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = (lane & 4) ? w4[i] : w4[i + 2], keep = (lane & 4) ? w4[i + 2] : w4[i];
-              w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            {
-              const float send = (lane & 2) ? w2[0] : w2[1], keep = (lane & 2) ? w2[1] : w2[0];
-              w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-            if ((lane & 1) == 0) {
-              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              part_s[(q * 2 + k) * 256 + c0 + col] = w1;
-            }
           }
         } else {
 #pragma unroll
@@ -290,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       constexpr int CPB = TcStage<OutT>::kColsPerBox;
       const int cpw = plan.cpw;
       const int k_total = ((n_chunks + TCG_EPQ - 1) / TCG_EPQ + cpw - 1) / cpw * cpw;   // same trip count for every warp
-      auto chunk_step = [&](uint32_t (&cur)[16], uint32_t (&nxt)[16], uint4 (&hc)[2], uint4 (&hn)[2], int k) {
+      auto chunk_step = [&](uint32_t (&cur)[16], uint32_t (&nxt)[16], int k) {
         const int ch = half + TCG_EPQ * k;
         const int pass = k / cpw;
         const int col0 = pass * cpw * (16 * TCG_EPQ);        // first tile column of this pass
@@ -301,8 +241,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
         }
         if (ch < n_chunks) {
           tmem_ld_wait();
-          if (ch + TCG_EPQ < n_chunks) { tmem_ld16(taddr + (ch + TCG_EPQ) * 16, nxt); load_h((ch + TCG_EPQ) * 16, hn); }
-          process(cur, hc, ch * 16, ch * 16 - col0);
+          if (ch + TCG_EPQ < n_chunks) tmem_ld16(taddr + (ch + TCG_EPQ) * 16, nxt);
+          process(cur, ch * 16, ch * 16 - col0);
         }
         if (k - pass * cpw == cpw - 1) {
           if (k == k_total - 1) {
@@ -316,35 +256,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
             const int cols = min(wk.bn - col0, cpw * (16 * TCG_EPQ));
             const int n_boxes = (cols + CPB - 1) / CPB;
             for (int j = 0; j < n_boxes; ++j)              // rows >= M and columns >= N are clipped by the tensor map
-              tma_store_2d(&tmD, cstage + (uint32_t)j * 16384u, n_base + col0 + j * CPB, m_blk * TC_BM);
+              tma_store_2d(&tmD, cstage + (uint32_t)j * 16384u, (n_base + col0 + j * CPB) * TcMemCols<OutT>::v, m_blk * TC_BM);
             tma_store_commit();
           }
         }
       };
       uint32_t ra[16], rb[16];
-      uint4 ha[2], hb[2];
-      if (half < n_chunks) { tmem_ld16(taddr + half * 16, ra); load_h(half * 16, ha); }
+      if (half < n_chunks) tmem_ld16(taddr + half * 16, ra);
       for (int k = 0; k < k_total; k += 2) {
-        chunk_step(ra, rb, ha, hb, k);
-        if (k + 1 < k_total) chunk_step(rb, ra, hb, ha, k + 1);
+        chunk_step(ra, rb, k);
+        if (k + 1 < k_total) chunk_step(rb, ra, k + 1);
       }
       const long long c3 = dbg ? clock64() : 0;
       w2 += c3 - c2;
       if (dbg) w4 += 1;
-      if (EPI == NFDPM_EPI_RELU_BWD) {
-        // combine the four row quadrants in order; one partial row per 128-row tile: part[m_blk][2N]
-        const int t = threadIdx.x - 64;
-        if (t < wk.bn && n_base + t < N) {
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            s0 += part_s[(qq * 2 + 0) * 256 + t];
-            s1 += part_s[(qq * 2 + 1) * 256 + t];
-          }
-          ep_part[(int64_t)m_blk * 2 * N + n_base + t] = s0;
-          ep_part[(int64_t)m_blk * 2 * N + N + n_base + t] = s1;
-        }
-      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -372,30 +297,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_nt_tc_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------- host side
-template <int EPI, typename OutT>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, int M, int N, int K, int BN,
-                     int split, const TcPlan& plan, const float* es, const float* eb, int grid, size_t smem, cudaStream_t st,
-                     const __nv_bfloat16* ep_h = nullptr, int64_t ld_h = 0, float* ep_part = nullptr) {
+template <int EPI, typename OutT, bool X3>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, int M, int N, int Kmem, int BN,
+                     int split, const TcPlan& plan, const float* es, const float* eb, int grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    NFDPM_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NFDPM_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI, OutT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     226 * 1024));
     attr_set = true;
   }
-  NFDPM_CUDA(launch_pdl(gemm_nt_tc_kernel<EPI, OutT>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, tmD, M, N, K, BN,
-                        split, plan, es, eb, ep_h, ld_h, ep_part));
+  NFDPM_CUDA(launch_pdl(gemm_nt_tc_kernel<EPI, OutT, X3>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, tmD, M, N, Kmem,
+                        BN, split, plan, es, eb));
   return 0;
 }
 
+// lda / ldb / ldd and K count LOGICAL elements; a split-pair row occupies 2 x ld bf16.
 int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
-               int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st,
-               const void* ep_h, int64_t ld_h, float* ep_part) {
-  NFDPM_REQUIRE(N % 16 == 0, "nfdpm_gemm_nt(bf16): N=%d must be a multiple of 16", N);
+               int in_dtype, int out_dtype, int epilogue, const float* ep_scale, const float* ep_bias, cudaStream_t st) {
+  const bool x3 = in_dtype == NFDPM_BF16X2, out_x2 = out_dtype == NFDPM_BF16X2;
+  NFDPM_REQUIRE(N % 16 == 0, "nfdpm_gemm_nt(tensor core): N=%d must be a multiple of 16", N);
+  NFDPM_REQUIRE(!out_x2 || (N % 32 == 0 && ldd % 32 == 0), "nfdpm_gemm_nt: split-pair output needs N and ldd multiples of 32");
   NFDPM_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bw % 16 == 0) && ((uintptr_t)D % 16 == 0),
-                "nfdpm_gemm_nt(bf16): operands must be 16-byte aligned");
-  NFDPM_REQUIRE(epilogue == NFDPM_EPI_RAW || N <= 2048, "nfdpm_gemm_nt(bf16): fused ActNorm epilogue supports N <= 2048");
-  // N tile: multiple of 16 that splits N evenly; <= 256 columns for bf16 output, <= 128 for fp32 output (the staging
-  // tile holds 128 x 256 bf16 or 128 x 128 fp32)
+                "nfdpm_gemm_nt(tensor core): operands must be 16-byte aligned");
+  NFDPM_REQUIRE(epilogue == NFDPM_EPI_RAW || N <= 2048, "nfdpm_gemm_nt(tensor core): fused ActNorm epilogue supports N <= 2048");
+  // N tile: multiple of 16 that splits N evenly; <= 256 columns for bf16 / split output, <= 128 for fp32 output (the
+  // classic staging tile holds 128 x 256 bf16 or 128 x 128 fp32 / split pairs)
   static int bn_cap = -1;
   if (bn_cap < 0) {
     const char* e = getenv("NFDPM_TC_BN");
@@ -407,7 +333,7 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   // few rows (deep levels): narrower tiles put more CTAs to work (measured at M = 2048, N = 512: 6.1 vs 7.2 us)
   const int m_tiles = (M + TC_BM - 1) / TC_BM;
   while (bn_max > 64 && N >= 2 * bn_max / 2 && m_tiles * ((N + bn_max - 1) / bn_max) <= 48 && N % (bn_max / 2) == 0) bn_max >>= 1;
-  const int cpb = (out_dtype == NFDPM_F32) ? 32 : 64;     // columns per 128-byte TMA store box
+  const int cpb = (out_dtype == NFDPM_BF16) ? 64 : 32;    // logical columns per 128-byte TMA store box
   const int nblk = (N + bn_max - 1) / bn_max;
   // one N block: any multiple of 16 (columns >= N are clipped by the D tensor map); several N blocks: BN must be a
   // whole number of store boxes, otherwise a tile's last box would spill into its neighbour's columns
@@ -427,13 +353,16 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
     const char* e = getenv("NFDPM_TC_SPLIT");
     split_on = (e && atoi(e) == 0) ? 0 : 1;
   }
-  const int split = (split_on && tc_split_ok(tiles, grid, BN, N) && epilogue != NFDPM_EPI_RELU_BWD) ? 1 : 0;
+  const int split = (split_on && tc_split_ok(tiles, grid, BN, N)) ? 1 : 0;
+  const int kmul = x3 ? 2 : 1;                           // bf16 columns per logical K
+  const int Kmem = K * kmul;
   CUtensorMap tmA, tmB, tmD;
-  if (make_map(&tmA, A, M, K, lda, TC_BM)) return 1;
-  if (make_map(&tmB, Bw, N, K, ldb, split ? BN / 2 : BN)) return 1;
-  if (make_map(&tmD, D, M, N, ldd, TC_BM, out_dtype == NFDPM_F32)) return 1;
+  if (make_map(&tmA, A, M, Kmem, lda * kmul, TC_BM)) return 1;
+  if (make_map(&tmB, Bw, N, Kmem, ldb * kmul, split ? BN / 2 : BN)) return 1;
+  if (out_x2) { if (make_map(&tmD, D, M, 2 * (int64_t)N, 2 * ldd, TC_BM)) return 1; }
+  else if (make_map(&tmD, D, M, N, ldd, TC_BM, out_dtype == NFDPM_F32)) return 1;
   const size_t n_pad = (size_t)((N + BN - 1) / BN) * BN;
-  const size_t extra = (epilogue != NFDPM_EPI_RAW ? 2 * n_pad * 4 : 0) + (epilogue == NFDPM_EPI_RELU_BWD ? 4 * 2 * 256 * 4 : 0);
+  const size_t extra = (epilogue != NFDPM_EPI_RAW ? 2 * n_pad * 4 : 0);
   // shared-memory plan (TcPlan): the deep ring pays when the main loop is long enough to be fed from L2 continuously;
   // NFDPM_TC_DEEP=0 keeps the classic plan everywhere, =2 forces the deep plan for every shape
   static int deep_on = -1;
@@ -441,30 +370,29 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
     const char* e = getenv("NFDPM_TC_DEEP");
     deep_on = e ? atoi(e) : 1;
   }
-  TcPlan plan = {TC_STAGES, TC_STAGE_BYTES, TC_CSTAGE_BYTES, 4};
+  // classic: the 64 KB staging buffer holds 256 bf16 / 128 fp32 / 128 split-pair columns of the tile per pass
+  TcPlan plan = {TC_STAGES, TC_STAGE_BYTES, TC_CSTAGE_BYTES, out_dtype == NFDPM_BF16 ? 4 : 2};
   // measured (tools/bench_gemms.py): M=32768 N=K=512 22.2 -> 21.7 us, N=112 fp32-out 11.0 -> 10.5 us; with ONE tile per CTA
   // (deep levels) the pass-wise epilogue has no next main loop to hide behind and costs 0.5 us, so those keep the classic plan
-  if (deep_on == 2 || (deep_on == 1 && K / TC_BK >= 4 && tiles > grid)) {
+  if (deep_on == 2 || (deep_on == 1 && Kmem / TC_BK >= 4 && tiles > grid)) {
     plan.stage_bytes = TC_A_BYTES + BN * TC_BK * 2;
-    plan.cstage_bytes = 128 * 64 * (out_dtype == NFDPM_F32 ? 4 : 2);
+    plan.cstage_bytes = 128 * 64 * (out_dtype == NFDPM_BF16 ? 2 : 4);     // one 64-column pass
     plan.cpw = 1;
     const size_t avail = 226 * 1024 - 1024 - (size_t)plan.cstage_bytes - extra;   // 226 KB dynamic (launch_tc) + static barriers
     plan.n_stages = (int)(avail / (size_t)plan.stage_bytes);
     if (plan.n_stages > TC_MAX_STAGES) plan.n_stages = TC_MAX_STAGES;
   }
   const size_t smem = 1024 + (size_t)plan.n_stages * plan.stage_bytes + plan.cstage_bytes + extra;
-  if (epilogue == NFDPM_EPI_RELU_BWD) {
-    NFDPM_REQUIRE(out_dtype == NFDPM_BF16 && ep_h && ep_part && ep_scale && ld_h % 8 == 0 && ((uintptr_t)ep_h % 16) == 0,
-                  "nfdpm_gemm_nt_relu_bwd: needs bf16 output, h (16-byte aligned, ld %% 8 == 0), scale and part");
-    return launch_tc<NFDPM_EPI_RELU_BWD, __nv_bfloat16>(tmA, tmB, tmD, M, N, K, BN, 0, plan, ep_scale, nullptr, grid, smem, st,
-                                                         (const __nv_bfloat16*)ep_h, ld_h, ep_part);
+#define GO(EPI, T, X) return launch_tc<EPI, T, X>(tmA, tmB, tmD, M, N, Kmem, BN, split, plan, ep_scale, ep_bias, grid, smem, st)
+  const bool raw = epilogue == NFDPM_EPI_RAW;
+  if (x3) {
+    if (out_dtype == NFDPM_F32) { if (raw) GO(NFDPM_EPI_RAW, float, true); else GO(NFDPM_EPI_ACTNORM_RELU, float, true); }
+    if (out_x2) { if (raw) GO(NFDPM_EPI_RAW, bf16x2_t, true); else GO(NFDPM_EPI_ACTNORM_RELU, bf16x2_t, true); }
+    return fail("nfdpm_gemm_nt: split-pair operands produce fp32 or split-pair output (out_dtype %d)", out_dtype);
   }
-#define GO(EPI, T) return launch_tc<EPI, T>(tmA, tmB, tmD, M, N, K, BN, split, plan, ep_scale, ep_bias, grid, smem, st)
-  if (out_dtype == NFDPM_F32) {
-    if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, float); else GO(NFDPM_EPI_ACTNORM_RELU, float);
-  } else {
-    if (epilogue == NFDPM_EPI_RAW) GO(NFDPM_EPI_RAW, __nv_bfloat16); else GO(NFDPM_EPI_ACTNORM_RELU, __nv_bfloat16);
-  }
+  if (out_dtype == NFDPM_F32) { if (raw) GO(NFDPM_EPI_RAW, float, false); else GO(NFDPM_EPI_ACTNORM_RELU, float, false); }
+  if (out_dtype == NFDPM_BF16) { if (raw) GO(NFDPM_EPI_RAW, __nv_bfloat16, false); else GO(NFDPM_EPI_ACTNORM_RELU, __nv_bfloat16, false); }
+  return fail("nfdpm_gemm_nt: bf16 operands produce fp32 or bf16 output (out_dtype %d)", out_dtype);
 #undef GO
 }
 

@@ -151,6 +151,50 @@ template <> struct TcStage<float> {
   }
 };
 
+// split bf16 pairs (common.cuh): a 16 KB box [128 rows][128 bytes] holds 32 LOGICAL columns, hi in the units 0..3 and lo in
+// the units 4..7 of a row
+template <> struct TcStage<bf16x2_t> {
+  static constexpr int kColsPerBox = 32;
+  static __device__ __forceinline__ void put16(uint32_t cbase, int row, int c0, const float (&v)[16]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 th = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      const float2 back = __bfloat1622float2(th);
+      __nv_bfloat162 tl = __floats2bfloat162_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+      h[i] = *reinterpret_cast<uint32_t*>(&th);
+      l[i] = *reinterpret_cast<uint32_t*>(&tl);
+    }
+    const uint32_t box = cbase + (uint32_t)(c0 >> 5) * 16384u + (uint32_t)row * 128u;
+    const int u0 = (c0 & 31) >> 3;                        // 0 or 2
+    st_shared_v4(box + (uint32_t)(((u0 + 0) ^ (row & 7)) << 4), h[0], h[1], h[2], h[3]);
+    st_shared_v4(box + (uint32_t)(((u0 + 1) ^ (row & 7)) << 4), h[4], h[5], h[6], h[7]);
+    st_shared_v4(box + (uint32_t)(((u0 + 4) ^ (row & 7)) << 4), l[0], l[1], l[2], l[3]);
+    st_shared_v4(box + (uint32_t)(((u0 + 5) ^ (row & 7)) << 4), l[4], l[5], l[6], l[7]);
+  }
+};
+// bf16 columns of the global row per logical column of the tile (TMA store coordinates)
+template <typename OutT> struct TcMemCols { static constexpr int v = 1; };
+template <> struct TcMemCols<bf16x2_t> { static constexpr int v = 2; };
+
+// The MMAs of one 64-bf16-column operand stage.  Plain bf16: four K=16 slices.  Split pairs: the stage is 32 logical K,
+// slices {hi0, hi1, lo0, lo1}; D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.  `first` = this stage starts the accumulation.
+template <bool X3>
+__device__ __forceinline__ void umma_stage(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool first) {
+  if (X3) {
+    umma_bf16(tmem_d, adesc + 0, bdesc + 0, idesc, first ? 0u : 1u);
+    umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+    umma_bf16(tmem_d, adesc + 4, bdesc + 0, idesc, 1u);
+    umma_bf16(tmem_d, adesc + 6, bdesc + 2, idesc, 1u);
+    umma_bf16(tmem_d, adesc + 0, bdesc + 4, idesc, 1u);
+    umma_bf16(tmem_d, adesc + 2, bdesc + 6, idesc, 1u);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)                           // +32 bytes (= 2 x 16 B) per K=16 slice inside the swizzle row
+      umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+  }
+}
+
 
 // ---------------------------------------------------------------- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -2,11 +2,15 @@
 launch sequences of one StepFlow / coupling network.  No arithmetic happens here — every number is
 produced by a kernel of the C-ABI library; torch supplies device memory and the current stream.
 
-Precision modes (env ``NFDPM_PRECISION``):
-  * ``bf16`` (default) — coupling-network GEMMs on tcgen05 tensor cores, bf16 operands, fp32 TMEM accumulators
-    (parity bar stated in DESIGN.md / tests).  Everything outside the coupling nets is fp32 in both modes.
-  * ``fp32`` — coupling-network GEMMs on CUDA cores with exact fp32 FMA accumulation
-    (parity bar: z / log-det within 1e-4 relative of the reference).
+Precision modes (env ``NFDPM_PRECISION``); everything outside the coupling networks is fp32 in every mode:
+  * ``fp32`` — the reference's arithmetic (fp32 convolutions, utils.py:36,64) on the tcgen05 tensor cores: operands are SPLIT
+    bf16 pairs (v = hi + lo, NFDPM_BF16X2) and every product is formed as hi*hi + lo*hi + hi*lo with fp32 TMEM
+    accumulation (2^-17 operand error instead of bf16's 2^-9).  Parity bar: z / log-det within 1e-4 relative of the
+    reference, reconstruction < 1e-4.  Training in this mode runs its GEMMs on CUDA cores (exact fp32).
+  * ``bf16`` — plain bf16 operands, one MMA per product: 3x the tensor throughput, stated tolerance in DESIGN.md / tests.
+  * ``auto`` (default) — inference (``torch.no_grad()`` transform / invert / sample: likelihood evaluation, decoding,
+    sampling) in ``fp32``, the training step (autograd-recorded transform + backward) in ``bf16``.
+  * ``fp32_simt`` — coupling GEMMs in exact fp32 FMA on CUDA cores everywhere (debugging reference, ~10x slower).
 """
 from __future__ import annotations
 
@@ -33,10 +37,26 @@ def channel_stats(x, layout: int, B: int, C: int, P: int, xs: int, scale, bias) 
 
 
 def precision() -> str:
-    p = os.environ.get("NFDPM_PRECISION", "bf16").lower()
-    if p not in ("fp32", "bf16"):
-        raise ValueError(f"NFDPM_PRECISION must be 'fp32' or 'bf16', got {p!r}")
+    p = os.environ.get("NFDPM_PRECISION", "auto").lower()
+    if p not in ("auto", "fp32", "bf16", "fp32_simt"):
+        raise ValueError(f"NFDPM_PRECISION must be 'auto', 'fp32', 'bf16' or 'fp32_simt', got {p!r}")
     return p
+
+
+#: storage dtypes of the coupling-network operands: torch.float32 (CUDA-core GEMMs), torch.bfloat16, N.SPLIT (bf16 pairs)
+TC_DTYPES = (torch.bfloat16, N.SPLIT)
+
+
+def coupling_dtype(train: bool = False) -> torch.dtype:
+    """Operand format of the coupling-network GEMMs for the inference chains or (``train``) the training step."""
+    p = precision()
+    if p == "bf16":
+        return torch.bfloat16
+    if p == "fp32_simt":
+        return torch.float32
+    if p == "fp32":
+        return torch.float32 if train else N.SPLIT
+    return torch.bfloat16 if train else N.SPLIT
 
 
 def round_up(a: int, b: int) -> int:
@@ -191,40 +211,60 @@ def prepare_mix(entries: Sequence[Tuple[MixCache, Optional[torch.Tensor], Option
 
 
 # ------------------------------------------------------------------------------------------- coupling net
-class CouplingCache:
-    """GEMM-ready copies of the three conv weights of one coupling network (nfdpm_pack_matrix)."""
+class WeightSet:
+    """The three packed conv weights of one coupling network in ONE operand format."""
 
     def __init__(self):
         self.key = None
         self.w1 = self.w2 = self.w3 = None
+
+    def alloc(self, dt: torch.dtype, F: int, K1p: int, ldp: int, dev: torch.device) -> None:
+        if self.w1 is None or self.w1.numel() != F * K1p or self.w1.device != dev:
+            _bump_epoch()
+            self.w1 = torch.empty(F * K1p, dtype=dt, device=dev)
+            self.w3 = torch.empty(ldp * F, dtype=dt, device=dev)
+            self.w2 = torch.empty(F * F, dtype=dt, device=dev) if dt != torch.float32 else None
+            self.key = None
+
+
+class CouplingCache:
+    """GEMM-ready copies of the three conv weights of one coupling network (nfdpm_pack_matrix), one WeightSet per operand
+    format: evaluation (split pairs) and training (bf16) alternate in one process without re-allocating — and thereby
+    invalidating captured graphs and batched packing plans of — each other's buffers."""
+
+    def __init__(self):
+        self.sets = {}
         self.K1 = self.K1p = self.ldp = 0
-        self.ep = None            # [4, F] folded inner-ActNorm parameters for the fused tensor-core kernel
-        self.ep_key = None
+
+    def at(self, dt: torch.dtype) -> WeightSet:
+        ws = self.sets.get(dt)
+        if ws is None:
+            ws = self.sets[dt] = WeightSet()
+        return ws
+
+    def geometry(self, w1: torch.Tensor, w3: torch.Tensor) -> None:
+        self.K1 = w1.shape[1] * 9
+        self.K1p = round_up(self.K1, 64)
+        self.ldp = round_up(9 * w3.shape[0], 16)
 
 
-def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, dt: torch.dtype):
-    key = (_vkey(w1, w2, w3), dt)
-    if cache_hit(cache.key, key):
-        return
-    F, Ch = w1.shape[0], w1.shape[1]
-    C = w3.shape[0]
-    dev = w1.device
-    K1 = Ch * 9
-    K1p = round_up(K1, 64)
-    ldp = round_up(9 * C, 16)
-    if cache.w1 is None or cache.w1.dtype != dt or cache.w1.numel() != F * K1p:
-        _bump_epoch()
-        cache.w1 = torch.empty(F * K1p, dtype=dt, device=dev)
-        cache.w3 = torch.empty(ldp * F, dtype=dt, device=dev)
-        cache.w2 = torch.empty(F * F, dtype=dt, device=dev) if dt != torch.float32 else None
+def _pack_coupling(cache: CouplingCache, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, dt: torch.dtype) -> WeightSet:
+    ws = cache.at(dt)
+    key = _vkey(w1, w2, w3)
+    if cache_hit(ws.key, key):
+        return ws
+    F, C = w1.shape[0], w3.shape[0]
+    cache.geometry(w1, w3)
+    K1, K1p, ldp = cache.K1, cache.K1p, cache.ldp
+    ws.alloc(dt, F, K1p, ldp, w1.device)
     # conv1 [F, Ch, 3, 3] -> rows n, cols c*9+tap (natural), zero-padded to K1p
-    N.pack_matrix(w1, cache.w1, 1, F, K1, 0, K1, 1, K1p, F)
+    N.pack_matrix(w1, ws.w1, 1, F, K1, 0, K1, 1, K1p, F)
     if dt != torch.float32:
-        N.pack_matrix(w2, cache.w2, 1, F, F, 0, F, 1, F, F)
+        N.pack_matrix(w2, ws.w2, 1, F, F, 0, F, 1, F, F)
     # zero conv [C, F, 3, 3] -> rows (tap, co), cols ci ("taps as N"); rows 9C..ldp zero
-    N.pack_matrix(w3, cache.w3, 9, C, F, 1, F * 9, 9, F, ldp)
-    cache.K1, cache.K1p, cache.ldp = K1, K1p, ldp
-    cache.key = key
+    N.pack_matrix(w3, ws.w3, 9, C, F, 1, F * 9, 9, F, ldp)
+    ws.key = key
+    return ws
 
 
 class PackPlan:
@@ -237,7 +277,8 @@ class PackPlan:
         from . import _train as T
         self.dt, self.train = dt, train
         self.weights, self.marks, jobs = [], [], []
-        code = N.F32 if dt == torch.float32 else N.BF16
+        self.owners = [(s.affcoupling, s.affcoupling._cache) for s in steps]
+        code = {torch.float32: N.F32, torch.bfloat16: N.BF16, N.SPLIT: N.BF16X2}[dt]
         pe = N.pack_elems()
         blocks = 0
 
@@ -254,13 +295,9 @@ class PackPlan:
             F, Ch, C = w1.shape[0], w1.shape[1], w3.shape[0]
             dev = w1.device
             K1, K1p, ldp, Kp3 = Ch * 9, round_up(Ch * 9, 64), round_up(9 * C, 16), round_up(9 * C, 64)
-            c = cp._cache
-            if c.w1 is None or c.w1.dtype != dt or c.w1.numel() != F * K1p:
-                _bump_epoch()
-                c.w1 = torch.empty(F * K1p, dtype=dt, device=dev)
-                c.w3 = torch.empty(ldp * F, dtype=dt, device=dev)
-                c.w2 = torch.empty(F * F, dtype=dt, device=dev) if dt != torch.float32 else None
-            c.K1, c.K1p, c.ldp = K1, K1p, ldp
+            cp._cache.geometry(w1, w3)
+            c = cp._cache.at(dt)
+            c.alloc(dt, F, K1p, ldp, dev)
             job(w1, c.w1, 1, F, K1, 0, K1, 1, K1p, F)
             if dt != torch.float32:
                 job(w2, c.w2, 1, F, F, 0, F, 1, F, F)
@@ -286,6 +323,11 @@ class PackPlan:
         self.table = torch.tensor(np.asarray(jobs, dtype=np.int64).reshape(-1), device=self.weights[0].device)
         self.key = None
 
+    def valid(self) -> bool:
+        """False once a coupling network started a new cache (its own load_state_dict / .to()): the job table then
+        points at orphaned buffers and the plan must be rebuilt."""
+        return all(cp._cache is c for cp, c in self.owners)
+
     def refresh(self) -> None:
         key = _vkey(*self.weights)
         if cache_hit(self.key, key):
@@ -293,13 +335,9 @@ class PackPlan:
         N.pack_batch(self.table, self.n_jobs, self.n_blocks)
         self.key = key
         for caches, ws in self.marks:
-            k = (_vkey(*ws), self.dt)
+            k = _vkey(*ws)
             for c in caches:
                 c.key = k
-
-
-def coupling_dtype() -> torch.dtype:
-    return torch.float32 if precision() == "fp32" else torch.bfloat16
 
 
 def coupling_a1(cp, B: int, C: int, H: int, W: int, dev: torch.device) -> Tuple[torch.Tensor, int]:
@@ -308,48 +346,19 @@ def coupling_a1(cp, B: int, C: int, H: int, W: int, dev: torch.device) -> Tuple[
     dt = coupling_dtype()
     _pack_coupling(cp._cache, conv1.weight, conv2.weight, zc.weight, dt)
     K1p = cp._cache.K1p
-    return WS.get("A1", B * H * W * K1p, dt, dev), K1p
-
-
-def fused_coupling_enabled() -> bool:
-    # Opt-in: the single-kernel coupling network keeps h1/h2 on chip but (round-1 measurement, profiles/) is still
-    # slower than the three pipelined GEMMs: both are L2->SM operand-bandwidth bound and the fused kernel cannot
-    # overlap its epilogues with MMAs.  It becomes the default once weights are multicast across a CTA cluster.
-    return os.environ.get("NFDPM_FUSED_COUPLING", "0") == "1"
-
-
-def refresh_folded(cp) -> None:
-    """(Re)compute the folded inner-ActNorm parameters of coupling network ``cp`` if they changed."""
-    _, an1, _, an2, _ = cp._parts()
-    cache = cp._cache
-    key = _vkey(an1.scale, an1.bias, an2.scale, an2.bias)
-    if cache_hit(cache.ep_key, key):
-        return
-    F = an1.scale.shape[0]
-    if cache.ep is None or cache.ep.numel() != 4 * F:
-        _bump_epoch()
-        cache.ep = torch.empty(4 * F, dtype=torch.float32, device=an1.scale.device)
-    N.fold_actnorm(an1.scale, an1.bias, cache.ep, cache.ep[F:], F)
-    N.fold_actnorm(an2.scale, an2.bias, cache.ep[2 * F:], cache.ep[3 * F:], F)
-    cache.ep_key = key
+    return WS.get("A1", B * H * W * K1p, dt, dev), K1p     # (numel counts logical columns: a split pair is one int32)
 
 
 def coupling_gemms(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int) -> Tuple[torch.Tensor, int]:
     """GEMM1 -> GEMM2 -> GEMM3 of an initialised coupling network from its im2col rows ``A1``.
-    Returns the taps-as-N rows (pm, ldp).  bf16 mode with F = 512 and 9C <= 512 runs them as ONE fused
-    tcgen05 kernel (h1 / h2 stay in shared memory)."""
+    Returns the taps-as-N rows (pm, ldp)."""
     conv1, an1, conv2, an2, zc = cp._parts()
     F = conv1.weight.shape[0]
     dt = A1.dtype
-    cache = cp._cache
+    K1p, ldp = cp._cache.K1p, cp._cache.ldp
+    cache = cp._cache.at(dt)
     dev = A1.device
     M = B * H * W
-    K1p, ldp = cache.K1p, cache.ldp
-    if dt == torch.bfloat16 and F == 512 and ldp <= 512 and K1p <= 512 and fused_coupling_enabled():
-        refresh_folded(cp)
-        pm = WS.get("pm", M * ldp, torch.float32, dev)
-        N.coupling_fused(A1, K1p, cache.w1, cache.w2, cache.w3, pm, ldp, M, K1p, cache.ep)
-        return pm, ldp
     h1 = WS.get("h1", M * F, dt, dev)
     N.gemm_nt(A1, K1p, cache.w1, K1p, h1, F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
     w2 = cache.w2 if dt != torch.float32 else conv2.weight
@@ -364,13 +373,13 @@ def fused_g3_enabled() -> bool:
     return os.environ.get("NFDPM_FUSED_G3", "1") != "0"
 
 
-def fused_g3_ok(B: int, C: int, H: int, W: int, F: int, ldp: int) -> bool:
+def fused_g3_ok(B: int, C: int, H: int, W: int, F: int, ldp: int, dt: torch.dtype = torch.bfloat16) -> bool:
     """Use nfdpm_gemm3_boundary?  Measured in situ (tools/bench_levels.py, profiles/): with ONE image per CTA
     (16x16 images: 128 CTAs) it beats GEMM3 + boundary (54.6 vs 61.4 us per StepFlow chain); at the deeper levels a
     128-row tile holds 2..8 images, only 64 / 16 CTAs exist and the separate kernels win — so only H*W == 256 takes it
     unless NFDPM_FUSED_G3=all."""
     v = os.environ.get("NFDPM_FUSED_G3", "1")
-    if v == "0" or not N.gemm3_boundary_ok(B, C, H, W, F, ldp):
+    if v == "0" or dt not in TC_DTYPES or not N.gemm3_boundary_ok(B, C, H, W, F * (2 if dt == N.SPLIT else 1), ldp):
         return False
     return v == "all" or H * W == 256
 
@@ -384,17 +393,17 @@ def coupling_boundary(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int, src,
     conv1, an1, conv2, an2, zc = cp._parts()
     F = conv1.weight.shape[0]
     dt = A1.dtype
-    cache = cp._cache
+    K1p, ldp = cp._cache.K1p, cp._cache.ldp
+    cache = cp._cache.at(dt)
     dev = A1.device
     M = B * H * W
-    K1p, ldp = cache.K1p, cache.ldp
     if tiles > 0:
         # row-band boundary (images beyond one CTA, small batches): GEMM1 -> GEMM2 -> GEMM3, then nfdpm_flow_boundary_tiled
         pm, _ = coupling_gemms(cp, A1, B, C, H, W)
         N.flow_boundary_tiled(src, src_bs, False, pm, ldp, zc.bias, zc.logs, ld_part, mt, beta, y, y_bs, None, 0, a1_next,
                               lda1_next, B, C, H, W, inverse, tiles)
         return
-    fused = dt == torch.bfloat16 and not fused_coupling_enabled() and fused_g3_ok(B, C, H, W, F, ldp)
+    fused = fused_g3_ok(B, C, H, W, F, ldp, dt)
     if not fused:
         if pm_out is None:
             pm, _ = coupling_gemms(cp, A1, B, C, H, W)
@@ -423,12 +432,11 @@ def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int,
     if F % 64 != 0:
         raise ValueError(f"coupling_net_n_features must be a multiple of 64 (got {F})")
     need_init = init and not (an1._initialized() and an2._initialized())
-    dt = torch.float32 if (precision() == "fp32" or need_init) else torch.bfloat16
-    cache = cp._cache
-    _pack_coupling(cache, conv1.weight, conv2.weight, zc.weight, dt)
+    dt = torch.float32 if need_init else coupling_dtype()     # the data-dependent initialisation runs in exact fp32
+    cache = _pack_coupling(cp._cache, conv1.weight, conv2.weight, zc.weight, dt)
     dev = y.device
     M = B * H * W
-    K1p, ldp = cache.K1p, cache.ldp
+    K1p, ldp = cp._cache.K1p, cp._cache.ldp
     A1 = WS.get("A1", M * K1p, dt, dev)
     N.im2col3x3(y, A1, B, C // 2, H, W, ybs, K1p)
     h1 = WS.get("h1", M * F, dt, dev)

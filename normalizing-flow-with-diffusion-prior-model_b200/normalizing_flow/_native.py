@@ -12,8 +12,13 @@ from typing import Optional
 
 import torch
 
-F32, F64, BF16 = 0, 1, 2
+F32, F64, BF16, BF16X2 = 0, 1, 2, 3
 EPI_RAW, EPI_ACTNORM_RELU = 0, 1
+
+#: torch storage dtype of split bf16 pairs (NFDPM_BF16X2, include/nfdpm_b200.h): 4 bytes per LOGICAL element — a row of ld
+#: logical columns is 2*ld bf16 (hi / lo planes interleaved in groups of 32).  torch has no such dtype; int32 buffers carry
+#: the words and ``_dt`` maps them to the NFDPM_BF16X2 code.  Only the kernels interpret the contents.
+SPLIT = torch.int32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NFDPM_B200_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libnfdpm_b200.so"))
@@ -71,8 +76,6 @@ def _load() -> C.CDLL:
         "nfdpm_flow_boundary_smem": ([i32, i32, i32, i32, i32], C.c_size_t),
         "nfdpm_flow_boundary": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i32, i64, i32, i32, i32, i32,
                                  i32, vp], C.c_int),
-        "nfdpm_coupling_fused": ([vp, i64, vp, vp, vp, vp, i64, i32, i32, vp, vp], C.c_int),
-        "nfdpm_fold_actnorm": ([vp, vp, vp, vp, i32, vp], C.c_int),
         "nfdpm_coupling_bwd": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i64, vp, vp, vp, vp, vp, i32, i32,
                                 i32, i32, vp], C.c_int),
         "nfdpm_coupling_bwd_tiles": ([i32, i32, i32], C.c_int),
@@ -82,18 +85,10 @@ def _load() -> C.CDLL:
         "nfdpm_actnorm_relu_bwd": ([vp, i32, i64, vp, i32, i64, vp, vp, i32, i64, vp, i32, i32, i32, vp], C.c_int),
         "nfdpm_reduce_rows2": ([vp, vp, vp, i32, i32, i32, i64, vp], C.c_int),
         "nfdpm_gemm3_boundary_ok": ([i32, i32, i32, i32, i32, i64], C.c_int),
-        "nfdpm_gemm3_boundary": ([vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
+        "nfdpm_gemm3_boundary": ([vp, i32, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, i64, i32, i32,
                                   i32, i32, i32, i64, i32, vp], C.c_int),
-        "nfdpm_boundary_gemm1_ok": ([i32, i32, i32, i32, i64], C.c_int),
-        "nfdpm_boundary_gemm1": ([vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32,
-                                  i32, i32, i32, i64, i32, vp], C.c_int),
-        "nfdpm_deep_step_debug": ([vp], C.c_int),
         "nfdpm_gemm_debug": ([vp], C.c_int),
         "nfdpm_flow_boundary_debug": ([vp], C.c_int),
-        "nfdpm_deep_step_ok": ([i32, i32, i32, i32, i32, i64, i64], C.c_int),
-        "nfdpm_deep_step": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, i64,
-                             vp, i32, i64, i32, i32, i32, i32, i32, i64, i64, i32, vp], C.c_int),
-        "nfdpm_gemm_nt_relu_bwd": ([vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp, vp, vp], C.c_int),
         "nfdpm_opt_chunk": ([], C.c_int),
         "nfdpm_pack_elems": ([], C.c_int),
         "nfdpm_pack_batch": ([vp, i32, i32, vp], C.c_int),
@@ -128,12 +123,12 @@ EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_
            "nfdpm_copy_channels", "nfdpm_im2col3x3", "nfdpm_pack_matrix", "nfdpm_gemm_nt", "nfdpm_coupling_apply",
            "nfdpm_split_prior_logp", "nfdpm_split_prior_sample", "nfdpm_gauss_logp_const",
            "nfdpm_gauss_sample_const", "nfdpm_accumulate", "nfdpm_rows_to_nchw", "nfdpm_nchw_to_rows",
-           "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary", "nfdpm_coupling_fused", "nfdpm_fold_actnorm",
+           "nfdpm_flow_boundary_smem", "nfdpm_flow_boundary",
            "nfdpm_coupling_bwd", "nfdpm_actnorm_relu_bwd", "nfdpm_reduce_rows", "nfdpm_mix_bwd", "nfdpm_mix_param_grad",
            "nfdpm_gemm_tn_workspace", "nfdpm_gemm_tn", "nfdpm_split_prior_bwd", "nfdpm_gauss_const_bwd",
            "nfdpm_col2im_add", "nfdpm_flow_boundary_stash", "nfdpm_reduce_rows2",
            "nfdpm_opt_chunk", "nfdpm_fused_clip_adam", "nfdpm_pack_elems", "nfdpm_pack_batch",
-           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_nt_relu_bwd", "nfdpm_boundary_gemm1_ok", "nfdpm_boundary_gemm1", "nfdpm_deep_step_debug", "nfdpm_gemm_debug", "nfdpm_flow_boundary_debug", "nfdpm_deep_step_ok", "nfdpm_deep_step",
+           "nfdpm_gemm3_boundary_ok", "nfdpm_gemm3_boundary", "nfdpm_coupling_bwd_tiles", "nfdpm_mix_bwd_tiles", "nfdpm_gemm_debug", "nfdpm_flow_boundary_debug",
            "nfdpm_latent_format", "nfdpm_postprocess_u8", "nfdpm_preprocess",
            "nfdpm_flow_boundary_tiles", "nfdpm_flow_boundary_tiled"]
 
@@ -163,6 +158,8 @@ def _dt(t: torch.Tensor) -> int:
         return F64
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == SPLIT:
+        return BF16X2
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 
@@ -264,12 +261,8 @@ def flow_boundary(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, b
                                 H, W, int(inverse), _st()))
 
 
-def coupling_fused(a1, lda1, w1, w2, w3, pm, ldp, M, K1p, ep) -> None:
-    _ok(lib.nfdpm_coupling_fused(_p(a1), lda1, _p(w1), _p(w2), _p(w3), _p(pm), ldp, M, K1p, _p(ep), _st()))
 
 
-def fold_actnorm(scale, bias, e_out, eb_out, n) -> None:
-    _ok(lib.nfdpm_fold_actnorm(_p(scale), _p(bias), _p(e_out), _p(eb_out), n, _st()))
 
 
 # ---------------------------------------------------------------------------------------------- backward
@@ -382,36 +375,19 @@ def gemm3_boundary_ok(B, Cc, H, W, K, ldp) -> bool:
 
 def gemm3_boundary(h2, ldh, w3p, pm_out, ld_pm_out, src, src_bs, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1,
                    lda1, B, Cc, H, W, K, ldp, inverse) -> None:
-    _ok(lib.nfdpm_gemm3_boundary(_p(h2), ldh, _p(w3p), _p(pm_out), ld_pm_out, _p(src), src_bs, _p(bias3), _p(logs3),
+    _ok(lib.nfdpm_gemm3_boundary(_p(h2), _dt(h2), ldh, _p(w3p), _p(pm_out), ld_pm_out, _p(src), src_bs, _p(bias3), _p(logs3),
                                  _p(ld_part), _p(mt), _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1),
                                  _dt(a1) if a1 is not None else F32, lda1, B, Cc, H, W, K, ldp, int(inverse), _st()))
 
 
-def boundary_gemm1_ok(Cc, H, W, Fh, K1p) -> bool:
-    return bool(lib.nfdpm_boundary_gemm1_ok(Cc, H, W, Fh, K1p))
 
 
-def boundary_gemm1(src, src_bs, squeeze_in, pm, ldp, bias3, logs3, ld_part, mt, beta, y, y_bs, xs, xs_bs, a1, w1p, s1, b1, h1,
-                   B, Cc, H, W, Fh, K1p, inverse) -> None:
-    _ok(lib.nfdpm_boundary_gemm1(_p(src), src_bs, int(squeeze_in), _p(pm), ldp, _p(bias3), _p(logs3), _p(ld_part), _p(mt),
-                                 _p(beta), _p(y), y_bs, _p(xs), xs_bs, _p(a1), _p(w1p), _p(s1), _p(b1), _p(h1), B, Cc, H, W,
-                                 Fh, K1p, int(inverse), _st()))
 
 
-def deep_step_ok(B, Cc, H, W, Fh, K1p, ldp) -> bool:
-    return bool(lib.nfdpm_deep_step_ok(B, Cc, H, W, Fh, K1p, ldp))
 
 
-def deep_step(a1_in, w1p, w2p, w3p, s1, b1, s2, b2, h1, h2, pm, ld_pm, src, src_bs, bias3, logs3, ld_part, mt, beta, y, y_bs,
-              xs, xs_bs, a1, lda1, B, Cc, H, W, Fh, K1p, ldp, inverse) -> None:
-    _ok(lib.nfdpm_deep_step(_p(a1_in), _p(w1p), _p(w2p), _p(w3p), _p(s1), _p(b1), _p(s2), _p(b2), _p(h1), _p(h2), _p(pm),
-                            ld_pm, _p(src), src_bs, _p(bias3), _p(logs3), _p(ld_part), _p(mt), _p(beta), _p(y), y_bs,
-                            _p(xs), xs_bs, _p(a1), _dt(a1) if a1 is not None else F32, lda1, B, Cc, H, W, Fh, K1p, ldp,
-                            int(inverse), _st()))
 
 
-def gemm_nt_relu_bwd(A, lda, Bw, ldb, dpre, ldd, M, Nn, K, h, ldh, scale, part) -> None:
-    _ok(lib.nfdpm_gemm_nt_relu_bwd(_p(A), lda, _p(Bw), ldb, _p(dpre), ldd, M, Nn, K, _p(h), ldh, _p(scale), _p(part), _st()))
 
 
 def latent_format(parts, cat, B, Ct, Ht, Wt, to_cat: bool) -> None:

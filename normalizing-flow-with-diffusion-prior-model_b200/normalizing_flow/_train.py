@@ -94,7 +94,7 @@ def forward_train(glow, x: Tensor, with_logp: bool):
     steps = [s for flows, _ in levels for s in flows]
     E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
     K = glow.K
-    dt = E.coupling_dtype()
+    dt = E.coupling_dtype(train=True)
     glow._pack_plan(steps, dt, True).refresh()      # every forward / transposed weight layout in one launch
     st = Stash()
     st.B, st.with_logp, st.in_shape, st.dt = B, with_logp, (B, c, H, W), dt
@@ -141,7 +141,7 @@ def forward_train(glow, x: Tensor, with_logp: bool):
         for k, step in enumerate(flows):
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
-            cache = cp._cache
+            cache = cp._cache.at(dt)
             if not fast:      # images larger than one CTA: unfused K-A + im2col (any size)
                 N.channel_mix(lv.x[k], lv.u[k], step._mix.fwd_mt, step._mix.fwd_beta, B, C, P, C * P, C * P)
                 N.im2col3x3(lv.u[k], lv.A1[k], B, C // 2, h, w, C * P, K1p)
@@ -296,9 +296,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         pong = (torch.empty(B, C, P, **f32), torch.empty(B, C, P, **f32))   # dx of successive steps alternate
         Kp3 = E.round_up(9 * C, 64)
         dh = torch.empty(M * F, dtype=dt, device=dev)
-        n_mt = (M + 127) // 128
         tc = dt == torch.bfloat16            # tensor-core wgrad: in-kernel split reduction + direct weight layouts
-        fused_rb = tc and os.environ.get("NFDPM_FUSED_RELU_BWD", "0") == "1"
         # The weight-gradient GEMMs feed only the optimiser: they run on a SIDE stream, concurrently with the
         # dgrad / elementwise chain of the same and the next StepFlow.  Their operands (dpm, dpre2, dpre1) are therefore
         # double-buffered across steps, and a buffer set is rewritten only after the side stream has read it.
@@ -311,7 +309,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         read_done = [None, None]
         dA1 = torch.empty(M * K1p, **f32)
         # ActNorm partial-sum buffers: one per (buffer set, layer) so their reductions can run on the side stream too
-        an_part_b = [[torch.empty(max(n_cta, n_mt) * 2 * F, **f32) for _ in range(2)] for _ in range(nbuf)]
+        an_part_b = [[torch.empty(n_cta * 2 * F, **f32) for _ in range(2)] for _ in range(nbuf)]
         T_c, T_m = N.coupling_bwd_tiles(C, h, w), N.mix_bwd_tiles(C, h, w)     # pixel tiles per image (1: image per CTA)
         dpar3 = torch.empty(B * T_c * 2 * C, **f32)
         dp_scratch = torch.empty(M * C, **f32) if T_c > 1 else None
@@ -360,27 +358,20 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             else:
                 N.gemm_tn(dpm, Kp3, lv.h2[k], F, d3, M, ldp, F, ws, fused_reduce=False)
                 N.pack_matrix(d3, sink.get(zc.weight), C, F, 9, F, 1, C * F, 9, C * F)
-            # second Conv2dActNorm (1x1).  The dgrad GEMM with the ActNorm+ReLU backward fused into its epilogue exists
-            # (nfdpm_gemm_nt_relu_bwd) but is epilogue-bound today (measured in graph, level 0: 32.9 / 40.7 us fused vs
-            # 10.8+18.3 / 18.2+18.3 us GEMM + elementwise kernel; profiles/r01_levels_bwd_in_graph.txt): opt-in.
-            if fused_rb:
-                N.gemm_nt_relu_bwd(dpm, Kp3, bc.w3t, Kp3, dpre, F, M, F, Kp3, lv.h2[k], F, an2.scale, an_part)
-                n_red = n_mt
-            else:
-                N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
-                N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, rows_cta)
-                n_red = n_cta
+            # second Conv2dActNorm (1x1).  (A dgrad GEMM with the ActNorm+ReLU backward fused into its epilogue was measured
+            # in round 1 and was epilogue-bound: 32.9 / 40.7 us against 10.8+18.3 / 18.2+18.3 us for GEMM + elementwise
+            # kernel at level 0, profiles/r01_levels_bwd_in_graph.txt; it left the library.)
+            N.gemm_nt(dpm, Kp3, bc.w3t, Kp3, dh, F, M, F, Kp3)
+            N.actnorm_relu_bwd(dh, F, lv.h2[k], F, an2.scale, dpre, F, an_part, M, F, rows_cta)
+            n_red = n_cta
 
             def side2():
                 N.reduce_rows2(an_part, sink.get(an2.scale), sink.get(an2.bias), n_red, F, F, 2 * F)
                 N.gemm_tn(dpre, F, lv.h1[k], F, sink.get(conv2.weight), M, F, F, ws, fused_reduce=tc)
             wgrad(side2)
             # first Conv2dActNorm (3x3)
-            if fused_rb:
-                N.gemm_nt_relu_bwd(dpre, F, bc.w2t, F, dpre1, F, M, F, F, lv.h1[k], F, an1.scale, an_part1)
-            else:
-                N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
-                N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre1, F, an_part1, M, F, rows_cta)
+            N.gemm_nt(dpre, F, bc.w2t, F, dh, F, M, F, F)
+            N.actnorm_relu_bwd(dh, F, lv.h1[k], F, an1.scale, dpre1, F, an_part1, M, F, rows_cta)
 
             def side1():
                 N.reduce_rows2(an_part1, sink.get(an1.scale), sink.get(an1.bias), n_red, F, F, 2 * F)

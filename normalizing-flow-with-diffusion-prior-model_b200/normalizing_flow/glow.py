@@ -138,7 +138,7 @@ class Glow(Transform):
         """The batched weight-packing job table for (dtype, train); built once, dropped when the module moves."""
         key = (dt, train)
         plan = self._plans.get(key)
-        if plan is None:
+        if plan is None or not plan.valid():
             plan = self._plans[key] = E.PackPlan(steps, dt, train)
         return plan
 
@@ -179,11 +179,7 @@ class Glow(Transform):
     def _refresh_caches(self, steps, slots) -> None:
         """Re-run LU/fold and weight packing for parameters that changed (outside any graph)."""
         E.prepare_mix([s._mix_entry(slots[i:i + 1]) for i, s in enumerate(steps)])
-        dt = torch.float32 if E.precision() == "fp32" else torch.bfloat16
-        self._pack_plan(steps, dt, False).refresh()
-        if dt == torch.bfloat16 and E.fused_coupling_enabled():
-            for s in steps:
-                E.refresh_folded(s.affcoupling)
+        self._pack_plan(steps, E.coupling_dtype(), False).refresh()
         for blk in self.blocks:
             E.refresh_split(blk.split, blk.flows[0]._C)
 

@@ -12,7 +12,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "normalizing-flow-with-diffusion-prior-model_b200")
-for p in (ROOT, PKG):
+for p in (ROOT, PKG, os.path.join(ROOT, "tests")):        # tests/: helper modules (split_pairs)
     if p not in sys.path:
         sys.path.insert(0, p)
 GOLDEN = os.path.join(ROOT, "tests", "golden")

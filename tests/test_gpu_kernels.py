@@ -9,6 +9,7 @@ import torch.nn.functional as F
 
 from normalizing_flow import _native as N
 from oracle import glow_oracle as O
+import split_pairs as SP
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -21,6 +22,13 @@ def rnd(*shape, seed=0, scale=1.0):
 
 def sync():
     torch.cuda.synchronize()
+
+
+def a1f(t):
+    """im2col rows of any operand format as fp32 values on the CPU."""
+    if t.dtype == N.SPLIT:
+        return SP.value(t.cpu(), t.shape[0], t.shape[1]).float()
+    return t.float().cpu()
 
 
 @pytest.mark.parametrize("C,P,B", [(3, 784, 2), (4, 256, 3), (8, 64, 5), (12, 256, 4), (16, 16, 9), (24, 64, 4),
@@ -350,9 +358,76 @@ def test_gemm_nt_bf16_tensor_core(M, N_, K, epi, out_dt):
         assert torch.allclose(got, ref, rtol=6e-3, atol=6e-3)
 
 
+# ------------------------------------------------------------------ split bf16 pairs (NFDPM_BF16X2): fp32-faithful tensor-core mode
+def test_split_pair_layout_pack_and_im2col():
+    """pack_matrix / im2col3x3 writing split pairs == the host-side encoding of the same fp32 values, BIT EXACT
+    (hi = bf16(v), lo = bf16(v - hi), groups of 32 columns interleaved), and hi + lo reproduces v to 2^-16."""
+    C, Fe, ldp = 12, 64, 112
+    w3 = rnd(C, Fe, 3, 3, seed=10)
+    out = torch.full((ldp, Fe), 5, dtype=N.SPLIT, device=DEV)
+    N.pack_matrix(w3.cuda(), out, 9, C, Fe, 1, Fe * 9, 9, Fe, ldp)
+    ref = torch.zeros(ldp, Fe)
+    ref[:9 * C] = w3.permute(2, 3, 0, 1).reshape(9 * C, Fe)
+    sync()
+    assert torch.equal(out.cpu(), SP.encode(ref))
+    assert float((SP.value(out.cpu(), ldp, Fe) - ref.double()).abs().max()) <= 2.0 ** -16 * float(ref.abs().max())
+    B, Cin, H, W, ld = 3, 6, 16, 16, 64
+    x = rnd(B, 2 * Cin, H, W, seed=9)
+    a = torch.full((B * H * W, ld), 7, dtype=N.SPLIT, device=DEV)
+    N.im2col3x3(x.cuda(), a, B, Cin, H, W, 2 * Cin * H * W, ld)
+    sync()
+    cols = torch.zeros(B * H * W, ld)
+    cols[:, :Cin * 9] = F.unfold(x[:, :Cin], 3, padding=1).permute(0, 2, 1).reshape(B * H * W, Cin * 9)
+    assert torch.equal(a.cpu(), SP.encode(cols))
+
+
+@pytest.mark.parametrize("M,N_,K", [(128, 256, 64), (300, 512, 64), (77, 112, 512), (4096, 224, 512), (2048, 432, 512),
+                                    (129, 32, 128), (32768, 512, 512), (1000, 512, 256), (8192, 512, 128), (50000, 64, 64)])
+@pytest.mark.parametrize("epi", [N.EPI_RAW, N.EPI_ACTNORM_RELU])
+@pytest.mark.parametrize("out", ["f32", "split"])
+def test_gemm_nt_split_pairs_reach_fp32_accuracy(M, N_, K, epi, out):
+    """Split-pair operands, three tcgen05.mma per K slice (hi*hi + lo*hi + hi*lo), fp32 TMEM accumulation: the product of
+    fp32 matrices within 2e-5 of the fp64 product relative to |A||B| row/column norms (bf16 operands: ~4e-3), i.e. the
+    accuracy of an fp32 GEMM.  Split-pair OUTPUT carries the fp32 result to 2^-16 relative."""
+    if out == "split" and N_ % 32:
+        pytest.skip("split-pair rows hold whole groups of 32 columns")
+    a, b = rnd(M, K, seed=M % 97), rnd(N_, K, seed=N_ + 1) * 0.1
+    es, eb = rnd(N_, seed=3, scale=0.2), rnd(N_, seed=4)
+    d = torch.full((M, N_), 3, dtype=torch.float32 if out == "f32" else N.SPLIT, device=DEV)
+    N.gemm_nt(SP.encode(a).cuda(), K, SP.encode(b).cuda(), K, d, N_, M, N_, K, epi, es.cuda(), eb.cuda())
+    sync()
+    ref = a.double() @ b.double().T
+    scale = a.double().norm(dim=1)[:, None] * b.double().norm(dim=1)[None, :]
+    if epi == N.EPI_ACTNORM_RELU:
+        ref = torch.relu(torch.exp(es.double()) * (ref + eb.double()))
+        scale = torch.exp(es.double()) * (scale + eb.double().abs())
+    got = d.cpu().double() if out == "f32" else SP.value(d.cpu(), M, N_)
+    err = float(((got - ref).abs() / scale).max())
+    assert err < 2e-5, err
+    if out == "split":
+        hi, lo = SP.decode(d.cpu(), M, N_)
+        assert bool((lo.abs() <= 2.0 ** -8 * hi.abs()).all())      # lo is the rounding residual of hi
+
+
+def test_gemm_nt_split_pairs_vs_plain_bf16_error():
+    """The same product with plain bf16 operands is > 100x less accurate: what the mode buys (measured 4.8e-6 vs 2.3e-3
+    relative L2; the split-pair figure is the 2^-18 rms representation error of hi + lo, twice)."""
+    M, N_, K = 2048, 512, 512
+    a, b = rnd(M, K, seed=1), rnd(N_, K, seed=2) * 0.1
+    ref = a.double() @ b.double().T
+    d3 = torch.empty(M, N_, device=DEV)
+    N.gemm_nt(SP.encode(a).cuda(), K, SP.encode(b).cuda(), K, d3, N_, M, N_, K)
+    d1 = torch.empty(M, N_, device=DEV)
+    N.gemm_nt(a.bfloat16().cuda(), K, b.bfloat16().cuda(), K, d1, N_, M, N_, K)
+    sync()
+    e3 = float((d3.cpu().double() - ref).norm() / ref.norm())
+    e1 = float((d1.cpu().double() - ref).norm() / ref.norm())
+    assert e3 < 1e-5 and e1 > 100 * e3, (e3, e1)
+
+
 # ------------------------------------------------------------------ fused step-boundary kernel
 @pytest.mark.parametrize("B,C,H,W", [(3, 4, 16, 16), (5, 12, 16, 16), (4, 24, 8, 8), (7, 48, 4, 4), (2, 6, 5, 7), (2, 16, 2, 2)])
-@pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16, N.SPLIT])
 def test_flow_boundary_equals_unfused_chain(B, C, H, W, a1_dt):
     """nfdpm_flow_boundary == coupling_apply -> channel_mix -> im2col3x3 (forward and inverse), and
     squeeze -> channel_mix -> im2col3x3 at a level entry."""
@@ -380,7 +455,7 @@ def test_flow_boundary_equals_unfused_chain(B, C, H, W, a1_dt):
                         B, C, H, W, inverse)
         sync()
         assert torch.allclose(u, u_ref, rtol=1e-5, atol=1e-5)
-        assert torch.allclose(a1.float(), a_ref.float(), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-5, atol=1e-5)
+        assert torch.allclose(a1f(a1), a1f(a_ref), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-5, atol=1e-5)
         if not inverse:
             assert torch.allclose(part, part_ref.reshape(-1, B).sum(0), rtol=1e-5, atol=1e-4)
         # coupling only, in place, no mix / no im2col (last step of a level)
@@ -409,7 +484,7 @@ def test_flow_boundary_equals_unfused_chain(B, C, H, W, a1_dt):
         N.flow_boundary(src, (C // 2) * 4 * P, True, None, 0, None, None, None, mt, beta, u, C * P, a1, lda, B, C, H, W, False)
         sync()
         assert torch.allclose(u, u_ref, rtol=1e-5, atol=1e-5)
-        assert torch.allclose(a1.float(), a_ref.float(), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-5, atol=1e-5)
+        assert torch.allclose(a1f(a1), a1f(a_ref), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-5, atol=1e-5)
 
 
 def test_flow_boundary_rejects_large_images():
@@ -420,42 +495,6 @@ def test_flow_boundary_rejects_large_images():
 
 
 # ------------------------------------------------------------------ fused coupling network (tcgen05)
-@pytest.mark.parametrize("M,K1p,ldp", [(300, 64, 112), (128, 64, 48), (8192, 128, 224), (2048, 256, 432),
-                                       (32768, 64, 112), (5000, 128, 224), (77, 192, 160)])
-def test_coupling_fused_equals_three_gemms(M, K1p, ldp):
-    """nfdpm_coupling_fused == gemm_nt(ACTNORM_RELU) -> gemm_nt(ACTNORM_RELU) -> gemm_nt(RAW) on the tensor-core path
-    (same bf16 roundings of h1/h2, same K order), and both agree with an fp64 reference of the bf16 pipeline."""
-    Fh = 512
-    a1 = rnd(M, K1p, seed=1).bfloat16().cuda()
-    w1 = (rnd(Fh, K1p, seed=2) * (1.0 / math.sqrt(K1p))).bfloat16().cuda()
-    w2 = (rnd(Fh, Fh, seed=3) * (1.0 / math.sqrt(Fh))).bfloat16().cuda()
-    w3 = (rnd(ldp, Fh, seed=4) * 0.05).bfloat16().cuda()
-    s1, b1 = rnd(Fh, seed=5, scale=0.2).cuda(), rnd(Fh, seed=6, scale=0.5).cuda()
-    s2, b2 = rnd(Fh, seed=7, scale=0.2).cuda(), rnd(Fh, seed=8, scale=0.5).cuda()
-    h1 = torch.empty(M, Fh, dtype=torch.bfloat16, device=DEV)
-    h2 = torch.empty(M, Fh, dtype=torch.bfloat16, device=DEV)
-    pm_ref = torch.empty(M, ldp, device=DEV)
-    N.gemm_nt(a1, K1p, w1, K1p, h1, Fh, M, Fh, K1p, N.EPI_ACTNORM_RELU, s1, b1)
-    N.gemm_nt(h1, Fh, w2, Fh, h2, Fh, M, Fh, Fh, N.EPI_ACTNORM_RELU, s2, b2)
-    N.gemm_nt(h2, Fh, w3, Fh, pm_ref, ldp, M, ldp, Fh)
-    ep = torch.empty(4 * Fh, device=DEV)
-    N.fold_actnorm(s1, b1, ep, ep[Fh:], Fh)
-    N.fold_actnorm(s2, b2, ep[2 * Fh:], ep[3 * Fh:], Fh)
-    pm = torch.full((M, ldp), 123.0, device=DEV)
-    N.coupling_fused(a1, K1p, w1, w2, w3, pm, ldp, M, K1p, ep)
-    sync()
-    assert torch.isfinite(pm).all()
-    assert torch.allclose(pm, pm_ref, rtol=1e-5, atol=1e-5), float((pm - pm_ref).abs().max())
-    # fp64 reference of the same bf16 pipeline (first 256 rows)
-    n = min(M, 256)
-    H1 = torch.relu(torch.exp(s1.double().cpu()) * (a1[:n].double().cpu() @ w1.double().cpu().T + b1.double().cpu()))
-    H1 = H1.float().bfloat16().double()
-    H2 = torch.relu(torch.exp(s2.double().cpu()) * (H1 @ w2.double().cpu().T + b2.double().cpu())).float().bfloat16().double()
-    ref = H2 @ w3.double().cpu().T
-    assert torch.allclose(pm[:n].cpu().double(), ref, rtol=2e-2, atol=2e-2)
-
-
-# ------------------------------------------------------------------ weight-gradient GEMM (TN)
 @pytest.mark.parametrize("M,N1,lda,N2,ldb", [(32768, 512, 512, 512, 512), (8192, 224, 256, 512, 512),
                                              (2048, 432, 448, 512, 512), (4096, 512, 512, 64, 64),
                                              (300, 112, 128, 512, 512), (64, 512, 512, 128, 128),
@@ -498,20 +537,25 @@ def test_gemm_tn_cuda_core(dta, dtb):
 # ------------------------------------------------------------------ ZeroConv GEMM + step boundary in one kernel
 @pytest.mark.parametrize("B,C,H,W", [(5, 12, 16, 16), (3, 4, 16, 16), (5, 24, 8, 8), (4, 8, 8, 8), (11, 48, 4, 4),
                                      (8, 16, 4, 4), (6, 32, 4, 2)])
-@pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16])
-def test_gemm3_boundary_equals_gemm_plus_boundary(B, C, H, W, a1_dt):
-    """nfdpm_gemm3_boundary == nfdpm_gemm_nt (bf16 tcgen05, fp32 out) -> nfdpm_flow_boundary_stash: every sink
-    (state, pre-mix stash, im2col rows, log-det partials, pm copy), forward and inverse, with and without the next mix;
-    B deliberately not a multiple of the images-per-CTA count."""
+@pytest.mark.parametrize("a1_dt,op_dt", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+                                         (N.SPLIT, N.SPLIT), (torch.float32, N.SPLIT)])
+def test_gemm3_boundary_equals_gemm_plus_boundary(B, C, H, W, a1_dt, op_dt):
+    """nfdpm_gemm3_boundary == nfdpm_gemm_nt (tcgen05, bf16 or split-pair operands, fp32 out) -> nfdpm_flow_boundary_stash:
+    every sink (state, pre-mix stash, im2col rows, log-det partials, pm copy), forward and inverse, with and without the
+    next mix; B deliberately not a multiple of the images-per-CTA count."""
     P, Ch, F = H * W, C // 2, 512
     ldp = (9 * C + 15) // 16 * 16
     lda = (9 * Ch + 63) // 64 * 64
     M = B * P
-    assert N.gemm3_boundary_ok(B, C, H, W, F, ldp)
+    assert N.gemm3_boundary_ok(B, C, H, W, F * (2 if op_dt == N.SPLIT else 1), ldp)
     x = rnd(B, C, H, W, seed=1).cuda()
-    h2 = (rnd(M, F, seed=2).cuda().clamp_min(0) * 0.5).to(torch.bfloat16)
-    w3 = (rnd(ldp, F, seed=3, scale=0.02).cuda()).to(torch.bfloat16)
+    h2 = rnd(M, F, seed=2).clamp_min(0) * 0.5
+    w3 = rnd(ldp, F, seed=3, scale=0.02)
     w3[9 * C:] = 0
+    if op_dt == N.SPLIT:
+        h2, w3 = SP.encode(h2).cuda(), SP.encode(w3).cuda()
+    else:
+        h2, w3 = h2.cuda().to(torch.bfloat16), w3.cuda().to(torch.bfloat16)
     bias3, logs3 = rnd(C, seed=4, scale=0.1).cuda(), rnd(C, seed=5, scale=0.1).cuda()
     mt, beta = rnd(C, C, seed=6, scale=0.4).cuda(), rnd(C, seed=7).cuda()
     pm_ref = torch.empty(M, ldp, device=DEV)
@@ -539,7 +583,7 @@ def test_gemm3_boundary_equals_gemm_plus_boundary(B, C, H, W, a1_dt):
             assert torch.equal(pm_out, pm_ref)
             assert torch.allclose(y, y_ref, rtol=1e-6, atol=1e-6), float((y - y_ref).abs().max())
             if with_mix:
-                assert torch.allclose(a1.float(), a_ref.float(), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-6, atol=1e-6)
+                assert torch.allclose(a1f(a1), a1f(a_ref), rtol=1e-2 if a1_dt == torch.bfloat16 else 1e-6, atol=1e-6)
             if not inverse:
                 assert torch.allclose(xs, xs_ref, rtol=1e-6, atol=1e-6)
                 assert torch.allclose(part, part_ref, rtol=1e-6, atol=1e-5)
@@ -559,153 +603,3 @@ def test_gemm3_boundary_support_query():
     assert not N.gemm3_boundary_ok(2, 96, 8, 8, 512, 864)        # 9C > 512 TMEM columns
     assert not N.gemm3_boundary_ok(3, 16, 2, 2, 512, 144)        # 32 images per tile: more than one per warp
     assert N.gemm3_boundary_ok(128, 48, 4, 4, 512, 432)
-
-
-# ------------------------------------------------------------------ step boundary + GEMM1 of the next StepFlow
-@pytest.mark.parametrize("B,C,H,W", [(3, 12, 16, 16), (5, 24, 8, 8), (7, 48, 4, 4), (4, 8, 8, 8), (6, 32, 4, 2),
-                                     (2, 16, 8, 16)])
-def test_boundary_gemm1_equals_boundary_plus_gemm(B, C, H, W):
-    """nfdpm_boundary_gemm1 == nfdpm_flow_boundary(_stash) -> nfdpm_gemm_nt(EPI_ACTNORM_RELU), BIT EXACT: state, pre-mix
-    stash, log-det partials, the optional global im2col copy and h1; coupling source (forward / inverse), plain source and
-    squeeze source; one and two 128-row tiles per image, resident and ring-fed weights."""
-    P, Ch, F = H * W, C // 2, 512
-    ldp = (9 * C + 15) // 16 * 16
-    K1p = (9 * Ch + 63) // 64 * 64
-    M = B * P
-    bf = torch.bfloat16
-    assert N.boundary_gemm1_ok(C, H, W, F, K1p)
-    pm = rnd(M, ldp, seed=1, scale=0.3).cuda()
-    w1 = (rnd(F, K1p, seed=2, scale=0.1).cuda()).to(bf)
-    w1[:, 9 * Ch:] = 0
-    s1, b1 = rnd(F, seed=3, scale=0.1).cuda(), rnd(F, seed=4, scale=0.3).cuda()
-    x = rnd(B, C, H, W, seed=5).cuda()
-    xsq = rnd(B, C // 4, 2 * H, 2 * W, seed=6).cuda()
-    mt, beta = rnd(C, C, seed=7, scale=0.3).cuda(), rnd(C, seed=8).cuda()
-    bias3, logs3 = rnd(C, seed=9, scale=0.1).cuda(), rnd(C, seed=10, scale=0.1).cuda()
-    for mode in ("coupling_fwd", "coupling_inv", "plain", "squeeze"):
-        for stash in (True, False):
-            cp, inv, sq = mode.startswith("coupling"), mode == "coupling_inv", mode == "squeeze"
-            src = xsq if sq else x
-            cargs = (pm, ldp, bias3, logs3) if cp else (None, 0, None, None)
-            y_ref, xs_ref = torch.empty_like(x), torch.empty_like(x)
-            a_ref = torch.empty(M, K1p, dtype=bf, device=DEV)
-            part_ref = torch.zeros(B, device=DEV)
-            if inv:
-                N.flow_boundary(src, C * P, False, *cargs, None, mt, beta, y_ref, C * P, a_ref, K1p, B, C, H, W, True)
-            else:
-                N.flow_boundary_stash(src, C * P, sq, *cargs, part_ref if cp else None, mt, beta, y_ref, C * P, xs_ref, C * P,
-                                      a_ref, K1p, B, C, H, W)
-            h1_ref = torch.empty(M, F, dtype=bf, device=DEV)
-            N.gemm_nt(a_ref, K1p, w1, K1p, h1_ref, F, M, F, K1p, N.EPI_ACTNORM_RELU, s1, b1)
-            y, xs = torch.empty_like(x), torch.empty_like(x)
-            a1 = torch.full((M, K1p), 7.0, dtype=bf, device=DEV) if stash else None
-            part = torch.zeros(B, device=DEV)
-            h1 = torch.full((M, F), float("nan"), dtype=bf, device=DEV)
-            N.boundary_gemm1(src, C * P, sq, *cargs, part if (cp and not inv) else None, mt, beta, y, C * P,
-                             None if inv else xs, 0 if inv else C * P, a1, w1, s1, b1, h1, B, C, H, W, F, K1p, inv)
-            sync()
-            assert torch.equal(y, y_ref) and torch.equal(h1, h1_ref), (mode, stash)
-            if stash:
-                assert torch.equal(a1, a_ref)
-            if not inv:
-                assert torch.equal(xs, xs_ref) and torch.equal(part, part_ref)
-
-
-def test_boundary_gemm1_support_query():
-    assert not N.boundary_gemm1_ok(12, 64, 64, 512, 64)         # image larger than two 128-row tiles
-    assert not N.boundary_gemm1_ok(6, 14, 14, 512, 64)          # 196 pixels
-    assert not N.boundary_gemm1_ok(12, 16, 16, 256, 64)         # hidden width other than 512
-    assert N.boundary_gemm1_ok(12, 16, 16, 512, 64) and N.boundary_gemm1_ok(48, 4, 4, 512, 256)
-
-
-# ------------------------------------------------------------------ cluster-fused StepFlow of a deep level
-@pytest.mark.parametrize("B,C,H,W", [(5, 24, 8, 8), (4, 8, 8, 8), (13, 48, 4, 4), (8, 16, 4, 4), (6, 32, 4, 2)])
-@pytest.mark.parametrize("a1_dt", [torch.float32, torch.bfloat16])
-def test_deep_step_equals_four_kernel_chain(B, C, H, W, a1_dt):
-    """nfdpm_deep_step (one launch: thread-block cluster per 128-row tile, GEMMs split along N, h1/h2/pm exchanged through
-    distributed shared memory) == 3 x nfdpm_gemm_nt + nfdpm_flow_boundary(_stash), BIT EXACT for every output (state,
-    pre-mix stash, im2col rows, log-det partials and the optional global copies of h1 / h2 / pm), forward and inverse,
-    with and without the next mix; B deliberately not a multiple of the images-per-tile count."""
-    P, Ch, F = H * W, C // 2, 512
-    ldp = (9 * C + 15) // 16 * 16
-    K1p = (9 * Ch + 63) // 64 * 64
-    M = B * P
-    assert N.deep_step_ok(B, C, H, W, F, K1p, ldp)
-    bf = torch.bfloat16
-    a1_in = (rnd(M, K1p, seed=1, scale=0.5).cuda()).to(bf)
-    a1_in[:, 9 * Ch:] = 0
-    w1 = (rnd(F, K1p, seed=2, scale=0.1).cuda()).to(bf)
-    w2 = (rnd(F, F, seed=3, scale=0.05).cuda()).to(bf)
-    w3 = (rnd(ldp, F, seed=4, scale=0.02).cuda()).to(bf)
-    w3[9 * C:] = 0
-    s1, b1, s2, b2 = (rnd(F, seed=5 + i, scale=0.2).cuda() for i in range(4))
-    x = rnd(B, C, H, W, seed=9).cuda()
-    bias3, logs3 = rnd(C, seed=10, scale=0.1).cuda(), rnd(C, seed=11, scale=0.1).cuda()
-    mt, beta = rnd(C, C, seed=12, scale=0.4).cuda(), rnd(C, seed=13).cuda()
-    h1_ref, h2_ref = torch.empty(M, F, dtype=bf, device=DEV), torch.empty(M, F, dtype=bf, device=DEV)
-    pm_ref = torch.empty(M, ldp, device=DEV)
-    N.gemm_nt(a1_in, K1p, w1, K1p, h1_ref, F, M, F, K1p, N.EPI_ACTNORM_RELU, s1, b1)
-    N.gemm_nt(h1_ref, F, w2, F, h2_ref, F, M, F, F, N.EPI_ACTNORM_RELU, s2, b2)
-    N.gemm_nt(h2_ref, F, w3, F, pm_ref, ldp, M, ldp, F)
-    for inverse in (False, True):
-        for with_mix in (True, False):
-            for stash in (True, False):
-                m_, b_ = (mt, beta) if with_mix else (None, None)
-                y_ref, xs_ref = torch.empty_like(x), torch.empty_like(x)
-                a_ref = torch.full((M, K1p), 3.0, dtype=a1_dt, device=DEV) if with_mix else None
-                part_ref = torch.zeros(B, device=DEV)
-                if inverse:
-                    N.flow_boundary(x, C * P, False, pm_ref, ldp, bias3, logs3, None, m_, b_, y_ref, C * P, a_ref,
-                                    K1p if with_mix else 0, B, C, H, W, True)
-                else:
-                    N.flow_boundary_stash(x, C * P, False, pm_ref, ldp, bias3, logs3, part_ref, m_, b_, y_ref, C * P, xs_ref,
-                                          C * P, a_ref, K1p if with_mix else 0, B, C, H, W)
-                y, xs = torch.empty_like(x), torch.empty_like(x)
-                a1 = torch.full((M, K1p), 5.0, dtype=a1_dt, device=DEV) if with_mix else None
-                part = torch.zeros(B, device=DEV)
-                h1 = torch.full((M, F), float("nan"), dtype=bf, device=DEV) if stash else None
-                h2 = torch.full((M, F), float("nan"), dtype=bf, device=DEV) if stash else None
-                pm = torch.full((M, ldp), float("nan"), device=DEV) if stash else None
-                N.deep_step(a1_in, w1, w2, w3, s1, b1, s2, b2, h1, h2, pm, ldp if stash else 0, x, C * P, bias3, logs3,
-                            None if inverse else part, m_, b_, y, C * P, None if inverse else xs, 0 if inverse else C * P,
-                            a1, K1p if with_mix else 0, B, C, H, W, F, K1p, ldp, inverse)
-                sync()
-                if stash:
-                    assert torch.equal(h1, h1_ref) and torch.equal(h2, h2_ref) and torch.equal(pm, pm_ref)
-                assert torch.equal(y, y_ref)
-                if with_mix:
-                    assert torch.equal(a1, a_ref)
-                if not inverse:
-                    assert torch.equal(xs, xs_ref) and torch.equal(part, part_ref)
-
-
-def test_deep_step_support_query():
-    assert not N.deep_step_ok(2, 12, 16, 16, 512, 64, 112)        # 256 pixels: an image is larger than a tile
-    assert not N.deep_step_ok(2, 6, 7, 7, 512, 64, 64)            # 49 pixels do not divide 128
-    assert not N.deep_step_ok(2, 96, 8, 8, 512, 448, 864)         # boundary scratch + operand buffers exceed 227 KB
-    assert N.deep_step_ok(128, 24, 8, 8, 512, 128, 224) and N.deep_step_ok(128, 48, 4, 4, 512, 256, 432)
-
-
-@pytest.mark.parametrize("M,N_,K", [(2048, 512, 512), (1000, 512, 128), (32768, 512, 512), (300, 64, 64)])
-def test_gemm_nt_relu_bwd_fused_epilogue(M, N_, K):
-    """dgrad GEMM with ActNorm+ReLU backward in the tcgen05 epilogue == GEMM followed by nfdpm_actnorm_relu_bwd:
-    dpre and the column sums (d scale, d bias), incl. rows beyond the last full 128-row tile."""
-    A = (rnd(M, K, seed=1, scale=0.5)).to(DEV).to(torch.bfloat16)
-    Bw = (rnd(N_, K, seed=2, scale=0.1)).to(DEV).to(torch.bfloat16)
-    h = rnd(M, N_, seed=3).to(DEV).clamp_min(0).to(torch.bfloat16)          # ~half the entries are zero (ReLU output)
-    scale = rnd(N_, seed=4, scale=0.2).to(DEV)
-    n_mt = (M + 127) // 128
-    dpre = torch.empty(M, N_, dtype=torch.bfloat16, device=DEV)
-    part = torch.full((n_mt * 2 * N_,), float("nan"), device=DEV)
-    N.gemm_nt_relu_bwd(A, K, Bw, K, dpre, N_, M, N_, K, h, N_, scale, part)
-    ds, db = torch.empty(N_, device=DEV), torch.empty(N_, device=DEV)
-    N.reduce_rows2(part, ds, db, n_mt, N_, N_, 2 * N_)
-    sync()
-    acc = A.float() @ Bw.float().T
-    g = torch.where(h.float() > 0, acc, torch.zeros_like(acc))
-    e = torch.exp(scale)
-    ref = g * e
-    assert float((dpre.float() - ref).norm() / ref.norm()) < 4e-3          # bf16 output rounding
-    ds_ref, db_ref = (g * h.float()).sum(0), ref.sum(0)
-    assert float((ds - ds_ref).norm() / ds_ref.norm()) < 1e-4
-    assert float((db - db_ref).norm() / db_ref.norm()) < 1e-4

@@ -72,8 +72,6 @@ for lvl, (C, hw) in enumerate([(12, 16), (24, 8), (48, 4)]):
     r["actnorm_relu_bwd"] = graph_time(lambda: N.actnorm_relu_bwd(dh, F, h2, F, scale, dpre, F, an_part, M, F, rows))
     n_mt = (M + 127) // 128
     part2 = torch.empty(n_mt * 2 * F, **f32)
-    r["dgrad3_fused"] = graph_time(lambda: N.gemm_nt_relu_bwd(dpm, Kp3, w3t, Kp3, dpre, F, M, F, Kp3, h2, F, scale, part2))
-    r["dgrad2_fused"] = graph_time(lambda: N.gemm_nt_relu_bwd(dh, F, w2t, F, dpre, F, M, F, F, h1, F, scale, part2))
     r["reduce_rows2"] = graph_time(lambda: N.reduce_rows2(an_part, gs, gbb, n_cta, F, F, 2 * F))
     r["wgrad2"] = graph_time(lambda: N.gemm_tn(dpre, F, h1, F, dw2, M, F, F, ws))
     r["dgrad2"] = graph_time(lambda: N.gemm_nt(dpre, F, w2t, F, dh, F, M, F, F))
