@@ -6,14 +6,24 @@ under torchrun for N>1 (one rank per GPU).  One "step" = one pass of the hot pat
 images: Glow.transform + GaussianPrior.compute_log_prob (x -> z, log-det, log-p) followed by Glow.invert (z -> x).
 Rank 0 prints ONE JSON line.
 
-  value        images/s (whole job), inputs already resident in HBM, device-timed with CUDA events, L2 flushed
-               between timed steps, max over ranks
+  value        images/s (whole job) in the DEFAULT precision mode (NFDPM_PRECISION=auto: inference in the fp32-faithful
+               split-bf16-pair tensor-core mode that meets the reference's 1e-4 parity bar), inputs resident in HBM,
+               device-timed with CUDA events, L2 flushed between timed steps, max over ranks
   e2e          same metric through the public module API with HOST (pinned) inputs: H2D of the batch and D2H of
                the per-image log-likelihood and the decoded images inside the timed region
-  roofline     the dominant kernel (coupling-net 512x512 GEMM at level 0) timed alone with CUDA events:
-               achieved TFLOP/s vs the measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline the CPU oracle (port of the reference's algorithm, torch-CPU fp32, all host threads) on a bounded
-               sample of the same workload, rank 0 / N=1 only
+  directions   forward(+log-det,+log-p), inverse (all L latents) and the sampling variant (last latent only) separately
+  modes        the same measurements + parity checks per precision mode ("fp32" = the headline, "bf16" = the opt-in fast
+               mode with its stated tolerance)
+  roofline     the dominant kernel (coupling-net 512x512 GEMM at level 0) timed alone (16 back-to-back launches per
+               CUDA-graph replay): algorithmic FLOP/s vs the measured bf16 BURST peak in MEASURED_PEAKS.json (peak/3 in
+               the 3-MMA fp32-faithful mode), with cuBLAS on the same shape beside it; roofline_hbm: the step-boundary
+               (ActNorm + 1x1 conv + affine coupling) kernels against the measured HBM copy bandwidth
+  cpu_baseline the UNMODIFIED reference module (baseline/_ref, staged by __graft_entry__.build()) on the host CPU, all
+               host threads, on a bounded sample of the same workload (rank 0 / N=1 only; own process)
+  gpu_eager_reference  the same unmodified module on cuda:0 through torch eager / cuDNN (the number the
+               kernels must beat), own process
+
+`--impl reference`: the reference arm — the unmodified reference module on the host CPU for the same config (batch 128).
 """
 from __future__ import annotations
 
@@ -28,14 +38,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "normalizing-flow-with-diffusion-prior-model_b200")
-for p in (ROOT, PKG):
-    if p not in sys.path:
-        sys.path.insert(0, p)
 
 CFG = dict(in_channel=3, L=3, K=16, S=32, batch=128)          # BASELINE.json configs[1]
 WORKLOAD = "Glow L3 K16, CIFAR-10 shape 3x32x32, batch 128 per GPU, fwd+logdet+logp then inverse"
-METRIC = "Glow L3/K16 32\u00d732 fwd+logdet & inverse imgs/sec"      # BASELINE.json's metric (its leading clause)
+METRIC = "Glow L3/K16 32×32 fwd+logdet & inverse imgs/sec"      # BASELINE.json's metric (its leading clause)
 FLOP_PER_IMG_FWD = 4.0119e9                                   # SURVEY.md §8 (verified with torch flop counter)
+WEIGHTS = ("reference constructors (seed 0) + data-dependent ActNorm init on the first batch + N(0,1e-3) on every "
+           "ZeroConv tensor (SURVEY 8d)")
+DTYPE_NAME = {"auto": "bf16x3 (split bf16 pairs on tcgen05, fp32 accumulate: fp32-faithful)",
+              "fp32": "bf16x3 (split bf16 pairs on tcgen05, fp32 accumulate: fp32-faithful)",
+              "bf16": "bf16", "fp32_simt": "fp32 (CUDA cores)"}
 
 
 def peaks():
@@ -89,22 +101,9 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_style_state(nf, SY, torch, dev):
-    """Weights as SURVEY §8(d) specifies them: the module constructors under torch.manual_seed(0) (QR-initialised 1x1
-    convs, N(0, 0.05) coupling convs, zero ZeroConvs: transforms.py:112-114, utils.py:37-38,64-65), the data-dependent
-    ActNorm initialisation on the first batch (transforms.py:74-78, always fp32), then N(0, 1e-3) (generator seed 1) on
-    every ZeroConv2d tensor so that no term of the path is degenerate.  Returns CPU state dicts (flow, prior)."""
-    c, L, K, S = CFG["in_channel"], CFG["L"], CFG["K"], CFG["S"]
-    torch.manual_seed(0)
-    flow = nf.Glow(c, L, K).to(dev)
-    prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
-    x = SY.seeded_input((CFG["batch"], c, S, S), 1).to(dev)         # rank 0's batch on every rank: identical replicas
-    with torch.no_grad():
-        ld, lp = nf.initialize_with_zeros(2, x.shape[0], dev)
-        flow.transform(x, ld, lp)
+def perturb_zero_convs(torch, sd, psd):
+    """N(0, 1e-3) (generator seed 1) on every ZeroConv2d tensor, in key order: no term of the path is degenerate."""
     g = torch.Generator().manual_seed(1)
-    sd = {k: v.detach().cpu().clone() for k, v in flow.state_dict().items()}
-    psd = {k: v.detach().cpu().clone() for k, v in prior.state_dict().items()}
     for d in (sd, psd):
         for k in d:
             if ".net.4." in k or ".split.conv." in k or "_GaussianPrior__conv." in k:
@@ -112,56 +111,164 @@ def reference_style_state(nf, SY, torch, dev):
     return sd, psd
 
 
-def oracle_step_fn(B: int, state=None, x=None, out=None):
-    """The reference's CPU path for this workload (oracle port): returns (fn, description)."""
-    import torch
-    from oracle import glow_oracle as O
-    c, L, K, S = CFG["in_channel"], CFG["L"], CFG["K"], CFG["S"]
-    sd, psd = state if state is not None else O.seeded_state(c, L, K, 0)
-    x = O.seeded_input((B, c, S, S), 1) if x is None else x
-
-    def step():
-        with torch.no_grad():
-            ld = torch.zeros(B, dtype=torch.float64)
-            lp = torch.zeros(B, dtype=torch.float64)
-            zs, ld, lp = O.glow_transform(sd, x, L, K, ld, lp)
-            lp += O.gaussian_prior_logp(psd, zs[-1])
-            if out is not None:
-                out["ll"] = ld + lp
-            return O.glow_invert(sd, zs, L, K)
-    return step
+def reference_style_state(nf, torch, dev, x_first):
+    """Weights as SURVEY §8(d) specifies them: the module constructors under torch.manual_seed(0) (QR-initialised 1x1
+    convs, N(0, 0.05) coupling convs, zero ZeroConvs: transforms.py:112-114, utils.py:37-38,64-65), the data-dependent
+    ActNorm initialisation on the first batch (transforms.py:74-78, always fp32), then `perturb_zero_convs`.  Works with
+    the product package AND with the unmodified reference (same constructors, same state_dict).  Returns CPU state dicts."""
+    c, L, K = CFG["in_channel"], CFG["L"], CFG["K"]
+    torch.manual_seed(0)
+    flow = nf.Glow(c, L, K).to(dev)
+    prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
+    x = x_first.to(dev)
+    with torch.no_grad():
+        ld, lp = nf.initialize_with_zeros(2, x.shape[0], dev)
+        flow.transform(x, ld, lp)
+    sd = {k: v.detach().cpu().clone() for k, v in flow.state_dict().items()}
+    psd = {k: v.detach().cpu().clone() for k, v in prior.state_dict().items()}
+    return perturb_zero_convs(torch, sd, psd)
 
 
-def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host CPU (oracle port; the reference is pure Python
-    on torch, so the port IS torch-CPU fp32 running the same op sequence), all host threads."""
-    import torch
+# ------------------------------------------------------------------------------------------- reference arms (own process)
+def run_reference(args, on_gpu: bool):
+    """--impl reference: the UNMODIFIED reference module (baseline/_ref) through its own public API — Glow.transform +
+    GaussianPrior.compute_log_prob + Glow.invert under no_grad, fp32 — on the host CPU with all host threads (the
+    reference arm / cpu_baseline), or with `--impl reference-gpu` on cuda:0 through torch eager + cuDNN (the
+    gpu_eager_reference comparator).  Falls back to the oracle port (kind "port") when no copy of the reference exists."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not on_gpu:
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""            # the reference picks cuda whenever it is visible (base.py:18)
+    import torch
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import synthetic as SY
+    from oracle import reference_module as RM
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the other ranks have exited, so rank 0 takes all host cores
-    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
-    B = 32                                   # bounded sample of the 128-image batch: ~1-2 s per step on 8+ cores
-    step = oracle_step_fn(B)
-    for _ in range(max(1, min(args.warmup, 1))):
+    if not on_gpu:
+        torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
+    c, L, K, S, B = CFG["in_channel"], CFG["L"], CFG["K"], CFG["S"], args.batch
+    dev = torch.device("cuda", 0) if on_gpu else torch.device("cpu")
+    x = SY.seeded_input((B, c, S, S), 1)
+    kind = "reference"
+    try:
+        nf = RM.import_reference()
+        sd, psd = reference_style_state(nf, torch, dev, x)
+        flow = nf.Glow(c, L, K).to(dev)
+        flow.load_state_dict(sd)
+        prior = nf.GaussianPrior(2 ** (L + 1) * c).to(dev)
+        prior.load_state_dict(psd)
+        flow.eval()
+        xd = x.to(dev)
+
+        def fwd():
+            ld, lp = nf.initialize_with_zeros(2, B, dev)
+            zs, ld, lp = flow.transform(xd, ld, lp)
+            lp = lp + prior.compute_log_prob(zs[-1])
+            return zs, ld + lp
+
+        def inv(zs):
+            return flow.invert(zs)
+    except ImportError as e:
+        if on_gpu:
+            print(json.dumps({"impl": "reference-gpu", "unavailable": str(e).splitlines()[0]}))
+            return
+        kind = "port"
+        from oracle import glow_oracle as O
+        sd, psd = O.seeded_state(c, L, K, 0)
+
+        def fwd():
+            ld = torch.zeros(B, dtype=torch.float64)
+            lp = torch.zeros(B, dtype=torch.float64)
+            zs, ld, lp = O.glow_transform(sd, x, L, K, ld, lp)
+            return zs, ld + lp + O.gaussian_prior_logp(psd, zs[-1])
+
+        def inv(zs):
+            return O.glow_invert(sd, zs, L, K)
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize()
+
+    def step():
+        zs, ll = fwd()
+        sync()
+        t_mid = time.perf_counter()
+        xr = inv(zs)
+        sync()
+        return t_mid, xr
+
+    tf32 = None
+    if on_gpu:
+        # torch's defaults: cuDNN convolutions may use TF32 (allow_tf32=True), matmuls may not
+        tf32 = bool(torch.backends.cudnn.allow_tf32) if args.tf32 is None else bool(args.tf32)
+        torch.backends.cudnn.allow_tf32 = tf32
+    budget = args.time_budget
+    with torch.no_grad():
+        t0 = time.perf_counter()
         step()
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
+        first = time.perf_counter() - t0
+        warm = max(0, min(args.warmup - 1, int(0.2 * budget / max(first, 1e-3))))
+        for _ in range(warm):
+            step()
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / steps
+        one = time.perf_counter() - t0
+        steps = max(1, min(args.steps, int(0.8 * budget / max(one, 1e-3))))
+        t_f = t_i = 0.0
+        recon = 0.0
+        for _ in range(steps):
+            sync()
+            a = time.perf_counter()
+            t_mid, xr = step()
+            b = time.perf_counter()
+            t_f += t_mid - a
+            t_i += b - t_mid
+        recon = float((xr.cpu() - x).abs().max())
+    dt = (t_f + t_i) / steps
     val = B / dt
     cores = torch.get_num_threads()
+    what = "unmodified reference module (baseline/_ref)" if kind == "reference" else "oracle port (no copy of the reference on this box)"
+    if on_gpu:
+        print(json.dumps({"impl": "reference-gpu", "value": val, "unit": "img/s", "ms_per_step": dt * 1e3, "steps": steps,
+                          "warmup": warm + 1, "batch": B, "forward_ms": t_f / steps * 1e3, "inverse_ms": t_i / steps * 1e3,
+                          "dtype": "fp32 tensors; cuDNN conv allow_tf32=%s" % tf32, "recon_max_abs_err": recon,
+                          "how": f"{what} on cuda:0, torch {torch.__version__} eager, wall clock around synchronised steps"}))
+        return
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm + 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"batch {B} of {CFG['batch']} per step"},
-            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
-                             "sample": f"batch {B} of {CFG['batch']}, {steps} steps, os.cpu_count={os.cpu_count()}"},
+            "config": {"workload": WORKLOAD, "global_batch": B, "weights": WEIGHTS,
+                       "steps_requested": args.steps, "warmup_requested": args.warmup,
+                       "note": f"steps bounded by a {budget:.0f} s budget" if steps < args.steps else "as requested"},
+            "directions": {"forward": {"value": B / (t_f / steps), "unit": "img/s", "ms": t_f / steps * 1e3},
+                           "inverse": {"value": B / (t_i / steps), "unit": "img/s", "ms": t_i / steps * 1e3}},
+            "checks": {"recon_max_abs_err": recon},
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": kind,
+                             "sample": f"{what}: batch {B}, {steps} steps after {warm + 1} warm-up, "
+                                       f"os.cpu_count={os.cpu_count()}"},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+def spawn_arm(impl: str, extra, timeout: float):
+    """Run a reference arm in its own process (it imports a package of the same name as the product's) -> parsed JSON."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", impl] + [str(a) for a in extra]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "NFDPM_PRECISION"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"timed out after {timeout:.0f} s"}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {"unavailable": (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+
+
+# ------------------------------------------------------------------------------------------- training step
 def bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, flush_buf, state):
     """Full training step of the reference recipe (normalizing_flow/trainer.py:150-167): dequantisation noise,
     transform, prior log-prob, bits/dim loss, backward, [gradient all-reduce over NCCL when N > 1], clip value 1,
@@ -266,16 +373,55 @@ def bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, fl
                     "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "ms": o_ms,
                     "bytes_per_launch": 32.0 * n_el}
     imgs = B * world * steps
+    exposed = dp.exposed_comm_us() if (dp is not None and hasattr(dp, "exposed_comm_us")) else None
     return {"metric": "Glow L3/K16 32x32 full train step imgs/sec (fwd + bwd + clip + Adam)", "value": imgs / (ms * 1e-3),
-            "unit": "img/s", "ms_per_step": ms / steps,
+            "unit": "img/s", "ms_per_step": ms / steps, "dtype": "bf16 coupling GEMMs (tcgen05), fp32 elsewhere",
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": launches, "cuda_graph": graph is not None,
             "optimizer": "torch clip_grad_value_/clip_grad_norm_/Adam(foreach)" if args.torch_optimizer else
                          "FusedClipAdam (clip value + clip norm + Adam, 3 launches)",
-            "grad_allreduce": (f"NCCL AVG, {len(flow.blocks) + 1} level buckets overlapped with backward" if dp else None),
+            "grad_allreduce": (dp.describe() if (dp is not None and hasattr(dp, "describe")) else
+                               ("NCCL AVG on per-level buckets overlapped with backward" if dp else None)),
+            "exposed_comm_us_per_step": exposed,
             "step_tflops": 3 * FLOP_PER_IMG_FWD * B / (ms / steps * 1e-3) / 1e12,
             "optimizer_roofline": opt_roof, "loss_first": first_loss, "loss_last": last_loss}
+
+
+def graph_time(torch, fn, reps=16, replays=10):
+    """us per call of fn the way the product runs it: `reps` back-to-back launches per CUDA-graph replay (no launch
+    gaps, operands L2-resident), CUDA events around `replays` replays on the launching stream."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        side.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(replays):
+            g.replay()
+        e.record()
+        side.synchronize()
+    torch.cuda.current_stream().wait_stream(side)
+    return s.elapsed_time(e) * 1e3 / (reps * replays)
+
+
+def ncu_traffic(kernel_key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full summary of THIS round
+    (profiles/r02_ncu_traffic.json, written by tools/summarise_ncu.py), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+        return d.get(kernel_key)
+    except Exception:
+        return None
 
 
 def main():
@@ -283,23 +429,31 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=CFG["batch"])
+    ap.add_argument("--time-budget", type=float, default=150.0, help="reference arms: seconds of steps at most")
+    ap.add_argument("--tf32", type=int, default=None, help="reference-gpu arm: force cuDNN allow_tf32 (default: torch's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the torch-eager-on-GPU reference comparator")
     ap.add_argument("--no-train", action="store_true", help="skip the full-train-step measurement")
     ap.add_argument("--train-eager", action="store_true", help="do not capture the train step in a CUDA graph")
     ap.add_argument("--torch-optimizer", action="store_true",
                     help="train arm: torch clip_grad_value_/clip_grad_norm_/Adam instead of the fused optimiser step")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, on_gpu=False)
+    if args.impl == "reference-gpu":
+        return run_reference(args, on_gpu=True)
     args.warmup = max(args.warmup, 3)
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
 
     import torch
     import torch.distributed as dist
     import normalizing_flow as nf
     from normalizing_flow import _native as N, _engine as E
-    import synthetic as SY            # synthetic inputs; the oracle is imported only by the cpu_baseline / reference legs
+    import synthetic as SY            # synthetic inputs; the oracle is imported only as the checker of `checks`
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -310,10 +464,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     c, L, K, S, B = CFG["in_channel"], CFG["L"], CFG["K"], CFG["S"], args.batch
-    mode = E.precision()
+    head_mode = E.precision()                       # "auto" unless the caller exported NFDPM_PRECISION
+    head_infer = "bf16" if head_mode == "bf16" else ("fp32_simt" if head_mode == "fp32_simt" else "fp32")
 
     # random-init weights of the named architecture (SURVEY §8(d) recipe), synthetic dequantised images
-    state = reference_style_state(nf, SY, torch, dev)
+    state = reference_style_state(nf, torch, dev, SY.seeded_input((CFG["batch"], c, S, S), 1))
     sd, psd = state
     flow = nf.Glow(c, L, K).to(dev)
     flow.load_state_dict(sd)
@@ -325,20 +480,21 @@ def main():
     xr_host = torch.empty(B, c, S, S).pin_memory()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step_dev():
+    def fwd_dev(x):
         ld, lp = nf.initialize_with_zeros(2, B, dev)
-        zs, ld, lp = flow.transform(x_dev, ld, lp)
+        zs, ld, lp = flow.transform(x, ld, lp)
         lp += prior.compute_log_prob(zs[-1])
-        xr = flow.invert(zs)
-        return ld + lp, xr
+        return zs, ld + lp
+
+    def step_dev():
+        zs, ll = fwd_dev(x_dev)
+        return ll, flow.invert(zs)
 
     def step_e2e():
         xd = x_host.to(dev, non_blocking=True)
-        ld, lp = nf.initialize_with_zeros(2, B, dev)
-        zs, ld, lp = flow.transform(xd, ld, lp)
-        lp += prior.compute_log_prob(zs[-1])
+        zs, ll = fwd_dev(xd)
         xr = flow.invert(zs)
-        ll_host.copy_(ld + lp, non_blocking=True)
+        ll_host.copy_(ll, non_blocking=True)
         xr_host.copy_(xr, non_blocking=True)
 
     def timed(fn, steps):
@@ -360,158 +516,225 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def rate(ms_total, steps):
+        return B * world * steps / (ms_total * 1e-3)
+
+    def oracle_checks(n_img=8):
+        """This mode's CUDA path against the CPU oracle on the first n_img images of the batch (the oracle is the checker
+        here, never the thing measured)."""
+        from oracle import glow_oracle as O
+        xs = x_host[:n_img].clone()
+        ld = torch.zeros(n_img, dtype=torch.float64)
+        lp = torch.zeros(n_img, dtype=torch.float64)
+        zo, ld, lp = O.glow_transform(sd, xs, L, K, ld, lp)
+        ll_o = ld + lp + O.gaussian_prior_logp(psd, zo[-1])
+        xo = O.glow_invert(sd, zo, L, K)
+        zs, ll = fwd_dev(x_dev)
+        xr_from_oracle_z = flow.invert([torch.cat([z, z.new_zeros(B - n_img, *z.shape[1:])]).to(dev) for z in zo])[:n_img].cpu()
+        n_px = S * S * 3.0
+        zg = torch.cat([z[:n_img].reshape(n_img, -1).cpu() for z in zs], 1).double()
+        zr = torch.cat([z.reshape(n_img, -1) for z in zo], 1).double()
+        bpd_g = float(nf.calculate_loss(ll[:n_img].cpu(), 32.0, n_px))
+        bpd_o = float(nf.calculate_loss(ll_o, 32.0, n_px))
+        return {"images": n_img,
+                "z_rel_l2_vs_oracle": float((zg - zr).norm() / zr.norm()),
+                "loglik_rel_err_vs_oracle": float(((ll[:n_img].cpu() - ll_o).abs() / ll_o.abs()).max()),
+                "bits_per_dim": bpd_g, "bits_per_dim_abs_err_vs_oracle": abs(bpd_g - bpd_o),
+                "inverse_max_abs_err_vs_oracle": float((xr_from_oracle_z - xo).abs().max()),
+                "oracle_own_recon_max_abs_err": float((xo - xs).abs().max())}
+
+    def measure_mode(mode, full):
+        """All device-timed numbers of one precision mode (the graphs are keyed on the mode string)."""
+        prev = os.environ.get("NFDPM_PRECISION")
+        os.environ["NFDPM_PRECISION"] = mode
+        try:
+            for _ in range(args.warmup):
+                step_dev()
+                step_e2e()
+            torch.cuda.synchronize()
+            l0 = N.launch_count
+            ms = timed(step_dev, args.steps)
+            launches = N.launch_count - l0
+            ms_e2e = timed(step_e2e, args.steps)
+            zs, _ = fwd_dev(x_dev)
+            flow.invert(zs)
+            ms_f = timed(lambda: fwd_dev(x_dev), args.steps)
+            ms_i = timed(lambda: flow.invert(zs), args.steps)
+            out = {"dtype": DTYPE_NAME[mode], "value": rate(ms, args.steps), "unit": "img/s", "ms_per_step": ms / args.steps,
+                   "e2e": {"value": rate(ms_e2e, args.steps), "unit": "img/s", "ms_per_step": ms_e2e / args.steps},
+                   "gpu_launches": launches,
+                   "forward": {"value": rate(ms_f, args.steps), "unit": "img/s", "ms": ms_f / args.steps},
+                   "inverse": {"value": rate(ms_i, args.steps), "unit": "img/s", "ms": ms_i / args.steps},
+                   "step_tflops_algorithmic": 2 * FLOP_PER_IMG_FWD * B / (ms / args.steps * 1e-3) / 1e12}
+            if full:
+                for _ in range(3):
+                    flow.invert([zs[-1]])
+                ms_s = timed(lambda: flow.invert([zs[-1]]), args.steps)
+                out["sample_last_latent"] = {"value": rate(ms_s, args.steps), "unit": "img/s", "ms": ms_s / args.steps,
+                                             "what": "Glow.invert([z_last]): every Split draws its half from the learned "
+                                                     "conditional prior (glow.py:203-246), T=1"}
+            ll, xr = step_dev()
+            torch.cuda.synchronize()
+            out["checks"] = {"recon_max_abs_err": float((xr - x_dev).abs().max())}
+            if rank == 0 and not args.no_cpu_baseline:
+                out["checks"].update(oracle_checks())
+            return out
+        finally:
+            if prev is None:
+                os.environ.pop("NFDPM_PRECISION", None)
+            else:
+                os.environ["NFDPM_PRECISION"] = prev
+
+    hbm, tf_burst, tf_sust, src = peaks()
     with torch.no_grad():
-        for _ in range(args.warmup):
-            step_dev()
-            step_e2e()
-        torch.cuda.synchronize()
         sampler = ClockSampler(local) if rank == 0 else None
         t_wall0 = time.time()
-        l0 = N.launch_count
-        ms = timed(step_dev, args.steps)
-        launches = N.launch_count - l0
-        ms_e2e = timed(step_e2e, args.steps)
+        head = measure_mode(head_infer, True)
         t_wall1 = time.time()
         clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-        ll, xr = step_dev()
-        torch.cuda.synchronize()
-        recon = float((xr - x_dev).abs().max())
+        modes = {head_infer: head}
+        if head_infer != "bf16":
+            modes["bf16"] = measure_mode("bf16", False)
 
         # ---- roofline of the dominant kernel: coupling-net conv2 (512x512) GEMM at level 0, M = B*256
-        hbm, tf_burst, tf_sust, src = peaks()
         M, F = B * (S // 2) * (S // 2), 512
-        dt = torch.float32 if mode == "fp32" else torch.bfloat16
-        # (a) LIVE: every launch of that GEMM inside one eager pass of the timed step (same kernel order and cache
-        #     state as the graph replays: its A operand was just written by the previous GEMM), CUDA events on the
-        #     launching stream; L2 flushed before the step like in the timed region
-        live = []
-        orig_gemm = N.gemm_nt
-
-        def timed_gemm(A_, lda, Bw, ldb, D_, ldd, M_, N_, K_, *rest, **kw):
-            if (M_, N_, K_) == (M, F, F):
-                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_.record()
-                orig_gemm(A_, lda, Bw, ldb, D_, ldd, M_, N_, K_, *rest, **kw)
-                e_.record()
-                live.append((s_, e_))
-            else:
-                orig_gemm(A_, lda, Bw, ldb, D_, ldd, M_, N_, K_, *rest, **kw)
-        prev_graphs = os.environ.get("NFDPM_GRAPHS")
-        os.environ["NFDPM_GRAPHS"] = "0"
-        N.gemm_nt = timed_gemm
-        try:
-            step_dev()                              # eager warm-up of the un-graphed path
-            torch.cuda.synchronize()
-            live.clear()
-            for _ in range(3):
-                flush_buf.zero_()
-                step_dev()
-            torch.cuda.synchronize()
-        finally:
-            N.gemm_nt = orig_gemm
-            if prev_graphs is None:
-                os.environ.pop("NFDPM_GRAPHS", None)
-            else:
-                os.environ["NFDPM_GRAPHS"] = prev_graphs
-        k_ms = sum(s_.elapsed_time(e_) for s_, e_ in live) / max(len(live), 1)
-        achieved = 2.0 * M * F * F / (k_ms * 1e-3) / 1e12
-        # (b) the same kernel alone, L2 flushed before every launch (cold operands)
-        a = (torch.randn(M, F, device=dev) * 0.5).to(dt)
-        w = (torch.randn(F, F, device=dev) * 0.05).to(dt)
-        d = torch.empty(M, F, dtype=dt, device=dev)
         es, eb = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
-        for _ in range(3):
-            N.gemm_nt(a, F, w, F, d, F, M, F, F, N.EPI_ACTNORM_RELU, es, eb)
-        reps = 10
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for s, e in evs:
-            flush_buf.zero_()
-            s.record()
-            N.gemm_nt(a, F, w, F, d, F, M, F, F, N.EPI_ACTNORM_RELU, es, eb)
-            e.record()
-        torch.cuda.synchronize()
-        cold_ms = sum(s.elapsed_time(e) for s, e in evs) / reps
-        cold_tf = 2.0 * M * F * F / (cold_ms * 1e-3) / 1e12
-        # (c) the way the product runs it: back to back inside a CUDA graph (no launch gaps, the A operand L2-resident
-        #     because the preceding GEMM has just written it), 16 launches per replay, CUDA events around 10 replays.
-        #     Event pairs around single eager launches (a) also count the idle gap before a ~20 us kernel starts.
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            gk = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gk):
-                for _ in range(16):
-                    N.gemm_nt(a, F, w, F, d, F, M, F, F, N.EPI_ACTNORM_RELU, es, eb)
-            gk.replay()
-            side.synchronize()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(10):
-                gk.replay()
-            e.record()
-            side.synchronize()
-        graph_ms = s.elapsed_time(e) / 160.0
-        graph_tf = 2.0 * M * F * F / (graph_ms * 1e-3) / 1e12
+
+        def operand(rows, cols, scale, dt):
+            v = torch.randn(rows, cols, device=dev) * scale
+            if dt != N.SPLIT:
+                return v.to(dt)
+            hi = v.bfloat16()
+            lo = (v - hi.float()).bfloat16()
+            w = torch.stack([hi.reshape(rows, cols // 32, 32), lo.reshape(rows, cols // 32, 32)], dim=2).contiguous()
+            return w.view(torch.int32).reshape(rows, cols)
+
+        def gemm_roofline(dt):
+            a, w = operand(M, F, 0.5, dt), operand(F, F, 0.05, dt)
+            d = torch.empty(M, F, dtype=dt, device=dev)
+            call = lambda: N.gemm_nt(a, F, w, F, d, F, M, F, F, N.EPI_ACTNORM_RELU, es, eb)
+            us = graph_time(torch, call)
+            for _ in range(3):
+                call()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for s_, e_ in evs:
+                flush_buf.zero_()
+                s_.record()
+                call()
+                e_.record()
+            torch.cuda.synchronize()
+            cold_us = sum(s_.elapsed_time(e_) for s_, e_ in evs) / len(evs) * 1e3
+            mmas = 3 if dt == N.SPLIT else 1
+            alg = 2.0 * M * F * F
+            tf = alg / (us * 1e-6) / 1e12
+            name = {torch.bfloat16: "gemm_nt_tc_kernel<ACTNORM_RELU, bf16, X3=false> (tcgen05, bf16 operands)",
+                    N.SPLIT: "gemm_nt_tc_kernel<ACTNORM_RELU, bf16x2, X3=true> (tcgen05, split bf16 pairs, 3 MMAs per product)",
+                    torch.float32: "gemm_nt_f32_kernel (CUDA cores)"}[dt]
+            key = {torch.bfloat16: "gemm_nt_tc_bf16", N.SPLIT: "gemm_nt_tc_x3", torch.float32: "gemm_nt_f32"}[dt]
+            tr = ncu_traffic(key)
+            return {"bound": "tensor", "kernel": f"{name} M={M} N=512 K=512", "achieved": tf, "peak": tf_burst / mmas,
+                    "unit": "TFLOP/s", "frac": tf / (tf_burst / mmas), "kernel_us": us, "launches_timed": 160,
+                    "flop_per_launch_algorithmic": alg, "mma_flop_issued_per_launch": alg * mmas,
+                    "issued_tflops": tf * mmas,
+                    "peak_source": f"{src} bf16 burst ({tf_burst:.1f} TFLOP/s)" + (" / 3 MMAs per product" if mmas == 3 else ""),
+                    "how": "16 back-to-back launches per CUDA-graph replay (as the product runs them), CUDA events around "
+                           "10 replays on the launching stream: a ~5 ms burst, hence the burst peak",
+                    "isolated_cold": {"kernel_us": cold_us, "achieved": alg / (cold_us * 1e-6) / 1e12,
+                                      "frac": alg / (cold_us * 1e-6) / 1e12 / (tf_burst / mmas),
+                                      "note": "event pair around single launches, L2 flushed before each (includes the launch gap)"},
+                    "traffic": tr.get("bytes") if tr else None, "traffic_source": tr.get("source") if tr else None}
+
+        head_dt = {"fp32": N.SPLIT, "bf16": torch.bfloat16, "fp32_simt": torch.float32}[head_infer]
+        roof = gemm_roofline(head_dt)
+        roof_bf16 = gemm_roofline(torch.bfloat16) if head_dt != torch.bfloat16 else None
+        # cuBLAS on the same shape, timed the same way: the bar for the kernel
+        a16 = (torch.randn(M, F, device=dev) * 0.5).bfloat16()
+        w16 = (torch.randn(F, F, device=dev) * 0.05).bfloat16()
+        a32, w32 = a16.float(), w16.float()
+        o16, o32 = torch.empty(M, F, dtype=torch.bfloat16, device=dev), torch.empty(M, F, device=dev)
+        cublas = {"bf16_us": graph_time(torch, lambda: torch.matmul(a16, w16.t(), out=o16))}
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        cublas["tf32_us"] = graph_time(torch, lambda: torch.matmul(a32, w32.t(), out=o32))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        cublas["fp32_us"] = graph_time(torch, lambda: torch.matmul(a32, w32.t(), out=o32))
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        cublas["note"] = ("torch.matmul (cuBLASLt) on M=%d N=K=512, no epilogue, same 16-per-replay timing; tf32 has 2^-11 "
+                          "operand rounding (not fp32-faithful), fp32 runs on CUDA cores" % M)
+        roof["cublas_same_shape"] = cublas
+
+        # ---- HBM roofline of the step-boundary kernels (ActNorm + 1x1 conv + affine coupling epilogue) at this batch
+        def boundary_roofline():
+            recs = []
+            for lvl, (C, hw) in enumerate([(12, 16), (24, 8), (48, 4)]):
+                P = hw * hw
+                Mr = B * P
+                K1p = (9 * (C // 2) + 63) // 64 * 64
+                ldp = (9 * C + 15) // 16 * 16
+                x = torch.randn(B, C, hw, hw, device=dev)
+                pm = torch.randn(Mr, ldp, device=dev) * 0.05
+                a1 = torch.empty(Mr, K1p, dtype=head_dt if head_dt != torch.float32 else torch.float32, device=dev)
+                mt, beta = torch.randn(C, C, device=dev) * 0.3, torch.randn(C, device=dev)
+                b3, l3 = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+                part = torch.empty(B, device=dev)
+                us = graph_time(torch, lambda: N.flow_boundary(x, C * P, False, pm, ldp, b3, l3, part, mt, beta, x, C * P, a1,
+                                                               K1p, B, C, hw, hw, False))
+                alg = 8.0 * C * P * B
+                moved = alg + 4.0 * Mr * ldp + a1.element_size() * Mr * K1p
+                recs.append({"level": lvl, "C": C, "P": P, "kernel_us": us, "algorithmic_bytes": alg,
+                             "achieved": alg / (us * 1e-6) / 1e9, "frac": alg / (us * 1e-6) / 1e9 / hbm,
+                             "bytes_moved_incl_pm_and_im2col": moved, "moved_gbs": moved / (us * 1e-6) / 1e9})
+            tr = ncu_traffic("flow_boundary_level1")
+            top = recs[1]
+            return {"bound": "hbm", "kernel": "flow_boundary_kernel<coupling, im2col sink> (levels 1-2 of the default path; "
+                    "level 0 runs it fused into gemm3_boundary_kernel)", "achieved": top["achieved"], "peak": hbm,
+                    "unit": "GB/s", "frac": top["frac"], "kernel_us": top["kernel_us"],
+                    "algorithmic_bytes_per_launch": top["algorithmic_bytes"],
+                    "what": "algorithmic bytes = read x + write y = 8*C*P per image per StepFlow (SURVEY 8d); the kernel also "
+                            "reads the ZeroConv taps (36*C*P) and writes the next im2col rows; one CTA per image: "
+                            "latency/issue-bound at batch 128, not bandwidth-bound",
+                    "per_level": recs, "peak_source": f"{src} copy bandwidth",
+                    "traffic": tr.get("bytes") if tr else None, "traffic_source": tr.get("source") if tr else None}
+        roof_hbm = boundary_roofline()
 
     train = None
     if not args.no_train:
         train = bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, flush_buf, state)
 
     if rank == 0:
-        imgs = B * world * args.steps
-        value = imgs / (ms * 1e-3)
-        e2e_v = imgs / (ms_e2e * 1e-3)
         line = {
-            "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": mode, "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world} (independent shards, "
-                       "no data-path collective)", "l2": "flushed between timed steps (256 MiB memset)",
-                       "weights": "reference constructors (seed 0) + data-dependent ActNorm init on the first batch + N(0,1e-3) on every ZeroConv tensor (SURVEY 8d)"},
-            "e2e": {"value": e2e_v, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": ll_host.numel() * 8 + xr_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": ("gemm_nt_f32_kernel (CUDA-core fp32)" if mode == "fp32" else
-                                                        "gemm_nt_tc_kernel (tcgen05 bf16)") + f" M={M} N=512 K=512",
-                         "achieved": graph_tf, "peak": tf_sust, "unit": "TFLOP/s", "frac": graph_tf / tf_sust,
-                         "kernel_ms": graph_ms, "launches_timed": 160,
-                         "how": "16 back-to-back launches per CUDA-graph replay (as the product runs them), CUDA events "
-                                "around 10 replays on the launching stream",
-                         "eager_live": {"kernel_ms": k_ms, "achieved": achieved, "frac": achieved / tf_sust,
-                                        "launches_timed": len(live),
-                                        "note": "event pair around every launch of this shape in 3 eager passes of the "
-                                                "step; includes the launch gap in front of each kernel"},
-                         "isolated_cold": {"kernel_ms": cold_ms, "achieved": cold_tf, "peak": tf_burst,
-                                           "frac": cold_tf / tf_burst, "note": "timed alone, L2 flushed before each launch"},
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture
-                         # profiles/r01_ncu_full_summary.md (34.10 MB read + 0.61 MB written back within the launch)
-                         "traffic": (34.86e6 if (mode == "bf16" and B == 128) else None), "peak_source": f"{src} bf16 sustained"},
+            "metric": METRIC, "value": head["value"], "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "precision_mode": head_mode,
+                       "parallelism": f"dp{world} (independent shards, no data-path collective)",
+                       "l2": "flushed between timed steps (256 MiB memset)", "weights": WEIGHTS},
+            "e2e": {"value": head["e2e"]["value"], "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": ll_host.numel() * 8 + xr_host.numel() * 4,
+                    "ms_per_step": head["e2e"]["ms_per_step"]},
+            "gpu_launches": head["gpu_launches"],
+            "directions": {k: head[k] for k in ("forward", "inverse", "sample_last_latent") if k in head},
+            "modes": modes,
+            "roofline": roof, "roofline_bf16_mode": roof_bf16, "roofline_hbm": roof_hbm,
             "clocks": clocks,
-            "checks": {"recon_max_abs_err": recon, "step_tflops": 2 * FLOP_PER_IMG_FWD * B / (ms / args.steps * 1e-3) / 1e12},
+            "checks": dict(head["checks"], step_tflops_algorithmic=head["step_tflops_algorithmic"]),
         }
         if train is not None:
             line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
-            Bs = 32
-            got = {}
-            st = oracle_step_fn(Bs, state, x_host[:Bs].clone(), got)
-            st()
-            # the same images through the CUDA path (this precision mode) vs the oracle: log-likelihood, bits/dim
-            with torch.no_grad():
-                ll_gpu = step_dev()[0][:Bs].cpu()
-            n_px = S * S * 3.0
-            line["checks"]["loglik_rel_err_vs_oracle"] = float(((ll_gpu - got["ll"]).abs() / got["ll"].abs()).max())
-            line["checks"]["bits_per_dim"] = float(nf.calculate_loss(ll_gpu, 32.0, n_px))
-            line["checks"]["bits_per_dim_abs_err_vs_oracle"] = abs(
-                line["checks"]["bits_per_dim"] - float(nf.calculate_loss(got["ll"], 32.0, n_px)))
-            best = 1e30
-            for _ in range(3):
-                t0 = time.perf_counter()
-                st()
-                best = min(best, time.perf_counter() - t0)
-            line["cpu_baseline"] = {"value": Bs / best, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"oracle (torch-CPU fp32) on batch {Bs} of {B}, best of 3, "
-                                              f"os.cpu_count={os.cpu_count()}"}
+            # the unmodified reference on the host CPU: bounded sample (same batch, few steps), own process
+            cpu = spawn_arm("reference", ["--batch", B, "--steps", 3, "--warmup", 1, "--time-budget", 25], 240)
+            if "cpu_baseline" in cpu:
+                line["cpu_baseline"] = cpu["cpu_baseline"]
+                line["cpu_baseline"]["directions"] = cpu.get("directions")
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "img/s", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "unavailable: " + str(cpu.get("unavailable"))}
+        if world == 1 and not args.no_eager_gpu:
+            torch.cuda.empty_cache()
+            g = spawn_arm("reference-gpu", ["--batch", B, "--steps", 10, "--warmup", 3, "--time-budget", 60], 300)
+            g["speedup_of_this_repo_device_timed"] = (head["value"] / g["value"]) if g.get("value") else None
+            line["gpu_eager_reference"] = g
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -35,6 +35,11 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
   return t;   // valid in thread 0
 }
 
+// clip_grad_value_ semantics of torch.clamp: a NaN gradient stays NaN (fminf / fmaxf would return the non-NaN operand and
+// turn a diverged step into a silent update by -clip_value); the NaN then reaches the norm and the parameters, as in the
+// reference's torch.nn.utils.clip_grad_value_ / clip_grad_norm_ (trainer.py:165-166).
+__device__ __forceinline__ float clampv(float v, float c) { return v < -c ? -c : (v > c ? c : v); }
+
 __global__ void __launch_bounds__(OPT_THREADS) opt_clip_sumsq_kernel(const OptRef* __restrict__ refs,
                                                                     const int2* __restrict__ chunks, float clip_value,
                                                                     float* __restrict__ partial) {
@@ -49,21 +54,21 @@ __global__ void __launch_bounds__(OPT_THREADS) opt_clip_sumsq_kernel(const OptRe
       const int n4 = n >> 2;
       for (int i = threadIdx.x; i < n4; i += OPT_THREADS) {
         float4 v = reinterpret_cast<float4*>(g)[i];
-        v.x = fminf(fmaxf(v.x, -clip_value), clip_value);
-        v.y = fminf(fmaxf(v.y, -clip_value), clip_value);
-        v.z = fminf(fmaxf(v.z, -clip_value), clip_value);
-        v.w = fminf(fmaxf(v.w, -clip_value), clip_value);
+        v.x = clampv(v.x, clip_value);
+        v.y = clampv(v.y, clip_value);
+        v.z = clampv(v.z, clip_value);
+        v.w = clampv(v.w, clip_value);
         reinterpret_cast<float4*>(g)[i] = v;
         acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       }
       for (int i = (n4 << 2) + threadIdx.x; i < n; i += OPT_THREADS) {
-        const float v = fminf(fmaxf(g[i], -clip_value), clip_value);
+        const float v = clampv(g[i], clip_value);
         g[i] = v;
         acc += v * v;
       }
     } else {
       for (int i = threadIdx.x; i < n; i += OPT_THREADS) {
-        const float v = fminf(fmaxf(g[i], -clip_value), clip_value);
+        const float v = clampv(g[i], clip_value);
         g[i] = v;
         acc += v * v;
       }

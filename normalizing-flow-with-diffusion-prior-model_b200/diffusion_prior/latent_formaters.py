@@ -165,8 +165,10 @@ class CatFormater(BaseFormater):
 
 
 def get_formater(name: str):
-    """'IdentityFormater' | 'CatFormater' -> class; anything else -> None (reference :251-263)."""
+    """'IdentityFormater' | 'CatFormater' -> class; anything else raises ValueError("Invalid formater name") like the
+    reference (latent_formaters.py:251-263)."""
     if name == "IdentityFormater":
         return IdentityFormater
     elif name == "CatFormater":
         return CatFormater
+    raise ValueError("Invalid formater name")

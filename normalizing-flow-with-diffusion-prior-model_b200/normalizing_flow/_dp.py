@@ -99,7 +99,10 @@ class GradAllReduce:
         mods = [self.flow] + ([self.prior] if self.prior is not None else [])
         with torch.no_grad():
             for m in mods:
-                ts = [p.data for p in m.parameters()] + [b for b in m.buffers()]
+                # the parameters THEMSELVES (not ``p.data``): an in-place copy under no_grad bumps the version counters that
+                # key every parameter-derived cache (LU/fold matrices, packed weights, captured chains); ``p.data.copy_``
+                # would leave a rank that already ran a forward on its stale caches
+                ts = list(m.parameters()) + list(m.buffers())
                 for dt in sorted({t.dtype for t in ts}, key=str):
                     grp = [t for t in ts if t.dtype == dt]
                     flat = torch.cat([t.reshape(-1) for t in grp])
@@ -108,9 +111,12 @@ class GradAllReduce:
                     for t in grp:
                         t.copy_(flat[off:off + t.numel()].view_as(t))
                         off += t.numel()
-        for m in self.flow.modules():                  # host-side caches of the flags / prepared matrices
-            if hasattr(m, "_init_known"):
-                m._init_known = None
+        for m in mods:                                 # host-side caches of the flags / prepared matrices
+            for sub in m.modules():
+                if hasattr(sub, "_init_known"):
+                    sub._init_known = None
+            if hasattr(m, "invalidate_caches"):
+                m.invalidate_caches()
 
     @contextlib.contextmanager
     def global_initialization(self):

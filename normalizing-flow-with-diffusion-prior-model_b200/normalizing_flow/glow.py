@@ -151,6 +151,26 @@ class Glow(Transform):
         self._plist = None
         return super()._apply(fn, *a, **k)
 
+    def invalidate_caches(self) -> None:
+        """Forget everything derived from the parameter VALUES (LU/fold matrices, packed weights, batched packing plans);
+        the next call recomputes them.  Needed only after writes that bypass the tensors' version counters
+        (``p.data.copy_(...)``, ``torch.Tensor.set_``): ordinary in-place updates, optimizer steps and
+        ``load_state_dict`` are detected on their own."""
+        for m in self.modules():
+            if isinstance(m, StepFlow):
+                m._mix.invalidate()
+            elif isinstance(m, AffineCoupling):
+                for ws in m._cache.sets.values():
+                    ws.key = None
+                b = getattr(m, "_bwd_cache", None)
+                if b is not None:
+                    b.key = None
+            elif isinstance(m, Split):
+                m._cache.key = None
+        for plan in self._plans.values():
+            plan.key = None
+        self._pver = None
+
     def _load_from_state_dict(self, *args, **kwargs):
         # the coupling networks start new weight caches on load (transforms.py): the batched packing plans hold the OLD
         # cache objects and buffer addresses, so they are rebuilt too (found by the checkpoint-resume test: a model that

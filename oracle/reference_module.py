@@ -1,0 +1,64 @@
+"""Load the UNMODIFIED reference package (davitpapikyan/Normalizing-Flow-with-Diffusion-Prior-Model) as a comparator.
+
+TEST INFRASTRUCTURE ONLY: used by ``bench.py --impl reference`` / ``--impl reference-gpu`` (the reference arms), by
+``tests/test_dropin_overlay.py`` and by the golden-vector generators — never by the product path.
+
+The reference is pure Python on PyTorch, so "building" it is staging a copy of its source tree where the GPU box can see
+it: ``stage()`` (called by ``__graft_entry__.build()`` in the build container, where ``/root/reference`` exists) copies the
+tree to ``baseline/_ref/`` — git-ignored, so no reference source enters the history, but shipped to the GPU box with the
+working tree.  ``import_reference()`` imports ``normalizing_flow`` from there with the reference's non-hot-path
+dependencies that this image lacks (aim, skimage, cleanfid, ignite: logging / data / metrics code, reference
+normalizing_flow/utils.py:4, trainer.py:8-13, data/utils.py:9, metrics/compute.py:21-30) stubbed by MagicMock.
+
+The reference package has the same import name as the product's drop-in mirror; a process imports ONE of them
+(``bench.py`` runs the reference arms in their own processes).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+from unittest.mock import MagicMock
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED = os.path.join(ROOT, "baseline", "_ref")
+SOURCE = os.environ.get("NFDPM_REFERENCE", "/root/reference")
+STUBS = ["aim", "skimage", "skimage.transform", "cleanfid", "cleanfid.fid", "cleanfid.features", "cleanfid.utils",
+         "cleanfid.resize", "ignite", "ignite.metrics"]
+
+
+def stage(src: str = SOURCE, dst: str = STAGED) -> bool:
+    """Copy the reference's Python tree (no media, no VCS data) to ``dst``.  Returns False when ``src`` is absent."""
+    if not os.path.isdir(os.path.join(src, "normalizing_flow")):
+        return False
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(src, dst, ignore=shutil.ignore_patterns("media", ".git", "__pycache__", "*.pyc", "*.png", "*.gif", "*.jpg"))
+    return True
+
+
+def find() -> str | None:
+    for p in (STAGED, SOURCE):
+        if os.path.isdir(os.path.join(p, "normalizing_flow")):
+            return p
+    return None
+
+
+def import_reference(path: str | None = None):
+    """-> the reference's ``normalizing_flow`` module (raises ImportError when no copy is available or when another
+    package of that name — the product's mirror — is already imported in this process)."""
+    path = path or find()
+    if path is None:
+        raise ImportError("no copy of the reference: neither baseline/_ref (staged by __graft_entry__.build()) nor "
+                          f"{SOURCE} exists")
+    have = sys.modules.get("normalizing_flow")
+    if have is not None:
+        if os.path.realpath(getattr(have, "__file__", "")).startswith(os.path.realpath(path)):
+            return have
+        raise ImportError("a different 'normalizing_flow' package is already imported in this process")
+    for m in STUBS:
+        sys.modules.setdefault(m, MagicMock())
+    sys.path.insert(0, path)
+    import normalizing_flow as nf  # noqa: E402
+    assert os.path.realpath(nf.__file__).startswith(os.path.realpath(path)), nf.__file__
+    return nf

@@ -1,5 +1,6 @@
-"""bench.py's reference arm (the reference's CPU path, timed through the oracle port) runs without a GPU and prints the
-contract line: one JSON object with the metric BASELINE.json names, the cpu_baseline description and an e2e block."""
+"""bench.py's reference arm (the UNMODIFIED reference module staged in baseline/_ref — or the oracle port when no copy of
+the reference exists — on the host CPU) runs without a GPU and prints the contract line: one JSON object with the metric
+BASELINE.json names, the cpu_baseline description and an e2e block."""
 import json
 import os
 import subprocess
@@ -11,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ, OMP_NUM_THREADS="1")                 # what torchrun exports: the arm must still take all cores
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1"], capture_output=True, text=True, env=env, timeout=900, cwd=ROOT)
+                        "--warmup", "1", "--batch", "8"], capture_output=True, text=True, env=env, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -24,7 +25,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["unit"] == "img/s" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["sample"]
+    sys.path.insert(0, ROOT)
+    from oracle import reference_module as RM
+    assert cb["kind"] == ("reference" if RM.find() else "port") and cb["value"] == d["value"] and cb["sample"]
+    assert set(d["directions"]) == {"forward", "inverse"} and d["checks"]["recon_max_abs_err"] < 1e-3
     assert cb["cores"] == (os.cpu_count() or 1), "rank 0 must use every host core even under OMP_NUM_THREADS=1"
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 

@@ -33,7 +33,11 @@ def _worker(rank, world, port, q):
             for m in flow.modules():
                 if hasattr(m, "is_initialized"):
                     m.is_initialized.fill_(1)
+        v0 = [p._version for p in flow.parameters()]
+        flow._pver = list(v0)                              # as if a forward had already keyed its caches on these versions
         dp.broadcast_parameters(src=0)
+        assert all(p._version > v for p, v in zip(flow.parameters(), v0)), "broadcast must bump the version counters"
+        assert flow._pver is None, "broadcast must invalidate the parameter-derived caches"
         chk = torch.stack([p.detach().double().sum() for p in flow.parameters()]).sum()
         allc = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)

@@ -46,7 +46,8 @@ def test_cat_formater_against_reference_golden(golden_dir, idx):
     assert isinstance(idf, IdentityFormater) and idf.get_num_latent_parts() == L
     assert np.array_equal(np.array(idf.get_input_shapes()), g[name + "_id_shapes"])
     assert idf.process_latents(lat) is lat and idf.postprocess(lat) is lat
-    assert get_formater("nope") is None
+    with pytest.raises(ValueError, match="Invalid formater name"):      # reference latent_formaters.py:261-262
+        get_formater("nope")
 
 
 def test_cat_formater_full_size_and_oracle(monkeypatch):
