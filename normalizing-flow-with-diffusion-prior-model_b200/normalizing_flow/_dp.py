@@ -77,9 +77,11 @@ class GradAllReduce:
         self.cuda = next(flow.parameters()).is_cuda
         self.stream = torch.cuda.Stream() if self.cuda else None
         self.sink = None
-        self.ranges: List = []
+        self.covered = 0
         self.launched = 0
-        flow._grad_hook = self
+        self.last_bucket_bytes = 0
+        self.enabled = True            # False: skip the collectives (bench.py: the step without communication, to report
+        flow._grad_hook = self         # the exposed communication time as the difference)
 
     def detach(self) -> None:
         if getattr(self.flow, "_grad_hook", None) is self:
@@ -133,31 +135,47 @@ class GradAllReduce:
     # ---- hooks called by _train.GlowTransformFn.backward
     def begin(self, glow, sink) -> None:
         self.sink = sink
-        self.ranges = sink.level_ranges(glow)
+        self.covered = 0
         self.launched = 0
         if self.cuda:
             sink.flat.record_stream(self.stream)
 
-    def level_done(self, li: int) -> None:
-        lo, hi = self.ranges[li]
+    def bucket_done(self, lo: int, hi: int, events=()) -> None:
+        """Average the flat-gradient range [lo, hi) over the ranks on the communication stream, once the current stream
+        and the streams that recorded ``events`` (the weight-gradient side stream) have produced it.  Buckets arrive in
+        backward order — a few StepFlows each (_train.BUCKET_STEPS) — so only the last, small one is not overlapped by
+        the rest of the backward."""
+        self.covered += hi - lo
+        self.launched += 1
+        if not self.enabled:
+            return
         buf = self.sink.flat[lo:hi]
         if self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
+            for ev in events:
+                self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
                 self._avg(buf)
         else:
             self._avg(buf)
-        self.launched += 1
+        self.last_bucket_bytes = 4 * (hi - lo)
+
+    def describe(self) -> str:
+        from . import _train as T
+        return (f"NCCL AVG on buckets of {T.BUCKET_STEPS} StepFlows of the flat gradient buffer ({self.launched} per step, "
+                f"last one {self.last_bucket_bytes / 1e6:.1f} MB), launched from inside the backward on a communication "
+                f"stream as soon as a bucket's last gradient kernel is enqueued")
 
     def finish(self) -> None:
         """Join the communication stream and average the (few, small) GaussianPrior gradients.  Call after
         ``loss.backward()`` and before clipping / the optimizer step."""
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.stream)
-        if self.sink is not None and self.launched != len(self.ranges):
-            raise RuntimeError("gradient all-reduce incomplete: backward did not visit every level")
+        if self.sink is not None and self.covered != self.sink.numel:
+            raise RuntimeError(f"gradient all-reduce incomplete: the backward reported {self.covered} of "
+                               f"{self.sink.numel} gradient elements")
         self.sink = None
-        if self.prior is not None:
+        if self.prior is not None and self.enabled:
             gs = [p.grad for p in self.prior.parameters() if p.grad is not None]
             if gs:
                 flat = torch.cat([g.reshape(-1) for g in gs])

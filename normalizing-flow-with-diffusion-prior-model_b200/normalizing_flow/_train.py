@@ -204,6 +204,12 @@ class GradSink:
         self.written.add(id(p))
         return self.flat[off:off + p.numel()].view(shape)
 
+    def span(self, first: Tensor, last: Tensor) -> Tuple[int, int]:
+        """[start, end) element range of the flat buffer from parameter ``first`` to the (padded) end of ``last``."""
+        lo = self.offsets[id(first)][0]
+        o, _ = self.offsets[id(last)]
+        return lo, o + (last.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+
     def level_ranges(self, glow) -> List[Tuple[int, int]]:
         """[start, end) element range of every level's parameters (levels are contiguous in parameters() order)."""
         out = []
@@ -221,10 +227,17 @@ def _strip_cols(src: Tensor, out: Tensor, rows: int, ld: int, cols: int) -> None
     N.pack_matrix(src, out, rows, 1, cols, ld, 0, 1, cols, rows)
 
 
+#: StepFlows per gradient bucket of the data-parallel all-reduce (``bucket_done``): K = 16 gives four buckets per level, the
+#: last (exposed) one of an L3/K16 CIFAR model is 4 x 0.35 M floats = 5.5 MB instead of a whole level's 22 MB
+BUCKET_STEPS = int(os.environ.get("NFDPM_BUCKET_STEPS", "4"))
+
+
 def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional[Tensor], dlp: Optional[Tensor],
-                   need_dx: bool, sink: GradSink, level_done=None) -> Optional[Tensor]:
-    """Writes every parameter gradient into ``sink`` and returns d x (or None).  ``level_done(li)`` is called after
-    the last kernel that writes level li's gradients has been enqueued (deepest level first): the hook the
+                   need_dx: bool, sink: GradSink, bucket_done=None) -> Optional[Tensor]:
+    """Writes every parameter gradient into ``sink`` and returns d x (or None).  ``bucket_done(lo, hi, events)`` is called
+    once every gradient in the flat-buffer range [lo, hi) has been enqueued — a group of BUCKET_STEPS consecutive
+    StepFlows, in backward order (deepest level first, last StepFlow first; the range of a level's first bucket also
+    holds its Split prior) — on the current stream or on the streams whose ``events`` are passed: the hook the
     data-parallel gradient all-reduce uses to overlap communication with the rest of the backward."""
     B = st.B
     levels = glow._levels()
@@ -310,6 +323,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         dA1 = torch.empty(M * K1p, **f32)
         # ActNorm partial-sum buffers: one per (buffer set, layer) so their reductions can run on the side stream too
         an_part_b = [[torch.empty(n_cta * 2 * F, **f32) for _ in range(2)] for _ in range(nbuf)]
+        keep = []                                  # scratch of the mix_param_grad launches (alive until the level is done)
         T_c, T_m = N.coupling_bwd_tiles(C, h, w), N.mix_bwd_tiles(C, h, w)     # pixel tiles per image (1: image per CTA)
         dpar3 = torch.empty(B * T_c * 2 * C, **f32)
         dp_scratch = torch.empty(M * C, **f32) if T_c > 1 else None
@@ -392,22 +406,35 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             if not (ablate & 4):
                     N.mix_bwd(du, C * P, dA1, K1p, lv.x[k], C * P, step._mix.fwd_mt, dxb, C * P, mix_part[k], B, C, h, w)
             dy = dxb
+            if k % BUCKET_STEPS == 0:
+                # a bucket of StepFlows [k, k_hi] is complete once their InvConv / ActNorm parameter gradients are folded
+                # (main stream) and their weight gradients have run (side stream)
+                k_hi = min(k + BUCKET_STEPS, K) - 1
+                items = []
+                for kk in range(k, k_hi + 1):
+                    stp = flows[kk]
+                    wgt, sc, bi = stp.invconv2d.weight, stp.actnorm.scale, stp.actnorm.bias
+                    scratch = torch.empty(C * C + C, **f32)
+                    keep.append(scratch)
+                    items.append(N.MixGradItem(part=mix_part[kk].data_ptr(), B=B * T_m, C=C, weight=wgt.data_ptr(),
+                                               scale=sc.data_ptr(), bias=bi.data_ptr(), winv=stp._mix.winv.data_ptr(),
+                                               dld_sum=dld_sum.data_ptr(), P=float(P), pad_=0,
+                                               d_weight=sink.get(wgt).data_ptr(), d_scale=sink.get(sc).data_ptr(),
+                                               d_bias=sink.get(bi).data_ptr(), scratch=scratch.data_ptr()))
+                N.mix_param_grad(items)
+                if bucket_done is not None:
+                    first_p = next(flows[k].parameters())
+                    last_mod = flows[k_hi] if (k_hi < K - 1 or split is None or split.conv is None) else split
+                    last_p = list(last_mod.parameters())[-1]
+                    lo_, hi_ = sink.span(first_p, last_p)
+                    evs = []
+                    if side is not None:
+                        ev_b = torch.cuda.Event()
+                        ev_b.record(side)
+                        evs.append(ev_b)
+                    bucket_done(lo_, hi_, evs)
         if side is not None:
-            main.wait_stream(side)                # every weight gradient of the level is complete (all-reduce, buffers)
-        items = []
-        keep = []
-        for k, step in enumerate(flows):
-            wgt, sc, bi = step.invconv2d.weight, step.actnorm.scale, step.actnorm.bias
-            dW, dS, dB = sink.get(wgt), sink.get(sc), sink.get(bi)
-            scratch = torch.empty(C * C + C, **f32)
-            keep.append(scratch)
-            items.append(N.MixGradItem(part=mix_part[k].data_ptr(), B=B * T_m, C=C, weight=wgt.data_ptr(), scale=sc.data_ptr(),
-                                       bias=bi.data_ptr(), winv=step._mix.winv.data_ptr(), dld_sum=dld_sum.data_ptr(),
-                                       P=float(P), pad_=0, d_weight=dW.data_ptr(), d_scale=dS.data_ptr(),
-                                       d_bias=dB.data_ptr(), scratch=scratch.data_ptr()))
-        N.mix_param_grad(items)
-        if level_done is not None:
-            level_done(li)
+            main.wait_stream(side)                # every weight gradient of the level is complete (buffers are reused)
         dx_next = dy
     dx = None
     if need_dx:
@@ -420,15 +447,16 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
 
 # ------------------------------------------------------------------------------------------- captured training chains
 # An UNCAPTURED training loop (the reference trainer as is) issues ~1 600 launches per step from Python and is host-bound
-# (25 ms vs 8.7 ms per 128-image step when the whole step sits in a torch.cuda.graph, bench.py --train-eager).  With
-# NFDPM_TRAIN_GRAPHS=1 the autograd Function captures its stash-forward chain and its backward chain once per
-# (shape, precision) and replays them, like the inference entry points do.  Bit-identical to the eager chain over several
-# optimiser steps (tests/test_gpu_train.py::test_captured_training_chains_equal_eager, run on a B200); opt-in until it has
-# been TIMED and run through the whole parity suite (round 1 ended without GPU time for that).  Not used under a caller's own capture or with the
-# data-parallel hook (NCCL launches from inside the backward); parameter caches are refreshed INSIDE the chains
-# (E.own_capture stays False), because the parameters change between replays.
+# (25.9 ms per 128-image step against 8.7 ms when the whole step sits in a torch.cuda.graph).  The autograd Function
+# therefore captures its stash-forward chain and its backward chain once per (shape, precision) and replays them, like the
+# inference entry points do: the reference trainer's unchanged step then takes 9.07 ms (bench.py --train-eager, round 2;
+# profiles/r02_train_chains.txt).  Bit-identical to the eager chain over several optimiser steps
+# (tests/test_gpu_train.py::test_captured_training_chains_equal_eager); the whole GPU suite passes with the chains on.
+# NFDPM_TRAIN_GRAPHS=0 turns them off.  Not used under a caller's own capture or with the data-parallel hook (NCCL launches
+# from inside the backward); parameter caches are refreshed INSIDE the chains (E.own_capture stays False), because the
+# parameters change between replays.
 def train_graphs_enabled() -> bool:
-    return os.environ.get("NFDPM_TRAIN_GRAPHS", "0") == "1"
+    return os.environ.get("NFDPM_TRAIN_GRAPHS", "1") != "0"
 
 
 class _TrainChains:
@@ -612,7 +640,7 @@ class GlowTransformFn(torch.autograd.Function):
         if hook is not None:
             hook.begin(glow, sink)
         dx = backward_train(glow, st, g_lat, g_ld, g_lp, ctx.needs_input_grad[1], sink,
-                            hook.level_done if hook is not None else None)
+                            hook.bucket_done if hook is not None else None)
         ctx.stash = None
         ctx.params = None
         glow._last_grad_flat = sink.flat                   # contiguous view of all gradients of this step

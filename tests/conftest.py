@@ -42,8 +42,8 @@ def golden_dir():
 
 
 @pytest.fixture(autouse=True)
-def _optional_captured_training_chains(monkeypatch):
-    """NFDPM_TEST_TRAIN_GRAPHS=1 runs EVERY test with the opt-in captured training chains (NFDPM_TRAIN_GRAPHS=1,
-    normalizing_flow/_train.py) — the switch for promoting them to the default: the whole parity suite must stay green."""
-    if os.environ.get("NFDPM_TEST_TRAIN_GRAPHS", "0") == "1":
-        monkeypatch.setenv("NFDPM_TRAIN_GRAPHS", "1")
+def _optional_eager_training_chains(monkeypatch):
+    """The captured training chains (normalizing_flow/_train.py) are the default; NFDPM_TEST_TRAIN_GRAPHS=0 runs EVERY test
+    with the eager kernel chain instead (both must stay green)."""
+    if os.environ.get("NFDPM_TEST_TRAIN_GRAPHS", "1") == "0":
+        monkeypatch.setenv("NFDPM_TRAIN_GRAPHS", "0")

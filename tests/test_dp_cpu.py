@@ -1,5 +1,5 @@
 """Host logic of the data-parallel path on CPU: world_size-2 ``gloo`` processes exercise the bucketed gradient
-all-reduce (per-level slices of the flat gradient buffer, deepest level first), the parameter/buffer broadcast and the
+all-reduce (StepFlow-group slices of the flat gradient buffer, in backward order), the parameter/buffer broadcast and the
 batch sharding.  No kernels run here; the NCCL path is the same code with backend "nccl" (bench.py --gpus N)."""
 import os
 import socket
@@ -51,9 +51,18 @@ def _worker(rank, world, port, q):
         ranges = sink.level_ranges(flow)
         assert len(ranges) == 3 and ranges[0][0] == 0 and ranges[-1][1] == sink.numel
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(2)), "levels must tile the flat buffer"
+        # the buckets the backward reports: per level (deepest first) groups of StepFlows, last group first; the first
+        # bucket of a level with a Split also holds the Split prior's parameters
+        levels = [(blk.flows, blk.split) for blk in flow.blocks] + [(flow.final_flows, None)]
+        buckets = []
+        for flows, split in reversed(levels):
+            last = list((split if split is not None else flows[-1]).parameters())[-1]
+            buckets.append(sink.span(next(flows[1].parameters()), last))          # K = 2, one StepFlow per bucket here
+            buckets.append(sink.span(next(flows[0].parameters()), list(flows[0].parameters())[-1]))
+        assert sorted(buckets) == sorted(set(buckets)) and sum(h - l for l, h in buckets) == sink.numel
         dp.begin(flow, sink)
-        for li in (2, 1, 0):
-            dp.level_done(li)
+        for lo, hi in buckets:
+            dp.bucket_done(lo, hi)
         for p, v in zip(prior.parameters(), (1.0, 2.0, 3.0)):
             p.grad = torch.full_like(p, v * (rank + 1))
         dp.finish()
@@ -64,7 +73,7 @@ def _worker(rank, world, port, q):
             assert torch.allclose(p.grad, torch.full_like(p, v * mean_rank))
         # --- an incomplete backward is an error, not a silent partial average
         dp.begin(flow, sink)
-        dp.level_done(2)
+        dp.bucket_done(*buckets[0])
         try:
             dp.finish()
             raise AssertionError("finish() accepted an incomplete all-reduce")
