@@ -449,6 +449,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-gpu", action="store_true", help="skip the torch-eager-on-GPU reference comparator")
     ap.add_argument("--no-train", action="store_true", help="skip the full-train-step measurement")
+    ap.add_argument("--only-train", action="store_true", help="development: print only the training record")
     ap.add_argument("--train-eager", action="store_true", help="do not capture the train step in a CUDA graph")
     ap.add_argument("--torch-optimizer", action="store_true",
                     help="train arm: torch clip_grad_value_/clip_grad_norm_/Adam instead of the fused optimiser step")
@@ -599,6 +600,13 @@ def main():
                 os.environ["NFDPM_PRECISION"] = prev
 
     hbm, tf_burst, tf_sust, src = peaks()
+    if args.only_train:                             # development switch: just the training record
+        train = bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, flush_buf, state)
+        if rank == 0:
+            print(json.dumps({"only_train": True, "n_gpus": world, "train": train}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     with torch.no_grad():
         sampler = ClockSampler(local) if rank == 0 else None
         t_wall0 = time.time()

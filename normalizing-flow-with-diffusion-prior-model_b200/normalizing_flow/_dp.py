@@ -24,6 +24,7 @@ normalizing_flow/utils.py:275-292) instead of rank 0's shard:
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import List, Optional
 
 import torch
@@ -71,6 +72,17 @@ class GradAllReduce:
     def __init__(self, flow, prior: Optional[torch.nn.Module] = None, group=None):
         if not dist.is_initialized():
             raise RuntimeError("GradAllReduce needs torch.distributed.init_process_group(...) first")
+        max_ctas = int(os.environ.get("NFDPM_NCCL_MAX_CTAS", "8"))          # 0: NCCL's default communicator
+        if group is None and dist.get_backend() == "nccl" and max_ctas > 0:
+            # The gradient all-reduces overlap the backward: every SM an NCCL CTA occupies is one the persistent GEMM grids
+            # (one CTA per SM, statically partitioned tiles) have to queue behind.  A communicator with few CTAs trades
+            # collective bandwidth (irrelevant: the buckets are overlapped) for less interference.  Measured at N = 2, config-2
+            # train step (tools/dp_cta_sweep.sh, profiles/r02_dp_cta_sweep.txt): exposed communication 211 us with NCCL's
+            # default, 151 / 126 / 204 / 302 us with at most 16 / 8 / 4 / 2 CTAs.
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = max_ctas
+            opts.config.min_ctas = 1
+            group = dist.new_group(backend="nccl", pg_options=opts)
         self.flow, self.prior, self.group = flow, prior, group
         self.world = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
@@ -82,6 +94,14 @@ class GradAllReduce:
         self.last_bucket_bytes = 0
         self.enabled = True            # False: skip the collectives (bench.py: the step without communication, to report
         flow._grad_hook = self         # the exposed communication time as the difference)
+        # The GaussianPrior's (few, small) gradients are complete at the very START of the backward (the prior term is the
+        # last thing the forward computes): average them on the communication stream as soon as autograd has accumulated
+        # them, instead of after the backward, where every launch of that small chain would be exposed.
+        self._prior_params = [p for p in prior.parameters() if p.requires_grad] if prior is not None else []
+        self._prior_ready = 0
+        self._prior_done = False
+        for p in self._prior_params:
+            p.register_post_accumulate_grad_hook(self._prior_grad_ready)
 
     def detach(self) -> None:
         if getattr(self.flow, "_grad_hook", None) is self:
@@ -132,6 +152,30 @@ class GradAllReduce:
         finally:
             E.stats_hook = prev
 
+    def _avg_prior(self) -> None:
+        gs = [p.grad for p in self._prior_params if p.grad is not None]
+        if gs:
+            flat = torch.cat([g.reshape(-1) for g in gs])
+            self._avg(flat)
+            off = 0
+            for g in gs:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+
+    def _prior_grad_ready(self, p) -> None:
+        self._prior_ready += 1
+        if self._prior_ready < len(self._prior_params) or not self.enabled:
+            return
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self._avg_prior()
+            for q in self._prior_params:
+                q.grad.record_stream(self.stream)
+        else:
+            self._avg_prior()
+        self._prior_done = True
+
     # ---- hooks called by _train.GlowTransformFn.backward
     def begin(self, glow, sink) -> None:
         self.sink = sink
@@ -169,18 +213,13 @@ class GradAllReduce:
     def finish(self) -> None:
         """Join the communication stream and average the (few, small) GaussianPrior gradients.  Call after
         ``loss.backward()`` and before clipping / the optimizer step."""
-        if self.cuda:
+        if self.cuda and self.enabled:
             torch.cuda.current_stream().wait_stream(self.stream)
         if self.sink is not None and self.covered != self.sink.numel:
             raise RuntimeError(f"gradient all-reduce incomplete: the backward reported {self.covered} of "
                                f"{self.sink.numel} gradient elements")
         self.sink = None
-        if self.prior is not None and self.enabled:
-            gs = [p.grad for p in self.prior.parameters() if p.grad is not None]
-            if gs:
-                flat = torch.cat([g.reshape(-1) for g in gs])
-                self._avg(flat)
-                off = 0
-                for g in gs:
-                    g.copy_(flat[off:off + g.numel()].view_as(g))
-                    off += g.numel()
+        if self.prior is not None and self.enabled and not self._prior_done:
+            self._avg_prior()                   # (gradients that did not come through autograd's accumulation)
+        self._prior_ready = 0
+        self._prior_done = False
