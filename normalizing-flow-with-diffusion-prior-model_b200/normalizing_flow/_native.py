@@ -118,6 +118,49 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
+
+#: NVTX ranges per kernel family around every launch (NFDPM_NVTX=1; off by default: a range push/pop per launch costs host
+#: time in the un-captured paths).  Families group the entry points the way DESIGN.md's kernel table does.
+_FAMILIES = (("gemm", ("nfdpm_gemm_nt", "nfdpm_gemm_tn")),
+             ("step_boundary", ("nfdpm_flow_boundary", "nfdpm_gemm3_boundary", "nfdpm_channel_mix", "nfdpm_coupling_apply",
+                                "nfdpm_im2col3x3", "nfdpm_actnorm_apply", "nfdpm_squeeze", "nfdpm_unsqueeze", "nfdpm_copy_channels")),
+             ("prior", ("nfdpm_split_prior", "nfdpm_gauss", "nfdpm_accumulate")),
+             ("prepare", ("nfdpm_mix_prepare", "nfdpm_pack", "nfdpm_channel_stats", "nfdpm_rows_to_nchw", "nfdpm_nchw_to_rows")),
+             ("backward", ("nfdpm_coupling_bwd", "nfdpm_mix_bwd", "nfdpm_mix_param_grad", "nfdpm_actnorm_relu_bwd", "nfdpm_reduce_rows",
+                           "nfdpm_col2im_add")),
+             ("optimizer", ("nfdpm_fused_clip_adam",)),
+             ("formats", ("nfdpm_latent_format", "nfdpm_postprocess_u8", "nfdpm_preprocess")))
+
+
+def _family(name: str) -> str:
+    for fam, prefixes in _FAMILIES:
+        if any(name.startswith(p) for p in prefixes):
+            return fam
+    return "misc"
+
+
+class _RangedLib:
+    """The bound library with an NVTX range ("family:entry point") around every call."""
+
+    def __init__(self, inner: C.CDLL):
+        self._inner = inner
+
+    def __getattr__(self, name: str):
+        fn = getattr(self._inner, name)
+        label = f"{_family(name)}:{name}"
+
+        def call(*args):
+            torch.cuda.nvtx.range_push(label)
+            try:
+                return fn(*args)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        setattr(self, name, call)
+        return call
+
+
+if os.environ.get("NFDPM_NVTX", "0") == "1":
+    lib = _RangedLib(lib)
 EXPORTS = ["nfdpm_version", "nfdpm_last_error_string", "nfdpm_sm_count", "nfdpm_ld_tiles", "nfdpm_mix_prepare",
            "nfdpm_channel_mix", "nfdpm_actnorm_apply", "nfdpm_channel_stats", "nfdpm_squeeze", "nfdpm_unsqueeze",
            "nfdpm_copy_channels", "nfdpm_im2col3x3", "nfdpm_pack_matrix", "nfdpm_gemm_nt", "nfdpm_coupling_apply",

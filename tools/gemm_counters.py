@@ -7,13 +7,25 @@ import torch
 from normalizing_flow import _native as N
 
 dev = torch.device("cuda")
-dt = torch.bfloat16
+dt = N.SPLIT if os.environ.get("MODE", "bf16") == "split" else torch.bfloat16       # MODE=split: fp32-faithful operand pairs
 F = 512
+
+
+def operand(rows, cols, scale):
+    v = torch.randn(rows, cols, device=dev) * scale
+    if dt != N.SPLIT:
+        return v.to(dt)
+    hi = v.bfloat16()
+    lo = (v - hi.float()).bfloat16()
+    w = torch.stack([hi.reshape(rows, cols // 32, 32), lo.reshape(rows, cols // 32, 32)], dim=2).contiguous()
+    return w.view(torch.int32).reshape(rows, cols)
+
+
 for name, M, Nn, K, out_dt, epi in [("L0 gemm1", 32768, 512, 64, dt, 1), ("L0 gemm2", 32768, 512, 512, dt, 1),
                                     ("L0 gemm3", 32768, 112, 512, torch.float32, 0), ("L1 gemm2", 8192, 512, 512, dt, 1),
                                     ("L2 gemm2", 2048, 512, 512, dt, 1)]:
-    a = (torch.randn(M, K, device=dev) * 0.5).to(dt)
-    w = (torch.randn(Nn, K, device=dev) * 0.05).to(dt)
+    a = operand(M, K, 0.5)
+    w = operand(Nn, K, 0.05)
     d = torch.empty(M, Nn, dtype=out_dt, device=dev)
     es, eb = torch.zeros(Nn, device=dev), torch.zeros(Nn, device=dev)
     args = (a, K, w, K, d, Nn, M, Nn, K) + ((N.EPI_ACTNORM_RELU, es, eb) if epi else ())
