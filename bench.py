@@ -721,6 +721,16 @@ def main():
     train = None
     if not args.no_train:
         train = bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, flush_buf, state)
+        if head_mode == "auto" and world == 1:
+            # the same step with the fp32-faithful (split bf16 pair) operand format in the stash, dgrad and wgrad GEMMs
+            os.environ["NFDPM_PRECISION"] = "fp32"
+            try:
+                t32 = bench_train(args, torch, dist, nf, N, dev, world, rank, B, x_host, timed, flush_buf, state)
+            finally:
+                os.environ.pop("NFDPM_PRECISION", None)
+            t32["dtype"] = "bf16x3 coupling GEMMs (split bf16 pairs on tcgen05: forward, dgrad, wgrad), fp32 elsewhere"
+            train["fp32_faithful_mode"] = {k: t32[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e", "gpu_launches",
+                                                               "step_tflops", "loss_first", "loss_last")}
 
     if rank == 0:
         line = {

@@ -20,38 +20,60 @@ template <typename T> __device__ __forceinline__ void stf(T* p, float v);
 template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// 8-element vector load / store helpers (16-byte bf16, 2 x 16-byte fp32)
+// 8-element vector load / store helpers: columns k0..k0+7 (k0 % 8 == 0) of row `row` of a row-major [rows, ld] matrix
+// (16-byte bf16, 2 x 16-byte fp32, 2 x 16-byte hi/lo for split pairs; ld counts logical columns)
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+  static __device__ __forceinline__ void load(const float* base, int64_t row, int64_t ld, int k0, float (&v)[8]) {
+    const float* p = base + row * ld + k0;
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+  static __device__ __forceinline__ void store(float* base, int64_t row, int64_t ld, int k0, const float (&v)[8]) {
+    float* p = base + row * ld + k0;
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
 };
-template <> struct Vec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+__device__ __forceinline__ void unpack_bf16x8(const uint4 u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[2 * i] = __uint_as_float(w[i] << 16);
-      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+}
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* base, int64_t row, int64_t ld, int k0, float (&v)[8]) {
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(base + row * ld + k0), v);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* base, int64_t row, int64_t ld, int k0, const float (&v)[8]) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t*>(&t);
     }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(base + row * ld + k0) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
+template <> struct Vec8<bf16x2_t> {
+  static __device__ __forceinline__ void load(const bf16x2_t* base, int64_t row, int64_t ld, int k0, float (&v)[8]) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + 2 * row * ld + split_col(k0);
+    float lo[8];
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(p), v);
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(p + 32), lo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += lo[i];
+  }
+  static __device__ __forceinline__ void store(bf16x2_t* base, int64_t row, int64_t ld, int k0, const float (&v)[8]) {
+    split_store8(reinterpret_cast<__nv_bfloat16*>(base) + 2 * row * ld, k0, v);
+  }
+};
+// scalar element (row, k) of the same matrices
+template <typename T> __device__ __forceinline__ void st_rc(T* base, int64_t row, int64_t ld, int64_t k, float v) {
+  put_rc<T>(base, row, ld, k, v);
+}
 
 // ------------------------------------------------------------------------------------------------ coupling backward
 struct CouplingBwdArgs {
@@ -196,7 +218,8 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
   // dpm rows: dpm[p', tap*C+co] = dP[co][p' - shift(tap)] = dP_pad[kt_s[col] + py'*(W+2) + px'] (zero outside the image and
   // in the padding columns).  A thread produces 8 consecutive columns (one 16-byte bf16 / two 16-byte fp32 stores).
   const int ldp = (int)a.ld_dpm;
-  TD* dpmb = reinterpret_cast<TD*>(a.dpm) + (int64_t)b * P * ldp;
+  TD* dpmb = reinterpret_cast<TD*>(a.dpm);
+  const int64_t row0 = (int64_t)b * P;
   if ((ldp & 7) == 0 && (((uintptr_t)dpmb) & 15) == 0) {
     const int n_g = ldp >> 3, K = 9 * C;
     for (int it = tid; it < P * n_g; it += nt) {
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
         const int col = g * 8 + e;
         v[e] = (col < K) ? win[kt_s[col]] : 0.f;
       }
-      Vec8<TD>::store(dpmb + (int64_t)pp * ldp + g * 8, v);
+      Vec8<TD>::store(dpmb, row0 + pp, ldp, g * 8, v);
     }
   } else {
     for (int i = tid; i < P * ldp; i += nt) {
@@ -219,7 +242,7 @@ __global__ void __launch_bounds__(1024) coupling_bwd_kernel(const CouplingBwdArg
         const int py = fdiv(pp, a.dW), px = pp - py * W;
         v = dP_pad[kt_s[col] + py * W2p + px];
       }
-      stf<TD>(dpmb + i, v);
+      st_rc<TD>(dpmb, row0 + pp, ldp, col, v);
     }
   }
   // per-image parameter partials: one warp per (kind, j) row of r_s, fixed order
@@ -374,7 +397,7 @@ __global__ void dpm_expand_kernel(const float* __restrict__ dP, TD* __restrict__
       const int yy = py - (tap / 3 - 1), xx = px - (tap % 3 - 1);
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(dP + (b * P + yy * W + xx) * C + co);
     }
-    stf<TD>(dpm + i, v);
+    st_rc<TD>(dpm, m, ld, col, v);
   }
 }
 
@@ -402,8 +425,8 @@ __global__ void __launch_bounds__(256) actnorm_relu_bwd_kernel(const TD* __restr
 #pragma unroll 4
     for (int m = m0 + r0; m < m1; m += rg) {
       float gv[8], hv[8], o[8];
-      Vec8<TD>::load(dh + (int64_t)m * ld_dh + g * 8, gv);
-      Vec8<TH>::load(h + (int64_t)m * ld_h + g * 8, hv);
+      Vec8<TD>::load(dh, m, ld_dh, g * 8, gv);
+      Vec8<TH>::load(h, m, ld_h, g * 8, hv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float gg = (hv[j] > 0.f) ? gv[j] : 0.f;
@@ -411,7 +434,7 @@ __global__ void __launch_bounds__(256) actnorm_relu_bwd_kernel(const TD* __restr
         o[j] = gg * e[j];
         db[j] += o[j];
       }
-      Vec8<TO>::store(dpre + (int64_t)m * ld_o + g * 8, o);
+      Vec8<TO>::store(dpre, m, ld_o, g * 8, o);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -847,7 +870,7 @@ __global__ void col2im_add_kernel(const float* __restrict__ da, int64_t lda, flo
 void gemm_tn_tc_plan(int M, int N1, int N2, int* BN, int* tiles, int* splits, int* kb_per_split);
 bool gemm_tn_tc_ok(const void* A, int64_t lda, const void* Bm, int64_t ldb, int N1, int N2);
 int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* ws, int M, int N1, int N2, int* splits_out,
-               float* D, int accumulate, int* counters, int out_mode, int out_c, cudaStream_t st);
+               float* D, int accumulate, int* counters, int out_mode, int out_c, int x3, cudaStream_t st);
 
 }  // namespace nfdpm
 
@@ -879,7 +902,8 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
   NFDPM_REQUIRE(dy && u && pm && bias3 && logs3 && du && dpm && dpar, "nfdpm_coupling_bwd: null pointer");
   NFDPM_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && H > 0 && W > 0 && ldp >= 9 * (int64_t)C && ld_dpm >= 9 * (int64_t)C,
                 "nfdpm_coupling_bwd: bad shape");
-  NFDPM_REQUIRE(dpm_dtype == NFDPM_F32 || dpm_dtype == NFDPM_BF16, "nfdpm_coupling_bwd: bad dpm dtype");
+  NFDPM_REQUIRE(dpm_dtype == NFDPM_F32 || dpm_dtype == NFDPM_BF16 || (dpm_dtype == NFDPM_BF16X2 && ld_dpm % 32 == 0),
+                "nfdpm_coupling_bwd: bad dpm dtype");
   NFDPM_REQUIRE(counter == nullptr || (dbias && dlogs), "nfdpm_coupling_bwd: the fused reduction needs dbias/dlogs");
   const int P = H * W, Ch = C / 2;
   cudaStream_t st = as_stream(stream);
@@ -887,6 +911,7 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
   if (!attr_set) {
     NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_kernel<bf16x2_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NFDPM_CUDA(cudaFuncSetAttribute(coupling_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
@@ -902,6 +927,7 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
     int threads = (P * Ch + 31) / 32 * 32;
     threads = threads > 1024 ? 1024 : (threads < 128 ? 128 : threads);
     if (dpm_dtype == NFDPM_F32) coupling_bwd_kernel<float><<<B, threads, smem, st>>>(a);
+    else if (dpm_dtype == NFDPM_BF16X2) coupling_bwd_kernel<bf16x2_t><<<B, threads, smem, st>>>(a);
     else coupling_bwd_kernel<__nv_bfloat16><<<B, threads, smem, st>>>(a);
     NFDPM_CHECK_LAUNCH("coupling_bwd_kernel");
     return 0;
@@ -921,6 +947,7 @@ extern "C" int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* d
   int64_t g = (n + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;
   if (dpm_dtype == NFDPM_F32) dpm_expand_kernel<float><<<(int)g, 256, 0, st>>>(dp_scratch, (float*)dpm, ld_dpm, C, H, W, n);
+  else if (dpm_dtype == NFDPM_BF16X2) dpm_expand_kernel<bf16x2_t><<<(int)g, 256, 0, st>>>(dp_scratch, (bf16x2_t*)dpm, ld_dpm, C, H, W, n);
   else dpm_expand_kernel<__nv_bfloat16><<<(int)g, 256, 0, st>>>(dp_scratch, (__nv_bfloat16*)dpm, ld_dpm, C, H, W, n);
   NFDPM_CHECK_LAUNCH("dpm_expand_kernel");
   return 0;
@@ -942,6 +969,14 @@ extern "C" int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_d
   const size_t smem = sizeof(float) * (size_t)rg * 2 * N;
   cudaStream_t st = as_stream(stream);
 #define GO(TD, TH, TO) actnorm_relu_bwd_kernel<TD, TH, TO><<<grid, 256, smem, st>>>((const TD*)dh, (const TH*)h, scale, (TO*)dpre, part, M, N, ld_dh, ld_h, ld_o, rows_per_cta)
+  if (h_dtype == NFDPM_BF16X2 || o_dtype == NFDPM_BF16X2) {
+    // fp32-faithful training: fp32 dh from the split-pair dgrad GEMM, split-pair stash h, split-pair dpre for the next GEMMs
+    NFDPM_REQUIRE(dh_dtype == NFDPM_F32 && h_dtype == NFDPM_BF16X2 && o_dtype == NFDPM_BF16X2 && ld_h % 32 == 0 && ld_o % 32 == 0,
+                  "nfdpm_actnorm_relu_bwd: the split-pair form is (fp32 dh, split h) -> split dpre with ld %% 32 == 0");
+    GO(float, bf16x2_t, bf16x2_t);
+    NFDPM_CHECK_LAUNCH("actnorm_relu_bwd_kernel");
+    return 0;
+  }
   const int key = (dh_dtype == NFDPM_BF16 ? 4 : 0) | (h_dtype == NFDPM_BF16 ? 2 : 0) | (o_dtype == NFDPM_BF16 ? 1 : 0);
   NFDPM_REQUIRE((dh_dtype == NFDPM_F32 || dh_dtype == NFDPM_BF16) && (h_dtype == NFDPM_F32 || h_dtype == NFDPM_BF16) &&
                 (o_dtype == NFDPM_F32 || o_dtype == NFDPM_BF16), "nfdpm_actnorm_relu_bwd: bad dtypes");
@@ -1048,7 +1083,12 @@ extern "C" int64_t nfdpm_gemm_tn_workspace(int M, int N1, int N2, int* splits_ou
   int bn, t, s_tc, per;
   gemm_tn_tc_plan(M, N1, N2, &bn, &t, &s_tc, &per);
   const int smax = splits > s_tc ? splits : s_tc;
-  return (int64_t)smax * N1 * N2;
+  // split-pair operands: the accumulator covers 2 x 2 bf16 columns per logical element (whole groups of 64)
+  const int n1m = 2 * ((N1 + 31) / 32 * 32), n2m = 2 * ((N2 + 31) / 32 * 32);
+  int s_x3;
+  gemm_tn_tc_plan(M, n1m, n2m, &bn, &t, &s_x3, &per);
+  const int64_t plain = (int64_t)smax * N1 * N2, x3 = (int64_t)s_x3 * n1m * n2m;
+  return plain > x3 ? plain : x3;
 }
 
 extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void* Bm, int b_dtype, int64_t ldb, float* D,
@@ -1060,9 +1100,17 @@ extern "C" int nfdpm_gemm_tn(const void* A, int a_dtype, int64_t lda, const void
                 "nfdpm_gemm_tn: bad output mode");
   cudaStream_t st = as_stream(stream);
   const int n = N1 * N2;
+  if (a_dtype == NFDPM_BF16X2 || b_dtype == NFDPM_BF16X2) {
+    NFDPM_REQUIRE(a_dtype == b_dtype && lda % 32 == 0 && ldb % 32 == 0 && N2 % 4 == 0 && lda >= (N1 + 31) / 32 * 32 &&
+                  ldb >= (N2 + 31) / 32 * 32 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)Bm % 16 == 0) && counters != nullptr,
+                  "nfdpm_gemm_tn: split-pair operands need both operands split, ld %% 32 == 0 covering whole column groups, "
+                  "N2 %% 4 == 0 and counters");
+    int s_tc = 1;
+    return gemm_tn_tc(A, lda, Bm, ldb, ws, M, N1, N2, &s_tc, D, accumulate, counters, out_mode, out_c, 1, st);
+  }
   if (a_dtype == NFDPM_BF16 && b_dtype == NFDPM_BF16 && gemm_tn_tc_ok(A, lda, Bm, ldb, N1, N2)) {
     int s_tc = 1;
-    if (gemm_tn_tc(A, lda, Bm, ldb, ws, M, N1, N2, &s_tc, D, accumulate, counters, out_mode, out_c, st)) return 1;
+    if (gemm_tn_tc(A, lda, Bm, ldb, ws, M, N1, N2, &s_tc, D, accumulate, counters, out_mode, out_c, 0, st)) return 1;
     if (s_tc > 0) {                                     // not reduced in-kernel
       reduce_rows_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, D, s_tc, n, n, accumulate);
       NFDPM_CHECK_LAUNCH("reduce_rows_kernel");

@@ -1,4 +1,9 @@
-// tcgen05 / TMEM / TMA weight-gradient GEMM:  D[N1,N2] (+)= sum_m A[m,N1] * B[m,N2]   (bf16 in, fp32 out)
+// tcgen05 / TMEM / TMA weight-gradient GEMM:  D[N1,N2] (+)= sum_m A[m,N1] * B[m,N2]   (bf16 or split bf16 pairs in, fp32 out)
+//
+// Split pairs (NFDPM_BF16X2, the fp32-faithful mode): the kernel runs on the operands' bf16 columns (2 per logical column,
+// groups of [32 hi | 32 lo]), so the accumulator tile holds, for every logical (n1, n2), the four partial products
+// hi*hi, hi*lo, lo*hi, lo*lo at (row, row + 32) x (column, column + 32) of its group; the in-kernel slab reduction adds the
+// four (their sum is the exact product of the represented values hi + lo) while it sums the split-M slabs.
 //
 // Both operands are read straight from their row-major activation layouts ([M, ld], channel fastest): the reduction
 // index m is the STRIDED dimension, i.e. both UMMA operands are "MN-major".  No transposed copies are made:
@@ -38,7 +43,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(const __grid_
                                                                    float* __restrict__ ws, int M, int N1, int N2, int BN,
                                                                    int num_n2, int splits, int kb_per_split,
                                                                    float* __restrict__ D, int accumulate,
-                                                                   int* __restrict__ counters, int out_mode, int out_c) {
+                                                                   int* __restrict__ counters, int out_mode, int out_c,
+                                                                   int x3, int N1L, int N2L) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TN_STAGES + 1];
   __shared__ uint32_t s_tmem_base;
@@ -160,72 +166,73 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(const __grid_
     __threadfence();
   }
   __syncthreads();
-  const int band = (128 + splits - 1) / splits;
+  // logical geometry of the tile: with split pairs 128 accumulator rows / BN columns are 64 / BN/2 logical ones
+  const int RL = x3 ? 64 : 128, CL = x3 ? (BN >> 1) : BN;
+  const int band = (RL + splits - 1) / splits;
   const int r_lo = split * band;
-  const int r_hi = min(min(128, r_lo + band), N1 - t1 * 128);     // rows of this CTA's band that exist
-  const int cols = min(BN, N2 - t2 * BN);
+  const int r_hi = min(min(RL, r_lo + band), N1L - t1 * RL);      // logical rows of this CTA's band that exist
+  const int cols = min(CL, N2L - t2 * CL);
   const int64_t slab = (int64_t)N1 * N2;
-  if (r_hi > r_lo) {
-    if (out_mode == NFDPM_TN_OUT_PLAIN) {
-      // items = (row, float4 column) flattened over all threads; two items and all their slab loads in flight
-      const int c4 = cols >> 2, n_items = (r_hi - r_lo) * c4;
-      for (int it = threadIdx.x; it < n_items; it += TN_THREADS) {
-        const int r = it / c4, c = it - r * c4;
-        const int64_t off = (int64_t)(t1 * 128 + r_lo + r) * N2 + t2 * BN;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r_hi > r_lo && cols > 0) {
+    const int c4 = cols >> 2, n_items = (r_hi - r_lo) * c4;
+    for (int it = threadIdx.x; it < n_items; it += TN_THREADS) {
+      const int r = it / c4, c = it - r * c4;
+      const int rr = r_lo + r, cc = 4 * c;
+      const int n1 = t1 * RL + rr, n2 = t2 * CL + cc;             // logical output element (first of four columns)
+      int tap = 0, co = 0;
+      if (out_mode == NFDPM_TN_OUT_TAPS) {              // n1 = tap*out_c + co  ->  [co][n2][tap]  (ZeroConv weight)
+        tap = n1 / out_c;
+        co = n1 - tap * out_c;
+        if (tap >= 9) continue;
+      } else if (out_mode == NFDPM_TN_OUT_STRIP && n2 >= out_c) {   // keep the first out_c columns
+        continue;
+      }
+      // accumulator coordinates of the (hi, hi) entry; the other three components sit 32 rows / columns further
+      const int mrow = x3 ? t1 * 128 + ((rr >> 5) << 6) + (rr & 31) : n1;
+      const int mcol = x3 ? t2 * BN + ((cc >> 5) << 6) + (cc & 31) : n2;
+      const float* src = ws + (int64_t)mrow * N2 + mcol;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x3) {
+        for (int s2 = 0; s2 < splits; ++s2) {            // slab order, then hh, hl, lh, ll: fixed => bitwise reproducible
+          const float* p = src + s2 * slab;
+          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(p));
+          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(p + 32));
+          const float4 v2 = __ldcg(reinterpret_cast<const float4*>(p + 32 * (int64_t)N2));
+          const float4 v3 = __ldcg(reinterpret_cast<const float4*>(p + 32 * (int64_t)N2 + 32));
+          acc.x += ((v0.x + v1.x) + v2.x) + v3.x;
+          acc.y += ((v0.y + v1.y) + v2.y) + v3.y;
+          acc.z += ((v0.z + v1.z) + v2.z) + v3.z;
+          acc.w += ((v0.w + v1.w) + v2.w) + v3.w;
+        }
+      } else {
         int s2 = 0;
-        for (; s2 + 4 <= splits; s2 += 4) {            // four slab loads in flight, added in slab order
+        for (; s2 + 4 <= splits; s2 += 4) {              // four slab loads in flight, added in slab order
           float4 v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(ws + (s2 + j) * slab + off) + c);
+          for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(src + (s2 + j) * slab));
 #pragma unroll
           for (int j = 0; j < 4; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
         }
         for (; s2 < splits; ++s2) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + s2 * slab + off) + c);
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + s2 * slab));
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        float4* d = reinterpret_cast<float4*>(D + off) + c;
+      }
+      if (out_mode == NFDPM_TN_OUT_PLAIN) {
+        float4* d = reinterpret_cast<float4*>(D + (int64_t)n1 * N2L + n2);
         if (accumulate) {
           const float4 o = *d;
           acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
         }
         *d = acc;
-      }
-    } else {
-      // layout-changing outputs (the weight tensors' own layouts): float4 slab loads, four scalar stores
-      const int c4 = cols >> 2, n_items = (r_hi - r_lo) * c4;
-      for (int it = threadIdx.x; it < n_items; it += TN_THREADS) {
-        const int r = it / c4, c = it - r * c4;
-        const int n1 = t1 * 128 + r_lo + r, n2 = t2 * BN + 4 * c;
-        int tap = 0, co = 0;
-        if (out_mode == NFDPM_TN_OUT_TAPS) {            // n1 = tap*out_c + co  ->  [co][n2][tap]  (ZeroConv weight)
-          tap = n1 / out_c;
-          co = n1 - tap * out_c;
-          if (tap >= 9) continue;
-        } else if (n2 >= out_c) {                        // NFDPM_TN_OUT_STRIP: keep the first out_c columns
-          continue;
-        }
-        const float4* src = reinterpret_cast<const float4*>(ws + (int64_t)n1 * N2 + t2 * BN) + c;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int s2 = 0;
-        for (; s2 + 4 <= splits; s2 += 4) {
-          float4 v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (s2 + j) * slab));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
-        }
-        for (; s2 < splits; ++s2) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + s2 * slab));
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+      } else {
+        // layout-changing outputs (the weight tensors' own layouts): four scalar stores
         const float av[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           int64_t o;
           if (out_mode == NFDPM_TN_OUT_TAPS) {
-            o = ((int64_t)co * N2 + n2 + j) * 9 + tap;
+            o = ((int64_t)co * N2L + n2 + j) * 9 + tap;
           } else {
             if (n2 + j >= out_c) break;
             o = (int64_t)n1 * out_c + n2 + j;
@@ -283,16 +290,20 @@ bool gemm_tn_tc_ok(const void* A, int64_t lda, const void* Bm, int64_t ldb, int 
          ((uintptr_t)Bm % 16 == 0) && N1 > 0;
 }
 
-int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* ws, int M, int N1, int N2, int* splits_out,
-               float* D, int accumulate, int* counters, int out_mode, int out_c, cudaStream_t st) {
+// x3: A and Bm are split bf16 pairs (lda / ldb / N1 / N2 count logical columns; a row is 2 x ld bf16)
+int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* ws, int M, int N1L, int N2L, int* splits_out,
+               float* D, int accumulate, int* counters, int out_mode, int out_c, int x3, cudaStream_t st) {
+  // the kernel's own dimensions: bf16 columns of the operands (whole groups of 64 for split pairs)
+  const int N1 = x3 ? 2 * ((N1L + 31) / 32 * 32) : N1L, N2 = x3 ? 2 * ((N2L + 31) / 32 * 32) : N2L;
+  const int kmul = x3 ? 2 : 1;
   int BN, tiles, splits, per;
   gemm_tn_tc_plan(M, N1, N2, &BN, &tiles, &splits, &per);
   const int num_n2 = (N2 + BN - 1) / BN;
   // the tensor maps cover the physical row width (lda / ldb): padding columns inside it are real memory, columns
   // beyond it and rows >= M are zero-filled by TMA
   CUtensorMap tmA, tmB;
-  if (make_map(&tmA, A, M, lda, lda, TN_BK)) return 1;
-  if (make_map(&tmB, Bm, M, ldb, ldb, TN_BK)) return 1;
+  if (make_map(&tmA, A, M, lda * kmul, lda * kmul, TN_BK)) return 1;
+  if (make_map(&tmB, Bm, M, ldb * kmul, ldb * kmul, TN_BK)) return 1;
   static bool attr_set = false;
   const size_t smem = 1024 + (size_t)TN_STAGES * TN_STAGE_BYTES;
   if (!attr_set) {
@@ -300,10 +311,10 @@ int gemm_tn_tc(const void* A, int64_t lda, const void* Bm, int64_t ldb, float* w
     attr_set = true;
   }
   if (tiles > 500 || tiles * splits > sm_count()) counters = nullptr;     // co-residency not guaranteed: reduce separately
-  NFDPM_REQUIRE(out_mode == NFDPM_TN_OUT_PLAIN || counters != nullptr,
-                "nfdpm_gemm_tn: a layout-changing output needs the in-kernel reduction (counters)");
+  NFDPM_REQUIRE((out_mode == NFDPM_TN_OUT_PLAIN && !x3) || counters != nullptr,
+                "nfdpm_gemm_tn: layout-changing outputs and split-pair operands need the in-kernel reduction (counters)");
   gemm_tn_tc_kernel<<<tiles * splits, TN_THREADS, smem, st>>>(tmA, tmB, ws, M, N1, N2, BN, num_n2, splits, per, D,
-                                                             accumulate, counters, out_mode, out_c);
+                                                             accumulate, counters, out_mode, out_c, x3, N1L, N2L);
   NFDPM_CHECK_LAUNCH("gemm_tn_tc_kernel");
   *splits_out = counters != nullptr ? 0 : splits;     // 0: already reduced into D
   return 0;

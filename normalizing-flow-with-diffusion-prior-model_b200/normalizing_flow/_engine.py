@@ -6,7 +6,8 @@ Precision modes (env ``NFDPM_PRECISION``); everything outside the coupling netwo
   * ``fp32`` — the reference's arithmetic (fp32 convolutions, utils.py:36,64) on the tcgen05 tensor cores: operands are SPLIT
     bf16 pairs (v = hi + lo, NFDPM_BF16X2) and every product is formed as hi*hi + lo*hi + hi*lo with fp32 TMEM
     accumulation (2^-17 operand error instead of bf16's 2^-9).  Parity bar: z / log-det within 1e-4 relative of the
-    reference, reconstruction < 1e-4.  Training in this mode runs its GEMMs on CUDA cores (exact fp32).
+    reference, reconstruction < 1e-4.  Training in this mode uses the same operand format for the stash, the dgrad
+    GEMMs and the weight-gradient GEMMs (gradients within 2e-4 of the reference's autograd).
   * ``bf16`` — plain bf16 operands, one MMA per product: 3x the tensor throughput, stated tolerance in DESIGN.md / tests.
   * ``auto`` (default) — inference (``torch.no_grad()`` transform / invert / sample: likelihood evaluation, decoding,
     sampling) in ``fp32``, the training step (autograd-recorded transform + backward) in ``bf16``.
@@ -55,7 +56,7 @@ def coupling_dtype(train: bool = False) -> torch.dtype:
     if p == "fp32_simt":
         return torch.float32
     if p == "fp32":
-        return torch.float32 if train else N.SPLIT
+        return N.SPLIT
     return torch.bfloat16 if train else N.SPLIT
 
 
@@ -304,10 +305,11 @@ class PackPlan:
             job(w3, c.w3, 9, C, F, 1, F * 9, 9, F, ldp)
             caches = [c]
             if train:
-                b = getattr(cp, "_bwd_cache", None)
+                # one set of transposed operands per operand format (like the forward WeightSets)
+                b = cp.__dict__.setdefault("_bwd_caches", {}).get(dt)
                 if b is None:
-                    b = cp._bwd_cache = T._BwdCache()
-                if b.w1t is None or b.w1t.dtype != dt:
+                    b = cp._bwd_caches[dt] = T._BwdCache()
+                if b.w1t is None or b.w1t.device != dev:
                     b.w1t = torch.empty(K1p * F, dtype=dt, device=dev)
                     b.w2t = torch.empty(F * F, dtype=dt, device=dev)
                     b.w3t = torch.empty(F * Kp3, dtype=dt, device=dev)

@@ -129,7 +129,7 @@ def forward_train(glow, x: Tensor, with_logp: bool):
         lv.h2 = torch.empty(K, M, F, dtype=dt, device=dev)
         lv.pm = torch.empty(K, M, ldp, **f32)
         lv.state_out = torch.empty(B, C, h, w, **f32)
-        fused_g3 = dt == torch.bfloat16 and E.fused_g3_ok(B, C, h, w, F, ldp)
+        fused_g3 = E.fused_g3_ok(B, C, h, w, F, ldp, dt)
         fast = _level_fast(C, h, w)
         T_ld = 1 if fast else N.ld_tiles(P)
         if fast:
@@ -308,8 +308,9 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         du = torch.empty(B, C, P, **f32)
         pong = (torch.empty(B, C, P, **f32), torch.empty(B, C, P, **f32))   # dx of successive steps alternate
         Kp3 = E.round_up(9 * C, 64)
-        dh = torch.empty(M * F, dtype=dt, device=dev)
-        tc = dt == torch.bfloat16            # tensor-core wgrad: in-kernel split reduction + direct weight layouts
+        # dgrad GEMM output: bf16 in bf16 mode; fp32 in the fp32-faithful (split-pair) and CUDA-core modes
+        dh = torch.empty(M * F, dtype=dt if dt == torch.bfloat16 else torch.float32, device=dev)
+        tc = dt in E.TC_DTYPES               # tensor-core wgrad: in-kernel split reduction + direct weight layouts
         # The weight-gradient GEMMs feed only the optimiser: they run on a SIDE stream, concurrently with the
         # dgrad / elementwise chain of the same and the next StepFlow.  Their operands (dpm, dpre2, dpre1) are therefore
         # double-buffered across steps, and a buffer set is rewritten only after the side stream has read it.
@@ -355,7 +356,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
                 main.wait_event(read_done[sb])          # the wgrads of two steps ago have read this buffer set
             cp = step.affcoupling
             conv1, an1, conv2, an2, zc = cp._parts()
-            bc = cp._bwd_cache                   # refreshed by the forward's PackPlan
+            bc = cp._bwd_caches[dt]              # refreshed by the forward's PackPlan
             if ablate & 2:
                 pass
             elif T_c == 1:

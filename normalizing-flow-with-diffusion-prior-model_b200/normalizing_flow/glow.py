@@ -162,8 +162,7 @@ class Glow(Transform):
             elif isinstance(m, AffineCoupling):
                 for ws in m._cache.sets.values():
                     ws.key = None
-                b = getattr(m, "_bwd_cache", None)
-                if b is not None:
+                for b in getattr(m, "_bwd_caches", {}).values():
                     b.key = None
             elif isinstance(m, Split):
                 m._cache.key = None

@@ -521,6 +521,62 @@ def test_gemm_tn_bf16_tensor_core(M, N1, lda, N2, ldb):
     assert float((D2.view(N1, N2).double() - 2 * ref).norm() / ref.norm()) < 2e-5
 
 
+@pytest.mark.parametrize("M,N1,lda,N2,ldb,mode,out_c", [(32768, 512, 512, 512, 512, 0, 0), (8192, 224, 256, 512, 512, 1, 24),
+                                                       (2048, 432, 448, 512, 512, 1, 48), (4096, 512, 512, 128, 128, 2, 108),
+                                                       (300, 112, 128, 512, 512, 1, 12), (1000, 512, 512, 256, 256, 0, 0),
+                                                       (64, 512, 512, 64, 64, 2, 54)])
+def test_gemm_tn_split_pairs(M, N1, lda, N2, ldb, mode, out_c):
+    """Weight-gradient GEMM on split bf16 pairs: the accumulator holds hi*hi, hi*lo, lo*hi, lo*lo of every logical element
+    and the in-kernel slab reduction adds them — the fp64 product of the fp32 operands to 1e-5 relative (plain bf16
+    operands: ~3e-3), in the three output layouts (plain, ZeroConv weight [C,F,3,3], im2col padding stripped), bitwise
+    reproducible."""
+    A = torch.zeros(M, lda)
+    A[:, :N1] = rnd(M, N1, seed=1)
+    B = torch.zeros(M, ldb)
+    B[:, :N2] = rnd(M, N2, seed=2)
+    As, Bs = SP.encode(A).to(DEV), SP.encode(B).to(DEV)
+    ref = A[:, :N1].double().T @ B[:, :N2].double()
+    if mode == N.TN_OUT_TAPS:                       # n1 = tap*C + co -> [co][n2][tap]
+        n_out = out_c * N2 * 9
+        want = ref[:9 * out_c].reshape(9, out_c, N2).permute(1, 2, 0).reshape(-1)
+    elif mode == N.TN_OUT_STRIP:
+        n_out = N1 * out_c
+        want = ref[:, :out_c].reshape(-1)
+    else:
+        n_out = N1 * N2
+        want = ref.reshape(-1)
+    D = torch.full((n_out,), float("nan"), device=DEV)
+    ws = torch.empty(N.gemm_tn_workspace(M, N1, N2), device=DEV)
+    N.gemm_tn(As, lda, Bs, ldb, D, M, N1, N2, ws, out_mode=mode, out_c=out_c)
+    D2 = torch.full((n_out,), float("nan"), device=DEV)
+    N.gemm_tn(As, lda, Bs, ldb, D2, M, N1, N2, ws, out_mode=mode, out_c=out_c)
+    sync()
+    got = D.double().cpu()
+    assert torch.isfinite(got).all() and torch.equal(D, D2)
+    assert float((got - want).norm() / want.norm()) < 1e-5
+
+
+@pytest.mark.parametrize("M,Nn", [(300, 512), (4096, 512), (77, 64)])
+def test_actnorm_relu_bwd_split_pairs(M, Nn):
+    """(fp32 dh, split-pair h) -> split-pair dpre + column partials == the fp32 kernel on the decoded operands."""
+    dh = rnd(M, Nn, seed=1).to(DEV)
+    h = torch.relu(rnd(M, Nn, seed=2))
+    scale = rnd(Nn, seed=3, scale=0.2).to(DEV)
+    hs = SP.encode(h).to(DEV)
+    h_val = SP.value(hs.cpu(), M, Nn).float().to(DEV)         # what the kernel sees: hi + lo
+    rows = 32
+    n_cta = (M + rows - 1) // rows
+    dpre = torch.zeros(M, Nn, dtype=N.SPLIT, device=DEV)
+    part = torch.zeros(n_cta * 2 * Nn, device=DEV)
+    N.actnorm_relu_bwd(dh, Nn, hs, Nn, scale, dpre, Nn, part, M, Nn, rows)
+    dpre_ref = torch.zeros(M, Nn, device=DEV)
+    part_ref = torch.zeros(n_cta * 2 * Nn, device=DEV)
+    N.actnorm_relu_bwd(dh, Nn, h_val, Nn, scale, dpre_ref, Nn, part_ref, M, Nn, rows)
+    sync()
+    assert torch.equal(dpre.cpu(), SP.encode(dpre_ref.cpu()))
+    assert torch.allclose(part, part_ref, rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("dta,dtb", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
 def test_gemm_tn_cuda_core(dta, dtb):
     M, N1, N2 = 1500, 24, 112

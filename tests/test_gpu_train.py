@@ -2,9 +2,12 @@
 (``Glow.transform`` + ``GaussianPrior.compute_log_prob`` under autograd -> hand-written backward kernels) against
 (a) the unmodified reference's autograd (tests/golden/glow_grad_*.npz) and (b) the CPU oracle on fresh seeded inputs.
 
-Tolerances: fp32 mode — every gradient tensor within 2e-4 relative L2 of the reference (fp32 summation order
-differs); bf16 tensor-core mode (stated) — within 8e-2 relative L2 per tensor (measured worst 4.2e-2: the first
-conv's weight at the deepest level, three bf16 GEMMs downstream of the loss), loss within 1e-3 bits/dim.
+Tolerances: exact fp32 (NFDPM_PRECISION=fp32_simt, CUDA-core GEMMs) — every gradient tensor within 2e-4 relative L2 of
+the reference (fp32 summation order differs); fp32-faithful tensor-core mode (NFDPM_PRECISION=fp32, split bf16 pairs in the
+stash, the dgrad and the weight-gradient GEMMs) — loss within 1e-5, the whole gradient within 1e-4 relative L2 (measured
+1.4e-5), single tensors within 1e-2 (X3_TOL below); bf16 tensor-core mode (stated) — within 8e-2 relative L2 per tensor
+(measured worst 4.2e-2: the first conv's weight at the deepest level, three bf16 GEMMs downstream of the loss), loss within
+1e-3 bits/dim.
 """
 import os
 
@@ -40,13 +43,21 @@ def _train_step(flow, prior, x, S):
     return loss
 
 
+#: fp32-faithful (split bf16 pair) training on the tensor cores: per-tensor relative L2 of the gradients.  The error of a
+#: tensor is cancellation-dominated (entries ~1e-5 that are sums of ~1e-3 terms): measured worst 5.6e-3 in this file's
+#: cases against 2.8e-4 for exact fp32 FMA arithmetic on such tensors; the WHOLE gradient is within 1.4e-5 relative L2
+#: (exact fp32: 9.2e-6, bf16: 1.3e-3) — tools/measure_grad_parity.py, profiles/r02_grad_parity.jsonl.
+X3_TOL = 1e-2
+X3_TOTAL_TOL = 1e-4
+
+
 def _rel(a, b):
     a, b = a.detach().cpu().double().reshape(-1), torch.as_tensor(b).detach().cpu().double().reshape(-1)
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
 @pytest.mark.parametrize("name", GRAD_CASES)
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("bf16", 8e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32_simt", 2e-4), ("fp32", X3_TOL), ("bf16", 8e-2)])
 def test_gradients_against_reference_golden(golden_dir, name, mode, tol, monkeypatch):
     monkeypatch.setenv("NFDPM_PRECISION", mode)
     g = np.load(os.path.join(golden_dir, name + ".npz"))
@@ -55,7 +66,7 @@ def test_gradients_against_reference_golden(golden_dir, name, mode, tol, monkeyp
     assert np.allclose(np.array(O.state_checksum(sd)), g["checksum"], atol=1e-9)
     x = torch.from_numpy(g["x"]).to(DEV)
     loss = _train_step(flow, prior, x, S)
-    assert abs(float(loss) - float(g["loss"])) < (1e-5 if mode == "fp32" else 1e-3)
+    assert abs(float(loss) - float(g["loss"])) < (1e-5 if mode != "bf16" else 1e-3)
     params = dict(flow.named_parameters())
     params.update({"prior/" + k: p for k, p in prior.named_parameters()})
     for i, k in enumerate(g["names"]):
@@ -76,7 +87,7 @@ def test_gradients_against_reference_golden(golden_dir, name, mode, tol, monkeyp
 
 
 @pytest.mark.parametrize("cfg", [(3, 3, 2, 4, 32, 71), (1, 3, 2, 5, 32, 72)])
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("bf16", 8e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32_simt", 2e-4), ("fp32", X3_TOL), ("bf16", 8e-2)])
 def test_gradients_against_oracle(cfg, mode, tol, monkeypatch):
     """Every gradient tensor, full comparison, on seeded inputs at a three-level shape (incl. d loss / d x)."""
     monkeypatch.setenv("NFDPM_PRECISION", mode)
@@ -86,7 +97,7 @@ def test_gradients_against_oracle(cfg, mode, tol, monkeypatch):
     loss_o, g_o, pg_o = O.train_grads(sd, psd, x_cpu, L, K, 32.0, S * S * 3.0)
     x = x_cpu.to(DEV).requires_grad_(True)
     loss = _train_step(flow, prior, x, S)
-    assert abs(float(loss) - float(loss_o)) < (1e-5 if mode == "fp32" else 1e-3)
+    assert abs(float(loss) - float(loss_o)) < (1e-5 if mode != "bf16" else 1e-3)
     worst = ("", 0.0)
     for k, p in flow.named_parameters():
         r = _rel(p.grad, g_o[k])
@@ -103,11 +114,15 @@ def test_gradients_against_oracle(cfg, mode, tol, monkeypatch):
     with torch.enable_grad():
         O.nll_bpd(sd, psd, xo, L, K, 32.0, S * S * 3.0).backward()
     assert _rel(x.grad, xo.grad) <= tol
+    if mode == "fp32":                       # the whole gradient vector, where cancellation inside single tensors averages out
+        num = sum(float((p.grad.cpu().double() - g_o[k].double()).pow(2).sum()) for k, p in flow.named_parameters())
+        den = sum(float(g_o[k].double().pow(2).sum()) for k, p in flow.named_parameters())
+        assert (num / den) ** 0.5 <= X3_TOTAL_TOL, (num / den) ** 0.5
     print("worst parameter", worst)
 
 
 @pytest.mark.parametrize("cfg", [(3, 2, 1, 2, 64, 75), (3, 3, 1, 1, 128, 76)])
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 8e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32_simt", 2e-3), ("fp32", X3_TOL), ("bf16", 8e-2)])
 def test_gradients_large_images(cfg, mode, tol, monkeypatch):
     """Images larger than one CTA (BASELINE config 4 geometry: 64x64 / 32x32 / 16x16 levels with 12 / 24 / 48 channels):
     unfused forward with stash, pixel-tiled coupling / K-A backward kernels.  fp32 tolerance 2e-3: the weight-gradient
@@ -118,12 +133,12 @@ def test_gradients_large_images(cfg, mode, tol, monkeypatch):
     x_cpu = O.seeded_input((B, c, S, S), seed + 1)
     loss_o, g_o, pg_o = O.train_grads(sd, psd, x_cpu, L, K, 32.0, S * S * 3.0)
     loss = _train_step(flow, prior, x_cpu.to(DEV), S)
-    assert abs(float(loss) - float(loss_o)) < (1e-5 if mode == "fp32" else 1e-3)
+    assert abs(float(loss) - float(loss_o)) < (1e-5 if mode != "bf16" else 1e-3)
     for k, p in flow.named_parameters():
         assert _rel(p.grad, g_o[k]) <= tol, (k, _rel(p.grad, g_o[k]))
 
 
-@pytest.mark.parametrize("mode,tol,ztol", [("fp32", 2e-4, 1e-4), ("bf16", 8e-2, 5e-3)])
+@pytest.mark.parametrize("mode,tol,ztol", [("fp32_simt", 2e-4, 1e-4), ("fp32", X3_TOL, 1e-4), ("bf16", 8e-2, 5e-3)])
 def test_ragged_shapes_mnist_28(mode, tol, ztol, monkeypatch):
     """Non-power-of-two geometry (MNIST 1x28x28, L=2: 14x14 = 196 and 7x7 = 49 pixels per image, batch 5, K=3): forward,
     inverse and every gradient against the oracle — neither level fits the whole-image GEMM tiling, ragged tail tiles."""
@@ -140,12 +155,12 @@ def test_ragged_shapes_mnist_28(mode, tol, ztol, monkeypatch):
     zo, ld_o, lp_o = O.glow_transform(sd, x_cpu, L, K, ld_o, lp_o)
     for a, b in zip(zs, zo):
         assert _rel(a, b) < ztol
-    assert torch.allclose(ld.cpu(), ld_o, rtol=1e-4 if mode == "fp32" else 2e-4)
-    assert torch.allclose(lp.cpu(), lp_o, rtol=1e-4 if mode == "fp32" else 2e-3)
-    assert float((xr.cpu() - x_cpu).abs().max()) < (1e-4 if mode == "fp32" else 5e-2)
+    assert torch.allclose(ld.cpu(), ld_o, rtol=1e-4 if mode != "bf16" else 2e-4)
+    assert torch.allclose(lp.cpu(), lp_o, rtol=1e-4 if mode != "bf16" else 2e-3)
+    assert float((xr.cpu() - x_cpu).abs().max()) < (1e-4 if mode != "bf16" else 5e-2)
     loss_o, g_o, pg_o = O.train_grads(sd, psd, x_cpu, L, K, 32.0, S * S * 3.0)
     loss = _train_step(flow, prior, x_cpu.to(DEV), S)
-    assert abs(float(loss) - float(loss_o)) < (1e-5 if mode == "fp32" else 1e-3)
+    assert abs(float(loss) - float(loss_o)) < (1e-5 if mode != "bf16" else 1e-3)
     for k, p in flow.named_parameters():
         assert _rel(p.grad, g_o[k]) <= tol, (k, _rel(p.grad, g_o[k]))
 
@@ -153,7 +168,7 @@ def test_ragged_shapes_mnist_28(mode, tol, ztol, monkeypatch):
 def test_batch_of_one_and_repeated_backward(monkeypatch):
     """B = 1 (every per-image reduction degenerates) and two training steps in a row on the same module (the stash of
     the first step is released, caches are refreshed after the parameter update)."""
-    monkeypatch.setenv("NFDPM_PRECISION", "fp32")
+    monkeypatch.setenv("NFDPM_PRECISION", "fp32_simt")
     c, L, K, B, S, seed = 3, 3, 1, 1, 32, 85
     flow, prior, sd, psd = _build(c, L, K, seed)
     x_cpu = O.seeded_input((B, c, S, S), seed + 1)
@@ -173,7 +188,7 @@ def test_batch_of_one_and_repeated_backward(monkeypatch):
 
 def test_logp_none_and_latent_gradients(monkeypatch):
     """NFBackbone-style call (logp=None, diffusion_prior/trainer.py:139): gradients arrive through the latents."""
-    monkeypatch.setenv("NFDPM_PRECISION", "fp32")
+    monkeypatch.setenv("NFDPM_PRECISION", "fp32_simt")
     c, L, K, B, S, seed = 3, 3, 1, 3, 16, 81
     flow, _, sd, _ = _build(c, L, K, seed)
     x_cpu = O.seeded_input((B, c, S, S), seed + 1)
@@ -202,7 +217,7 @@ def test_logp_none_and_latent_gradients(monkeypatch):
 def test_adam_steps_track_the_oracle(monkeypatch):
     """Three optimiser steps of the reference recipe (clip value 1, clip norm 1, Adam 1e-4; trainer.py:161-167):
     the loss trajectory follows the oracle's."""
-    monkeypatch.setenv("NFDPM_PRECISION", "fp32")
+    monkeypatch.setenv("NFDPM_PRECISION", "fp32_simt")
     c, L, K, B, S, seed = 3, 3, 1, 4, 16, 91
     flow, prior, sd, psd = _build(c, L, K, seed)
     x_cpu = O.seeded_input((B, c, S, S), seed + 1)
