@@ -330,9 +330,16 @@ int gemm_nt_tc(const void* A, int64_t lda, const void* Bw, int64_t ldb, void* D,
   }
   int bn_max = (out_dtype == NFDPM_F32) ? 128 : 256;
   if (bn_max > bn_cap) bn_max = bn_cap;
-  // few rows (deep levels): narrower tiles put more CTAs to work (measured at M = 2048, N = 512: 6.1 vs 7.2 us)
+  // few rows (deep levels): narrower tiles put more CTAs to work (measured at M = 2048, N = 512: 6.1 vs 7.2 us; round 2,
+  // per-StepFlow chain over the three levels with narrowing below 48 / 74 / 100 / 148 tiles: 172.3 / 170.1 / 170.9 / 175.4 us
+  // in the split-pair mode, 110.4 / 108.7 / 108.9 / 112.3 us in bf16)
   const int m_tiles = (M + TC_BM - 1) / TC_BM;
-  while (bn_max > 64 && N >= 2 * bn_max / 2 && m_tiles * ((N + bn_max - 1) / bn_max) <= 48 && N % (bn_max / 2) == 0) bn_max >>= 1;
+  static int narrow_below = -1;
+  if (narrow_below < 0) {
+    const char* e = getenv("NFDPM_TC_NARROW");
+    narrow_below = e ? atoi(e) : 74;
+  }
+  while (bn_max > 64 && N >= 2 * bn_max / 2 && m_tiles * ((N + bn_max - 1) / bn_max) <= narrow_below && N % (bn_max / 2) == 0) bn_max >>= 1;
   const int cpb = (out_dtype == NFDPM_BF16) ? 64 : 32;    // logical columns per 128-byte TMA store box
   const int nblk = (N + bn_max - 1) / bn_max;
   // one N block: any multiple of 16 (columns >= N are clipped by the D tensor map); several N blocks: BN must be a
