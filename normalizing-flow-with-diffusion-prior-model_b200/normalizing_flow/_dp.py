@@ -72,13 +72,14 @@ class GradAllReduce:
     def __init__(self, flow, prior: Optional[torch.nn.Module] = None, group=None):
         if not dist.is_initialized():
             raise RuntimeError("GradAllReduce needs torch.distributed.init_process_group(...) first")
-        max_ctas = int(os.environ.get("NFDPM_NCCL_MAX_CTAS", "8"))          # 0: NCCL's default communicator
+        max_ctas = int(os.environ.get("NFDPM_NCCL_MAX_CTAS", "16"))          # 0: NCCL's default communicator
         if group is None and dist.get_backend() == "nccl" and max_ctas > 0:
             # The gradient all-reduces overlap the backward: every SM an NCCL CTA occupies is one the persistent GEMM grids
             # (one CTA per SM, statically partitioned tiles) have to queue behind.  A communicator with few CTAs trades
             # collective bandwidth (irrelevant: the buckets are overlapped) for less interference.  Measured at N = 2, config-2
             # train step (tools/dp_cta_sweep.sh, profiles/r02_dp_cta_sweep.txt): exposed communication 211 us with NCCL's
-            # default, 151 / 126 / 204 / 302 us with at most 16 / 8 / 4 / 2 CTAs.
+            # default, 151 / 126 / 204 / 302 us with at most 16 / 8 / 4 / 2 CTAs; at N = 8: 375 us default, 342 / 276 / 451 us with
+            # 32 / 16 / 8.  16 is the default.
             opts = dist.ProcessGroupNCCL.Options()
             opts.config.max_ctas = max_ctas
             opts.config.min_ctas = 1
