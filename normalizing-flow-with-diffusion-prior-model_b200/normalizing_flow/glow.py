@@ -329,20 +329,45 @@ class Glow(Transform):
             return 1
         return n
 
-    def _fork_join(self, n: int, fn):
+    @staticmethod
+    def _deep_sub(B: int, h: int, w: int) -> int:
+        """Concurrent sub-batches for ONE level's StepFlow chain.  At the deep levels (8x8 and smaller) every kernel of the
+        chain is latency-bound on a fraction of the SMs (one 128-row tile per CTA: 16...128 CTAs, 8-15 us per launch of which
+        2-6 us are MMA work), and the images of a batch are independent: running the chain of several image groups on
+        concurrent streams inside the captured graph overlaps those latencies.  Level 0 stays on one stream (its persistent
+        GEMM grids already fill the GPU; splitting it was measured 6 % slower).  NFDPM_DEEP_STREAMS="n1:n2" = sub-batches
+        at 64-pixel / 16-pixel-and-smaller levels.  MEASURED SLOWER in every combination (profiles/r02_deep_streams.txt:
+        5.60 ms per config-2 step on one stream, 5.90 / 5.92 / 6.71 ms with 2:2 / 2:4 / 4:4) — the deep-level GEMMs turn out
+        to be bound by the depth of their TMA operand ring (two 32 KB stages in flight per ~1 us L2 round trip = 64 GB/s per
+        CTA), not by idle SMs, and concurrent chains compete for the same L2 — so the default is one stream ("1:1")."""
+        if h * w >= 256:
+            return 1
+        spec = os.environ.get("NFDPM_DEEP_STREAMS", "1:1").split(":")
+        try:
+            n = int(spec[0] if h * w >= 64 else spec[-1])
+        except ValueError:
+            n = 1
+        while n > 1 and (B % n != 0 or (B // n) * h * w < 256):      # whole sub-batches of at least two 128-row tiles
+            n -= 1
+        return max(n, 1)
+
+    def _fork_join(self, n: int, fn, pool: str = "_streams"):
+        """fn(0) ... fn(n-1) on n concurrent streams forked from / joined into the current one (inside a capture: parallel
+        branches of the graph).  `pool`: attribute holding the streams, so that nested forks do not share them."""
         if n == 1:
             return [fn(0)]
         cur = torch.cuda.current_stream()
-        if getattr(self, "_streams", None) is None or len(self._streams) < n:
-            self._streams = [torch.cuda.Stream() for _ in range(n)]
+        if getattr(self, pool, None) is None or len(getattr(self, pool)) < n:
+            setattr(self, pool, [torch.cuda.Stream() for _ in range(n)])
+        streams = getattr(self, pool)
         out = []
         for i in range(n):
-            s = self._streams[i]
+            s = streams[i]
             s.wait_stream(cur)
             with torch.cuda.stream(s):
                 out.append(fn(i))
         for i in range(n):
-            cur.wait_stream(self._streams[i])
+            cur.wait_stream(streams[i])
         return out
 
     def _transform_autograd(self, x, log_det_jac, logp, levels, slots, steps, ready):
@@ -552,23 +577,34 @@ class Glow(Transform):
                 cur, cur_bs, ch = st, C * P, C // 2
                 continue
             st = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)     # flow state of this level (in place)
-            first = flows[0]
-            A1, K1p = E.coupling_a1(first.affcoupling, B, C, h, w, dev)
-            # level entry: squeeze + K-A of step 0 + im2col
-            N.flow_boundary(cur, cur_bs, True, None, 0, None, None, None, first._mix.fwd_mt, first._mix.fwd_beta,
-                            st, C * P, A1, K1p, B, C, h, w, False)
-            for k, step in enumerate(flows):
-                cp = step.affcoupling
-                nxt = flows[k + 1] if k + 1 < len(flows) else None
-                if nxt is not None:
-                    A1n, K1p = E.coupling_a1(nxt.affcoupling, B, C, h, w, dev)     # same scratch buffer as A1
-                    E.coupling_boundary(cp, A1, B, C, h, w, st, C * P, ld_part[row * B:], nxt._mix.fwd_mt,
-                                        nxt._mix.fwd_beta, st, C * P, A1n, K1p, False)
-                    A1 = A1n
-                else:
-                    E.coupling_boundary(cp, A1, B, C, h, w, st, C * P, ld_part[row * B:], None, None, st, C * P,
-                                        None, 0, False)
-                row += 1
+            nsub = self._deep_sub(B, h, w) if torch.cuda.is_current_stream_capturing() else 1
+            Bs = B // nsub
+            row0 = row
+
+            def level_chain(i, cur=cur, cur_bs=cur_bs, st=st, flows=flows, C=C, h=h, w=w, P=P, Bs=Bs, row0=row0):
+                """The K StepFlows of this level for images [i*Bs, (i+1)*Bs): views of the level's tensors."""
+                src_i, st_i = cur[i * Bs:(i + 1) * Bs], st[i * Bs:(i + 1) * Bs]
+                first = flows[0]
+                A1, K1p = E.coupling_a1(first.affcoupling, Bs, C, h, w, dev)
+                # level entry: squeeze + K-A of step 0 + im2col
+                N.flow_boundary(src_i, cur_bs, True, None, 0, None, None, None, first._mix.fwd_mt, first._mix.fwd_beta,
+                                st_i, C * P, A1, K1p, Bs, C, h, w, False)
+                r = row0
+                for k, step in enumerate(flows):
+                    cp = step.affcoupling
+                    nxt = flows[k + 1] if k + 1 < len(flows) else None
+                    part = ld_part[r * B + i * Bs:]
+                    if nxt is not None:
+                        A1n, K1p = E.coupling_a1(nxt.affcoupling, Bs, C, h, w, dev)     # same scratch buffer as A1
+                        E.coupling_boundary(cp, A1, Bs, C, h, w, st_i, C * P, part, nxt._mix.fwd_mt,
+                                            nxt._mix.fwd_beta, st_i, C * P, A1n, K1p, False)
+                        A1 = A1n
+                    else:
+                        E.coupling_boundary(cp, A1, Bs, C, h, w, st_i, C * P, part, None, None, st_i, C * P,
+                                            None, 0, False)
+                    r += 1
+            self._fork_join(nsub, level_chain, pool="_deep_streams")
+            row += len(flows)
             if split is None:
                 latents.append(st)
                 break
@@ -669,25 +705,32 @@ class Glow(Transform):
         return cur
 
     def _invert_level_fast(self, flows, src, own: bool, B: int, C: int, h: int, w: int, dev) -> Tensor:
-        """K inverse StepFlows of one level with the fused kernels; returns the level's input state."""
+        """K inverse StepFlows of one level with the fused kernels; returns the level's input state.  Deep levels run as
+        concurrent sub-batches inside a captured graph (`_deep_sub`)."""
         P = h * w
         st = src if own else torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
-        last = flows[-1]
-        A1, K1p = E.coupling_a1(last.affcoupling, B, C, h, w, dev)
-        N.flow_boundary(src, C * P, False, None, 0, None, None, None, None, None, None, 0, A1, K1p, B, C, h, w,
-                        False)                     # im2col of the level's entry state
-        for k in range(len(flows) - 1, -1, -1):
-            step = flows[k]
-            cp = step.affcoupling
-            if k > 0:
-                A1n, K1p = E.coupling_a1(flows[k - 1].affcoupling, B, C, h, w, dev)
-                E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
-                                    st, C * P, A1n, K1p, True)
-                A1 = A1n
-            else:
-                E.coupling_boundary(cp, A1, B, C, h, w, src, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
-                                    st, C * P, None, 0, True)
-            src = st
+        nsub = self._deep_sub(B, h, w) if torch.cuda.is_current_stream_capturing() else 1
+        Bs = B // nsub
+
+        def level_chain(i):
+            src_i, st_i = src[i * Bs:(i + 1) * Bs], st[i * Bs:(i + 1) * Bs]
+            last = flows[-1]
+            A1, K1p = E.coupling_a1(last.affcoupling, Bs, C, h, w, dev)
+            N.flow_boundary(src_i, C * P, False, None, 0, None, None, None, None, None, None, 0, A1, K1p, Bs, C, h, w,
+                            False)                     # im2col of the level's entry state
+            for k in range(len(flows) - 1, -1, -1):
+                step = flows[k]
+                cp = step.affcoupling
+                if k > 0:
+                    A1n, K1p = E.coupling_a1(flows[k - 1].affcoupling, Bs, C, h, w, dev)
+                    E.coupling_boundary(cp, A1, Bs, C, h, w, src_i, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
+                                        st_i, C * P, A1n, K1p, True)
+                    A1 = A1n
+                else:
+                    E.coupling_boundary(cp, A1, Bs, C, h, w, src_i, C * P, None, step._mix.inv_mt, step._mix.inv_beta,
+                                        st_i, C * P, None, 0, True)
+                src_i = st_i
+        self._fork_join(nsub, level_chain, pool="_deep_streams")
         return st
 
     def _invert_core(self, latents, temperature, levels, slots, steps, ready: bool) -> Tensor:
