@@ -424,24 +424,37 @@ def coupling_boundary(cp, A1: torch.Tensor, B: int, C: int, H: int, W: int, src,
                      inverse)
 
 
-def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int, init: bool = False) -> Tuple[torch.Tensor, int]:
+#: set by coupling_rows(stash=True): the operands the backward of a stand-alone AffineCoupling needs (normalizing_flow/_modgrad.py)
+last_coupling_stash = None
+
+
+def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int, init: bool = False,
+                  stash: bool = False) -> Tuple[torch.Tensor, int]:
     """Run the coupling network of AffineCoupling ``cp`` on the first C/2 channels of ``y`` ([B,C,P], batch
     stride ``ybs``).  Returns (pm, ldp): the taps-as-N ZeroConv rows consumed by nfdpm_coupling_apply.
     ``init`` performs the data-dependent initialisation of inner ActNorms that are not initialised yet
-    (always in exact fp32)."""
+    (always in exact fp32).  ``stash``: the training form — operands in the TRAINING format, in fresh tensors that are
+    published as ``last_coupling_stash`` for the module's backward."""
+    global last_coupling_stash
     conv1, an1, conv2, an2, zc = cp._parts()
     F = conv1.weight.shape[0]
     if F % 64 != 0:
         raise ValueError(f"coupling_net_n_features must be a multiple of 64 (got {F})")
     need_init = init and not (an1._initialized() and an2._initialized())
-    dt = torch.float32 if need_init else coupling_dtype()     # the data-dependent initialisation runs in exact fp32
+    if stash and need_init:
+        coupling_rows(cp, y, ybs, B, C, H, W, init=True)          # initialise first (exact fp32), then run the stash pass
+        need_init = False
+    dt = torch.float32 if need_init else coupling_dtype(train=stash)     # the data-dependent initialisation runs in exact fp32
     cache = _pack_coupling(cp._cache, conv1.weight, conv2.weight, zc.weight, dt)
     dev = y.device
     M = B * H * W
     K1p, ldp = cp._cache.K1p, cp._cache.ldp
-    A1 = WS.get("A1", M * K1p, dt, dev)
+
+    def buf(tag, numel, dtype):
+        return torch.empty(numel, dtype=dtype, device=dev) if stash else WS.get(tag, numel, dtype, dev)
+    A1 = buf("A1", M * K1p, dt)
     N.im2col3x3(y, A1, B, C // 2, H, W, ybs, K1p)
-    h1 = WS.get("h1", M * F, dt, dev)
+    h1 = buf("h1", M * F, dt)
     if need_init and not an1._initialized():
         raw = WS.get("raw", M * F, torch.float32, dev)
         N.gemm_nt(A1, K1p, cache.w1, K1p, raw, F, M, F, K1p)
@@ -449,15 +462,18 @@ def coupling_rows(cp, y: torch.Tensor, ybs: int, B: int, C: int, H: int, W: int,
         an1._mark_initialized()
     N.gemm_nt(A1, K1p, cache.w1, K1p, h1, F, M, F, K1p, N.EPI_ACTNORM_RELU, an1.scale, an1.bias)
     w2 = cache.w2 if dt != torch.float32 else conv2.weight
-    h2 = WS.get("h2", M * F, dt, dev)
+    h2 = buf("h2", M * F, dt)
     if need_init and not an2._initialized():
         raw = WS.get("raw", M * F, torch.float32, dev)
         N.gemm_nt(h1, F, w2, F, raw, F, M, F, F)
         channel_stats(raw, 1, B, F, H * W, F, an2.scale, an2.bias)
         an2._mark_initialized()
     N.gemm_nt(h1, F, w2, F, h2, F, M, F, F, N.EPI_ACTNORM_RELU, an2.scale, an2.bias)
-    pm = WS.get("pm", M * ldp, torch.float32, dev)
+    pm = buf("pm", M * ldp, torch.float32)
     N.gemm_nt(h2, F, cache.w3, F, pm, ldp, M, ldp, F)
+    if stash:
+        from types import SimpleNamespace
+        last_coupling_stash = SimpleNamespace(A1=A1, h1=h1, h2=h2, pm=pm, dt=dt, K1p=K1p, ldp=ldp)
     return pm, ldp
 
 

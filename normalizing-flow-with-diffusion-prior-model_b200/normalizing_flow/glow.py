@@ -70,6 +70,13 @@ class StepFlow(Transform):
         self.affcoupling._run(y, ybs, t, tbs, B, C, H, W, True, None)
         N.channel_mix(t, x, self._mix.inv_mt, self._mix.inv_beta, B, C, P, tbs, xbs)
 
+    def _transform_composed(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """Under autograd a stand-alone StepFlow is the composition of its three differentiable parts, like the reference's
+        (glow.py:46-48); the fused single-kernel form below serves the no-grad call."""
+        y, log_det_jac, logp = self.actnorm.transform(x, log_det_jac, logp)
+        y, log_det_jac, logp = self.invconv2d.transform(y, log_det_jac, logp)
+        return self.affcoupling.transform(y, log_det_jac, logp)
+
     @_granular("StepFlow")
     def transform(self, x: Tensor, log_det_jac: Tensor, logp: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         x = E.check_input(x)

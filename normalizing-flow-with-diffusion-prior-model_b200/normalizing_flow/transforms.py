@@ -18,11 +18,11 @@ from .utils import ZeroConv2d, coupling_network
 
 
 class _NoBackward(torch.autograd.Function):
-    """Identity whose backward raises: granular modules (ActNorm, InvConv2d, AffineCoupling, Split, StepFlow, GlowBlock
-    called on their own) compute their FORWARD with the kernels in any grad mode — the reference's own unit tests call
-    them with autograd enabled (tests/transformations.py) — but only the whole-Glow path has backward kernels
-    (normalizing_flow/_train.py).  Back-propagating through a granular call therefore fails loudly instead of
-    silently dropping gradients."""
+    """Identity whose backward raises.  ``transform`` of the granular modules (ActNorm, InvConv2d, AffineCoupling, Squeeze,
+    Split — and StepFlow / GlowBlock, which compose them) is differentiable through normalizing_flow/_modgrad.py; ``invert``
+    has no backward kernels (the reference inverts only under ``torch.no_grad()``: sampling and decoding), so its forward
+    runs in any grad mode — the reference's own unit tests call it with autograd enabled (tests/transformations.py) —
+    and back-propagating through it fails loudly instead of silently dropping gradients."""
 
     @staticmethod
     def forward(ctx, t, what, inplace, *deps):
@@ -35,8 +35,8 @@ class _NoBackward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         raise NotImplementedError(
-            f"{ctx.what}: backward through a stand-alone transform is not implemented; train through Glow.transform "
-            f"(its autograd Function covers every parameter) or call this module under torch.no_grad().")
+            f"{ctx.what}: backward through invert() is not implemented (the reference inverts under torch.no_grad(): "
+            f"sampling and decoding); transform() is differentiable.")
 
 
 def _no_autograd(x: Tensor, mod: nn.Module, what: str) -> None:
@@ -46,12 +46,21 @@ def _no_autograd(x: Tensor, mod: nn.Module, what: str) -> None:
 
 
 def _granular(what: str):
-    """Decorator for stand-alone transform / invert methods: run the kernels without recording, then attach the
-    loud-failure node to every floating-point tensor result (in place for the accumulators that were updated in place)."""
+    """Decorator for stand-alone transform / invert methods.  Without autograd: the kernels, nothing recorded.  Under
+    autograd ``transform`` goes through the module's autograd Function (normalizing_flow/_modgrad.py; StepFlow composes its
+    three parts); ``invert`` runs the kernels without recording and attaches the loud-failure node to its result."""
     def deco(fn):
         def wrapper(self, x, *args, **kw):
             if not E.autograd_needed(x, self):
                 return fn(self, x, *args, **kw)
+            if fn.__name__ == "transform":
+                from . import _modgrad as MG
+                ld = args[0] if len(args) > 0 else kw.get("log_det_jac")
+                lp = args[1] if len(args) > 1 else kw.get("logp")
+                if what == "StepFlow":
+                    return self._transform_composed(x, ld, lp)
+                if what in MG.SUPPORTED:
+                    return MG.transform(self, what, fn, E.check_input(x), ld, lp)
             ins = [t for t in (x,) + tuple(args) + tuple(kw.values()) if isinstance(t, Tensor)]
             deps = [t for t in ins if t.requires_grad] + [p for p in self.parameters() if p.requires_grad]
             with torch.no_grad():

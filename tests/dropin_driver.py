@@ -20,7 +20,7 @@ ov = os.path.join(work, "overlay")
 nf_dir = os.path.join(ov, "normalizing_flow")
 shutil.copytree(os.path.join(ref, "normalizing_flow"), nf_dir)                      # cp -r $REF/normalizing_flow overlay_nf
 shutil.copy(os.path.join(nf_dir, "utils.py"), os.path.join(nf_dir, "_ref_utils.py"))  # keep the non-hot-path helpers
-for f in ("_native.py", "_engine.py", "_train.py", "_dp.py", "_optim.py", "base.py", "transforms.py", "glow.py", "prior.py",
+for f in ("_native.py", "_engine.py", "_train.py", "_modgrad.py", "_dp.py", "_optim.py", "base.py", "transforms.py", "glow.py", "prior.py",
           "utils.py"):
     shutil.copy(os.path.join(pkg, "normalizing_flow", f), os.path.join(nf_dir, f))
 with open(os.path.join(nf_dir, "utils.py"), "a") as fh:
