@@ -705,6 +705,27 @@ def main():
                 recs.append({"level": lvl, "C": C, "P": P, "kernel_us": us, "algorithmic_bytes": alg,
                              "achieved": alg / (us * 1e-6) / 1e9, "frac": alg / (us * 1e-6) / 1e9 / hbm,
                              "bytes_moved_incl_pm_and_im2col": moved, "moved_gbs": moved / (us * 1e-6) / 1e9})
+            # the unfused K-A kernel (fused ActNorm + invertible 1x1 conv, north-star item 2) at a size beyond L2, where it IS
+            # bandwidth-bound: x [8192, 12, 256] fp32 read once, y written once = 201 MB
+            Bk, Ck, Pk = 8192, 12, 256
+            xk = torch.randn(Bk, Ck, Pk, device=dev)
+            yk = torch.empty_like(xk)
+            mk, bk = torch.randn(Ck, Ck, device=dev) * 0.3, torch.randn(Ck, device=dev)
+            for _ in range(3):
+                N.channel_mix(xk, yk, mk, bk, Bk, Ck, Pk, Ck * Pk, Ck * Pk)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for s_, e_ in evs:
+                s_.record()
+                N.channel_mix(xk, yk, mk, bk, Bk, Ck, Pk, Ck * Pk, Ck * Pk)
+                e_.record()
+            torch.cuda.synchronize()
+            ka_us = sorted(s_.elapsed_time(e_) for s_, e_ in evs)[len(evs) // 2] * 1e3
+            ka_bytes = 8.0 * Bk * Ck * Pk
+            ka = {"kernel": "chanmix kernel (nfdpm_channel_mix: fused ActNorm + 1x1 conv, unfused form) on [8192,12,256] fp32",
+                  "bytes_per_launch": ka_bytes, "kernel_us": ka_us, "achieved": ka_bytes / (ka_us * 1e-6) / 1e9,
+                  "frac": ka_bytes / (ka_us * 1e-6) / 1e9 / hbm,
+                  "note": "inputs larger than L2 (201 MB), timed alone with CUDA events; not on the default fused path at batch 128"}
+            del xk, yk
             tr = ncu_traffic("flow_boundary_level1")
             top = recs[1]
             return {"bound": "hbm", "kernel": "flow_boundary_kernel<coupling, im2col sink> (levels 1-2 of the default path; "
@@ -714,7 +735,7 @@ def main():
                     "what": "algorithmic bytes = read x + write y = 8*C*P per image per StepFlow (SURVEY 8d); the kernel also "
                             "reads the ZeroConv taps (36*C*P) and writes the next im2col rows; one CTA per image: "
                             "latency/issue-bound at batch 128, not bandwidth-bound",
-                    "per_level": recs, "peak_source": f"{src} copy bandwidth",
+                    "per_level": recs, "bandwidth_bound_size": ka, "peak_source": f"{src} copy bandwidth",
                     "traffic": tr.get("bytes") if tr else None, "traffic_source": tr.get("source") if tr else None}
         roof_hbm = boundary_roofline()
 
