@@ -1,5 +1,5 @@
 """In-graph time (16 back-to-back launches per replay) of the coupling-network GEMM shapes of BASELINE config 2.
-Run under different switches (NFDPM_TC2=1, NFDPM_TC_BN=...) to compare GEMM variants."""
+Run under different switches (NFDPM_TC_BN=..., NFDPM_TC_SPLIT=0, NFDPM_TC_DEEP=0|2, NFDPM_TC_NARROW=...) to compare GEMM variants."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "normalizing-flow-with-diffusion-prior-model_b200"))
