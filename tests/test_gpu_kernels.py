@@ -556,6 +556,45 @@ def test_gemm_tn_split_pairs(M, N1, lda, N2, ldb, mode, out_c):
     assert float((got - want).norm() / want.norm()) < 1e-5
 
 
+@pytest.mark.parametrize("B,C,H,W", [(3, 12, 16, 16), (5, 24, 8, 8), (4, 48, 4, 4), (2, 12, 32, 32)])
+def test_coupling_bwd_operand_formats_agree(B, C, H, W):
+    """nfdpm_coupling_bwd writes d(pm) as the K operand of the ZeroConv dgrad / wgrad GEMMs in the training format: the bf16
+    and split-pair sinks must hold exactly the encodings of the fp32 sink's values (one-CTA-per-image and tiled forms), and
+    every other output must not depend on the sink format."""
+    P, Ch = H * W, C // 2
+    ldp = (9 * C + 15) // 16 * 16
+    Kp3 = (9 * C + 63) // 64 * 64
+    M = B * P
+    dy = rnd(B, C, P, seed=1).to(DEV)
+    dld = rnd(B, seed=2).to(DEV)
+    u = rnd(B, C, P, seed=3).to(DEV)
+    pm = (rnd(M, ldp, seed=4) * 0.1).to(DEV)
+    bias3, logs3 = rnd(C, seed=5, scale=0.1).to(DEV), rnd(C, seed=6, scale=0.1).to(DEV)
+    T_c = N.coupling_bwd_tiles(C, H, W)
+    outs = {}
+    for dt in (torch.float32, torch.bfloat16, N.SPLIT):
+        du = torch.zeros(B, C, P, device=DEV)
+        dpm = torch.full((M, Kp3), 7, dtype=dt, device=DEV)
+        dpar = torch.zeros(B * T_c * 2 * C, device=DEV)
+        if T_c == 1:
+            db, dl = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            N.coupling_bwd(dy, C * P, dld, u, C * P, pm, ldp, bias3, logs3, du, C * P, dpm, Kp3, dpar, B, C, H, W, db, dl)
+        else:
+            N.coupling_bwd(dy, C * P, dld, u, C * P, pm, ldp, bias3, logs3, du, C * P, dpm, Kp3, dpar, B, C, H, W,
+                           dp_scratch=torch.empty(M * C, device=DEV))
+            db, dl = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            N.reduce_rows2(dpar, db, dl, B * T_c, C, C, 2 * C)
+        sync()
+        outs[dt] = (du.cpu(), dpm.cpu(), db.cpu(), dl.cpu())
+    du32, dpm32, db32, dl32 = outs[torch.float32]
+    assert float(dpm32[:, 9 * C:].abs().max()) == 0.0 and float(dpm32.abs().max()) > 0
+    for dt in (torch.bfloat16, N.SPLIT):
+        du_, dpm_, db_, dl_ = outs[dt]
+        assert torch.equal(du_, du32) and torch.equal(db_, db32) and torch.equal(dl_, dl32)
+    assert torch.equal(outs[torch.bfloat16][1].float(), dpm32.bfloat16().float())
+    assert torch.equal(outs[N.SPLIT][1], SP.encode(dpm32))
+
+
 @pytest.mark.parametrize("M,Nn", [(300, 512), (4096, 512), (77, 64)])
 def test_actnorm_relu_bwd_split_pairs(M, Nn):
     """(fp32 dh, split-pair h) -> split-pair dpre + column partials == the fp32 kernel on the decoded operands."""
