@@ -325,6 +325,7 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
         # ActNorm partial-sum buffers: one per (buffer set, layer) so their reductions can run on the side stream too
         an_part_b = [[torch.empty(n_cta * 2 * F, **f32) for _ in range(2)] for _ in range(nbuf)]
         keep = []                                  # scratch of the mix_param_grad launches (alive until the level is done)
+        bucket = BUCKET_STEPS if bucket_done is not None else K      # without a data-parallel hook: one fold per level
         T_c, T_m = N.coupling_bwd_tiles(C, h, w), N.mix_bwd_tiles(C, h, w)     # pixel tiles per image (1: image per CTA)
         dpar3 = torch.empty(B * T_c * 2 * C, **f32)
         dp_scratch = torch.empty(M * C, **f32) if T_c > 1 else None
@@ -407,10 +408,10 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
             if not (ablate & 4):
                     N.mix_bwd(du, C * P, dA1, K1p, lv.x[k], C * P, step._mix.fwd_mt, dxb, C * P, mix_part[k], B, C, h, w)
             dy = dxb
-            if k % BUCKET_STEPS == 0:
+            if k % bucket == 0:
                 # a bucket of StepFlows [k, k_hi] is complete once their InvConv / ActNorm parameter gradients are folded
-                # (main stream) and their weight gradients have run (side stream)
-                k_hi = min(k + BUCKET_STEPS, K) - 1
+                # and their weight gradients have run (both on the side stream)
+                k_hi = min(k + bucket, K) - 1
                 items = []
                 for kk in range(k, k_hi + 1):
                     stp = flows[kk]
@@ -422,7 +423,8 @@ def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional
                                                dld_sum=dld_sum.data_ptr(), P=float(P), pad_=0,
                                                d_weight=sink.get(wgt).data_ptr(), d_scale=sink.get(sc).data_ptr(),
                                                d_bias=sink.get(bi).data_ptr(), scratch=scratch.data_ptr()))
-                N.mix_param_grad(items)
+                # (side stream: the fold feeds only the optimiser / the all-reduce, and one launch is ~50 us of latency)
+                wgrad(lambda items=items: N.mix_param_grad(items))
                 if bucket_done is not None:
                     first_p = next(flows[k].parameters())
                     last_mod = flows[k_hi] if (k_hi < K - 1 or split is None or split.conv is None) else split
