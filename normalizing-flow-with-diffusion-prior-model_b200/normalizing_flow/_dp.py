@@ -207,7 +207,7 @@ class GradAllReduce:
 
     def describe(self) -> str:
         from . import _train as T
-        return (f"NCCL AVG on buckets of {T.BUCKET_STEPS} StepFlows of the flat gradient buffer ({self.launched} per step, "
+        return (f"NCCL AVG on buckets of up to {T.BUCKET_STEPS} StepFlows of the flat gradient buffer ({self.launched} per step, "
                 f"last one {self.last_bucket_bytes / 1e6:.1f} MB), launched from inside the backward on a communication "
                 f"stream as soon as a bucket's last gradient kernel is enqueued")
 

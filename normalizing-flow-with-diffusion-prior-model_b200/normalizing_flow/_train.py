@@ -227,9 +227,12 @@ def _strip_cols(src: Tensor, out: Tensor, rows: int, ld: int, cols: int) -> None
     N.pack_matrix(src, out, rows, 1, cols, ld, 0, 1, cols, rows)
 
 
-#: StepFlows per gradient bucket of the data-parallel all-reduce (``bucket_done``): K = 16 gives four buckets per level, the
-#: last (exposed) one of an L3/K16 CIFAR model is 4 x 0.35 M floats = 5.5 MB instead of a whole level's 22 MB
-BUCKET_STEPS = int(os.environ.get("NFDPM_BUCKET_STEPS", "4"))
+#: StepFlows per gradient bucket of the data-parallel all-reduce (``bucket_done``).  Measured at N = 2 on the config-2 step
+#: (profiles/r02_dp_cta_sweep.txt): 2 / 4 / 8 / 16 StepFlows per bucket -> 9.16 / 9.01 / 8.88 / 8.70 ms per step (N = 1 on the
+#: same box: 8.73 ms).  Finer buckets shorten the last, exposed all-reduce (22 MB -> 5.6 MB at 4) but every bucket costs a
+#: parameter-gradient fold launch, stream events and an NCCL kernel that takes SMs from the persistent GEMM grids, which
+#: outweighs it — so the default is one bucket per level (K = 16 and larger values mean "the whole level").
+BUCKET_STEPS = int(os.environ.get("NFDPM_BUCKET_STEPS", "16"))
 
 
 def backward_train(glow, st: Stash, d_lat: List[Optional[Tensor]], dld: Optional[Tensor], dlp: Optional[Tensor],
