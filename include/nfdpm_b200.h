@@ -113,6 +113,8 @@ int nfdpm_copy_channels(const float* src, float* dst, int B, int Cn, int P, int6
  *   ZeroConv3x3(512->C): "taps as N": PM[m, tap*C+co] = sum_ci h2[m,ci]*W3[co,ci,tap] (one GEMM, N=9C);
  *                      the 3x3 gather-add over neighbouring pixels happens in nfdpm_coupling_apply.
  */
+ /* (out_dtype of nfdpm_im2col3x3 / nfdpm_pack_matrix / nfdpm_pack_batch and the a1_dtype of the step-boundary entry points:
+ *  NFDPM_F32, NFDPM_BF16 or NFDPM_BF16X2; for split pairs ld_out % 32 == 0.) */
 int nfdpm_im2col3x3(const float* x, void* out, int out_dtype, int B, int Cin, int H, int W, int64_t x_bstride,
                     int64_t ld_out, nfdpm_stream_t stream);
 
@@ -224,7 +226,7 @@ int nfdpm_nchw_to_rows(const float* x, void* out, int out_dtype, int B, int Cc, 
  */
 /* Affine coupling + log-det backward (transforms.py:179-184).  dy [B,C,P] grad of the coupling output, dld [B] grad of
  * log_det_jac (may be NULL), u [B,C,P] coupling input, pm as in the forward.  Outputs: du [B,C,P] (first half = dy_a;
- * the coupling-net part is added by nfdpm_mix_bwd), dpm [B*P, ld_dpm] (F32 or BF16, columns >= 9C zero-filled: the
+ * the coupling-net part is added by nfdpm_mix_bwd), dpm [B*P, ld_dpm] (F32, BF16 or BF16X2, columns >= 9C zero-filled: the
  * K operand of the ZeroConv dgrad GEMM), dpar [B][2C] per-image partials (dbias3[C], dlogs3[C]).  With `counter` (one
  * zero-initialised int32, re-armed by the kernel) the last CTA sums dpar over the images in order into dbias[C] /
  * dlogs[C]; with counter == NULL reduce dpar with nfdpm_reduce_rows2. */
@@ -236,7 +238,7 @@ int nfdpm_coupling_bwd(const float* dy, int64_t dy_bs, const float* dld, const f
  * with nfdpm_reduce_rows2), dp_scratch [B*H*W*C] floats is required and counter must be NULL. */
 int nfdpm_coupling_bwd_tiles(int C, int H, int W);
 /* ActNorm+ReLU backward on rows (utils.py:69,84-87): dpre = dh*(h>0)*exp(scale); part[cta][2N] partial d(scale), d(bias);
- * ctas = ceil(M/rows_per_cta). */
+ * ctas = ceil(M/rows_per_cta).  dtypes: any mix of F32 / BF16, or the fp32-faithful form (F32 dh, BF16X2 h) -> BF16X2 dpre. */
 int nfdpm_actnorm_relu_bwd(const void* dh, int dh_dtype, int64_t ld_dh, const void* h, int h_dtype, int64_t ld_h,
                            const float* scale, void* dpre, int o_dtype, int64_t ld_o, float* part, int M, int N,
                            int rows_per_cta, nfdpm_stream_t stream);
@@ -261,7 +263,9 @@ typedef struct {
   float* d_weight; float* d_scale; float* d_bias; float* scratch; /* scratch: C*C + C floats */
 } nfdpm_mix_grad_item;
 int nfdpm_mix_param_grad(const nfdpm_mix_grad_item* items_host, int n, nfdpm_stream_t stream);
-/* Weight gradients: D[N1,N2] (+)= sum_m A[m,N1]*B[m,N2] (A, B row-major, F32 or BF16; D fp32 with ldd == N2).
+/* Weight gradients: D[N1,N2] (+)= sum_m A[m,N1]*B[m,N2] (A, B row-major, F32, BF16 or both BF16X2; D fp32 with ldd == N2).
+ * Split pairs (needs counters): the tensor-core accumulator holds hi*hi, hi*lo, lo*hi, lo*lo of every logical element and the
+ * in-kernel reduction adds the four: the exact product of the represented values.
  * ws: nfdpm_gemm_tn_workspace(M,N1,N2,NULL) floats.  counters (may be NULL): >= 1024 int32, ZERO before the first use
  * and private to one stream; with it the bf16 tensor-core path sums its split-M partial slabs inside the GEMM kernel
  * (the CTAs of an output tile wait for each other; fixed slab order, so the result stays bitwise reproducible) instead
